@@ -1,0 +1,114 @@
+/*
+ * spx_oracle.h -- C API of the CPU oracle for SP-SLAM's plane-extraction front end.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * PARITY UNPINNED: the arithmetic of this path lives in PCL 1.8.0 (pinned by the reference's
+ * build.sh:4, README.md:25, CMakeLists.txt:42), which is neither vendored in /root/reference nor
+ * installed here, and the reference ships no tests or golden vectors for it.  This oracle restates
+ * the reference's own code (src/Frame.cc:854-1144) and the published PCL 1.8.0 algorithms it
+ * calls (see spx_oracle.cpp for per-function citations and the list of under-determined choices).
+ */
+#ifndef SPX_ORACLE_H
+#define SPX_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_config {
+    /* YAML keys read through Config::Get (Examples/RGB-D/TUM1.yaml:73-78,99-100) */
+    int32_t cloud_dis;          /* Cloud.Dis                src/Frame.cc:856 */
+    int32_t min_size;           /* Plane.MinSize            src/Frame.cc:888 */
+    float   angle_thr_deg;      /* Plane.AngleThreshold     src/Frame.cc:889 */
+    float   dist_thr;           /* Plane.DistanceThreshold  src/Frame.cc:890 */
+    double  line_ratio;         /* Line.Ratio               src/Frame.cc:941 */
+    float   line_dist_thr;      /* Line.DistanceThreshold   src/Frame.cc:942 */
+    /* Frame statics (src/Frame.cc:169-172) and image bounds (src/Frame.cc:536-564) */
+    float fx, fy, cx, cy;
+    float min_x, max_x, min_y, max_y;
+    /* hard-coded in src/Frame.cc:881-882,945 */
+    float   max_depth_change_factor;   /* 0.05f */
+    float   normal_smoothing_size;     /* 10.0f */
+    int32_t ransac_max_iter;           /* 1000  */
+    int32_t enable_supposed;           /* run GeneratePlanesFromBoundries (src/Frame.cc:194) */
+} orc_config;
+
+/* 16-byte packed point: xyz + packed rgba (a<<24|r<<16|g<<8|b), the payload of pcl::PointXYZRGB */
+typedef struct orc_point { float x, y, z; uint32_t rgba; } orc_point;
+
+typedef struct orc_ctx orc_ctx;
+
+void      orc_default_config(orc_config *cfg);
+orc_ctx * orc_create(const orc_config *cfg);
+void      orc_destroy(orc_ctx *);
+
+/* Run the whole path on one depth image (CV_32F metres, row-major, pitch in floats = cols).
+ * normals_in: NULL, or 3*N floats (nx[N],ny[N],nz[N] SoA) to bypass normal estimation
+ * ("feed the reference's normals" mode).  Returns 0. */
+int orc_run(orc_ctx *, const float *depth, int rows, int cols, const float *normals_in);
+
+/* ---- intermediates of the last orc_run (sizes: N = width*height of the organized cloud) ---- */
+void   orc_dims(const orc_ctx *, int *width, int *height);
+void   orc_get_cloud(const orc_ctx *, float *x, float *y, float *z);          /* N each */
+void   orc_get_distance_map(const orc_ctx *, float *dist);                    /* N, unclamped */
+void   orc_get_normals(const orc_ctx *, float *nx, float *ny, float *nz);     /* N each, NaN = invalid */
+void   orc_get_plane_d(const orc_ctx *, float *d);                            /* N */
+int    orc_get_labels_raw(const orc_ctx *, uint32_t *labels);                 /* N; returns label_indices.size() */
+void   orc_get_labels_refined(const orc_ctx *, uint32_t *labels);             /* N */
+/* models accepted by OrganizedMultiPlaneSegmentation::segment (before SP-SLAM's post filter) */
+int    orc_num_models(const orc_ctx *);
+void   orc_get_model(const orc_ctx *, int i, float coef[4], float centroid[3], float cov[9],
+                     float *curvature, uint32_t *label, int *n_inliers_segment,
+                     int *n_inliers_refined, int *n_contour);
+void   orc_get_model_inliers(const orc_ctx *, int i, int32_t *idx);           /* n_inliers_refined */
+void   orc_get_model_contour(const orc_ctx *, int i, int32_t *idx);           /* n_contour */
+/* was the SAT arithmetic exact (order independent)?  1 = every fp64 partial sum was exact */
+int    orc_sat_exact(const orc_ctx *);
+
+/* ---- final Frame fields (src/Frame.cc:187,199; include/Frame.h:223-244) ---- */
+int    orc_num_real_planes(const orc_ctx *);     /* mnRealPlaneNum */
+int    orc_num_planes(const orc_ctx *);          /* mnPlaneNum     */
+void   orc_get_plane(const orc_ctx *, int i, float coef[4], int *n_points, int *n_boundary,
+                     int *src_model /* model index for real planes, parent plane for supposed */);
+void   orc_get_plane_points(const orc_ctx *, int i, orc_point *pts);
+void   orc_get_plane_boundary(const orc_ctx *, int i, orc_point *pts);
+
+/* ---- RANSAC line log of GeneratePlanesFromBoundries: one record per segLine.segment call ---- */
+typedef struct orc_line_rec {
+    int32_t plane;          /* index into mvBoundaryPoints being processed */
+    int32_t round;          /* j in 0..3 */
+    int32_t n_points;       /* size of boundPoints at the call */
+    int32_t iterations;     /* RANSAC iterations_ at exit */
+    int32_t n_inliers;      /* refined inlier count returned by segment() */
+    int32_t in_range;       /* LineInRange */
+    int32_t is_border;      /* IsBorderLine (only evaluated if in_range) */
+    int32_t emitted;        /* CaculatePlanes returned true */
+    float   coef[6];        /* optimised line: centroid + direction */
+} orc_line_rec;
+int    orc_num_line_recs(const orc_ctx *);
+void   orc_get_line_recs(const orc_ctx *, orc_line_rec *out);
+
+/* seconds spent in the two Timer sections of the last run (src/Frame.cc:184-197) */
+void   orc_get_times(const orc_ctx *, double *t_plane, double *t_splane);
+
+/* ---- stage-level entry points used by known-answer tests ---- */
+/* two-pass chamfer of PCL's computeFeature on a caller-supplied mask (0 = edge) */
+void   orc_chamfer(const uint8_t *mask, int width, int height, float *dist);
+/* pcl::eigen33(mat, eigenvalue, eigenvector): smallest eigenpair of a symmetric 3x3 (row-major) */
+void   orc_eigen33_smallest(const float cov[9], float *eigenvalue, float eigenvector[3]);
+/* pcl::eigen33(mat, evals) + computeCorrespondingEigenVector(mat, evals[2]) */
+void   orc_eigen33_largest(const float cov[9], float evals[3], float eigenvector[3]);
+/* SACSegmentation<LINE>::segment on a point list; returns n_inliers, fills coef[6], inlier idx, iterations */
+int    orc_sac_line(const orc_point *pts, int n, double threshold, int max_iter,
+                    float coef[6], int32_t *inliers, int *iterations);
+/* the index pairs RANSAC would draw for a cloud of n points, ignoring isSampleGood rejections */
+void   orc_ransac_draws(int n, int n_draws, int32_t *pairs /* 2*n_draws */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
