@@ -1,0 +1,168 @@
+/*
+ * spx.h -- C ABI of the B200-native plane-extraction front end (drop-in for SP-SLAM's PCL path).
+ *
+ * The reference has no FFI: the path is two Frame member functions that fill public Frame fields
+ * (/root/reference/src/Frame.cc:186,194; fields at /root/reference/include/Frame.h:223-244).  Each entry point
+ * below names the reference interface it replaces.  Plain pointers and sizes only; the shared library
+ * (sp_slam_b200/libspx.so) is sm_100a CUDA with no CPU fallback: every call fails with SPX_ERR_CUDA when no
+ * usable device is present.
+ */
+#ifndef SPX_H
+#define SPX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPX_VERSION 100
+
+/* per-frame capacities (a frame exceeding one sets SPX_FRAME_OVERFLOW in spx_frame_header.flags) */
+#define SPX_MAX_CAND    96   /* connected components larger than Plane.MinSize                    */
+#define SPX_MAX_MODELS  64   /* planes accepted by the curvature test                             */
+#define SPX_MAX_PLANES  128  /* real + supposed planes (mvPlaneCoefficients.size())               */
+#define SPX_MAX_LINES   4    /* line fits per real plane (src/Frame.cc:962)                       */
+
+enum {
+    SPX_OK = 0,
+    SPX_ERR_ARG = 1,       /* bad argument (null pointer, size beyond the context's capacity, ...) */
+    SPX_ERR_CUDA = 2,      /* CUDA runtime error or no device; see spx_last_error()                */
+    SPX_ERR_STATE = 3      /* call order violated (e.g. results fetched before an extract)         */
+};
+
+enum { SPX_FRAME_OVERFLOW = 1u };
+
+/* Thresholds the reference reads from YAML through Config::Get (Examples/RGB-D/TUM1.yaml:73-78,99-100), the Frame
+ * statics (src/Frame.cc:169-177,536-564) and the constants hard-coded in src/Frame.cc:881-882,945. */
+typedef struct spx_config {
+    int32_t cloud_dis;                 /* Cloud.Dis                 src/Frame.cc:856 */
+    int32_t min_size;                  /* Plane.MinSize             src/Frame.cc:888 */
+    float   angle_thr_deg;             /* Plane.AngleThreshold      src/Frame.cc:889 */
+    float   dist_thr;                  /* Plane.DistanceThreshold   src/Frame.cc:890 */
+    double  line_ratio;                /* Line.Ratio                src/Frame.cc:941 */
+    float   line_dist_thr;             /* Line.DistanceThreshold    src/Frame.cc:942 */
+    float   fx, fy, cx, cy;            /* Frame::fx..cy             src/Frame.cc:169-172 */
+    float   min_x, max_x, min_y, max_y;/* Frame::mnMinX..mnMaxY     src/Frame.cc:536-564 */
+    float   max_depth_change_factor;   /* 0.05f                     src/Frame.cc:881 */
+    float   normal_smoothing_size;     /* 10.0f (only 10 is supported)  src/Frame.cc:882 */
+    int32_t ransac_max_iter;           /* 1000                      src/Frame.cc:945 */
+    int32_t enable_supposed;           /* 0 skips GeneratePlanesFromBoundries (src/Frame.cc:194) */
+    /* capacity of the context */
+    int32_t max_frames;                /* frames per batch */
+    int32_t max_rows, max_cols;        /* depth image size */
+    int32_t device;                    /* CUDA device ordinal */
+} spx_config;
+
+/* payload of pcl::PointXYZRGB: xyz + rgba packed as (a<<24 | r<<16 | g<<8 | b) */
+typedef struct spx_point { float x, y, z; uint32_t rgba; } spx_point;
+
+/* one entry of mvPlaneCoefficients / mvPlanePoints / mvBoundaryPoints (include/Frame.h:223-230) */
+typedef struct spx_plane {
+    float    coef[4];        /* unit normal + d, d >= 0 (src/Frame.cc:918-919,1087-1089) */
+    int32_t  n_points;       /* mvPlanePoints[i].points.size()    */
+    int32_t  n_boundary;     /* mvBoundaryPoints[i].points.size() */
+    int64_t  points_off;     /* offset into spx_batch_result.points   */
+    int64_t  boundary_off;   /* offset into spx_batch_result.boundary */
+    int32_t  src;            /* real plane: index of the segmentation model; supposed plane: parent plane index */
+    int32_t  is_supposed;
+} spx_plane;
+
+typedef struct spx_frame_header {
+    int32_t  n_real;         /* mnRealPlaneNum (src/Frame.cc:187) */
+    int32_t  n_planes;       /* mnPlaneNum     (src/Frame.cc:199) */
+    int32_t  first_plane;    /* index of this frame's first entry in spx_batch_result.planes */
+    uint32_t flags;
+} spx_frame_header;
+
+/* Results of the last extract call; all pointers are host memory owned by the context, valid until the next
+ * extract / fetch / destroy on that context. */
+typedef struct spx_batch_result {
+    int32_t  n_frames;
+    int32_t  n_planes_total;
+    int64_t  n_points_total;
+    int64_t  n_boundary_total;
+    const spx_frame_header *frames;
+    const spx_plane        *planes;
+    const spx_point        *points;
+    const spx_point        *boundary;
+} spx_batch_result;
+
+typedef struct spx_ctx spx_ctx;
+
+/* fills the reference's defaults (TUM1.yaml) and capacity 1 frame of 480x640 on device 0 */
+void spx_default_config(spx_config *cfg);
+
+/* replaces: Config::SetParameterFile + the Frame statics set on the first frame (src/Frame.cc:162-177) */
+int  spx_create(const spx_config *cfg, spx_ctx **out);
+void spx_destroy(spx_ctx *ctx);
+const char *spx_last_error(const spx_ctx *ctx);   /* ctx may be NULL: error of the last failed spx_create */
+
+/* Use a caller-owned CUDA stream (cudaStream_t) for all work of this context; NULL restores the context's own. */
+int spx_set_stream(spx_ctx *ctx, void *cuda_stream);
+
+/* replaces: Frame::ComputePlanesFromOrganizedPointCloud + Frame::GeneratePlanesFromBoundries for one frame
+ * (src/Frame.cc:186-201).  depth: HOST memory, CV_32F metres, `rows` x `cols`, row pitch in bytes.  Host->device
+ * copy, kernels and device->host copy of the results all happen inside the call. */
+int spx_extract(spx_ctx *ctx, const float *depth, int rows, int cols, size_t pitch_bytes, spx_batch_result *out);
+
+/* the same for `n_frames` frames of one sequence (offline processing, frames are independent);
+ * frame f starts at (const char*)depth + f * frame_stride_bytes */
+int spx_extract_batch(spx_ctx *ctx, const float *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
+                      size_t frame_stride_bytes, spx_batch_result *out);
+
+/* device-resident variant: `depth_dev` is DEVICE memory; only kernels run (asynchronously on the context's stream),
+ * results stay on the device until spx_fetch_results (which synchronises and copies them to the host). */
+int spx_extract_batch_device(spx_ctx *ctx, const float *depth_dev, int n_frames, int rows, int cols,
+                             size_t pitch_bytes, size_t frame_stride_bytes);
+int spx_fetch_results(spx_ctx *ctx, spx_batch_result *out);
+/* only the frame headers and plane records (coefficients and counts), not the clouds */
+int spx_fetch_planes(spx_ctx *ctx, spx_batch_result *out);
+
+/* "feed the reference's normals": like spx_extract for one frame, but integral-image normal estimation is replaced by
+ * the caller's normals (HOST memory, 3*N floats: nx[N], ny[N], nz[N], N = organized cloud size, NaN = invalid). */
+int spx_segment_from_normals(spx_ctx *ctx, const float *depth, int rows, int cols, size_t pitch_bytes,
+                             const float *normals, spx_batch_result *out);
+
+/* organized-cloud size for an image: width = ceil(cols / Cloud.Dis), height = ceil(rows / Cloud.Dis) (src/Frame.cc:873-874) */
+int spx_cloud_dims(const spx_ctx *ctx, int rows, int cols, int *width, int *height);
+
+/* replaces: Timer::SetTPlane / SetTSPlane (src/Frame.cc:184-197): device time in seconds of the two sections of the
+ * last extract call (whole batch), measured with CUDA events on the context's stream. */
+int spx_get_times(spx_ctx *ctx, double *t_plane, double *t_splane);
+/* number of kernel launches issued by the last extract call */
+int spx_last_launch_count(const spx_ctx *ctx);
+
+/* ---- debug taps for the parity tests: intermediates of frame `frame` of the last extract call, copied to host ---- */
+int spx_get_cloud(spx_ctx *ctx, int frame, float *x, float *y, float *z);                 /* N each */
+int spx_get_distance_map(spx_ctx *ctx, int frame, float *dist);                           /* N, min(PCL distance map, 10) */
+int spx_get_normals(spx_ctx *ctx, int frame, float *nx, float *ny, float *nz, float *plane_d);
+int spx_get_labels_raw(spx_ctx *ctx, int frame, uint32_t *labels, int *n_label_lists);    /* CCL labels before refine */
+int spx_get_plane_ids(spx_ctx *ctx, int frame, int8_t *ids);     /* after refine: model index per pixel, -1 = none */
+
+typedef struct spx_model_info {
+    float    coef[4];          /* OrganizedMultiPlaneSegmentation model_coefficients (sign as PCL leaves it) */
+    float    centroid[3];
+    float    cov[9];
+    float    curvature;
+    uint32_t label;            /* CCL label of the component */
+    int32_t  n_segment;        /* inliers after segment() */
+    int32_t  n_inliers;        /* inliers after refine()  */
+    int32_t  n_contour;
+} spx_model_info;
+int spx_get_models(spx_ctx *ctx, int frame, spx_model_info *models /* SPX_MAX_MODELS */, int *n_models);
+int spx_get_model_inliers(spx_ctx *ctx, int frame, int model, int32_t *idx /* n_inliers */);
+int spx_get_model_contour(spx_ctx *ctx, int frame, int model, int32_t *idx /* n_contour */);
+
+typedef struct spx_line_info {
+    int32_t plane, round, n_points, iterations, n_inliers, in_range, is_border, emitted;
+    float   coef[6];
+} spx_line_info;
+/* one record per SACSegmentation::segment call of GeneratePlanesFromBoundries, in the reference's call order */
+int spx_get_lines(spx_ctx *ctx, int frame, spx_line_info *lines /* SPX_MAX_MODELS*SPX_MAX_LINES */, int *n_lines);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

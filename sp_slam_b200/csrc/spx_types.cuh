@@ -1,0 +1,126 @@
+// spx_types.cuh -- device-side records shared by the kernels and the host API.
+#pragma once
+#include <cstdint>
+#include "../../include/spx.h"
+
+namespace spx {
+
+// geometry + thresholds, passed by value to every kernel
+struct Params {
+    // depth image
+    int rows, cols;
+    size_t pitch;          // bytes
+    size_t frame_stride;   // bytes
+    int n_frames;
+    // organized cloud (src/Frame.cc:856-874)
+    int dis, w, h, N;
+    float fx, fy, cx, cy;
+    float min_x, max_x, min_y, max_y;
+    float mdcf;            // max depth change factor
+    int   min_size;
+    float ang_cos;         // cosf(float(0.017453 * AngTh))   src/Frame.cc:900
+    float dist_thr;        // Plane.DistanceThreshold
+    double line_ratio;
+    double line_thr;       // double(float Line.DistanceThreshold)
+    int   ransac_max_iter;
+    int   enable_supposed;
+    int   n_grid;          // iterations of the `for(float i=-0.25;i<0.25;i=i+0.01)` loop (src/Frame.cc:1095)
+    // per-frame arena capacities (elements)
+    int contour_cap;       // contour index arena (2N + 16*SPX_MAX_MODELS)
+    int pts_cap;           // point arena
+    int bnd_cap;           // boundary arena
+};
+
+struct Cand {              // connected component with size > Plane.MinSize
+    int   root;            // minimum pixel index of the component
+    int   label;           // PCL label = rank of the component by first raster pixel
+    int   size;
+    int   idx_off;         // offset of its raster-ordered index list in the frame's cand_idx arena
+    float vec[3];          // smallest eigenvector (sign as eigen33 leaves it)
+    float eigenvalue;
+    float centroid[3];
+    float curvature;
+    float cov[9];
+};
+
+struct Model {             // accepted by the curvature test (model_coefficients[i] of segment())
+    float coef[4];
+    float centroid[3];
+    float curvature;
+    float cov[9];
+    int   label;
+    int   root;
+    int   n0;              // inliers after segment()
+    int   n1, n2;          // claimed in refine pass 1 / pass 2
+    int   cand_off;        // raster-ordered originals in cand_idx
+    int   last_inlier;     // inlier_indices[i].indices.back() after refine
+    int   contour_off;     // slice of the frame's contour arena (capacity 2*(n0+n1+n2)+16)
+    int   n_contour;
+    int   plane;           // index into planes[] after the post filter, -1 = dropped by PlaneNotSeen
+    int   n_rounds;        // SACSegmentation::segment calls made on this model's contour (0..4)
+};
+
+struct Line {              // one SACSegmentation::segment call of GeneratePlanesFromBoundries
+    int   model;           // segmentation model whose contour is being fitted
+    int   round;
+    int   n_points, iterations, n_inliers, in_range, is_border, emitted;
+    int   pts_off;         // line inlier points in the frame's line arena
+    float coef[6];
+};
+
+struct PlaneRec {          // device-side spx_plane (frame-local offsets)
+    float coef[4];
+    int   n_points, n_boundary;
+    int   points_off, boundary_off;
+    int   src;
+    int   is_supposed;
+    int   line;            // supposed: index into lines[]; real: -1
+    int   pad;
+};
+
+struct FrameCtl {
+    int n_labels;          // label_indices.size() = number of components + 1
+    int n_cand;
+    int n_models;
+    int n_real, n_planes;
+    unsigned flags;
+    int pts_used, bnd_used;
+    int n_lines;
+    int pad[3];
+    Cand     cand[SPX_MAX_CAND];
+    Model    models[SPX_MAX_MODELS];
+    PlaneRec planes[SPX_MAX_PLANES];
+    Line     lines[SPX_MAX_MODELS * SPX_MAX_LINES];
+};
+
+// all device buffers of a context; per-frame arrays are frame-major (frame f at f * stride)
+struct Buffers {
+    float *px, *py, *pz;          // organized cloud, N per frame
+    float *dist;                  // chamfer distance, clamped at 10
+    float *nx, *ny, *nz, *pd;     // normals (NaN = invalid) and plane_d
+    uint8_t *conn;                // bit0: comparator edge to the left pixel, bit1: to the upper pixel
+    int   *parent;                // union-find forest, then flattened roots
+    int   *cnt;                   // component size at its root
+    int   *lab;                   // PCL labels (rank of the component)
+    int16_t *root_model;          // model index at component roots, -1 otherwise
+    int8_t *pid;                  // plane (model) id per pixel, -1 = none
+    int   *pos;                   // position of the pixel in its model's inlier list
+    int   *cand_idx;              // raster-ordered index lists of the candidates
+    int   *contour_idx;           // contour arena, contour_cap per frame
+    float4 *line_a, *line_b;      // RANSAC working clouds (contour_cap per frame)
+    int   *line_sh;               // shuffled indices (contour_cap per frame)
+    int   *line_inl;              // inlier index scratch (contour_cap per frame)
+    spx_point *line_pts;          // accepted line inlier points (contour_cap per frame)
+    spx_point *pts;               // point arena, pts_cap per frame
+    spx_point *bnd;               // boundary arena, bnd_cap per frame
+    FrameCtl *ctl;
+    // compacted outputs
+    spx_frame_header *out_frames;
+    spx_plane *out_planes;
+    spx_point *out_pts;
+    spx_point *out_bnd;
+    long long *out_totals;        // [0] planes, [1] points, [2] boundary
+    long long *frame_offs;        // per frame: plane, point, boundary offsets (3 per frame)
+};
+
+}  // namespace spx
