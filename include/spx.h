@@ -134,7 +134,9 @@ int spx_get_times(spx_ctx *ctx, double *t_plane, double *t_splane);
 /* number of kernel launches issued by the last extract call */
 int spx_last_launch_count(const spx_ctx *ctx);
 
-/* ---- debug taps for the parity tests: intermediates of frame `frame` of the last extract call, copied to host ---- */
+/* ---- debug taps for the parity tests: intermediates of frame `frame` of the last extract call, copied to host.
+ * They need spx_set_debug(ctx, 1) BEFORE the extract call (it adds the per-pixel label kernel to the schedule). ---- */
+int spx_set_debug(spx_ctx *ctx, int on);
 int spx_get_cloud(spx_ctx *ctx, int frame, float *x, float *y, float *z);                 /* N each */
 int spx_get_distance_map(spx_ctx *ctx, int frame, float *dist);                           /* N, min(PCL distance map, 10) */
 int spx_get_normals(spx_ctx *ctx, int frame, float *nx, float *ny, float *nz, float *plane_d);

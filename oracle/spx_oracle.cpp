@@ -28,6 +28,8 @@
  *   E7  Frame::IsBorderPoint reads imDepth.ptr<float>(j)[i] with no bounds check (src/Frame.cc:1039-1050).
  *       We define it by flat addressing on the continuous image, data[j*cols+i]; indices outside the buffer
  *       count as invalid samples, and a non-finite projection (PcZ == 0) makes the point "not border".
+ *   E8  computeRoots' atan2 / cos / sin on floats resolve to the platform libm's atan2f / cosf / sinf, whose last
+ *       bit is implementation defined; we take the correctly rounded value (evaluate in double, round to float).
  */
 #include "spx_oracle.h"
 
@@ -85,9 +87,10 @@ static void compute_roots(const float m[9], float roots[3]) {
         float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
         if (q > 0.0f) q = 0.0f;
         float rho = std::sqrt(-a_over_3);
-        float theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
-        float cos_theta = std::cos(theta);
-        float sin_theta = std::sin(theta);
+        // E8: the three transcendental calls are evaluated in double and rounded to float
+        float theta = float(std::atan2(double(std::sqrt(-q)), double(half_b))) * s_inv3;
+        float cos_theta = float(std::cos(double(theta)));
+        float sin_theta = float(std::sin(double(theta)));
         roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
         roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
         roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);

@@ -1,0 +1,310 @@
+"""ctypes binding of the C ABI (include/spx.h, sp_slam_b200/libspx.so).
+
+The library is sm_100a CUDA only.  Loading works anywhere (so the symbol table can be checked on a CPU box); every
+compute entry point fails with SPX_ERR_CUDA when no B200-class device is present -- there is no CPU path.
+
+``PlaneExtractor`` mirrors the two reference calls it replaces, Frame::ComputePlanesFromOrganizedPointCloud and
+Frame::GeneratePlanesFromBoundries (/root/reference/src/Frame.cc:186,194), and hands back the same fields
+(mvPlanePoints, mvBoundaryPoints, mvPlaneCoefficients, mnRealPlaneNum, mnPlaneNum; include/Frame.h:223-244).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspx.so")
+
+SPX_OK, SPX_ERR_ARG, SPX_ERR_CUDA, SPX_ERR_STATE = 0, 1, 2, 3
+SPX_FRAME_OVERFLOW = 1
+SPX_MAX_CAND, SPX_MAX_MODELS, SPX_MAX_PLANES, SPX_MAX_LINES = 96, 64, 128, 4
+
+POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgba", "<u4")])
+PLANE_DTYPE = np.dtype([("coef", "<f4", 4), ("n_points", "<i4"), ("n_boundary", "<i4"), ("points_off", "<i8"),
+                        ("boundary_off", "<i8"), ("src", "<i4"), ("is_supposed", "<i4")])
+HEADER_DTYPE = np.dtype([("n_real", "<i4"), ("n_planes", "<i4"), ("first_plane", "<i4"), ("flags", "<u4")])
+MODEL_DTYPE = np.dtype([("coef", "<f4", 4), ("centroid", "<f4", 3), ("cov", "<f4", 9), ("curvature", "<f4"),
+                        ("label", "<u4"), ("n_segment", "<i4"), ("n_inliers", "<i4"), ("n_contour", "<i4")])
+LINE_DTYPE = np.dtype([("plane", "<i4"), ("round", "<i4"), ("n_points", "<i4"), ("iterations", "<i4"),
+                       ("n_inliers", "<i4"), ("in_range", "<i4"), ("is_border", "<i4"), ("emitted", "<i4"),
+                       ("coef", "<f4", 6)])
+
+# every symbol include/spx.h declares (tests check the built library exports exactly these)
+EXPORTS = (
+    "spx_default_config", "spx_create", "spx_destroy", "spx_last_error", "spx_set_stream", "spx_extract",
+    "spx_extract_batch", "spx_extract_batch_device", "spx_fetch_results", "spx_fetch_planes",
+    "spx_segment_from_normals", "spx_cloud_dims", "spx_get_times", "spx_last_launch_count", "spx_set_debug",
+    "spx_get_cloud", "spx_get_distance_map", "spx_get_normals", "spx_get_labels_raw", "spx_get_plane_ids",
+    "spx_get_models", "spx_get_model_inliers", "spx_get_model_contour", "spx_get_lines",
+)
+
+
+class SpxConfig(C.Structure):
+    _fields_ = [
+        ("cloud_dis", C.c_int32), ("min_size", C.c_int32), ("angle_thr_deg", C.c_float), ("dist_thr", C.c_float),
+        ("line_ratio", C.c_double), ("line_dist_thr", C.c_float),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+        ("max_depth_change_factor", C.c_float), ("normal_smoothing_size", C.c_float),
+        ("ransac_max_iter", C.c_int32), ("enable_supposed", C.c_int32),
+        ("max_frames", C.c_int32), ("max_rows", C.c_int32), ("max_cols", C.c_int32), ("device", C.c_int32),
+    ]
+
+
+class SpxBatchResult(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int32), ("n_planes_total", C.c_int32), ("n_points_total", C.c_int64),
+        ("n_boundary_total", C.c_int64),
+        ("frames", C.c_void_p), ("planes", C.c_void_p), ("points", C.c_void_p), ("boundary", C.c_void_p),
+    ]
+
+
+class SpxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"spx error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libspx.so; raises if the CUDA extension has not been built (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C sp_slam_b200/csrc` "
+                               "(or `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+        L.spx_default_config.argtypes = [C.POINTER(SpxConfig)]
+        L.spx_default_config.restype = None
+        L.spx_create.argtypes = [C.POINTER(SpxConfig), C.POINTER(vp)]
+        L.spx_destroy.argtypes = [vp]
+        L.spx_destroy.restype = None
+        L.spx_last_error.argtypes = [vp]
+        L.spx_last_error.restype = C.c_char_p
+        L.spx_set_stream.argtypes = [vp, vp]
+        L.spx_set_debug.argtypes = [vp, i32]
+        L.spx_extract.argtypes = [vp, vp, i32, i32, sz, C.POINTER(SpxBatchResult)]
+        L.spx_extract_batch.argtypes = [vp, vp, i32, i32, i32, sz, sz, C.POINTER(SpxBatchResult)]
+        L.spx_extract_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz]
+        L.spx_fetch_results.argtypes = [vp, C.POINTER(SpxBatchResult)]
+        L.spx_fetch_planes.argtypes = [vp, C.POINTER(SpxBatchResult)]
+        L.spx_segment_from_normals.argtypes = [vp, vp, i32, i32, sz, vp, C.POINTER(SpxBatchResult)]
+        L.spx_cloud_dims.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+        L.spx_get_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.spx_last_launch_count.argtypes = [vp]
+        L.spx_get_cloud.argtypes = [vp, i32, vp, vp, vp]
+        L.spx_get_distance_map.argtypes = [vp, i32, vp]
+        L.spx_get_normals.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.spx_get_labels_raw.argtypes = [vp, i32, vp, C.POINTER(i32)]
+        L.spx_get_plane_ids.argtypes = [vp, i32, vp]
+        L.spx_get_models.argtypes = [vp, i32, vp, C.POINTER(i32)]
+        L.spx_get_model_inliers.argtypes = [vp, i32, i32, vp]
+        L.spx_get_model_contour.argtypes = [vp, i32, i32, vp]
+        L.spx_get_lines.argtypes = [vp, i32, vp, C.POINTER(i32)]
+        for name in EXPORTS:
+            getattr(L, name)   # AttributeError here = the library is stale
+        _lib = L
+    return _lib
+
+
+def default_config(**overrides) -> SpxConfig:
+    cfg = SpxConfig()
+    lib().spx_default_config(C.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _view(ptr, count, dtype):
+    if not ptr or count == 0:
+        return np.empty(0, dtype)
+    buf = (C.c_char * (int(count) * dtype.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(count))
+
+
+@dataclass
+class FramePlanes:
+    """The plane fields of one Frame (include/Frame.h:223-244)."""
+    mnRealPlaneNum: int
+    mnPlaneNum: int
+    mvPlaneCoefficients: np.ndarray          # (mnPlaneNum, 4) float32, unit normal + d, d >= 0
+    mvPlanePoints: list                      # per plane: POINT_DTYPE array
+    mvBoundaryPoints: list                   # per plane: POINT_DTYPE array
+    src: np.ndarray                          # real: segmentation model index; supposed: parent plane index
+    is_supposed: np.ndarray
+    flags: int
+
+
+class BatchResult:
+    """Copies of the context-owned result buffers of one extract call."""
+
+    def __init__(self, r: SpxBatchResult, copy: bool = True):
+        f = _view(r.frames, r.n_frames, HEADER_DTYPE)
+        p = _view(r.planes, r.n_planes_total, PLANE_DTYPE)
+        pts = _view(r.points, r.n_points_total, POINT_DTYPE)
+        bnd = _view(r.boundary, r.n_boundary_total, POINT_DTYPE)
+        if copy:
+            f, p, pts, bnd = f.copy(), p.copy(), pts.copy(), bnd.copy()
+        self.frames, self.planes, self.points, self.boundary = f, p, pts, bnd
+
+    def __len__(self):
+        return len(self.frames)
+
+    def frame(self, i: int) -> FramePlanes:
+        h = self.frames[i]
+        pl = self.planes[h["first_plane"]: h["first_plane"] + h["n_planes"]]
+        have_clouds = len(self.points) > 0 or len(self.boundary) > 0
+        pts = [self.points[q["points_off"]: q["points_off"] + q["n_points"]] for q in pl] if have_clouds else []
+        bnd = [self.boundary[q["boundary_off"]: q["boundary_off"] + q["n_boundary"]] for q in pl] if have_clouds else []
+        return FramePlanes(int(h["n_real"]), int(h["n_planes"]), pl["coef"].copy(), pts, bnd, pl["src"].copy(),
+                           pl["is_supposed"].copy(), int(h["flags"]))
+
+
+class PlaneExtractor:
+    """One context = one CUDA device + fixed capacity (frames per batch, image size)."""
+
+    def __init__(self, cfg: SpxConfig | None = None, debug: bool = False, **overrides):
+        self.cfg = cfg if cfg is not None else default_config(**overrides)
+        self._h = C.c_void_p()
+        rc = lib().spx_create(C.byref(self.cfg), C.byref(self._h))
+        if rc != SPX_OK:
+            self._h = C.c_void_p()
+            raise SpxError(rc, (lib().spx_last_error(None) or b"").decode())
+        if debug:
+            self._ck(lib().spx_set_debug(self._h, 1))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().spx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != SPX_OK:
+            raise SpxError(rc, (lib().spx_last_error(self._h) or b"").decode())
+
+    # ---- extraction ----
+    def extract(self, depth: np.ndarray) -> FramePlanes:
+        """One frame: CV_32F metres, rows x cols (host)."""
+        return self.extract_batch(depth[None]).frame(0)
+
+    def extract_batch(self, depth: np.ndarray) -> BatchResult:
+        """(n_frames, rows, cols) float32 host array; H2D copy, kernels and D2H copy inside the call."""
+        if depth.dtype != np.float32 or depth.ndim != 3 or depth.strides[2] != 4:
+            depth = np.ascontiguousarray(depth, dtype=np.float32)
+        n, rows, cols = depth.shape
+        r = SpxBatchResult()
+        self._ck(lib().spx_extract_batch(self._h, depth.ctypes.data, n, rows, cols, depth.strides[1],
+                                         depth.strides[0], C.byref(r)))
+        return BatchResult(r)
+
+    def extract_batch_ptr(self, host_ptr: int, n: int, rows: int, cols: int, copy: bool = False) -> BatchResult:
+        """Same, from a raw host pointer (e.g. a pinned torch tensor's data_ptr()); tight row-major layout."""
+        r = SpxBatchResult()
+        self._ck(lib().spx_extract_batch(self._h, host_ptr, n, rows, cols, cols * 4, rows * cols * 4, C.byref(r)))
+        return BatchResult(r, copy=copy)
+
+    def extract_device(self, dev_ptr: int, n: int, rows: int, cols: int, pitch: int | None = None,
+                       frame_stride: int | None = None):
+        """Asynchronous, device-resident depth; results stay on the device until fetch()."""
+        pitch = cols * 4 if pitch is None else pitch
+        frame_stride = pitch * rows if frame_stride is None else frame_stride
+        self._ck(lib().spx_extract_batch_device(self._h, dev_ptr, n, rows, cols, pitch, frame_stride))
+
+    def fetch(self, clouds: bool = True, copy: bool = True) -> BatchResult:
+        r = SpxBatchResult()
+        self._ck((lib().spx_fetch_results if clouds else lib().spx_fetch_planes)(self._h, C.byref(r)))
+        return BatchResult(r, copy=copy)
+
+    def segment_from_normals(self, depth: np.ndarray, normals: np.ndarray) -> FramePlanes:
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        normals = np.ascontiguousarray(normals, dtype=np.float32)
+        rows, cols = depth.shape
+        r = SpxBatchResult()
+        self._ck(lib().spx_segment_from_normals(self._h, depth.ctypes.data, rows, cols, cols * 4, normals.ctypes.data,
+                                                C.byref(r)))
+        return BatchResult(r).frame(0)
+
+    def set_stream(self, cuda_stream: int | None):
+        self._ck(lib().spx_set_stream(self._h, cuda_stream))
+
+    def cloud_dims(self, rows: int, cols: int):
+        w, h = C.c_int(), C.c_int()
+        self._ck(lib().spx_cloud_dims(self._h, rows, cols, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def times(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(lib().spx_get_times(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @property
+    def launches(self) -> int:
+        return lib().spx_last_launch_count(self._h)
+
+    # ---- debug taps (need debug=True) ----
+    def _n(self, rows, cols):
+        w, h = self.cloud_dims(rows, cols)
+        return w, h, w * h
+
+    def cloud(self, frame, n):
+        a = [np.empty(n, np.float32) for _ in range(3)]
+        self._ck(lib().spx_get_cloud(self._h, frame, *(x.ctypes.data for x in a)))
+        return np.stack(a)
+
+    def distance_map(self, frame, n):
+        d = np.empty(n, np.float32)
+        self._ck(lib().spx_get_distance_map(self._h, frame, d.ctypes.data))
+        return d
+
+    def normals(self, frame, n):
+        a = [np.empty(n, np.float32) for _ in range(4)]
+        self._ck(lib().spx_get_normals(self._h, frame, *(x.ctypes.data for x in a)))
+        return np.stack(a[:3]), a[3]
+
+    def labels_raw(self, frame, n):
+        l = np.empty(n, np.uint32)
+        k = C.c_int()
+        self._ck(lib().spx_get_labels_raw(self._h, frame, l.ctypes.data, C.byref(k)))
+        return l, k.value
+
+    def plane_ids(self, frame, n):
+        p = np.empty(n, np.int8)
+        self._ck(lib().spx_get_plane_ids(self._h, frame, p.ctypes.data))
+        return p
+
+    def models(self, frame):
+        m = np.zeros(SPX_MAX_MODELS, MODEL_DTYPE)
+        k = C.c_int()
+        self._ck(lib().spx_get_models(self._h, frame, m.ctypes.data, C.byref(k)))
+        out = []
+        for i in range(k.value):
+            inl = np.full(int(m[i]["n_inliers"]), -1, np.int32)
+            con = np.empty(int(m[i]["n_contour"]), np.int32)
+            if len(inl):
+                self._ck(lib().spx_get_model_inliers(self._h, frame, i, inl.ctypes.data))
+            if len(con):
+                self._ck(lib().spx_get_model_contour(self._h, frame, i, con.ctypes.data))
+            out.append(dict(coef=m[i]["coef"].copy(), centroid=m[i]["centroid"].copy(),
+                            cov=m[i]["cov"].reshape(3, 3).copy(), curvature=float(m[i]["curvature"]),
+                            label=int(m[i]["label"]), n_segment=int(m[i]["n_segment"]), inliers=inl, contour=con))
+        return out
+
+    def lines(self, frame):
+        l = np.zeros(SPX_MAX_MODELS * SPX_MAX_LINES, LINE_DTYPE)
+        k = C.c_int()
+        self._ck(lib().spx_get_lines(self._h, frame, l.ctypes.data, C.byref(k)))
+        return l[:k.value].copy()

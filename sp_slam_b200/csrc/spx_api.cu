@@ -1,0 +1,602 @@
+// spx_api.cu -- the C ABI of include/spx.h: context, device memory layout, kernel schedule, result transfer.
+//
+// Replaces the two Frame member functions of the reference (/root/reference/src/Frame.cc:186 and :194, bodies
+// :854-936 and :938-999) for a batch of independent frames.  Compiled for sm_100a with -fmad=false: every product
+// and sum of the reference's fp32 arithmetic is rounded separately, as in the PCL path.
+//
+// There is no CPU fallback: without a usable CUDA device spx_create fails with SPX_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "spx_lines.cuh"
+#include "spx_normals.cuh"
+#include "spx_refine.cuh"
+#include "spx_segment.cuh"
+
+using namespace spx;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevArena {
+    char *base = nullptr;
+    size_t size = 0, used = 0;
+    template <typename T>
+    T *take(size_t n) {
+        const size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+        T *p = reinterpret_cast<T *>(base + used);
+        used += bytes;
+        return p;
+    }
+};
+template <typename T>
+size_t padded(size_t n) { return (n * sizeof(T) + 255) & ~size_t(255); }
+
+}  // namespace
+
+struct spx_ctx {
+    spx_config cfg;
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    Params P;           // geometry of the last call (capacities fixed at create)
+    Buffers B;
+    DevArena arena;
+    float *d_depth = nullptr;          // staging for host-side depth (tight pitch)
+    int capN = 0, cap_w = 0, cap_h = 0;
+    int n_grid = 0;
+    // host results (pinned, grown on demand)
+    spx_frame_header *h_frames = nullptr;
+    spx_plane *h_planes = nullptr;
+    spx_point *h_pts = nullptr, *h_bnd = nullptr;
+    size_t h_planes_cap = 0, h_pts_cap = 0, h_bnd_cap = 0;
+    long long *h_totals = nullptr;
+    // state of the last extract
+    bool have_run = false;
+    bool debug = false;
+    int last_frames = 0;
+    const float *last_depth_dev = nullptr;
+    int launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(spx_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define SPX_CK(c, call)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail((c), SPX_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));   \
+    } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// organized-cloud size (src/Frame.cc:873-874): ceil(cols / dis) x ceil(rows / dis), evaluated in float as there
+void cloud_dims(int rows, int cols, int dis, int *w, int *h) {
+    *h = int(std::ceil(rows / float(dis)));
+    *w = int(std::ceil(cols / float(dis)));
+}
+
+void mt19937_seeded_state(uint32_t seed, uint32_t s[624]) {
+    s[0] = seed;
+    for (uint32_t i = 1; i < 624; ++i) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + i;
+}
+
+// the values visited by `for(float i = -0.25; i < 0.25;) { ...; i = i + 0.01; }` (src/Frame.cc:1095-1106)
+int grid_values(float out[64]) {
+    int n = 0;
+    for (float i = -0.25; i < 0.25;) {
+        if (n < 64) out[n] = i;
+        ++n;
+        i = i + 0.01;
+    }
+    return n;
+}
+
+int set_geometry(spx_ctx *c, int n_frames, int rows, int cols, size_t pitch, size_t frame_stride) {
+    if (n_frames < 1 || n_frames > c->cfg.max_frames) return fail(c, SPX_ERR_ARG, "n_frames %d outside [1, %d]", n_frames, c->cfg.max_frames);
+    if (rows < 1 || cols < 1 || rows > c->cfg.max_rows || cols > c->cfg.max_cols)
+        return fail(c, SPX_ERR_ARG, "image %dx%d exceeds the context capacity %dx%d", rows, cols, c->cfg.max_rows, c->cfg.max_cols);
+    if (pitch < size_t(cols) * sizeof(float) || pitch % sizeof(float)) return fail(c, SPX_ERR_ARG, "bad pitch");
+    if (n_frames > 1 && frame_stride < pitch * size_t(rows)) return fail(c, SPX_ERR_ARG, "bad frame stride");
+    Params &P = c->P;
+    P.rows = rows; P.cols = cols; P.pitch = pitch; P.frame_stride = frame_stride; P.n_frames = n_frames;
+    cloud_dims(rows, cols, P.dis, &P.w, &P.h);
+    P.N = P.w * P.h;
+    if (P.N > c->capN) return fail(c, SPX_ERR_ARG, "organized cloud exceeds the context capacity");
+    return SPX_OK;
+}
+
+// ---- the kernel schedule -----------------------------------------------------------------------------------
+int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given) {
+    const Params &P = c->P;
+    const Buffers &B = c->B;
+    cudaStream_t st = c->stream;
+    const int F = P.n_frames, N = P.N;
+    const dim3 gpix(cdiv(N, 256), F);
+    int &L = c->launches;
+    L = 0;
+
+    SPX_CK(c, cudaEventRecord(c->ev[0], st));
+    SPX_CK(c, cudaMemsetAsync(B.ctl, 0, sizeof(FrameCtl) * size_t(F), st));
+    k_backproject<<<gpix, 256, 0, st>>>(depth_dev, P, B); ++L;
+    if (!normals_given) {
+        if (P.w >= 3 && P.h >= 3) {
+            k_chamfer<<<cdiv(F, kChamferWarps), kChamferWarps * 32, size_t(kChamferWarps) * 3 * P.w * sizeof(float), st>>>(P, B); ++L;
+        }
+        k_normals<<<dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), 256, kNormalsSmem, st>>>(P, B); ++L;
+    } else {
+        k_plane_d<<<gpix, 256, 0, st>>>(P, B); ++L;
+    }
+    k_ccl_link<<<dim3(cdiv(P.w, 32), cdiv(P.h, 8), F), dim3(32, 8), 0, st>>>(P, B); ++L;
+    k_ccl_merge<<<gpix, 256, 0, st>>>(P, B); ++L;
+    k_ccl_flatten<<<gpix, 256, 0, st>>>(P, B); ++L;
+    k_ccl_rank<<<F, 1024, 0, st>>>(P, B); ++L;
+    if (c->debug) { k_ccl_label<<<gpix, 256, 0, st>>>(P, B); ++L; }
+    k_moments_fit<<<dim3(SPX_MAX_CAND / 4, F), 128, 0, st>>>(P, B); ++L;
+    k_models<<<cdiv(F, 128), 128, 0, st>>>(P, B); ++L;
+    k_pid_init<<<gpix, 256, 0, st>>>(P, B); ++L;
+    k_refine<<<cdiv(F, kRefWarps), kRefWarps * 32, 0, st>>>(P, B); ++L;
+    k_contour<<<F, 32, 0, st>>>(P, B); ++L;
+    k_postfilter<<<cdiv(F, 128), 128, 0, st>>>(P, B); ++L;
+    SPX_CK(c, cudaEventRecord(c->ev[1], st));
+    if (P.enable_supposed) {
+        k_lines<<<dim3(SPX_MAX_MODELS, F), kLineThreads, 0, st>>>(depth_dev, P, B); ++L;
+        k_supposed<<<cdiv(F, 128), 128, 0, st>>>(P, B); ++L;
+    }
+    SPX_CK(c, cudaEventRecord(c->ev[2], st));
+    k_scan_frames<<<1, 1024, 0, st>>>(P, B); ++L;
+    k_emit_records<<<F, 128, 0, st>>>(P, B); ++L;
+    k_pack_points<<<gpix, 256, 0, st>>>(P, B); ++L;
+    k_pack_contours<<<dim3(SPX_MAX_MODELS, F), 128, 0, st>>>(P, B); ++L;
+    if (P.enable_supposed) { k_pack_supposed<<<dim3(SPX_MAX_PLANES, F), 128, 0, st>>>(P, B); ++L; }
+    SPX_CK(c, cudaEventRecord(c->ev[3], st));
+    SPX_CK(c, cudaGetLastError());
+    c->have_run = true;
+    c->last_frames = F;
+    c->last_depth_dev = depth_dev;
+    return SPX_OK;
+}
+
+template <typename T>
+int grow_pinned(spx_ctx *c, T **p, size_t *cap, size_t need) {
+    if (need <= *cap) return SPX_OK;
+    size_t ncap = *cap ? *cap : 1024;
+    while (ncap < need) ncap *= 2;
+    if (*p) SPX_CK(c, cudaFreeHost(*p));
+    *p = nullptr; *cap = 0;
+    SPX_CK(c, cudaHostAlloc(reinterpret_cast<void **>(p), ncap * sizeof(T), cudaHostAllocDefault));
+    *cap = ncap;
+    return SPX_OK;
+}
+
+int fetch(spx_ctx *c, spx_batch_result *out, bool with_clouds) {
+    if (!c->have_run) return fail(c, SPX_ERR_STATE, "no extract call has been made on this context");
+    cudaStream_t st = c->stream;
+    const int F = c->last_frames;
+    SPX_CK(c, cudaMemcpyAsync(c->h_totals, c->B.out_totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    SPX_CK(c, cudaMemcpyAsync(c->h_frames, c->B.out_frames, sizeof(spx_frame_header) * size_t(F), cudaMemcpyDeviceToHost, st));
+    SPX_CK(c, cudaStreamSynchronize(st));
+    const long long n_pl = c->h_totals[0], n_pt = c->h_totals[1], n_bd = c->h_totals[2];
+    int rc;
+    if ((rc = grow_pinned(c, &c->h_planes, &c->h_planes_cap, size_t(n_pl))) != SPX_OK) return rc;
+    if (n_pl) SPX_CK(c, cudaMemcpyAsync(c->h_planes, c->B.out_planes, sizeof(spx_plane) * size_t(n_pl), cudaMemcpyDeviceToHost, st));
+    if (with_clouds) {
+        if ((rc = grow_pinned(c, &c->h_pts, &c->h_pts_cap, size_t(n_pt))) != SPX_OK) return rc;
+        if ((rc = grow_pinned(c, &c->h_bnd, &c->h_bnd_cap, size_t(n_bd))) != SPX_OK) return rc;
+        if (n_pt) SPX_CK(c, cudaMemcpyAsync(c->h_pts, c->B.out_pts, sizeof(spx_point) * size_t(n_pt), cudaMemcpyDeviceToHost, st));
+        if (n_bd) SPX_CK(c, cudaMemcpyAsync(c->h_bnd, c->B.out_bnd, sizeof(spx_point) * size_t(n_bd), cudaMemcpyDeviceToHost, st));
+    }
+    SPX_CK(c, cudaStreamSynchronize(st));
+    if (out) {
+        out->n_frames = F;
+        out->n_planes_total = int(n_pl);
+        out->n_points_total = with_clouds ? n_pt : 0;
+        out->n_boundary_total = with_clouds ? n_bd : 0;
+        out->frames = c->h_frames;
+        out->planes = c->h_planes;
+        out->points = with_clouds ? c->h_pts : nullptr;
+        out->boundary = with_clouds ? c->h_bnd : nullptr;
+    }
+    return SPX_OK;
+}
+
+int upload_depth(spx_ctx *c, const float *depth, int n_frames, int rows, int cols, size_t pitch, size_t frame_stride) {
+    const size_t tight = size_t(cols) * sizeof(float);
+    if (pitch == tight && (n_frames == 1 || frame_stride == tight * rows)) {
+        SPX_CK(c, cudaMemcpyAsync(c->d_depth, depth, tight * rows * size_t(n_frames), cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (int f = 0; f < n_frames; ++f)
+            SPX_CK(c, cudaMemcpy2DAsync(reinterpret_cast<char *>(c->d_depth) + tight * rows * size_t(f), tight,
+                                        reinterpret_cast<const char *>(depth) + frame_stride * size_t(f), pitch, tight, size_t(rows),
+                                        cudaMemcpyHostToDevice, c->stream));
+    }
+    return SPX_OK;
+}
+
+int check_frame(spx_ctx *c, int frame) {
+    if (!c) return SPX_ERR_ARG;
+    if (!c->have_run) return fail(c, SPX_ERR_STATE, "no extract call has been made on this context");
+    if (!c->debug) return fail(c, SPX_ERR_STATE, "debug taps are off: call spx_set_debug(ctx, 1) before the extract");
+    if (frame < 0 || frame >= c->last_frames) return fail(c, SPX_ERR_ARG, "frame %d outside the last batch", frame);
+    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_CK(c, cudaStreamSynchronize(c->stream));
+    return SPX_OK;
+}
+
+template <typename T>
+int d2h(spx_ctx *c, T *dst, const T *src, size_t n) {
+    if (!dst) return SPX_OK;
+    SPX_CK(c, cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost));
+    return SPX_OK;
+}
+
+int get_ctl(spx_ctx *c, int frame, FrameCtl *out) {
+    SPX_CK(c, cudaMemcpy(out, c->B.ctl + frame, sizeof(FrameCtl), cudaMemcpyDeviceToHost));
+    return SPX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void spx_default_config(spx_config *cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->cloud_dis = 3; cfg->min_size = 500; cfg->angle_thr_deg = 3.0f; cfg->dist_thr = 0.05f;
+    cfg->line_ratio = 0.2; cfg->line_dist_thr = 0.01f;
+    cfg->fx = 517.306408f; cfg->fy = 516.469215f; cfg->cx = 318.643040f; cfg->cy = 255.313989f;
+    cfg->min_x = 0.0f; cfg->max_x = 640.0f; cfg->min_y = 0.0f; cfg->max_y = 480.0f;
+    cfg->max_depth_change_factor = 0.05f; cfg->normal_smoothing_size = 10.0f;
+    cfg->ransac_max_iter = 1000; cfg->enable_supposed = 1;
+    cfg->max_frames = 1; cfg->max_rows = 480; cfg->max_cols = 640; cfg->device = 0;
+}
+
+int spx_create(const spx_config *cfg, spx_ctx **out) {
+    if (!cfg || !out) return fail(nullptr, SPX_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->cloud_dis < 1 || cfg->max_frames < 1 || cfg->max_frames > 65535 || cfg->max_rows < 1 || cfg->max_cols < 1)
+        return fail(nullptr, SPX_ERR_ARG, "bad capacity / Cloud.Dis (1 <= max_frames <= 65535)");
+    if (cfg->normal_smoothing_size != 10.0f) return fail(nullptr, SPX_ERR_ARG, "only normal_smoothing_size = 10 is supported");
+    if (cfg->min_size < 0 || cfg->ransac_max_iter < 1) return fail(nullptr, SPX_ERR_ARG, "bad Plane.MinSize / RANSAC iteration count");
+    int w, h;
+    cloud_dims(cfg->max_rows, cfg->max_cols, cfg->cloud_dis, &w, &h);
+    if (w > kMaxW) return fail(nullptr, SPX_ERR_ARG, "organized cloud wider than %d columns", kMaxW);
+    if (size_t(w) * h >= (1u << 20)) return fail(nullptr, SPX_ERR_ARG, "organized cloud larger than 2^20 points");
+
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, SPX_ERR_CUDA, "no CUDA device (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, SPX_ERR_ARG, "device %d out of range (%d devices)", cfg->device, n_dev);
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess)
+        return fail(nullptr, SPX_ERR_CUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, SPX_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+    spx_ctx *c = new (std::nothrow) spx_ctx();
+    if (!c) return fail(nullptr, SPX_ERR_ARG, "out of host memory");
+    c->cfg = *cfg;
+    c->device = cfg->device;
+    c->cap_w = w; c->cap_h = h; c->capN = w * h;
+    float grid[64];
+    c->n_grid = grid_values(grid);
+
+    Params &P = c->P;
+    std::memset(&P, 0, sizeof(P));
+    P.dis = cfg->cloud_dis;
+    P.fx = cfg->fx; P.fy = cfg->fy; P.cx = cfg->cx; P.cy = cfg->cy;
+    P.min_x = cfg->min_x; P.max_x = cfg->max_x; P.min_y = cfg->min_y; P.max_y = cfg->max_y;
+    P.mdcf = cfg->max_depth_change_factor;
+    P.min_size = cfg->min_size;
+    P.ang_cos = cosf(float(0.017453 * cfg->angle_thr_deg));   // src/Frame.cc:900 -> setAngularThreshold stores cosf()
+    P.dist_thr = cfg->dist_thr;
+    P.line_ratio = cfg->line_ratio;
+    P.line_thr = double(cfg->line_dist_thr);
+    P.ransac_max_iter = cfg->ransac_max_iter;
+    P.enable_supposed = cfg->enable_supposed ? 1 : 0;
+    P.n_grid = c->n_grid;
+    const size_t N = size_t(c->capN), F = size_t(cfg->max_frames);
+    P.contour_cap = int(2 * N + 16 * SPX_MAX_MODELS);
+    P.pts_cap = int(N + size_t(P.contour_cap) + size_t(32) * c->n_grid * c->n_grid);
+    P.bnd_cap = 2 * P.contour_cap;
+
+#define SPX_CK_CREATE(call)                                                                                   \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) {                                                                              \
+            fail(nullptr, SPX_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                             \
+            spx_destroy(c);                                                                                   \
+            return SPX_ERR_CUDA;                                                                              \
+        }                                                                                                     \
+    } while (0)
+
+    SPX_CK_CREATE(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int i = 0; i < 4; ++i) SPX_CK_CREATE(cudaEventCreate(&c->ev[i]));
+
+    const size_t FN = F * N, FC = F * size_t(P.contour_cap);
+    size_t total = 0;
+    total += 8 * padded<float>(FN);                        // px py pz dist nx ny nz pd
+    total += padded<uint8_t>(FN) + 5 * padded<int>(FN);    // conn | parent cnt lab pos cand_idx
+    total += padded<int16_t>(FN) + padded<int8_t>(FN);     // root_model pid
+    total += 3 * padded<int>(FC) + 2 * padded<float4>(FC) + padded<spx_point>(FC);
+    total += padded<FrameCtl>(F);
+    total += padded<spx_frame_header>(F) + padded<spx_plane>(F * SPX_MAX_PLANES);
+    total += padded<spx_point>(F * size_t(P.pts_cap)) + padded<spx_point>(F * size_t(P.bnd_cap));
+    total += padded<long long>(4) + padded<long long>(3 * F);
+    total += padded<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols));
+    SPX_CK_CREATE(cudaMalloc(reinterpret_cast<void **>(&c->arena.base), total));
+    c->arena.size = total;
+    DevArena &A = c->arena;
+    Buffers &B = c->B;
+    B.px = A.take<float>(FN); B.py = A.take<float>(FN); B.pz = A.take<float>(FN); B.dist = A.take<float>(FN);
+    B.nx = A.take<float>(FN); B.ny = A.take<float>(FN); B.nz = A.take<float>(FN); B.pd = A.take<float>(FN);
+    B.conn = A.take<uint8_t>(FN);
+    B.parent = A.take<int>(FN); B.cnt = A.take<int>(FN); B.lab = A.take<int>(FN); B.pos = A.take<int>(FN); B.cand_idx = A.take<int>(FN);
+    B.root_model = A.take<int16_t>(FN); B.pid = A.take<int8_t>(FN);
+    B.contour_idx = A.take<int>(FC); B.line_sh = A.take<int>(FC); B.line_inl = A.take<int>(FC);
+    B.line_a = A.take<float4>(FC); B.line_b = A.take<float4>(FC); B.line_pts = A.take<spx_point>(FC);
+    B.ctl = A.take<FrameCtl>(F);
+    B.out_frames = A.take<spx_frame_header>(F); B.out_planes = A.take<spx_plane>(F * SPX_MAX_PLANES);
+    B.out_pts = A.take<spx_point>(F * size_t(P.pts_cap)); B.out_bnd = A.take<spx_point>(F * size_t(P.bnd_cap));
+    B.out_totals = A.take<long long>(4); B.frame_offs = A.take<long long>(3 * F);
+    c->d_depth = A.take<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols));
+    if (A.used > A.size) { fail(nullptr, SPX_ERR_ARG, "internal: arena accounting"); spx_destroy(c); return SPX_ERR_ARG; }
+
+    uint32_t mt[624];
+    mt19937_seeded_state(12345u, mt);   // boost::mt19937 rng_alg_ seeded in SampleConsensusModel's ctor (random = false)
+    SPX_CK_CREATE(cudaMemcpyToSymbol(c_mt_init, mt, sizeof(mt)));
+    SPX_CK_CREATE(cudaMemcpyToSymbol(c_grid, grid, sizeof(grid)));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kNormalsSmem)));
+    SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_totals), 4 * sizeof(long long), cudaHostAllocDefault));
+    SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_frames), F * sizeof(spx_frame_header), cudaHostAllocDefault));
+#undef SPX_CK_CREATE
+    *out = c;
+    return SPX_OK;
+}
+
+void spx_destroy(spx_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    if (c->arena.base) cudaFree(c->arena.base);
+    if (c->h_totals) cudaFreeHost(c->h_totals);
+    if (c->h_frames) cudaFreeHost(c->h_frames);
+    if (c->h_planes) cudaFreeHost(c->h_planes);
+    if (c->h_pts) cudaFreeHost(c->h_pts);
+    if (c->h_bnd) cudaFreeHost(c->h_bnd);
+    for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char *spx_last_error(const spx_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int spx_set_stream(spx_ctx *c, void *cuda_stream) {
+    if (!c) return SPX_ERR_ARG;
+    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_CK(c, cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return SPX_OK;
+}
+
+int spx_set_debug(spx_ctx *c, int on) {
+    if (!c) return SPX_ERR_ARG;
+    c->debug = on != 0;
+    return SPX_OK;
+}
+
+int spx_extract_batch_device(spx_ctx *c, const float *depth_dev, int n_frames, int rows, int cols, size_t pitch_bytes,
+                             size_t frame_stride_bytes) {
+    if (!c) return SPX_ERR_ARG;
+    if (!depth_dev) return fail(c, SPX_ERR_ARG, "null depth pointer");
+    SPX_CK(c, cudaSetDevice(c->device));
+    int rc = set_geometry(c, n_frames, rows, cols, pitch_bytes, frame_stride_bytes);
+    if (rc != SPX_OK) return rc;
+    return run_pipeline(c, depth_dev, false);
+}
+
+int spx_fetch_results(spx_ctx *c, spx_batch_result *out) {
+    if (!c || !out) return SPX_ERR_ARG;
+    SPX_CK(c, cudaSetDevice(c->device));
+    return fetch(c, out, true);
+}
+
+int spx_fetch_planes(spx_ctx *c, spx_batch_result *out) {
+    if (!c || !out) return SPX_ERR_ARG;
+    SPX_CK(c, cudaSetDevice(c->device));
+    return fetch(c, out, false);
+}
+
+int spx_extract_batch(spx_ctx *c, const float *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
+                      size_t frame_stride_bytes, spx_batch_result *out) {
+    if (!c) return SPX_ERR_ARG;
+    if (!depth || !out) return fail(c, SPX_ERR_ARG, "null argument");
+    SPX_CK(c, cudaSetDevice(c->device));
+    const size_t tight = size_t(cols) * sizeof(float);
+    int rc = set_geometry(c, n_frames, rows, cols, pitch_bytes, frame_stride_bytes);
+    if (rc != SPX_OK) return rc;
+    if ((rc = upload_depth(c, depth, n_frames, rows, cols, pitch_bytes, frame_stride_bytes)) != SPX_OK) return rc;
+    c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);
+    if ((rc = run_pipeline(c, c->d_depth, false)) != SPX_OK) return rc;
+    return fetch(c, out, true);
+}
+
+int spx_extract(spx_ctx *c, const float *depth, int rows, int cols, size_t pitch_bytes, spx_batch_result *out) {
+    return spx_extract_batch(c, depth, 1, rows, cols, pitch_bytes, pitch_bytes * size_t(rows > 0 ? rows : 0), out);
+}
+
+int spx_segment_from_normals(spx_ctx *c, const float *depth, int rows, int cols, size_t pitch_bytes, const float *normals,
+                             spx_batch_result *out) {
+    if (!c) return SPX_ERR_ARG;
+    if (!depth || !normals || !out) return fail(c, SPX_ERR_ARG, "null argument");
+    SPX_CK(c, cudaSetDevice(c->device));
+    const size_t tight = size_t(cols) * sizeof(float);
+    int rc = set_geometry(c, 1, rows, cols, pitch_bytes, pitch_bytes * size_t(rows));
+    if (rc != SPX_OK) return rc;
+    if ((rc = upload_depth(c, depth, 1, rows, cols, pitch_bytes, pitch_bytes * size_t(rows))) != SPX_OK) return rc;
+    c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);
+    const size_t N = size_t(c->P.N);
+    SPX_CK(c, cudaMemcpyAsync(c->B.nx, normals, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    SPX_CK(c, cudaMemcpyAsync(c->B.ny, normals + N, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    SPX_CK(c, cudaMemcpyAsync(c->B.nz, normals + 2 * N, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = run_pipeline(c, c->d_depth, true)) != SPX_OK) return rc;
+    return fetch(c, out, true);
+}
+
+int spx_cloud_dims(const spx_ctx *c, int rows, int cols, int *width, int *height) {
+    if (!c || !width || !height || rows < 1 || cols < 1) return SPX_ERR_ARG;
+    cloud_dims(rows, cols, c->P.dis, width, height);
+    return SPX_OK;
+}
+
+int spx_get_times(spx_ctx *c, double *t_plane, double *t_splane) {
+    if (!c) return SPX_ERR_ARG;
+    if (!c->have_run) return fail(c, SPX_ERR_STATE, "no extract call has been made on this context");
+    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_CK(c, cudaEventSynchronize(c->ev[3]));
+    float a = 0, b = 0, d = 0;
+    SPX_CK(c, cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+    SPX_CK(c, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+    SPX_CK(c, cudaEventElapsedTime(&d, c->ev[2], c->ev[3]));
+    if (t_plane) *t_plane = (double(a) + double(d)) * 1e-3;   // segmentation + packing of the clouds
+    if (t_splane) *t_splane = double(b) * 1e-3;
+    return SPX_OK;
+}
+
+int spx_last_launch_count(const spx_ctx *c) { return c ? c->launches : 0; }
+
+// ---- debug taps ----------------------------------------------------------------------------------------------
+int spx_get_cloud(spx_ctx *c, int frame, float *x, float *y, float *z) {
+    int rc = check_frame(c, frame);
+    if (rc != SPX_OK) return rc;
+    const size_t N = size_t(c->P.N), o = N * size_t(frame);
+    if ((rc = d2h(c, x, c->B.px + o, N)) != SPX_OK) return rc;
+    if ((rc = d2h(c, y, c->B.py + o, N)) != SPX_OK) return rc;
+    return d2h(c, z, c->B.pz + o, N);
+}
+
+int spx_get_distance_map(spx_ctx *c, int frame, float *dist) {
+    int rc = check_frame(c, frame);
+    if (rc != SPX_OK) return rc;
+    return d2h(c, dist, c->B.dist + size_t(c->P.N) * size_t(frame), size_t(c->P.N));
+}
+
+int spx_get_normals(spx_ctx *c, int frame, float *nx, float *ny, float *nz, float *plane_d) {
+    int rc = check_frame(c, frame);
+    if (rc != SPX_OK) return rc;
+    const size_t N = size_t(c->P.N), o = N * size_t(frame);
+    if ((rc = d2h(c, nx, c->B.nx + o, N)) != SPX_OK) return rc;
+    if ((rc = d2h(c, ny, c->B.ny + o, N)) != SPX_OK) return rc;
+    if ((rc = d2h(c, nz, c->B.nz + o, N)) != SPX_OK) return rc;
+    return d2h(c, plane_d, c->B.pd + o, N);
+}
+
+int spx_get_labels_raw(spx_ctx *c, int frame, uint32_t *labels, int *n_label_lists) {
+    int rc = check_frame(c, frame);
+    if (rc != SPX_OK) return rc;
+    if ((rc = d2h(c, reinterpret_cast<int *>(labels), c->B.lab + size_t(c->P.N) * size_t(frame), size_t(c->P.N))) != SPX_OK) return rc;
+    if (n_label_lists) {
+        int n = 0;
+        SPX_CK(c, cudaMemcpy(&n, &c->B.ctl[frame].n_labels, sizeof(int), cudaMemcpyDeviceToHost));
+        *n_label_lists = n;
+    }
+    return SPX_OK;
+}
+
+int spx_get_plane_ids(spx_ctx *c, int frame, int8_t *ids) {
+    int rc = check_frame(c, frame);
+    if (rc != SPX_OK) return rc;
+    return d2h(c, ids, c->B.pid + size_t(c->P.N) * size_t(frame), size_t(c->P.N));
+}
+
+int spx_get_models(spx_ctx *c, int frame, spx_model_info *models, int *n_models) {
+    int rc = check_frame(c, frame);
+    if (rc != SPX_OK) return rc;
+    std::vector<FrameCtl> ctl(1);
+    if ((rc = get_ctl(c, frame, ctl.data())) != SPX_OK) return rc;
+    const FrameCtl &K = ctl[0];
+    if (n_models) *n_models = K.n_models;
+    if (models)
+        for (int i = 0; i < K.n_models; ++i) {
+            const Model &M = K.models[i];
+            spx_model_info &o = models[i];
+            std::memcpy(o.coef, M.coef, sizeof(o.coef));
+            std::memcpy(o.centroid, M.centroid, sizeof(o.centroid));
+            std::memcpy(o.cov, M.cov, sizeof(o.cov));
+            o.curvature = M.curvature; o.label = uint32_t(M.label);
+            o.n_segment = M.n0; o.n_inliers = M.n0 + M.n1 + M.n2; o.n_contour = M.n_contour;
+        }
+    return SPX_OK;
+}
+
+int spx_get_model_inliers(spx_ctx *c, int frame, int model, int32_t *idx) {
+    int rc = check_frame(c, frame);
+    if (rc != SPX_OK) return rc;
+    if (model < 0 || model >= SPX_MAX_MODELS || !idx) return fail(c, SPX_ERR_ARG, "bad model index");
+    const size_t N = size_t(c->P.N), o = N * size_t(frame);
+    std::vector<int8_t> pid(N);
+    std::vector<int> pos(N);
+    if ((rc = d2h(c, pid.data(), c->B.pid + o, N)) != SPX_OK) return rc;
+    if ((rc = d2h(c, pos.data(), c->B.pos + o, N)) != SPX_OK) return rc;
+    for (size_t q = 0; q < N; ++q)
+        if (pid[q] == model) idx[pos[q]] = int32_t(q);   // inlier_indices[model].indices[pos] = q
+    return SPX_OK;
+}
+
+int spx_get_model_contour(spx_ctx *c, int frame, int model, int32_t *idx) {
+    int rc = check_frame(c, frame);
+    if (rc != SPX_OK) return rc;
+    if (model < 0 || model >= SPX_MAX_MODELS || !idx) return fail(c, SPX_ERR_ARG, "bad model index");
+    Model M;
+    SPX_CK(c, cudaMemcpy(&M, &c->B.ctl[frame].models[model], sizeof(Model), cudaMemcpyDeviceToHost));
+    return d2h(c, idx, c->B.contour_idx + size_t(frame) * size_t(c->P.contour_cap) + M.contour_off, size_t(M.n_contour));
+}
+
+int spx_get_lines(spx_ctx *c, int frame, spx_line_info *lines, int *n_lines) {
+    int rc = check_frame(c, frame);
+    if (rc != SPX_OK) return rc;
+    std::vector<FrameCtl> ctl(1);
+    if ((rc = get_ctl(c, frame, ctl.data())) != SPX_OK) return rc;
+    const FrameCtl &K = ctl[0];
+    int n = 0;
+    if (c->P.enable_supposed)
+        for (int i = K.n_real - 1; i >= 0; --i) {   // the reference visits the real planes last to first
+            const int m = K.planes[i].src;
+            const Model &M = K.models[m];
+            if (M.n_contour < 50) continue;
+            for (int j = 0; j < M.n_rounds; ++j) {
+                const Line &Ln = K.lines[m * SPX_MAX_LINES + j];
+                if (lines) {
+                    spx_line_info &o = lines[n];
+                    o.plane = i; o.round = j; o.n_points = Ln.n_points; o.iterations = Ln.iterations; o.n_inliers = Ln.n_inliers;
+                    o.in_range = Ln.in_range; o.is_border = Ln.is_border; o.emitted = Ln.emitted;
+                    std::memcpy(o.coef, Ln.coef, sizeof(o.coef));
+                }
+                ++n;
+            }
+        }
+    if (n_lines) *n_lines = n;
+    return SPX_OK;
+}
+
+}  // extern "C"

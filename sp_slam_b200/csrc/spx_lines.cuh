@@ -1,7 +1,7 @@
 // spx_lines.cuh -- K8: supposed planes from plane edges.  RANSAC line fits on every kept plane's contour (seeded
 // mt19937 draw sequence replayed exactly, hypotheses scored in parallel, adaptive stop replayed in order), PCA
-// refinement, border tests on the full-resolution depth image, emission of perpendicular planes, and the final
-// compaction of all per-frame results into contiguous output buffers.
+// refinement, border tests on the full-resolution depth image, emission of perpendicular planes, and the offsets
+// of every frame's results in the contiguous output buffers.
 //
 // Reference: /root/reference/src/Frame.cc:938-1114 (GeneratePlanesFromBoundries, IsBorderLine, IsBorderPoint,
 // LineInRange, CaculatePlanes) and PCL 1.8.0 segmentation/impl/sac_segmentation.hpp (segment),
@@ -10,6 +10,7 @@
 #pragma once
 #include <climits>
 #include "spx_math.cuh"
+#include "spx_refine.cuh"   // plane_not_seen
 #include "spx_types.cuh"
 
 namespace spx {
@@ -412,8 +413,8 @@ __global__ void __launch_bounds__(128) k_pack_supposed(Params P, Buffers B) {
     const FrameCtl &ctl = B.ctl[f];
     if (k >= ctl.n_planes) return;
     const PlaneRec &R = ctl.planes[k];
-    spx_point *pts = B.pts + size_t(f) * P.pts_cap + R.points_off;
-    spx_point *bnd = B.bnd + size_t(f) * P.bnd_cap + R.boundary_off;
+    spx_point *pts = B.out_pts + B.frame_offs[size_t(f) * 3 + 1] + R.points_off;
+    spx_point *bnd = B.out_bnd + B.frame_offs[size_t(f) * 3 + 2] + R.boundary_off;
     if (!R.is_supposed) {
         if (ctl.models[R.src].n_contour == 0 && P.enable_supposed) {
             for (int j = threadIdx.x; j < R.n_boundary; j += blockDim.x) {
@@ -445,7 +446,8 @@ __global__ void __launch_bounds__(128) k_pack_supposed(Params P, Buffers B) {
     }
 }
 
-// exclusive scan of the per-frame totals (one CTA), then a gather into contiguous output buffers
+// exclusive scan of the per-frame totals (one CTA): where each frame's planes / points / boundary points start in the
+// contiguous output buffers the pack kernels write to
 __global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B) {
     __shared__ long long s_run[3];
     __shared__ long long s_w[3][32];
@@ -486,17 +488,17 @@ __global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B) {
     if (tid < 3) B.out_totals[tid] = s_run[tid];
 }
 
-__global__ void __launch_bounds__(256) k_gather(Params P, Buffers B) {
-    const int f = blockIdx.y;
+// frame headers and plane records with batch-global offsets; one CTA per frame
+__global__ void __launch_bounds__(128) k_emit_records(Params P, Buffers B) {
+    const int f = blockIdx.x;
     const FrameCtl &ctl = B.ctl[f];
     const long long o_pl = B.frame_offs[size_t(f) * 3 + 0], o_pt = B.frame_offs[size_t(f) * 3 + 1], o_bd = B.frame_offs[size_t(f) * 3 + 2];
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    if (gtid == 0) {
+    if (threadIdx.x == 0) {
         spx_frame_header h;
         h.n_real = ctl.n_real; h.n_planes = ctl.n_planes; h.first_plane = int(o_pl); h.flags = ctl.flags;
         B.out_frames[f] = h;
     }
-    for (int k = gtid; k < ctl.n_planes; k += gsz) {
+    for (int k = threadIdx.x; k < ctl.n_planes; k += blockDim.x) {
         const PlaneRec &R = ctl.planes[k];
         spx_plane o;
         o.coef[0] = R.coef[0]; o.coef[1] = R.coef[1]; o.coef[2] = R.coef[2]; o.coef[3] = R.coef[3];
@@ -505,12 +507,6 @@ __global__ void __launch_bounds__(256) k_gather(Params P, Buffers B) {
         o.src = R.src; o.is_supposed = R.is_supposed;
         B.out_planes[o_pl + k] = o;
     }
-    const uint4 *sp = reinterpret_cast<const uint4 *>(B.pts + size_t(f) * P.pts_cap);
-    uint4 *dp = reinterpret_cast<uint4 *>(B.out_pts + o_pt);
-    for (int k = gtid; k < ctl.pts_used; k += gsz) dp[k] = sp[k];
-    const uint4 *sb = reinterpret_cast<const uint4 *>(B.bnd + size_t(f) * P.bnd_cap);
-    uint4 *db = reinterpret_cast<uint4 *>(B.out_bnd + o_bd);
-    for (int k = gtid; k < ctl.bnd_used; k += gsz) db[k] = sb[k];
 }
 
 }  // namespace spx

@@ -11,6 +11,7 @@
 #include <cstdint>
 
 #define SPX_HD __host__ __device__ __forceinline__
+#define SPX_FULL 0xffffffffu
 
 namespace spx {
 

@@ -10,7 +10,6 @@
 
 namespace spx {
 
-#define SPX_FULL 0xffffffffu
 constexpr float kDistCap = 10.0f;   // normal_smoothing_size_: the distance map is only consumed through min(d, 10)
 
 // ---------------------------------------------------------------------------------------------------------------

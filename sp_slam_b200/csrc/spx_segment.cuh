@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) k_ccl_link(Params P, Buffers B) {
                 (dot3f(n1x, n1y, n1z, B.nx[fo + o], B.ny[fo + o], B.nz[fo + o]) > P.ang_cos);
         }
         B.conn[fo + q] = uint8_t((L ? 1 : 0) | (U ? 2 : 0));
+        B.cnt[fo + q] = 0;
     }
     const unsigned linked = __ballot_sync(SPX_FULL, valid && L);
     const unsigned starts = ~linked | 1u;                       // lane 0 always starts a run inside the segment

@@ -27,8 +27,8 @@ struct Params {
     int   n_grid;          // iterations of the `for(float i=-0.25;i<0.25;i=i+0.01)` loop (src/Frame.cc:1095)
     // per-frame arena capacities (elements)
     int contour_cap;       // contour index arena (2N + 16*SPX_MAX_MODELS)
-    int pts_cap;           // point arena
-    int bnd_cap;           // boundary arena
+    int pts_cap;           // points a frame may emit (N + line inliers + 32 supposed-plane grids)
+    int bnd_cap;           // boundary points a frame may emit
 };
 
 struct Cand {              // connected component with size > Plane.MinSize
@@ -111,10 +111,8 @@ struct Buffers {
     int   *line_sh;               // shuffled indices (contour_cap per frame)
     int   *line_inl;              // inlier index scratch (contour_cap per frame)
     spx_point *line_pts;          // accepted line inlier points (contour_cap per frame)
-    spx_point *pts;               // point arena, pts_cap per frame
-    spx_point *bnd;               // boundary arena, bnd_cap per frame
     FrameCtl *ctl;
-    // compacted outputs
+    // compacted outputs: frame f's planes / points / boundary points start at frame_offs[3f + 0/1/2]
     spx_frame_header *out_frames;
     spx_plane *out_planes;
     spx_point *out_pts;
