@@ -5,8 +5,8 @@ import numpy as np
 
 
 def angle_between(n1, n2):
-    c = float(np.clip(np.dot(n1.astype(np.float64), n2.astype(np.float64)), -1.0, 1.0))
-    return float(np.arccos(c))
+    a, b = np.asarray(n1, np.float64), np.asarray(n2, np.float64)
+    return float(np.arctan2(np.linalg.norm(np.cross(a, b)), np.dot(a, b)))   # well conditioned near 0
 
 
 def bits(a):
@@ -40,8 +40,8 @@ def compare_frame(ext, orc, depth, frame_planes=None, tol_angle=1e-4, tol_d=1e-4
         rep["normals_bit_exact"] = same_f32(nrm_gpu, nrm_ref)
         if not rep["normals_bit_exact"]:
             ok = ~nan_r
-            dots = np.clip(np.sum(nrm_gpu[:, ok].astype(np.float64) * nrm_ref[:, ok].astype(np.float64), axis=0), -1, 1)
-            rep["normals_max_angle"] = float(np.arccos(dots).max())
+            a, b = nrm_gpu[:, ok].astype(np.float64), nrm_ref[:, ok].astype(np.float64)
+            rep["normals_max_angle"] = float(np.arctan2(np.linalg.norm(np.cross(a.T, b.T), axis=1), np.sum(a * b, axis=0)).max())
             assert rep["normals_max_angle"] < 1e-4, rep
         else:
             assert same_f32(pd_gpu, orc.plane_d()), "plane_d differs"
