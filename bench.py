@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- 640x480 plane-extraction frames/s (BASELINE.json metric) on N B200s, one process per GPU.
+
+A step = one pass of the whole hot path (back-projection .. supposed planes .. packed Frame fields) over one batch of
+synthetic depth frames (the box-room orbit of SURVEY.md section 8d, configs[1]); every rank owns its own batch (weak
+scaling, frames are independent) and the plane lists are gathered over NCCL at the end of every step.
+
+  value        frames/s, depth batch already resident in HBM, CUDA-event timed, max over ranks
+  e2e          frames/s through the C ABI with HOST buffers: pinned host depth -> device, kernels, Frame fields -> host
+  roofline     the kernel with the largest share of the step, its algorithmic bytes (table below) over its
+               CUDA-event duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline the CPU oracle (a port of the reference's PCL path; oracle/) on the host cores, bounded sample
+
+`--impl reference` times that CPU oracle on all host threads instead (the reference's own PCL build cannot be compiled
+here: PCL / Eigen / Boost / OpenCV C++ are absent).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "640x480 plane-extraction frames/s"
+UNIT = "frames/s"
+ROWS, COLS = 480, 640
+
+
+def algorithmic_bytes_per_frame(rows=ROWS, cols=COLS, dis=3):
+    """Compulsory bytes per frame: whole path and per kernel (inputs read once + outputs written once,
+    upper bound = every pixel an inlier).  N = organized-cloud size."""
+    w, h = -(-cols // dis), -(-rows // dis)
+    n = w * h
+    path = rows * cols * 4 + n * 4 + n * 4 + n * 16 + 65536
+    k = {
+        "k_backproject": n * 4 + n * 16,                 # 1 depth sample in, x y z dist out
+        "k_chamfer": 2 * (n * 4 + n * 4),                # two passes over the distance map
+        "k_normals": n * 16 + n * 16,                    # x y z dist in, nx ny nz plane_d out
+        "k_ccl_link": n * 28 + n * 9,                    # x y z n d in, conn parent cnt out
+        "k_ccl_merge": n * 1 + n * 4,                    # conn in, parent forest touched
+        "k_ccl_flatten": n * 4 + n * 4 + n * 4,          # parent in/out, counts
+        "k_ccl_rank": n * 8 + n * 4,                     # parent + cnt in, root labels out
+        "k_ccl_label": n * 8,
+        "k_moments_fit": n * 4 + n * 12 + n * 8,         # parent + xyz of members in, index list + positions out
+        "k_models": 8192,
+        "k_pid_init": n * 4 + n * 1,
+        "k_refine": 2 * 2 * n + n * 12 + n * 4,          # plane ids in/out twice, xyz of free pixels, positions
+        "k_contour": n * 1 + 16384,                      # plane-id map in, contour indices out
+        "k_postfilter": 8192,
+        "k_lines": 4 * 4096 * 16 + 2 * 160000,           # <=4 rounds over a ~4k point contour + 20x20 depth windows
+        "k_supposed": 8192,
+        "k_scan_frames": 64,
+        "k_emit_records": 8192,
+        "k_pack_points": n * 17 + n * 16,                # pid pos xyz in, 16-byte points out
+        "k_pack_contours": 4096 * (4 + 12 + 16),
+        "k_pack_supposed": 2 * 2500 * 16,
+    }
+    return path, k, n
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_frames(n_frames: int, rank: int, noise: str, res: str):
+    from sp_slam_b200 import scenes
+    start = (rank * 125) % 1000
+    if res == "720p":
+        d = scenes.realsense_sequence(n_frames, start=start)
+        model = "realsense"
+    else:
+        d = scenes.boxroom_sequence(n_frames, start=start)
+        model = "kinect"
+    if noise != "none":
+        for k in range(n_frames):
+            d[k] = scenes.add_noise(d[k], start + k, model)
+    return d
+
+
+def oracle_fps(depth: np.ndarray, n_threads: int, res: str):
+    from oracle import pyoracle
+    cfg = oracle_config(res)
+    t0 = time.perf_counter()
+    nr, na, tp, ts = pyoracle.run_batch(depth, n_threads, cfg)
+    dt = time.perf_counter() - t0
+    return len(depth) / dt, dt, int(na.sum()), tp, ts
+
+
+def intrinsics(res):
+    from sp_slam_b200 import scenes
+    return scenes.REALSENSE if res == "720p" else scenes.TUM1
+
+
+def oracle_config(res):
+    from oracle import pyoracle
+    it = intrinsics(res)
+    return pyoracle.default_config(fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy, max_x=float(it.width), max_y=float(it.height))
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference's PCL path, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = min(args.frames, args.ref_frames)
+    depth = make_frames(n, 0, args.noise, args.res)
+    for _ in range(args.warmup):
+        oracle_fps(depth[: max(cores, 8)], cores, args.res)
+    t0 = time.perf_counter()
+    planes = 0
+    for _ in range(args.steps):
+        _, _, p, _, _ = oracle_fps(depth, cores, args.res)
+        planes += p
+    dt = time.perf_counter() - t0
+    fps = args.steps * n / dt
+    line = {
+        "impl": "reference", "metric": METRIC if args.res == "480p" else "1280x720 plane-extraction frames/s",
+        "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "frames_per_step": n, "noise": args.noise},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} frames of the workload per step, frame-parallel on {cores} host threads; "
+                                   "oracle/ C++ port of the reference's PCL 1.8 path (PCL itself cannot be built here)"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "planes_per_frame": planes / (args.steps * n),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    if args.res == "720p":
+        return f"{args.frames}-frame synthetic 1280x720 RealSense-shaped clutter sequence, batched plane extraction"
+    return f"{args.frames}-frame synthetic 640x480 box-room orbit (BASELINE configs[1]), batched plane extraction"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1000, help="frames per step and per GPU")
+    ap.add_argument("--ref-frames", type=int, default=500, help="frames per step of the CPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="frames of the cpu_baseline leg")
+    ap.add_argument("--noise", default="none", choices=["none", "sensor"])
+    ap.add_argument("--res", default="480p", choices=["480p", "720p"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    from sp_slam_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    rows, cols = (720, 1280) if args.res == "720p" else (ROWS, COLS)
+    F = args.frames
+    it = intrinsics(args.res)
+    depth_np = make_frames(F, rank, args.noise, args.res)
+    host = torch.from_numpy(depth_np).pin_memory()
+    dev = host.cuda(non_blocking=False)
+    ext = api.PlaneExtractor(max_frames=F, max_rows=rows, max_cols=cols, device=local_rank, fx=it.fx, fy=it.fy, cx=it.cx,
+                             cy=it.cy, max_x=float(it.width), max_y=float(it.height))
+    stream = torch.cuda.current_stream()
+    ext.set_stream(stream.cuda_stream)
+    ext.set_profile(True)
+
+    def gather_planes():
+        """the one collective of the path: plane lists (frame headers + plane records) to every rank over NCCL"""
+        if world == 1:
+            return
+        from sp_slam_b200 import sharding
+        sharding.gather_plane_lists(ext, F)
+
+    def step_device():
+        ext.extract_device(dev.data_ptr(), F, rows, cols)
+        gather_planes()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    ktimes: dict[str, float] = {}
+    launches = 0
+    with ClockSampler(local_rank) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+            launches += ext.launches
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        for name, t in ext.kernel_times():   # events of the last timed step
+            ktimes[name] = ktimes.get(name, 0.0) + t
+        # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+        res = None
+        for _ in range(2):
+            res = ext.extract_batch_ptr(host.data_ptr(), F, rows, cols)
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.steps):
+            res = ext.extract_batch_ptr(host.data_ptr(), F, rows, cols)
+            d2h += res.frames.nbytes + res.planes.nbytes + res.points.nbytes + res.boundary.nbytes + 24
+            launches_e2e = ext.launches
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    planes_per_frame = float(res.frames["n_planes"].mean())
+    overflow = int((res.frames["flags"] != 0).sum())
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    value = world * F * args.steps / (ms * 1e-3)
+    e2e_val = world * F * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        path_bytes, kbytes, n = algorithmic_bytes_per_frame(rows, cols)
+        top = max(ktimes, key=ktimes.get)
+        step_kernel_ms = sum(ktimes.values())
+        achieved = kbytes.get(top, 0) * F / (ktimes[top] * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src,
+            "kernel_ms_per_launch": ktimes[top], "kernel_share_of_step": ktimes[top] / step_kernel_ms,
+            "algorithmic_bytes_per_frame": kbytes.get(top, 0),
+            "path": {"algorithmic_bytes_per_frame": path_bytes,
+                     "achieved": (value / world) * path_bytes / 1e9, "frac": (value / world) * path_bytes / 1e9 / peak},
+            "kernels_ms": {k: round(v, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1])},
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            ns = min(F, args.cpu_sample)
+            fps, dt, _, tp, ts = oracle_fps(depth_np[:ns], cores, args.res)
+            cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"first {ns} frames of the workload, frame-parallel on {cores} host threads, {dt:.1f} s; "
+                             f"oracle/ C++ port of the reference's PCL 1.8 path; per-frame 1-core time "
+                             f"{1e3 * (tp + ts) / ns:.2f} ms (plane {1e3 * tp / ns:.2f} + supposed {1e3 * ts / ns:.2f})"}
+        line = {
+            "metric": METRIC if args.res == "480p" else "1280x720 plane-extraction frames/s",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "frames_per_step_per_gpu": F, "noise": args.noise,
+                       "cloud_dis": 3, "organized_cloud": n, "l2": "inputs larger than L2 (depth batch "
+                       f"{F * rows * cols * 4 / 1e6:.0f} MB per GPU)", "parallelism": f"frame-sharded x{world}",
+                       "planes_per_frame": planes_per_frame, "overflow_frames": overflow},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": F * rows * cols * 4,
+                    "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "latency_ms_per_frame_in_batch": ms / args.steps / F,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    ext.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,20 @@ int spx_fetch_results(spx_ctx *ctx, spx_batch_result *out);
 /* only the frame headers and plane records (coefficients and counts), not the clouds */
 int spx_fetch_planes(spx_ctx *ctx, spx_batch_result *out);
 
+/* Device-side view of the last extract's results (valid until the next extract on the context; read them on the
+ * context's stream or after synchronising it).  This is what a multi-GPU caller hands to NCCL for the end-of-sequence
+ * gather of plane lists without a host round trip. */
+typedef struct spx_device_result {
+    int32_t  n_frames;
+    const spx_frame_header *frames;    /* n_frames */
+    const spx_plane        *planes;    /* totals[0] records */
+    const spx_point        *points;    /* totals[1] */
+    const spx_point        *boundary;  /* totals[2] */
+    const long long        *totals;    /* 3 values: planes, points, boundary points of the batch */
+    int64_t  planes_capacity;          /* records the planes buffer can hold */
+} spx_device_result;
+int spx_get_device_results(spx_ctx *ctx, spx_device_result *out);
+
 /* "feed the reference's normals": like spx_extract for one frame, but integral-image normal estimation is replaced by
  * the caller's normals (HOST memory, 3*N floats: nx[N], ny[N], nz[N], N = organized cloud size, NaN = invalid). */
 int spx_segment_from_normals(spx_ctx *ctx, const float *depth, int rows, int cols, size_t pitch_bytes,
@@ -133,6 +147,10 @@ int spx_cloud_dims(const spx_ctx *ctx, int rows, int cols, int *width, int *heig
 int spx_get_times(spx_ctx *ctx, double *t_plane, double *t_splane);
 /* number of kernel launches issued by the last extract call */
 int spx_last_launch_count(const spx_ctx *ctx);
+/* per-kernel device times of the last extract call: with profiling on, every launch is bracketed by CUDA events on
+ * the context's stream.  names[k] (static strings) / ms[k] for launch k, k < min(*n, cap). */
+int spx_set_profile(spx_ctx *ctx, int on);
+int spx_get_kernel_times(spx_ctx *ctx, const char **names, float *ms, int cap, int *n);
 
 /* ---- debug taps for the parity tests: intermediates of frame `frame` of the last extract call, copied to host.
  * They need spx_set_debug(ctx, 1) BEFORE the extract call (it adds the per-pixel label kernel to the schedule). ---- */

@@ -80,6 +80,9 @@ def lib():
         L.orc_get_plane_boundary.argtypes = [vp, i32, vp]
         L.orc_get_line_recs.argtypes = [vp, vp]
         L.orc_get_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_run_batch.argtypes = [C.POINTER(OrcConfig), vp, i32, i32, i32, i32, vp, vp, C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double)]
+        L.orc_run_batch.restype = i32
         L.orc_chamfer.argtypes = [vp, i32, i32, vp]
         L.orc_eigen33_smallest.argtypes = [vp, C.POINTER(C.c_float), vp]
         L.orc_eigen33_largest.argtypes = [vp, vp, vp]
@@ -216,6 +219,19 @@ class Oracle:
         a, b = C.c_double(), C.c_double()
         lib().orc_get_times(self._h, C.byref(a), C.byref(b))
         return a.value, b.value
+
+
+def run_batch(depth: np.ndarray, n_threads: int, cfg: OrcConfig | None = None):
+    """Frame-parallel oracle over (n, rows, cols) float32 frames; returns (n_real[n], n_planes[n], t_plane_sum, t_splane_sum)."""
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    n, rows, cols = depth.shape
+    cfg = cfg if cfg is not None else default_config()
+    nr = np.zeros(n, np.int32)
+    na = np.zeros(n, np.int32)
+    a, b = C.c_double(), C.c_double()
+    lib().orc_run_batch(C.byref(cfg), depth.ctypes.data, n, rows, cols, int(n_threads), nr.ctypes.data, na.ctypes.data,
+                        C.byref(a), C.byref(b))
+    return nr, na, a.value, b.value
 
 
 def chamfer(mask: np.ndarray) -> np.ndarray:

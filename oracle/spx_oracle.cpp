@@ -39,7 +39,9 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <random>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -985,6 +987,33 @@ void orc_get_line_recs(const orc_ctx *c, orc_line_rec *out) {
     std::memcpy(out, c->line_recs.data(), c->line_recs.size() * sizeof(orc_line_rec));
 }
 void orc_get_times(const orc_ctx *c, double *a, double *b) { *a = c->t_plane; *b = c->t_splane; }
+
+int orc_run_batch(const orc_config *cfg, const float *depth, int n_frames, int rows, int cols, int n_threads,
+                  int32_t *n_real, int32_t *n_planes, double *t_plane_sum, double *t_splane_sum) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_frames) n_threads = n_frames > 0 ? n_frames : 1;
+    std::mutex mu;
+    double tp = 0, ts = 0;
+    std::vector<std::thread> pool;
+    for (int tid = 0; tid < n_threads; ++tid)
+        pool.emplace_back([&, tid]() {
+            orc_ctx *c = orc_create(cfg);
+            double a = 0, b = 0;
+            for (int f = tid; f < n_frames; f += n_threads) {
+                orc_run(c, depth + size_t(f) * rows * cols, rows, cols, nullptr);
+                if (n_real) n_real[f] = c->n_real;
+                if (n_planes) n_planes[f] = c->n_all;
+                a += c->t_plane; b += c->t_splane;
+            }
+            orc_destroy(c);
+            std::lock_guard<std::mutex> lk(mu);
+            tp += a; ts += b;
+        });
+    for (auto &t : pool) t.join();
+    if (t_plane_sum) *t_plane_sum = tp;
+    if (t_splane_sum) *t_splane_sum = ts;
+    return 0;
+}
 
 void orc_chamfer(const uint8_t *mask, int w, int h, float *dist) { chamfer(mask, w, h, dist); }
 void orc_eigen33_smallest(const float cov[9], float *ev, float vec[3]) { eigen33_smallest(cov, *ev, vec); }

@@ -95,6 +95,12 @@ void   orc_get_line_recs(const orc_ctx *, orc_line_rec *out);
 /* seconds spent in the two Timer sections of the last run (src/Frame.cc:184-197) */
 void   orc_get_times(const orc_ctx *, double *t_plane, double *t_splane);
 
+/* Frame-parallel run of the whole path on host threads (one orc_ctx per thread; frames are independent): the CPU
+ * baseline of bench.py.  depth: n_frames contiguous images.  Fills per-frame mnRealPlaneNum / mnPlaneNum and the summed
+ * Timer sections (seconds of CPU time over all frames).  Returns 0. */
+int    orc_run_batch(const orc_config *cfg, const float *depth, int n_frames, int rows, int cols, int n_threads,
+                     int32_t *n_real, int32_t *n_planes, double *t_plane_sum, double *t_splane_sum);
+
 /* ---- stage-level entry points used by known-answer tests ---- */
 /* two-pass chamfer of PCL's computeFeature on a caller-supplied mask (0 = edge) */
 void   orc_chamfer(const uint8_t *mask, int width, int height, float *dist);

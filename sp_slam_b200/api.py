@@ -37,6 +37,7 @@ EXPORTS = (
     "spx_default_config", "spx_create", "spx_destroy", "spx_last_error", "spx_set_stream", "spx_extract",
     "spx_extract_batch", "spx_extract_batch_device", "spx_fetch_results", "spx_fetch_planes",
     "spx_segment_from_normals", "spx_cloud_dims", "spx_get_times", "spx_last_launch_count", "spx_set_debug",
+    "spx_set_profile", "spx_get_kernel_times", "spx_get_device_results",
     "spx_get_cloud", "spx_get_distance_map", "spx_get_normals", "spx_get_labels_raw", "spx_get_plane_ids",
     "spx_get_models", "spx_get_model_inliers", "spx_get_model_contour", "spx_get_lines",
 )
@@ -59,6 +60,13 @@ class SpxBatchResult(C.Structure):
         ("n_frames", C.c_int32), ("n_planes_total", C.c_int32), ("n_points_total", C.c_int64),
         ("n_boundary_total", C.c_int64),
         ("frames", C.c_void_p), ("planes", C.c_void_p), ("points", C.c_void_p), ("boundary", C.c_void_p),
+    ]
+
+
+class SpxDeviceResult(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int32), ("frames", C.c_void_p), ("planes", C.c_void_p), ("points", C.c_void_p),
+        ("boundary", C.c_void_p), ("totals", C.c_void_p), ("planes_capacity", C.c_int64),
     ]
 
 
@@ -98,6 +106,9 @@ def lib():
         L.spx_cloud_dims.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32)]
         L.spx_get_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.spx_last_launch_count.argtypes = [vp]
+        L.spx_get_device_results.argtypes = [vp, C.POINTER(SpxDeviceResult)]
+        L.spx_set_profile.argtypes = [vp, i32]
+        L.spx_get_kernel_times.argtypes = [vp, vp, vp, i32, C.POINTER(i32)]
         L.spx_get_cloud.argtypes = [vp, i32, vp, vp, vp]
         L.spx_get_distance_map.argtypes = [vp, i32, vp]
         L.spx_get_normals.argtypes = [vp, i32, vp, vp, vp, vp]
@@ -238,6 +249,11 @@ class PlaneExtractor:
                                                 C.byref(r)))
         return BatchResult(r).frame(0)
 
+    def device_results(self) -> SpxDeviceResult:
+        r = SpxDeviceResult()
+        self._ck(lib().spx_get_device_results(self._h, C.byref(r)))
+        return r
+
     def set_stream(self, cuda_stream: int | None):
         self._ck(lib().spx_set_stream(self._h, cuda_stream))
 
@@ -254,6 +270,17 @@ class PlaneExtractor:
     @property
     def launches(self) -> int:
         return lib().spx_last_launch_count(self._h)
+
+    def set_profile(self, on: bool):
+        self._ck(lib().spx_set_profile(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """[(kernel name, device ms)] of the last extract call (needs set_profile(True) before it)."""
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = C.c_int()
+        self._ck(lib().spx_get_kernel_times(self._h, names, ms, 64, C.byref(n)))
+        return [(names[k].decode(), float(ms[k])) for k in range(min(n.value, 64))]
 
     # ---- debug taps (need debug=True) ----
     def _n(self, rows, cols):

@@ -65,6 +65,11 @@ struct spx_ctx {
     int last_frames = 0;
     const float *last_depth_dev = nullptr;
     int launches = 0;
+    // optional per-kernel timing (spx_set_profile): event k is recorded before launch k, one more after the last
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<const char *> prof_names;
+    int prof_n = 0;
     std::string err;
 };
 
@@ -134,40 +139,62 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given) {
     int &L = c->launches;
     L = 0;
 
+    c->prof_n = 0;
+    // LAUNCH(kernel, grid, block, smem, args...): counts the launch and, when profiling, brackets it with events
+#define LAUNCH(kern, grid, block, smem, ...)                                                        \
+    do {                                                                                            \
+        if (c->profile) {                                                                           \
+            if (int(c->prof_ev.size()) <= c->prof_n + 1) {                                          \
+                cudaEvent_t pe_;                                                                    \
+                SPX_CK(c, cudaEventCreate(&pe_));                                                   \
+                c->prof_ev.push_back(pe_);                                                          \
+                SPX_CK(c, cudaEventCreate(&pe_));                                                   \
+                c->prof_ev.push_back(pe_);                                                          \
+            }                                                                                       \
+            if (int(c->prof_names.size()) <= c->prof_n) c->prof_names.resize(c->prof_n + 1);        \
+            c->prof_names[c->prof_n] = #kern;                                                       \
+            SPX_CK(c, cudaEventRecord(c->prof_ev[c->prof_n], st));                                  \
+            ++c->prof_n;                                                                            \
+        }                                                                                           \
+        kern<<<grid, block, smem, st>>>(__VA_ARGS__);                                               \
+        ++L;                                                                                        \
+    } while (0)
+
     SPX_CK(c, cudaEventRecord(c->ev[0], st));
     SPX_CK(c, cudaMemsetAsync(B.ctl, 0, sizeof(FrameCtl) * size_t(F), st));
-    k_backproject<<<gpix, 256, 0, st>>>(depth_dev, P, B); ++L;
+    LAUNCH(k_backproject, gpix, 256, 0, depth_dev, P, B);
     if (!normals_given) {
-        if (P.w >= 3 && P.h >= 3) {
-            k_chamfer<<<cdiv(F, kChamferWarps), kChamferWarps * 32, size_t(kChamferWarps) * 3 * P.w * sizeof(float), st>>>(P, B); ++L;
-        }
-        k_normals<<<dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), 256, kNormalsSmem, st>>>(P, B); ++L;
+        if (P.w >= 3 && P.h >= 3)
+            LAUNCH(k_chamfer, cdiv(F, kChamferWarps), kChamferWarps * 32, size_t(kChamferWarps) * 3 * P.w * sizeof(float), P, B);
+        LAUNCH(k_normals, dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), 256, kNormalsSmem, P, B);
     } else {
-        k_plane_d<<<gpix, 256, 0, st>>>(P, B); ++L;
+        LAUNCH(k_plane_d, gpix, 256, 0, P, B);
     }
-    k_ccl_link<<<dim3(cdiv(P.w, 32), cdiv(P.h, 8), F), dim3(32, 8), 0, st>>>(P, B); ++L;
-    k_ccl_merge<<<gpix, 256, 0, st>>>(P, B); ++L;
-    k_ccl_flatten<<<gpix, 256, 0, st>>>(P, B); ++L;
-    k_ccl_rank<<<F, 1024, 0, st>>>(P, B); ++L;
-    if (c->debug) { k_ccl_label<<<gpix, 256, 0, st>>>(P, B); ++L; }
-    k_moments_fit<<<dim3(SPX_MAX_CAND / 4, F), 128, 0, st>>>(P, B); ++L;
-    k_models<<<cdiv(F, 128), 128, 0, st>>>(P, B); ++L;
-    k_pid_init<<<gpix, 256, 0, st>>>(P, B); ++L;
-    k_refine<<<cdiv(F, kRefWarps), kRefWarps * 32, 0, st>>>(P, B); ++L;
-    k_contour<<<F, 32, 0, st>>>(P, B); ++L;
-    k_postfilter<<<cdiv(F, 128), 128, 0, st>>>(P, B); ++L;
+    LAUNCH(k_ccl_link, dim3(cdiv(P.w, 32), cdiv(P.h, 8), F), dim3(32, 8), 0, P, B);
+    LAUNCH(k_ccl_merge, gpix, 256, 0, P, B);
+    LAUNCH(k_ccl_flatten, gpix, 256, 0, P, B);
+    LAUNCH(k_ccl_rank, F, 1024, 0, P, B);
+    if (c->debug) LAUNCH(k_ccl_label, gpix, 256, 0, P, B);
+    LAUNCH(k_moments_fit, dim3(SPX_MAX_CAND / 4, F), 128, 0, P, B);
+    LAUNCH(k_models, cdiv(F, 128), 128, 0, P, B);
+    LAUNCH(k_pid_init, gpix, 256, 0, P, B);
+    LAUNCH(k_refine, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
+    LAUNCH(k_contour, F, 32, 0, P, B);
+    LAUNCH(k_postfilter, cdiv(F, 128), 128, 0, P, B);
     SPX_CK(c, cudaEventRecord(c->ev[1], st));
     if (P.enable_supposed) {
-        k_lines<<<dim3(SPX_MAX_MODELS, F), kLineThreads, 0, st>>>(depth_dev, P, B); ++L;
-        k_supposed<<<cdiv(F, 128), 128, 0, st>>>(P, B); ++L;
+        LAUNCH(k_lines, dim3(SPX_MAX_MODELS, F), kLineThreads, 0, depth_dev, P, B);
+        LAUNCH(k_supposed, cdiv(F, 128), 128, 0, P, B);
     }
     SPX_CK(c, cudaEventRecord(c->ev[2], st));
-    k_scan_frames<<<1, 1024, 0, st>>>(P, B); ++L;
-    k_emit_records<<<F, 128, 0, st>>>(P, B); ++L;
-    k_pack_points<<<gpix, 256, 0, st>>>(P, B); ++L;
-    k_pack_contours<<<dim3(SPX_MAX_MODELS, F), 128, 0, st>>>(P, B); ++L;
-    if (P.enable_supposed) { k_pack_supposed<<<dim3(SPX_MAX_PLANES, F), 128, 0, st>>>(P, B); ++L; }
+    LAUNCH(k_scan_frames, 1, 1024, 0, P, B);
+    LAUNCH(k_emit_records, F, 128, 0, P, B);
+    LAUNCH(k_pack_points, gpix, 256, 0, P, B);
+    LAUNCH(k_pack_contours, dim3(SPX_MAX_MODELS, F), 128, 0, P, B);
+    if (P.enable_supposed) LAUNCH(k_pack_supposed, dim3(SPX_MAX_PLANES, F), 128, 0, P, B);
     SPX_CK(c, cudaEventRecord(c->ev[3], st));
+    if (c->profile) SPX_CK(c, cudaEventRecord(c->prof_ev[c->prof_n], st));
+#undef LAUNCH
     SPX_CK(c, cudaGetLastError());
     c->have_run = true;
     c->last_frames = F;
@@ -385,6 +412,7 @@ void spx_destroy(spx_ctx *c) {
     if (c->h_pts) cudaFreeHost(c->h_pts);
     if (c->h_bnd) cudaFreeHost(c->h_bnd);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -425,6 +453,16 @@ int spx_fetch_planes(spx_ctx *c, spx_batch_result *out) {
     if (!c || !out) return SPX_ERR_ARG;
     SPX_CK(c, cudaSetDevice(c->device));
     return fetch(c, out, false);
+}
+
+int spx_get_device_results(spx_ctx *c, spx_device_result *out) {
+    if (!c || !out) return SPX_ERR_ARG;
+    if (!c->have_run) return fail(c, SPX_ERR_STATE, "no extract call has been made on this context");
+    out->n_frames = c->last_frames;
+    out->frames = c->B.out_frames; out->planes = c->B.out_planes; out->points = c->B.out_pts; out->boundary = c->B.out_bnd;
+    out->totals = c->B.out_totals;
+    out->planes_capacity = int64_t(c->cfg.max_frames) * SPX_MAX_PLANES;
+    return SPX_OK;
 }
 
 int spx_extract_batch(spx_ctx *c, const float *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
@@ -484,6 +522,25 @@ int spx_get_times(spx_ctx *c, double *t_plane, double *t_splane) {
 }
 
 int spx_last_launch_count(const spx_ctx *c) { return c ? c->launches : 0; }
+
+int spx_set_profile(spx_ctx *c, int on) {
+    if (!c) return SPX_ERR_ARG;
+    c->profile = on != 0;
+    return SPX_OK;
+}
+
+int spx_get_kernel_times(spx_ctx *c, const char **names, float *ms, int cap, int *n) {
+    if (!c || !n) return SPX_ERR_ARG;
+    if (!c->have_run || !c->profile || c->prof_n == 0) return fail(c, SPX_ERR_STATE, "no profiled extract call (spx_set_profile) on this context");
+    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_CK(c, cudaEventSynchronize(c->prof_ev[c->prof_n]));
+    *n = c->prof_n;
+    for (int k = 0; k < c->prof_n && k < cap; ++k) {
+        if (names) names[k] = c->prof_names[k];
+        if (ms) SPX_CK(c, cudaEventElapsedTime(&ms[k], c->prof_ev[k], c->prof_ev[k + 1]));
+    }
+    return SPX_OK;
+}
 
 // ---- debug taps ----------------------------------------------------------------------------------------------
 int spx_get_cloud(spx_ctx *c, int frame, float *x, float *y, float *z) {

@@ -1,0 +1,69 @@
+"""Frame sharding across the GPUs of one box and the one collective of the path: the gather of plane lists.
+
+The reference is single-process; for offline sequences frames are independent
+(PlaneNotSeen only sees the planes of its own frame, /root/reference/src/Frame.cc:1116-1144), so rank r of G owns the
+contiguous frame range [r*F/G, (r+1)*F/G) and nothing is exchanged until the per-frame headers (mnRealPlaneNum,
+mnPlaneNum) and plane records (mvPlaneCoefficients + cloud sizes) are gathered.  The payload is small (16 B per frame
++ 48 B per plane), so the gather is latency bound; clouds stay on the rank that produced them.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+
+
+def shard_range(n_frames: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous frame range of `rank`; the first n_frames % world ranks get one frame more."""
+    base, extra = divmod(n_frames, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class _DevBuf:
+    """A raw device range exposed through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def _as_tensor(ptr: int, nbytes: int, device):
+    import torch
+    return torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
+
+
+def gather_plane_lists(ext: "api.PlaneExtractor", n_frames: int, to_host: bool = False):
+    """NCCL all-gather of every rank's frame headers and plane records (device buffers of the last extract).
+
+    Returns (headers[world, n_frames], planes[world, max_planes], counts[world]) as device uint8/int64 tensors, or
+    numpy structured arrays per rank when ``to_host``."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    r = ext.device_results()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    hdr = _as_tensor(r.frames, n_frames * api.HEADER_DTYPE.itemsize, dev)
+    totals = _as_tensor(r.totals, 24, dev).view(torch.int64)
+    counts = torch.empty(world * 3, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, totals)
+    hdrs = torch.empty(world * hdr.numel(), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(hdrs, hdr)
+    counts_h = counts.view(world, 3).cpu()
+    max_planes = int(counts_h[:, 0].max())
+    rec = api.PLANE_DTYPE.itemsize
+    planes = torch.empty(world * max(max_planes, 1) * rec, dtype=torch.uint8, device=dev)
+    if max_planes > 0:
+        mine = _as_tensor(r.planes, max_planes * rec, dev)   # the buffer is max_frames * SPX_MAX_PLANES records long
+        dist.all_gather_into_tensor(planes, mine)
+    if not to_host:
+        return hdrs.view(world, -1), planes.view(world, -1), counts_h
+    out = []
+    hdrs_h = hdrs.view(world, -1).cpu().numpy()
+    planes_h = planes.view(world, -1).cpu().numpy()
+    for k in range(world):
+        n_pl = int(counts_h[k, 0])
+        out.append((np.frombuffer(hdrs_h[k].tobytes(), dtype=api.HEADER_DTYPE),
+                    np.frombuffer(planes_h[k].tobytes(), dtype=api.PLANE_DTYPE)[:n_pl]))
+    return out
