@@ -168,7 +168,8 @@ def run_reference(args, rank, world):
         "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "frames_per_step": n, "noise": args.noise},
+        "config": {"workload": workload_name(args), "frames_per_step_per_gpu": args.frames, "noise": args.noise,
+                   "cloud_dis": 3, "sample_frames_per_step": n},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n} frames of the workload per step, frame-parallel on {cores} host threads; "
                                    "oracle/ C++ port of the reference's PCL 1.8 path (PCL itself cannot be built here)"},
@@ -226,7 +227,9 @@ def main():
     dev = host.cuda(non_blocking=False)
     ext = api.PlaneExtractor(max_frames=F, max_rows=rows, max_cols=cols, device=local_rank, fx=it.fx, fy=it.fy, cx=it.cx,
                              cy=it.cy, max_x=float(it.width), max_y=float(it.height))
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch and the library, so torch.cuda.Event brackets the kernels
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     ext.set_stream(stream.cuda_stream)
     ext.set_profile(True)
 
