@@ -33,19 +33,19 @@ def _as_tensor(ptr: int, nbytes: int, device):
     return torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
 
 
-def gather_plane_lists(ext: "api.PlaneExtractor", n_frames: int, to_host: bool = False):
-    """NCCL all-gather of every rank's frame headers and plane records (device buffers of the last extract).
+def gather_records(hdr, planes_buf, totals, to_host: bool = False):
+    """All-gather of per-rank frame headers and plane records; works on any backend (NCCL on device buffers, gloo on
+    host tensors in the CPU tests).
 
-    Returns (headers[world, n_frames], planes[world, max_planes], counts[world]) as device uint8/int64 tensors, or
-    numpy structured arrays per rank when ``to_host``."""
+    hdr: uint8 tensor, n_frames * 16 bytes (same n_frames on every rank);  planes_buf: uint8 tensor holding at least
+    this rank's plane records (48 bytes each), and at least max-over-ranks records of capacity;  totals: int64[3]
+    (planes, points, boundary points).  Plane counts differ per rank, so counts are gathered first and the records
+    padded to the maximum."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size()
-    r = ext.device_results()
-    dev = torch.device("cuda", torch.cuda.current_device())
-    hdr = _as_tensor(r.frames, n_frames * api.HEADER_DTYPE.itemsize, dev)
-    totals = _as_tensor(r.totals, 24, dev).view(torch.int64)
+    dev = hdr.device
     counts = torch.empty(world * 3, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts, totals)
     hdrs = torch.empty(world * hdr.numel(), dtype=torch.uint8, device=dev)
@@ -55,8 +55,9 @@ def gather_plane_lists(ext: "api.PlaneExtractor", n_frames: int, to_host: bool =
     rec = api.PLANE_DTYPE.itemsize
     planes = torch.empty(world * max(max_planes, 1) * rec, dtype=torch.uint8, device=dev)
     if max_planes > 0:
-        mine = _as_tensor(r.planes, max_planes * rec, dev)   # the buffer is max_frames * SPX_MAX_PLANES records long
-        dist.all_gather_into_tensor(planes, mine)
+        if planes_buf.numel() < max_planes * rec:
+            raise ValueError("plane buffer smaller than the largest rank's plane list")
+        dist.all_gather_into_tensor(planes, planes_buf[: max_planes * rec])
     if not to_host:
         return hdrs.view(world, -1), planes.view(world, -1), counts_h
     out = []
@@ -67,3 +68,16 @@ def gather_plane_lists(ext: "api.PlaneExtractor", n_frames: int, to_host: bool =
         out.append((np.frombuffer(hdrs_h[k].tobytes(), dtype=api.HEADER_DTYPE),
                     np.frombuffer(planes_h[k].tobytes(), dtype=api.PLANE_DTYPE)[:n_pl]))
     return out
+
+
+def gather_plane_lists(ext: "api.PlaneExtractor", n_frames: int, to_host: bool = False):
+    """NCCL all-gather of every rank's frame headers and plane records straight from the device buffers of the last
+    extract (no host round trip for the payload)."""
+    import torch
+
+    r = ext.device_results()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    hdr = _as_tensor(r.frames, n_frames * api.HEADER_DTYPE.itemsize, dev)
+    totals = _as_tensor(r.totals, 24, dev).view(torch.int64)
+    planes_buf = _as_tensor(r.planes, int(r.planes_capacity) * api.PLANE_DTYPE.itemsize, dev)
+    return gather_records(hdr, planes_buf, totals, to_host)
