@@ -265,6 +265,7 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         for name, t in ext.kernel_times():   # events of the last timed step
+            name = name.split("<")[0]
             ktimes[name] = ktimes.get(name, 0.0) + t
         # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
         res = None

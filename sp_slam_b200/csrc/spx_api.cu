@@ -173,12 +173,14 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given) {
     LAUNCH(k_ccl_link, dim3(cdiv(P.w, 32), cdiv(P.h, 8), F), dim3(32, 8), 0, P, B);
     LAUNCH(k_ccl_merge, gpix, 256, 0, P, B);
     LAUNCH(k_ccl_flatten, gpix, 256, 0, P, B);
-    LAUNCH(k_ccl_rank, F, 1024, 0, P, B);
+    LAUNCH(k_ccl_rank, F, kRankThreads, 0, P, B);
     if (c->debug) LAUNCH(k_ccl_label, gpix, 256, 0, P, B);
-    LAUNCH(k_moments_fit, dim3(SPX_MAX_CAND / 4, F), 128, 0, P, B);
+    LAUNCH(k_moments_fit, dim3(SPX_MAX_CAND / kMomWarps, F), kMomWarps * 32, 0, P, B);
     LAUNCH(k_models, cdiv(F, 128), 128, 0, P, B);
     LAUNCH(k_pid_init, gpix, 256, 0, P, B);
-    LAUNCH(k_refine, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
+    if (P.w <= 224) LAUNCH(k_refine<7>, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
+    else if (P.w <= 448) LAUNCH(k_refine<14>, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
+    else LAUNCH(k_refine<16>, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
     LAUNCH(k_contour, F, 32, 0, P, B);
     LAUNCH(k_postfilter, cdiv(F, 128), 128, 0, P, B);
     SPX_CK(c, cudaEventRecord(c->ev[1], st));

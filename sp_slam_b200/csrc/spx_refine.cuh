@@ -21,9 +21,7 @@ struct RefineSmem {
     int    n0[SPX_MAX_MODELS];
     int    cnt1[SPX_MAX_MODELS], cnt2[SPX_MAX_MODELS];
     int    last1[SPX_MAX_MODELS], last2[SPX_MAX_MODELS];
-    int8_t rowA[kMaxW], rowB[kMaxW];   // plane ids of the previously finished row / the row being processed
-    int8_t cmA[kMaxW];                 // model claimed sideways by claimer c  (pass 1: right, pass 2: left)
-    int8_t cmB[kMaxW];                 // model claimed vertically by claimer c (pass 1: down, pass 2: up)
+    int8_t cmA[kMaxW];                 // model claimed sideways by claimer column c  (pass 1: right, pass 2: left)
 };
 
 // point-to-plane test of PlaneRefinementComparator::compare (fp32 products and sums, no contraction)
@@ -32,91 +30,154 @@ __device__ __forceinline__ bool refine_dist_ok(const float *cf, float x, float y
     return fabsf(v) < kRefineThr;
 }
 
-// Ordered emission of the claims made by one row of claimers.  In visiting order claimer k issues its sideways claim
-// (cmA) and then its vertical claim (cmB); `lane` enumerates claimers in visiting order inside a 32-wide segment.
-// Every claimed pixel receives its position in inlier_indices[model] (= base[model] + running count).
-template <bool kReverse>
-__device__ __forceinline__ void refine_emit(RefineSmem &S, int w, int claimer_row, int *cnt, int *last, const int *pos_base,
-                                            int *pos, int lane) {
-    for (int base = 0; base < w; base += 32) {
-        const int k = base + lane;
-        const int c = kReverse ? (w - 1 - k) : k;
-        const bool valid = k < w;
-        const int mS = valid ? int(S.cmA[c]) : -1;
-        const int mV = valid ? int(S.cmB[c]) : -1;
-        unsigned todoS = __ballot_sync(SPX_FULL, mS >= 0), todoV = __ballot_sync(SPX_FULL, mV >= 0);
-        while (todoS | todoV) {
-            const int src = __ffs(todoS | todoV) - 1;
-            const int mine = mS >= 0 ? mS : mV;
-            const int mm = __shfl_sync(SPX_FULL, mine, src);
-            const unsigned bS = __ballot_sync(SPX_FULL, mS == mm), bV = __ballot_sync(SPX_FULL, mV == mm);
-            const unsigned lt = (1u << lane) - 1u;
-            const int before = __popc(bS & lt) + __popc(bV & lt);
-            const int b0 = cnt[mm];
-            int qS, qV;
-            if (kReverse) { qS = claimer_row * w + c - 1; qV = (claimer_row - 1) * w + c; }   // left (wraps at c == 0), up
-            else          { qS = claimer_row * w + c + 1; qV = (claimer_row + 1) * w + c; }   // right, down
-            if (mS == mm) pos[qS] = pos_base[mm] + b0 + before;
-            if (mV == mm) pos[qV] = pos_base[mm] + b0 + before + (mS == mm ? 1 : 0);
-            const int hl = 31 - __clz(bS | bV);
-            __syncwarp();
-            if (lane == hl) { last[mm] = (mV == mm) ? qV : qS; cnt[mm] = b0 + __popc(bS) + __popc(bV); }
-            __syncwarp();
-            todoS &= ~bS; todoV &= ~bV;
-        }
+// One raster pass of refine() over a frame, one warp.  kReverse = false: PCL's first pass (rows 0..h-2, cols 0..w-2,
+// right neighbour then lower neighbour, labels read live); kReverse = true: the second pass (rows h-1..1, cols
+// w-1..0, left neighbour -- which at c == 0 is the last pixel of the row above -- then upper neighbour).
+//
+// Rows are visited in pass order; lane l of chunk ch owns visiting index k = 32 ch + l (column c = k, or w-1-k in the
+// reverse pass).  For target row r:
+//   A) pixels claimed vertically by the finished previous row (the claimer sits in the same column),
+//   W) reverse pass only: the wrap claim of (r+1, 0) on (r, w-1),
+//   E) ordered emission of the claims made by the previous row's claimers: in visiting order claimer k issues its
+//      sideways claim and then its vertical claim; every claimed pixel gets its position in inlier_indices[model],
+//   B) the chain inside row r: a free pixel is claimed by its already-final neighbour on the claimer side.  With
+//      src = nearest labelled pixel on that side (or the carry from the previous chunk), a free pixel is claimed iff
+//      it and every free pixel between src and itself lie within 0.02 m of src's plane -- ballots and bit masks only.
+// Row r+1's plane ids and the xyz of its free pixels are prefetched into registers while row r is processed (plane ids
+// two rows ahead), so no global-load latency sits on the row-to-row dependency chain.
+template <int NCH, bool kReverse>
+__device__ __forceinline__ void refine_pass(RefineSmem &S, const Params &P, const float *__restrict__ px, const float *__restrict__ py,
+                                            const float *__restrict__ pz, int8_t *pid, int *pos, int *cnt, int *last,
+                                            const int *pos_base, int lane) {
+    const int w = P.w, h = P.h;
+    int a[NCH], prev[NCH], pn[NCH], pn2[NCH], mV[NCH];
+    float x[NCH], y[NCH], z[NCH], xn[NCH], yn[NCH], zn[NCH];
+    auto col = [&](int ch) { const int k = ch * 32 + lane; return kReverse ? (w - 1 - k) : k; };
+    auto row_of = [&](int t) { return kReverse ? (h - 1 - t) : t; };
+    // prologue: plane ids of rows t = 0 and 1, xyz of the free pixels of row 0
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        const bool valid = ch * 32 + lane < w;
+        const int c = col(ch);
+        pn[ch] = valid ? int(pid[row_of(0) * w + c]) : -2;
+        pn2[ch] = (valid && h > 1) ? int(pid[row_of(1) * w + c]) : -2;
+        prev[ch] = -2; mV[ch] = -1;
+        xn[ch] = yn[ch] = zn[ch] = 0.f;
     }
-}
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+        if (pn[ch] == -1) { const int q = row_of(0) * w + col(ch); xn[ch] = px[q]; yn[ch] = py[q]; zn[ch] = pz[q]; }
+    for (int c0 = lane; c0 < w; c0 += 32) S.cmA[c0] = -1;
+    __syncwarp();
 
-// In-row chain: every free pixel whose neighbour on the claimer side carries model m and that lies within 0.02 m of
-// plane m is claimed, and then claims onward.  For one model this is a carry ripple: F = free & near-plane pixels,
-// seeds = (sources shifted one step | carry-in) & F, claimed = F & ~(F + seeds).  Chains of different models never
-// overlap (a pixel's fate is decided by its single claimer-side neighbour), so each is resolved independently.
-// `lane` enumerates pixels in visiting order (pass 1: left to right; pass 2: right to left).
-template <bool kReverse>
-__device__ __forceinline__ void refine_chain(RefineSmem &S, int8_t *rowCur, int w, int r, const float *px, const float *py,
-                                             const float *pz, int lane) {
-    int carry = -1;
-    for (int base = 0; base < w; base += 32) {
-        const int k = base + lane;
-        const int c = kReverse ? (w - 1 - k) : k;
-        const bool valid = k < w;
-        const int cur = valid ? int(rowCur[c]) : -2;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (valid && cur == -1) { const int q = r * w + c; x = px[q]; y = py[q]; z = pz[q]; }
-        int newcur = cur;
-        unsigned todo = __ballot_sync(SPX_FULL, cur >= 0);
-        bool carry_pending = carry >= 0;
-        while (carry_pending || todo) {
-            int mm;
-            if (carry_pending) { mm = carry; carry_pending = false; }
-            else { mm = __shfl_sync(SPX_FULL, cur, __ffs(todo) - 1); }
-            const unsigned src = __ballot_sync(SPX_FULL, cur == mm);
-            todo &= ~src;
-            const unsigned F = __ballot_sync(SPX_FULL, cur == -1 && refine_dist_ok(S.coef[mm], x, y, z));
-            const unsigned seeds = ((src << 1) | (carry == mm ? 1u : 0u)) & F;
-            if (seeds == 0u) continue;
-            const unsigned claimed = F & ~(F + seeds);
-            if ((claimed >> lane) & 1u) {
-                newcur = mm;
-                S.cmA[kReverse ? c + 1 : c - 1] = int8_t(mm);   // the claimer is the previously visited pixel
+    for (int t = 0; t < h; ++t) {
+        const int r = row_of(t);
+        // rotate the prefetch registers and issue the loads of the rows ahead
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) { a[ch] = pn[ch]; x[ch] = xn[ch]; y[ch] = yn[ch]; z[ch] = zn[ch]; pn[ch] = pn2[ch]; }
+        if (t + 1 < h) {
+            const int rn = row_of(t + 1);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch)
+                if (pn[ch] == -1) { const int q = rn * w + col(ch); xn[ch] = px[q]; yn[ch] = py[q]; zn[ch] = pz[q]; }
+        }
+        if (t + 2 < h) {
+            const int rn2 = row_of(t + 2);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) pn2[ch] = (ch * 32 + lane < w) ? int(pid[rn2 * w + col(ch)]) : -2;
+        }
+        // A) vertical claims by the previous row
+        if (t >= 1) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                mV[ch] = -1;
+                const int m = prev[ch];
+                if (a[ch] == -1 && m >= 0 && (kReverse || col(ch) <= w - 2) && refine_dist_ok(S.coef[m], x[ch], y[ch], z[ch])) {
+                    a[ch] = m; mV[ch] = m;
+                }
+            }
+            // W) wrap claim of (r+1, 0) on (r, w-1): visiting index w-1 of the previous row claims visiting index 0
+            if (kReverse) {
+                int m0 = -1;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch)
+                    if (ch == ((w - 1) >> 5)) m0 = __shfl_sync(SPX_FULL, prev[ch], (w - 1) & 31);
+                if (m0 >= 0 && lane == 0 && a[0] == -1 && refine_dist_ok(S.coef[m0], x[0], y[0], z[0])) {
+                    a[0] = m0; S.cmA[0] = int8_t(m0);
+                }
+                __syncwarp();
+            }
+            // E) emission for the claimers of the previous row
+            const int claimer_row = kReverse ? r + 1 : r - 1;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const bool valid = ch * 32 + lane < w;
+                const int c = col(ch);
+                const int mS = valid ? int(S.cmA[c]) : -1;
+                const int mv = mV[ch];
+                unsigned todoS = __ballot_sync(SPX_FULL, mS >= 0), todoV = __ballot_sync(SPX_FULL, mv >= 0);
+                while (todoS | todoV) {
+                    const int src = __ffs(todoS | todoV) - 1;
+                    const int mine = mS >= 0 ? mS : mv;
+                    const int mm = __shfl_sync(SPX_FULL, mine, src);
+                    const unsigned bS = __ballot_sync(SPX_FULL, mS == mm), bV = __ballot_sync(SPX_FULL, mv == mm);
+                    const unsigned lt = (1u << lane) - 1u;
+                    const int before = __popc(bS & lt) + __popc(bV & lt);
+                    const int b0 = cnt[mm];
+                    int qS, qV;
+                    if (kReverse) { qS = claimer_row * w + c - 1; qV = (claimer_row - 1) * w + c; }   // left (wraps at c == 0), up
+                    else          { qS = claimer_row * w + c + 1; qV = (claimer_row + 1) * w + c; }   // right, down
+                    if (mS == mm) pos[qS] = pos_base[mm] + b0 + before;
+                    if (mv == mm) pos[qV] = pos_base[mm] + b0 + before + (mS == mm ? 1 : 0);
+                    const int hl = 31 - __clz(bS | bV);
+                    __syncwarp();
+                    if (lane == hl) { last[mm] = (mv == mm) ? qV : qS; cnt[mm] = b0 + __popc(bS) + __popc(bV); }
+                    __syncwarp();
+                    todoS &= ~bS; todoV &= ~bV;
+                }
+                if (valid) S.cmA[c] = -1;
+            }
+            __syncwarp();
+        }
+        // B) the chain inside row r (claimers: rows <= h-2 in the forward pass, rows >= 1 in the reverse pass)
+        if (kReverse ? (r >= 1) : (r <= h - 2)) {
+            int carry = -1;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const bool valid = ch * 32 + lane < w;
+                const int cur = a[ch];
+                const unsigned labelled = __ballot_sync(SPX_FULL, cur >= 0);
+                const unsigned below = labelled & ((1u << lane) - 1u);
+                const int src_lane = below ? (31 - __clz(below)) : -1;
+                const int m_lane = __shfl_sync(SPX_FULL, cur, src_lane < 0 ? 0 : src_lane);
+                const int m_src = src_lane < 0 ? carry : m_lane;
+                const bool isfree = valid && cur == -1;
+                const bool ok = isfree && m_src >= 0 && refine_dist_ok(S.coef[m_src], x[ch], y[ch], z[ch]);
+                const unsigned blocked = __ballot_sync(SPX_FULL, !valid || (cur == -1 && !ok));
+                // the free pixels visited between src and this one: bits src_lane+1 .. lane-1
+                const unsigned le_src = src_lane < 0 ? 0u : ((2u << src_lane) - 1u);
+                const unsigned mask = ((1u << lane) - 1u) & ~le_src;
+                const bool claimed = ok && (blocked & mask) == 0u;
+                if (claimed) {
+                    a[ch] = m_src;
+                    const int c = col(ch);
+                    S.cmA[kReverse ? c + 1 : c - 1] = int8_t(m_src);   // the claimer is the previously visited pixel
+                }
+                carry = __shfl_sync(SPX_FULL, a[ch], 31);
+                if (carry < 0) carry = -1;
             }
         }
-        if (valid) rowCur[c] = int8_t(newcur);
-        carry = __shfl_sync(SPX_FULL, newcur, 31);
-        if (carry < 0) carry = -1;
+        // final labels of row r
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            if (ch * 32 + lane < w) pid[r * w + col(ch)] = int8_t(a[ch]);
+            prev[ch] = a[ch];
+        }
+        __syncwarp();
     }
 }
 
-// K6: one warp per frame.
-// Pass 1 (PCL: rows 0..h-2, cols 0..w-2, right neighbour then lower neighbour, labels read live):
-//   target row r:  A) pixels claimed from above by the finished row r-1 (claimers c <= w-2), then
-//                  B) the left-to-right chain inside row r (only rows <= h-2 have claimers).
-// Pass 2 (PCL: rows h-1..1, cols w-1..0, left neighbour -- which at c == 0 is the last pixel of the row above --
-//   then upper neighbour):
-//   target row r:  A') claimed from below by the finished row r+1 (all columns), W) the wrap claim of (r+1, 0) on
-//                  (r, w-1), then B') the right-to-left chain inside row r (rows >= 1).
-// Claim order (= order of the appended inlier indices) is the visiting order of the CLAIMERS, so the claims of
-// claimer row k are emitted once both its sideways and its vertical claims are known.
+template <int NCH>
 __global__ void __launch_bounds__(kRefWarps * 32) k_refine(Params P, Buffers B) {
     __shared__ RefineSmem smem[kRefWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -126,7 +187,6 @@ __global__ void __launch_bounds__(kRefWarps * 32) k_refine(Params P, Buffers B) 
     FrameCtl &ctl = B.ctl[f];
     const int nm = ctl.n_models;
     if (nm == 0) return;
-    const int w = P.w, h = P.h;
     const size_t fo = size_t(f) * P.N;
     const float *px = B.px + fo, *py = B.py + fo, *pz = B.pz + fo;
     int8_t *pid = B.pid + fo;
@@ -137,72 +197,14 @@ __global__ void __launch_bounds__(kRefWarps * 32) k_refine(Params P, Buffers B) 
         S.coef[m][0] = M.coef[0]; S.coef[m][1] = M.coef[1]; S.coef[m][2] = M.coef[2]; S.coef[m][3] = M.coef[3];
         S.n0[m] = M.n0; S.cnt1[m] = 0; S.cnt2[m] = 0; S.last1[m] = -1; S.last2[m] = -1;
     }
-    for (int c = lane; c < w; c += 32) { S.cmA[c] = -1; S.cmB[c] = -1; }
     __syncwarp();
-
-    int8_t *rowPrev = S.rowA, *rowCur = S.rowB;
-    // ---------------- pass 1 ----------------
-    for (int r = 0; r < h; ++r) {
-        for (int c = lane; c < w; c += 32) { rowCur[c] = pid[r * w + c]; S.cmB[c] = -1; }
-        __syncwarp();
-        if (r >= 1) {
-            for (int c = lane; c < w - 1; c += 32) {
-                if (rowCur[c] < 0) {
-                    const int m = rowPrev[c];
-                    if (m >= 0) {
-                        const int q = r * w + c;
-                        if (refine_dist_ok(S.coef[m], px[q], py[q], pz[q])) { rowCur[c] = int8_t(m); S.cmB[c] = int8_t(m); }
-                    }
-                }
-            }
-            __syncwarp();
-            refine_emit<false>(S, w, r - 1, S.cnt1, S.last1, S.n0, pos, lane);
-        }
-        for (int c = lane; c < w; c += 32) S.cmA[c] = -1;
-        __syncwarp();
-        if (r <= h - 2) refine_chain<false>(S, rowCur, w, r, px, py, pz, lane);
-        __syncwarp();
-        for (int c = lane; c < w; c += 32) pid[r * w + c] = rowCur[c];
-        int8_t *t = rowPrev; rowPrev = rowCur; rowCur = t;
-    }
+    refine_pass<NCH, false>(S, P, px, py, pz, pid, pos, S.cnt1, S.last1, S.n0, lane);
     __threadfence_block();
     __syncwarp();
     // positions of pass-2 claims start after the originals and the pass-1 claims
     for (int m = lane; m < nm; m += 32) S.n0[m] += S.cnt1[m];
-    for (int c = lane; c < w; c += 32) { S.cmA[c] = -1; S.cmB[c] = -1; }
     __syncwarp();
-    // ---------------- pass 2 ----------------
-    for (int r = h - 1; r >= 0; --r) {
-        for (int c = lane; c < w; c += 32) { rowCur[c] = pid[r * w + c]; S.cmB[c] = -1; }
-        __syncwarp();
-        if (r <= h - 2) {
-            for (int c = lane; c < w; c += 32) {
-                if (rowCur[c] < 0) {
-                    const int m = rowPrev[c];
-                    if (m >= 0) {
-                        const int q = r * w + c;
-                        if (refine_dist_ok(S.coef[m], px[q], py[q], pz[q])) { rowCur[c] = int8_t(m); S.cmB[c] = int8_t(m); }
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) {   // wrap claim of (r+1, 0) on (r, w-1)
-                const int m = rowPrev[0];
-                if (m >= 0 && rowCur[w - 1] < 0) {
-                    const int q = r * w + w - 1;
-                    if (refine_dist_ok(S.coef[m], px[q], py[q], pz[q])) { rowCur[w - 1] = int8_t(m); S.cmA[0] = int8_t(m); }
-                }
-            }
-            __syncwarp();
-            refine_emit<true>(S, w, r + 1, S.cnt2, S.last2, S.n0, pos, lane);
-        }
-        for (int c = lane; c < w; c += 32) S.cmA[c] = -1;
-        __syncwarp();
-        if (r >= 1) refine_chain<true>(S, rowCur, w, r, px, py, pz, lane);
-        __syncwarp();
-        for (int c = lane; c < w; c += 32) pid[r * w + c] = rowCur[c];
-        int8_t *t = rowPrev; rowPrev = rowCur; rowCur = t;
-    }
+    refine_pass<NCH, true>(S, P, px, py, pz, pid, pos, S.cnt2, S.last2, S.n0, lane);
     __syncwarp();
     for (int m = lane; m < nm; m += 32) {
         Model &M = ctl.models[m];

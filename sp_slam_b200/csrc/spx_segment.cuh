@@ -105,22 +105,38 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(Params P, Buffers B) {
     if (valid && (__ffs(peers) - 1) == int(threadIdx.x & 31)) atomicAdd(B.cnt + fo + root, __popc(peers));
 }
 
-// K4d: one CTA per frame.  Exclusive prefix count of roots in raster order = PCL's dense label of each component;
-// components with size > Plane.MinSize become plane candidates, in label order.
-__global__ void __launch_bounds__(1024) k_ccl_rank(Params P, Buffers B) {
+// K4d: one CTA per frame, one pass over the frame in 1024-pixel chunks (raster order).
+//  (1) exclusive prefix count of roots = PCL's dense label of each component; components with size > Plane.MinSize
+//      become plane candidates, in label order, and get the offset of their index list;
+//  (2) order-preserving multi-way compaction: every pixel of a candidate component is appended to that candidate's
+//      raster-ordered index list (label_indices[l] of PCL) and learns its position in it.  A component's root is its
+//      first raster pixel, so the candidate is always known before (or in the same chunk as) its members.
+constexpr int kRankThreads = 1024;
+
+__global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) {
     __shared__ unsigned warp_tot[32];
     __shared__ unsigned running_s, block_tot;
+    __shared__ int s_off[SPX_MAX_CAND];          // start of the candidate's index list
+    __shared__ int s_cnt[SPX_MAX_CAND];          // members emitted so far
+    __shared__ int s_size[SPX_MAX_CAND];
+    __shared__ int s_wcnt[SPX_MAX_CAND][32];     // members of candidate c found by warp w in this chunk -> their base
+    __shared__ int s_ncand, s_noff;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t fo = size_t(f) * P.N;
     FrameCtl &ctl = B.ctl[f];
-    if (tid == 0) running_s = 0;
+    const int *parent = B.parent + fo;
+    int16_t *root_cand = B.root_model + fo;      // at roots: candidate index or -1 (re-used for model ids by k_models)
+    int *cand_idx = B.cand_idx + fo;
+    int *pos = B.pos + fo;
+    if (tid == 0) { running_s = 0; s_ncand = 0; s_noff = 0; }
     __syncthreads();
-    for (int base = 0; base < P.N; base += 1024) {
+    for (int base = 0; base < P.N; base += kRankThreads) {
         const int q = base + tid;
         bool isroot = false, iscand = false;
-        int sz = 0;
+        int sz = 0, root = -1;
         if (q < P.N) {
-            isroot = B.parent[fo + q] == q;
+            root = parent[q];
+            isroot = root == q;
             if (isroot) { sz = B.cnt[fo + q]; iscand = unsigned(sz) > unsigned(P.min_size); }
         }
         // roots are counted in bits 0..19 (N < 2^20), candidates in bits 20..31
@@ -145,22 +161,62 @@ __global__ void __launch_bounds__(1024) k_ccl_rank(Params P, Buffers B) {
             if (lane == 31) block_tot = s;
         }
         __syncthreads();
-        const unsigned excl = running_s + warp_tot[wid] + incl - v;
+        const unsigned run_before = running_s;   // thread 0 advances it after the next barrier
+        const unsigned chunk_tot = block_tot;
+        const unsigned excl = run_before + warp_tot[wid] + incl - v;
         if (isroot) {
             B.lab[fo + q] = int(excl & 0xFFFFFu);
-            B.root_model[fo + q] = -1;
-        }
-        if (iscand) {
-            const unsigned k = excl >> 20;
-            if (k < SPX_MAX_CAND) {
-                ctl.cand[k].root = q; ctl.cand[k].label = int(excl & 0xFFFFFu); ctl.cand[k].size = sz;
-            } else {
-                atomicOr(&ctl.flags, unsigned(SPX_FRAME_OVERFLOW));
+            int16_t rc = -1;
+            if (iscand) {
+                const unsigned k = excl >> 20;
+                if (k < SPX_MAX_CAND) {
+                    ctl.cand[k].root = q; ctl.cand[k].label = int(excl & 0xFFFFFu); ctl.cand[k].size = sz;
+                    s_size[k] = sz;
+                    rc = int16_t(k);
+                } else {
+                    atomicOr(&ctl.flags, unsigned(SPX_FRAME_OVERFLOW));
+                }
             }
+            root_cand[q] = rc;
         }
         __syncthreads();
-        if (tid == 0) running_s += block_tot;
+        int nc_now = int((run_before + chunk_tot) >> 20);
+        if (nc_now > SPX_MAX_CAND) nc_now = SPX_MAX_CAND;
+        if (tid == 0) {
+            int off = s_noff;
+            for (int k = s_ncand; k < nc_now; ++k) { s_off[k] = off; s_cnt[k] = 0; ctl.cand[k].idx_off = off; off += s_size[k]; }
+            s_noff = off; s_ncand = nc_now;
+            running_s = run_before + chunk_tot;
+        }
+        for (int i = tid; i < nc_now * 32; i += kRankThreads) s_wcnt[i >> 5][i & 31] = 0;
         __syncthreads();
+        if (nc_now > 0) {   // uniform over the CTA
+            const int c = (q < P.N) ? int(root_cand[root]) : -1;
+            const unsigned peers = __match_any_sync(SPX_FULL, c);
+            const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+            if (c >= 0 && rank_in_warp == 0) s_wcnt[c][wid] = __popc(peers);
+            __syncthreads();
+            for (int cc = wid; cc < nc_now; cc += 32) {
+                const int t = s_wcnt[cc][lane];
+                int sc = t;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(SPX_FULL, sc, o);
+                    if (lane >= o) sc += u;
+                }
+                const int b0 = s_cnt[cc];
+                s_wcnt[cc][lane] = b0 + sc - t;
+                __syncwarp();
+                if (lane == 31) s_cnt[cc] = b0 + sc;
+            }
+            __syncthreads();
+            if (c >= 0) {
+                const int k = s_wcnt[c][wid] + rank_in_warp;
+                cand_idx[s_off[c] + k] = q;
+                pos[q] = k;
+            }
+            __syncthreads();
+        }
     }
     if (tid == 0) {
         const unsigned tot = running_s;
@@ -168,8 +224,6 @@ __global__ void __launch_bounds__(1024) k_ccl_rank(Params P, Buffers B) {
         int nc = int(tot >> 20);
         if (nc > SPX_MAX_CAND) nc = SPX_MAX_CAND;
         ctl.n_cand = nc;
-        int off = 0;
-        for (int k = 0; k < nc; ++k) { ctl.cand[k].idx_off = off; off += ctl.cand[k].size; }
     }
 }
 
@@ -185,49 +239,66 @@ __global__ void __launch_bounds__(256) k_ccl_label(Params P, Buffers B) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // K5a: one warp per candidate.  computeMeanAndCovarianceMatrix accumulates nine fp32 moments over the component's
-// pixels IN RASTER ORDER, one rounding per add; a tree reduction would round differently, so the order is kept:
-// the warp walks the frame in 32-pixel chunks, ballots the members, and lanes 0..8 each carry one accumulator
-// through the members in order (values broadcast by shuffle).  The raster-ordered index list (label_indices[l])
-// and each pixel's position in it fall out of the same walk.  Lane 0 then solves the 3x3 eigenproblem.
+// pixels IN RASTER ORDER, one rounding per add; a tree reduction would round differently, so the chain is kept: the
+// warp walks the candidate's dense index list 32 members at a time (coalesced index loads, gathered xyz, next batch
+// prefetched while the current one is consumed), every lane forms the nine products of its member into shared
+// memory, and lanes 0..8 each carry one accumulator through the 32 staged products in order.  Lane 0 then solves
+// the 3x3 eigenproblem.  The time of the kernel is the longest chain: size x one dependent fp32 add.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_moments_fit(Params P, Buffers B) {
+constexpr int kMomWarps = 4;
+constexpr int kMomBatch = 128;   // members per iteration (4 per lane)
+
+__global__ void __launch_bounds__(kMomWarps * 32) k_moments_fit(Params P, Buffers B) {
+    __shared__ float s_prod[kMomWarps][2][kMomBatch * 9];
     const int f = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ci = blockIdx.x * 4 + warp;
+    const int ci = blockIdx.x * kMomWarps + warp;
     FrameCtl &ctl = B.ctl[f];
     if (ci >= ctl.n_cand) return;
     Cand &cd = ctl.cand[ci];
-    const int root = cd.root, size = cd.size, off = cd.idx_off;
+    const int size = cd.size;
     const size_t fo = size_t(f) * P.N;
-    const int *parent = B.parent + fo;
     const float *px = B.px + fo, *py = B.py + fo, *pz = B.pz + fo;
-    int *cand_idx = B.cand_idx + fo;
-    int *pos = B.pos + fo;
-    // factor selectors of accu[lane]: xx xy xz yy yz zz x y z
-    const int sa = (lane <= 2 || lane == 6) ? 0 : ((lane == 3 || lane == 4 || lane == 7) ? 1 : 2);
-    const int sb = (lane == 0) ? 0 : ((lane == 1 || lane == 3) ? 1 : ((lane == 2 || lane == 4 || lane == 5) ? 2 : 3));
+    const int *idx = B.cand_idx + fo + cd.idx_off;
     float accu = 0.0f;
-    int found = 0;
-    for (int base = (root >> 5) << 5; found < size && base < P.N; base += 32) {
-        const int p = base + lane;
-        const bool m = p < P.N && parent[p] == root;
-        unsigned bits = __ballot_sync(SPX_FULL, m);
-        if (bits == 0u) continue;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (m) {
-            x = px[p]; y = py[p]; z = pz[p];
-            const int k = found + __popc(bits & ((1u << lane) - 1u));
-            cand_idx[off + k] = p;
-            pos[p] = k;
+    // software pipeline: indices two batches ahead, coordinates one batch ahead of the dependent chain
+    float x[4], y[4], z[4];
+    int pnext[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int m = j * 32 + lane;
+        x[j] = y[j] = z[j] = 0.f;
+        if (m < size) { const int p = idx[m]; x[j] = px[p]; y[j] = py[p]; z[j] = pz[p]; }
+        const int m2 = kMomBatch + m;
+        pnext[j] = m2 < size ? idx[m2] : -1;
+    }
+    int buf = 0;
+    for (int base = 0; base < size; base += kMomBatch, buf ^= 1) {
+        float *pr = s_prod[warp][buf];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float *q = pr + (j * 32 + lane) * 9;
+            q[0] = x[j] * x[j]; q[1] = x[j] * y[j]; q[2] = x[j] * z[j]; q[3] = y[j] * y[j]; q[4] = y[j] * z[j]; q[5] = z[j] * z[j];
+            q[6] = x[j]; q[7] = y[j]; q[8] = z[j];
         }
-        found += __popc(bits);
-        while (bits) {
-            const int j = __ffs(bits) - 1;
-            bits &= bits - 1u;
-            const float xj = __shfl_sync(SPX_FULL, x, j), yj = __shfl_sync(SPX_FULL, y, j), zj = __shfl_sync(SPX_FULL, z, j);
-            const float a = sa == 0 ? xj : (sa == 1 ? yj : zj);
-            const float b = sb == 0 ? xj : (sb == 1 ? yj : (sb == 2 ? zj : 1.0f));
-            accu += a * b;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p = pnext[j];
+            x[j] = y[j] = z[j] = 0.f;
+            if (p >= 0) { x[j] = px[p]; y[j] = py[p]; z[j] = pz[p]; }
+            const int m2 = base + 2 * kMomBatch + j * 32 + lane;
+            pnext[j] = m2 < size ? idx[m2] : -1;
+        }
+        __syncwarp();
+        const int cnt = min(kMomBatch, size - base);
+        if (lane < 9) {
+            const float *src = pr + lane;
+            if (cnt == kMomBatch) {
+#pragma unroll 32
+                for (int j = 0; j < kMomBatch; ++j) accu += src[j * 9];
+            } else {
+                for (int j = 0; j < cnt; ++j) accu += src[j * 9];
+            }
         }
     }
     float acc[9];
@@ -282,6 +353,7 @@ __global__ void __launch_bounds__(128) k_models(Params P, Buffers B) {
             pp[3] = 0;
             pp[3] = -1 * dot4f(pp, cen);
         }
+        B.root_model[fo + cd.root] = -1;   // held the candidate index until here (k_ccl_rank)
         if (double(cd.curvature) < 0.001) {
             if (nm < SPX_MAX_MODELS) {
                 Model &m = ctl.models[nm];

@@ -63,3 +63,26 @@ def test_feed_oracle_normals_bit_exact_labels(ext, seq, oracle_lib):
     lab_ref, nl_ref = orc.labels_raw()
     assert np.array_equal(lab, lab_ref.ravel()) and nl == nl_ref
     compare_frame(ext, orc, d, fp, check_stages=False)
+
+
+def test_cpp_host_adapter_fills_frame_fields(ext, seq, tmp_path):
+    """The C++ adapter (sp_slam_b200/host/FramePlanes.h, the reference's member names) against the C ABI."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "adapter_check"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", str(exe), os.path.join(root, "tests", "host", "adapter_check.cpp"),
+                           "-L" + os.path.join(root, "sp_slam_b200"), "-lspx", "-Wl,-rpath," + os.path.join(root, "sp_slam_b200")])
+    d = seq[2]
+    raw = tmp_path / "depth.bin"
+    d.tofile(raw)
+    out = subprocess.check_output([str(exe), str(raw), "480", "640"], text=True).splitlines()
+    fp = ext.extract(d)
+    assert out[0] == f"real {fp.mnRealPlaneNum}" and out[1] == f"all {fp.mnPlaneNum}"
+    for i, line in enumerate(out[2:]):
+        t = line.split()
+        assert np.array_equal(np.array(t[2:6], np.float32).view(np.uint32), fp.mvPlaneCoefficients[i].view(np.uint32))
+        assert int(t[6]) == len(fp.mvPlanePoints[i]) and int(t[7]) == len(fp.mvBoundaryPoints[i])
+        p = fp.mvPlanePoints[i]
+        sx = float(np.sum(p["x"].astype(np.float64) + 2.0 * p["y"].astype(np.float64) + 3.0 * p["z"].astype(np.float64)))
+        assert abs(float(t[8]) - sx) <= 1e-9 * max(1.0, abs(sx))
