@@ -162,15 +162,19 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given) {
 
     SPX_CK(c, cudaEventRecord(c->ev[0], st));
     SPX_CK(c, cudaMemsetAsync(B.ctl, 0, sizeof(FrameCtl) * size_t(F), st));
-    LAUNCH(k_backproject, gpix, 256, 0, depth_dev, P, B);
     if (!normals_given) {
-        if (P.w >= 3 && P.h >= 3)
-            LAUNCH(k_chamfer, cdiv(F, kChamferWarps), kChamferWarps * 32, size_t(kChamferWarps) * 3 * P.w * sizeof(float), P, B);
-        LAUNCH(k_normals, dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), 256, kNormalsSmem, P, B);
+        const int nb = cdiv(P.h, kBandRows), nch = cdiv(P.w, 32);
+        const int dbg = c->debug ? 1 : 0;
+        const size_t csm = size_t(kChamferWarps) * (3 * P.w + kBandSpan * (nch <= 7 ? 7 : (nch <= 14 ? 14 : 16))) * sizeof(float);
+        if (nch <= 7) LAUNCH(k_edge_chamfer<7>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
+        else if (nch <= 14) LAUNCH(k_edge_chamfer<14>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
+        else LAUNCH(k_edge_chamfer<16>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
+        LAUNCH(k_normals_link, dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), 256, kNormalsSmem, depth_dev, P, B, dbg);
     } else {
+        LAUNCH(k_backproject, gpix, 256, 0, depth_dev, P, B);
         LAUNCH(k_plane_d, gpix, 256, 0, P, B);
+        LAUNCH(k_ccl_link, dim3(cdiv(P.w, 32), cdiv(P.h, 8), F), dim3(32, 8), 0, P, B);
     }
-    LAUNCH(k_ccl_link, dim3(cdiv(P.w, 32), cdiv(P.h, 8), F), dim3(32, 8), 0, P, B);
     LAUNCH(k_ccl_merge, gpix, 256, 0, P, B);
     LAUNCH(k_ccl_flatten, gpix, 256, 0, P, B);
     LAUNCH(k_ccl_rank, F, kRankThreads, 0, P, B);
@@ -365,7 +369,9 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     const size_t FN = F * N, FC = F * size_t(P.contour_cap);
     size_t total = 0;
     total += 8 * padded<float>(FN);                        // px py pz dist nx ny nz pd
-    total += padded<uint8_t>(FN) + 5 * padded<int>(FN);    // conn | parent cnt lab pos cand_idx
+    total += 2 * padded<uint8_t>(FN) + 5 * padded<int>(FN);    // conn kwin | parent cnt lab pos cand_idx
+    const size_t n_cham = F * size_t(cdiv(h, kBandRows)) * size_t(kBandRows + kBandHalo) * size_t(w);
+    total += padded<float>(n_cham);
     total += padded<int16_t>(FN) + padded<int8_t>(FN);     // root_model pid
     total += 3 * padded<int>(FC) + 2 * padded<float4>(FC) + padded<spx_point>(FC);
     total += padded<FrameCtl>(F);
@@ -379,7 +385,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     Buffers &B = c->B;
     B.px = A.take<float>(FN); B.py = A.take<float>(FN); B.pz = A.take<float>(FN); B.dist = A.take<float>(FN);
     B.nx = A.take<float>(FN); B.ny = A.take<float>(FN); B.nz = A.take<float>(FN); B.pd = A.take<float>(FN);
-    B.conn = A.take<uint8_t>(FN);
+    B.conn = A.take<uint8_t>(FN); B.kwin = A.take<uint8_t>(FN); B.cham_tmp = A.take<float>(n_cham);
     B.parent = A.take<int>(FN); B.cnt = A.take<int>(FN); B.lab = A.take<int>(FN); B.pos = A.take<int>(FN); B.cand_idx = A.take<int>(FN);
     B.root_model = A.take<int16_t>(FN); B.pid = A.take<int8_t>(FN);
     B.contour_idx = A.take<int>(FC); B.line_sh = A.take<int>(FC); B.line_inl = A.take<int>(FC);
@@ -395,7 +401,9 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     mt19937_seeded_state(12345u, mt);   // boost::mt19937 rng_alg_ seeded in SampleConsensusModel's ctor (random = false)
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_mt_init, mt, sizeof(mt)));
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_grid, grid, sizeof(grid)));
-    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kNormalsSmem)));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_link, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kNormalsSmem)));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_edge_chamfer<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_edge_chamfer<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_totals), 4 * sizeof(long long), cudaHostAllocDefault));
     SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_frames), F * sizeof(spx_frame_header), cudaHostAllocDefault));
 #undef SPX_CK_CREATE

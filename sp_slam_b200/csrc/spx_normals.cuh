@@ -1,5 +1,5 @@
-// spx_normals.cuh -- K1..K3: back-projection + depth-change mask, exact capped chamfer distance, integral-image
-// normals (AVERAGE_3D_GRADIENT) + plane_d.
+// spx_normals.cuh -- K1..K3: depth-change mask + exact capped chamfer distance (band parallel), and the fused tile
+// kernel: back-projection, integral-image normals (AVERAGE_3D_GRADIENT), plane_d, comparator links.
 //
 // Reference: /root/reference/src/Frame.cc:855-885 (cloud construction, IntegralImageNormalEstimation settings) and
 // PCL 1.8.0 features/impl/integral_image_normal.hpp (initAverage3DGradientMethod, computeFeature,
@@ -13,11 +13,8 @@ namespace spx {
 constexpr float kDistCap = 10.0f;   // normal_smoothing_size_: the distance map is only consumed through min(d, 10)
 
 // ---------------------------------------------------------------------------------------------------------------
-// K1: one thread per organized pixel.  z = d; x = (n - cx) * z / fx; y = (m - cy) * z / fy  (src/Frame.cc:861-865),
-// plus the depth-change mask of computeFeature evaluated from the pixel's four neighbours:
-//   index pixel (r<=h-2, c<=w-2): |z - zR| > t(z) or |z - zD| > t(z) marks it; it is also marked as the right
-//   neighbour of (r, c-1) and the lower neighbour of (r-1, c), with t taken at THAT pixel.
-// dist is initialised to 0 (edge) or 10 (= min(width + height, cap)).
+// K1 (feed-normals path only; the normal path back-projects inside k_normals_link): one thread per organized pixel.
+// z = d; x = (n - cx) * z / fx; y = (m - cy) * z / fy  (src/Frame.cc:861-865).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_backproject(const float *__restrict__ depth, Params P, Buffers B) {
     const int f = blockIdx.y;
@@ -25,66 +22,127 @@ __global__ void __launch_bounds__(256) k_backproject(const float *__restrict__ d
     if (i >= P.N) return;
     const int r = i / P.w, c = i - r * P.w;
     const char *img = reinterpret_cast<const char *>(depth) + size_t(f) * P.frame_stride;
-    auto Z = [&](int rr, int cc) -> float {
-        return *reinterpret_cast<const float *>(img + size_t(rr) * P.dis * P.pitch + size_t(cc) * P.dis * sizeof(float));
-    };
-    auto thr = [&](float z) -> float { return (P.mdcf * (fabsf(z) + 1.0f)) * 2.0f; };
-    const float z = Z(r, c);
+    const float z = *reinterpret_cast<const float *>(img + size_t(r) * P.dis * P.pitch + size_t(c) * P.dis * sizeof(float));
     const float x = (float(c * P.dis) - P.cx) * z / P.fx;
     const float y = (float(r * P.dis) - P.cy) * z / P.fy;
-    bool edge = false;
-    const bool zf = isfinite(z);
-    if (r <= P.h - 2 && c <= P.w - 2) {
-        const float zR = Z(r, c + 1), zD = Z(r + 1, c), t = thr(z);
-        if (fabsf(z - zR) > t || !zf || !isfinite(zR)) edge = true;
-        if (fabsf(z - zD) > t || !zf || !isfinite(zD)) edge = true;
-    }
-    if (c >= 1 && r <= P.h - 2) {
-        const float zL = Z(r, c - 1);
-        if (fabsf(zL - z) > thr(zL) || !zf || !isfinite(zL)) edge = true;
-    }
-    if (r >= 1 && c <= P.w - 2) {
-        const float zU = Z(r - 1, c);
-        if (fabsf(zU - z) > thr(zU) || !zf || !isfinite(zU)) edge = true;
-    }
     const size_t o = size_t(f) * P.N + i;
     B.px[o] = x; B.py[o] = y; B.pz[o] = z;
-    B.dist[o] = edge ? 0.0f : fminf(float(P.w + P.h), kDistCap);
+    B.dist[o] = 0.0f;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2: PCL's two-pass chamfer (1.0 / 1.4f), bit-exact under the cap min(d, 10).  One warp per frame; rows are
-// sequential (the recurrence needs the finished previous row), columns are parallel:
+// K2: depth-change mask + PCL's two-pass chamfer (1.0 / 1.4f), bit-exact under the cap min(d, 10), straight from the
+// depth image.  One warp per BAND of 32 organized rows; columns are parallel, rows sequential:
 //   cur[c] = min(B[c], cur[c-1] (+) 1.0f),  B[c] = min(init, prev[c-1] (+) 1.4f, prev[c] (+) 1.0f, prev[c+1] (+) 1.4f)
 // fp32 addition of a positive constant is monotone, so min commutes with it and
-//   cur[c] = min_j (B[c-j] (+) 1.0f j times);  every step costs >= 1, so j <= 10 suffices under the cap.
-// Each lane owns a contiguous chunk of columns and starts its sequential scan 10 columns early.
+//   cur[c] = min_j (B[c-j] (+) 1.0f j times);  every step costs >= 1, so j <= 10 suffices under the cap
+// (each lane owns a contiguous chunk of columns and starts its sequential scan 10 columns early).  For the same
+// reason a row only depends on the 10 rows before it in pass order: a band runs the forward pass over
+// [r0-10, r1+10) and the backward pass over [r1+9 .. r0], starting both from the initial values, and is exact on its
+// own rows [r0, r1) -- 5 independent warps per 160-row frame instead of one 320-step chain.
+// The depth-change mask of computeFeature is evaluated from the pixel's four neighbours:
+//   index pixel (r<=h-2, c<=w-2): |z - zR| > t(z) or |z - zD| > t(z) marks it; it is also marked as the right
+//   neighbour of (r, c-1) and the lower neighbour of (r-1, c), with t taken at THAT pixel.
 // The reference's row wrap-around (previous_row[w] aliases current_row[0]; next_row[-1] aliases current_row[w-1])
-// is reproduced.
+// is reproduced.  Output: kwin = int(min(dist, 10)) if that is > 2 else 0 (all the normal estimation consumes).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kChamferWarps = 4;
+constexpr int kBandRows = 32;
+constexpr int kBandHalo = 10;
+constexpr int kBandSpan = kBandRows + 2 * kBandHalo;   // mask rows a band looks at
 
-__global__ void __launch_bounds__(kChamferWarps * 32) k_chamfer(Params P, Buffers B) {
+template <int NCH>
+__global__ void __launch_bounds__(kChamferWarps * 32) k_edge_chamfer(const float *__restrict__ depth, Params P, Buffers B, int write_dist) {
     extern __shared__ float sm_f[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int f = blockIdx.x * kChamferWarps + warp;
-    if (f >= P.n_frames) return;
     const int w = P.w, h = P.h;
-    float *rowA = sm_f + size_t(warp) * 3 * w;
+    const int nb = (h + kBandRows - 1) / kBandRows;
+    const int g = blockIdx.x * kChamferWarps + warp;
+    const int f = g / nb, band = g - f * nb;
+    if (f >= P.n_frames) return;
+    float *rowA = sm_f + size_t(warp) * (3 * w + kBandSpan * NCH);
     float *rowB = rowA + w;
     float *Bv = rowB + w;
-    float *d = B.dist + size_t(f) * P.N;
+    unsigned *mbits = reinterpret_cast<unsigned *>(Bv + w);   // [kBandSpan][NCH]
+    const size_t fo = size_t(f) * P.N;
+    const int r0 = band * kBandRows, r1 = min(r0 + kBandRows, h);
+    const int ra = max(r0 - kBandHalo, 0), rb = min(r1 + kBandHalo, h);
+    const char *img = reinterpret_cast<const char *>(depth) + size_t(f) * P.frame_stride;
+    const float initv = fminf(float(w + h), kDistCap);
+
+    // ---- phase 1: mask bits of rows [ra, rb) ----
+    {
+        float zU[NCH], zC[NCH], zD[NCH], zN[NCH];
+        auto load_row = [&](int r, float (&dst)[NCH]) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int c = ch * 32 + lane;
+                dst[ch] = (r >= 0 && r < h && c < w)
+                              ? *reinterpret_cast<const float *>(img + size_t(r) * P.dis * P.pitch + size_t(c) * P.dis * sizeof(float))
+                              : 0.0f;
+            }
+        };
+        auto thr = [&](float z) -> float { return (P.mdcf * (fabsf(z) + 1.0f)) * 2.0f; };
+        load_row(ra - 1, zU); load_row(ra, zC); load_row(ra + 1, zD);
+        for (int r = ra; r < rb; ++r) {
+            load_row(r + 2, zN);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int c = ch * 32 + lane;
+                const float z = zC[ch];
+                float zR = __shfl_down_sync(SPX_FULL, z, 1), zL = __shfl_up_sync(SPX_FULL, z, 1);
+                if (ch + 1 < NCH) { const float t = __shfl_sync(SPX_FULL, zC[ch + 1 < NCH ? ch + 1 : ch], 0); if (lane == 31) zR = t; }
+                if (ch >= 1) { const float t = __shfl_sync(SPX_FULL, zC[ch >= 1 ? ch - 1 : ch], 31); if (lane == 0) zL = t; }
+                bool edge = false;
+                const bool zf = isfinite(z);
+                if (r <= h - 2 && c <= w - 2) {
+                    const float zDn = zD[ch], t = thr(z);
+                    if (fabsf(z - zR) > t || !zf || !isfinite(zR)) edge = true;
+                    if (fabsf(z - zDn) > t || !zf || !isfinite(zDn)) edge = true;
+                }
+                if (c >= 1 && r <= h - 2) {
+                    if (fabsf(zL - z) > thr(zL) || !zf || !isfinite(zL)) edge = true;
+                }
+                if (r >= 1 && c <= w - 2) {
+                    const float zUp = zU[ch];
+                    if (fabsf(zUp - z) > thr(zUp) || !zf || !isfinite(zUp)) edge = true;
+                }
+                const unsigned bits = __ballot_sync(SPX_FULL, c < w && edge);
+                if (lane == 0) mbits[(r - ra) * NCH + ch] = bits;
+            }
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) { zU[ch] = zC[ch]; zC[ch] = zD[ch]; zD[ch] = zN[ch]; }
+        }
+    }
+    __syncwarp();
+    // no edge anywhere near the band: the distance is the initial value everywhere
+    unsigned anyedge = 0u;
+    for (int i = lane; i < (rb - ra) * NCH; i += 32) anyedge |= mbits[i];
+    anyedge = __reduce_or_sync(SPX_FULL, anyedge);
+    uint8_t *kwin = B.kwin + fo;
+    float *dist = B.dist + fo;
+    if (anyedge == 0u) {
+        const uint8_t kk = initv > 2.0f ? uint8_t(int(initv)) : uint8_t(0);
+        for (int r = r0; r < r1; ++r)
+            for (int c = lane; c < w; c += 32) { kwin[r * w + c] = kk; if (write_dist) dist[r * w + c] = initv; }
+        return;
+    }
+    auto init_of = [&](int r, int c) -> float { return ((mbits[(r - ra) * NCH + (c >> 5)] >> (c & 31)) & 1u) ? 0.0f : initv; };
+    float *scratch = B.cham_tmp + (size_t(f) * nb + band) * size_t(kBandRows + kBandHalo) * w;   // forward rows [r0, rb)
     const int CH = (w + 31) / 32;
     const int c0 = lane * CH;
     const int c1 = min(c0 + CH, w);
 
     float *prev = rowA, *cur = rowB;
-    for (int c = lane; c < w; c += 32) prev[c] = d[c];
+    for (int c = lane; c < w; c += 32) {
+        const float v = init_of(ra, c);
+        prev[c] = v;
+        if (ra >= r0) scratch[(ra - r0) * w + c] = v;
+    }
     __syncwarp();
-    // forward pass: rows 1..h-1, columns 1..w-1
-    for (int r = 1; r < h; ++r) {
-        float *dr = d + size_t(r) * w;
-        for (int c = lane; c < w; c += 32) cur[c] = dr[c];
+    // forward pass: rows ra+1 .. rb-1, columns 1..w-1
+    for (int r = ra + 1; r < rb; ++r) {
+        for (int c = lane; c < w; c += 32) cur[c] = init_of(r, c);
         __syncwarp();
         const float cur0 = cur[0];
         for (int c = lane; c < w; c += 32) {
@@ -108,13 +166,20 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_chamfer(Params P, Buffer
             }
         }
         __syncwarp();
-        for (int c = lane; c < w; c += 32) dr[c] = cur[c];
+        if (r >= r0) for (int c = lane; c < w; c += 32) scratch[(r - r0) * w + c] = cur[c];
         float *t = prev; prev = cur; cur = t;
     }
-    // backward pass: rows h-2..0, columns w-2..0; `prev` holds the finished row below
-    for (int r = h - 2; r >= 0; --r) {
-        float *dr = d + size_t(r) * w;
-        for (int c = lane; c < w; c += 32) cur[c] = dr[c];
+    // backward pass: rows rb-2 .. r0, columns w-2..0; `prev` holds the finished row below (row rb-1: forward values)
+    auto emit = [&](int r, const float *row) {
+        for (int c = lane; c < w; c += 32) {
+            const float s = fminf(row[c], kDistCap);
+            kwin[r * w + c] = s > 2.0f ? uint8_t(int(s)) : uint8_t(0);
+            if (write_dist) dist[r * w + c] = s;
+        }
+    };
+    if (rb - 1 < r1) emit(rb - 1, prev);   // the frame's last row is never touched by the backward pass
+    for (int r = rb - 2; r >= r0; --r) {
+        for (int c = lane; c < w; c += 32) cur[c] = scratch[(r - r0) * w + c];
         __syncwarp();
         const float curLast = cur[w - 1];
         for (int c = lane; c < w; c += 32) {
@@ -138,89 +203,151 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_chamfer(Params P, Buffer
             }
         }
         __syncwarp();
-        for (int c = lane; c < w; c += 32) dr[c] = cur[c];
+        if (r < r1) emit(r, cur);
         float *t = prev; prev = cur; cur = t;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K3: normals.  One CTA per 32x16 tile of a frame.  The central differences of the tile plus a (5 left/up, 4
-// right/down) halo are summed into tile-local first-order integral images in fp64 (6 channels + a finite count),
-// then every pixel takes its k x k window sum (k = int(min(dist, 10)), rect [c - k/2, c - k/2 + k)) as
-//   ((I[y1][x1] + I[y0][x0]) - I[y0][x1]) - I[y1][x0]
-// and forms n = normalize(gy x gx) in fp64, casts to fp32 and flips it towards the origin.
+// K3: cloud + normals + plane_d + comparator links, one CTA per 32x16 tile of a frame.
+//  1. back-projection of the tile plus a 7-pixel halo straight from the depth image into shared memory
+//     (z = d; x = (n - cx) * z / fx; y = (m - cy) * z / fy, src/Frame.cc:861-865); the tile's own points go to HBM.
+//  2. the central differences of initAverage3DGradientMethod (zero on the image border) are summed into tile-local
+//     first-order integral images in fp64 (2 x 3 channels; a finite-count image only if the region holds a
+//     non-finite depth), rows then columns.
+//  3. every pixel of the tile AND of the column to its left / the row above takes its k x k window sum
+//     (k = int(min(dist, 10)), rect [c - k/2, c - k/2 + k)) as ((I[y1][x1] + I[y0][x0]) - I[y0][x1]) - I[y1][x0],
+//     forms n = normalize(gy x gx) in fp64, casts to fp32, flips it towards the origin, and plane_d = p . n.
+//  4. PlaneCoefficientComparator::compare(current, left / upper): |d1 - d2| < DisTh * z1^2 && n1 . n2 > cos(AngTh)
+//     -> 2 link bits per pixel + the row-run initialisation of the union-find forest.  Normals never reach HBM
+//     (unless the parity taps are on).
 // The fp64 sums of fp32 differences are exact for depth data (DESIGN.md "SAT exactness"), hence independent of the
 // summation origin/order and bit-identical to PCL's whole-image double integral image.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTW = 32, kTH = 16;
+constexpr int kNW = kTW + 1, kNH = kTH + 1;      // pixels that get a normal: the tile + one column left + one row up
 constexpr int kHaloL = 5, kHaloR = 4;
-constexpr int kRW = kTW + kHaloL + kHaloR;   // 41 region columns
-constexpr int kRH = kTH + kHaloL + kHaloR;   // 25 region rows
-constexpr int kSW = kRW + 1;                 // 42 integral columns
-constexpr int kSH = kRH + 1;                 // 26 integral rows
-constexpr int kSATStride = kSW + 1;          // 43 (odd: conflict-light column scans)
-constexpr size_t kNormalsSmem = size_t(6) * kSH * kSATStride * sizeof(double) + size_t(kSH) * kSATStride * sizeof(int);
+constexpr int kRW = kNW + kHaloL + kHaloR;       // 42 columns of differences: image columns [tc-6, tc+35]
+constexpr int kRH = kNH + kHaloL + kHaloR;       // 26 rows
+constexpr int kCW = kRW + 2, kCHt = kRH + 2;     // 44 x 28 cloud points (differences reach +-1)
+constexpr int kCStride = kCW + 1;
+constexpr int kSW = kRW + 1, kSH = kRH + 1;      // 43 x 27 integral-image nodes
+constexpr int kSATStride = kSW;                  // 43, odd
+constexpr int kNStride = kNW + 1;
+constexpr size_t kNormalsSmem = size_t(6) * kSH * kSATStride * sizeof(double) + size_t(3) * kCHt * kCStride * sizeof(float) +
+                                size_t(kSH) * kSATStride * sizeof(int);
 
-__global__ void __launch_bounds__(256) k_normals(Params P, Buffers B) {
+__global__ void __launch_bounds__(256) k_normals_link(const float *__restrict__ depth, Params P, Buffers B, int write_normals) {
     extern __shared__ double sm_d[];
-    double *S = sm_d;                                                   // [6][kSH][kSATStride]
-    int *Cn = reinterpret_cast<int *>(S + size_t(6) * kSH * kSATStride);  // [kSH][kSATStride]
+    double *S = sm_d;                                                    // [6][kSH][kSATStride]
+    float *C = reinterpret_cast<float *>(S + 6 * kSH * kSATStride);      // [3][kCHt][kCStride]
+    int *Cn = reinterpret_cast<int *>(C + 3 * kCHt * kCStride);          // [kSH][kSATStride], only with non-finite depth
+    float *Nrm = reinterpret_cast<float *>(S);                           // [4][kNH][kNStride], aliases S after step 3
+    constexpr int cs = kSH * kSATStride;          // channel stride of S
+    constexpr int ccs = kCHt * kCStride;          // channel stride of C
     const int f = blockIdx.z;
     const int tc = blockIdx.x * kTW, tr = blockIdx.y * kTH;
     const int w = P.w, h = P.h;
     const size_t fo = size_t(f) * P.N;
-    const float *px = B.px + fo, *py = B.py + fo, *pz = B.pz + fo;
     const int tid = threadIdx.x;
+    const char *img = reinterpret_cast<const char *>(depth) + size_t(f) * P.frame_stride;
 
+    // ---- 1. cloud region ----
+    int nonfinite = 0;
+    for (int i = tid; i < kCW * kCHt; i += 256) {
+        const int ly = i / kCW, lx = i - ly * kCW;
+        const int r = tr - 7 + ly, c = tc - 7 + lx;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (r >= 0 && r < h && c >= 0 && c < w) {
+            z = *reinterpret_cast<const float *>(img + size_t(r) * P.dis * P.pitch + size_t(c) * P.dis * sizeof(float));
+            x = (float(c * P.dis) - P.cx) * z / P.fx;
+            y = (float(r * P.dis) - P.cy) * z / P.fy;
+            if (!isfinite(z)) nonfinite = 1;
+            if (ly >= 7 && ly < 7 + kTH && lx >= 7 && lx < 7 + kTW) {
+                const size_t o = fo + size_t(r) * w + c;
+                B.px[o] = x; B.py[o] = y; B.pz[o] = z;
+            }
+        }
+        const int o = ly * kCStride + lx;
+        C[o] = x; C[ccs + o] = y; C[2 * ccs + o] = z;
+    }
     // zero row 0 and column 0 of every integral image
     for (int i = tid; i < 7 * kSW; i += 256) {
-        int ch = i / kSW, x = i - ch * kSW;
-        if (ch < 6) S[(size_t(ch) * kSH) * kSATStride + x] = 0.0; else Cn[x] = 0;
+        const int ch = i / kSW, x = i - ch * kSW;
+        if (ch < 6) S[ch * cs + x] = 0.0; else Cn[x] = 0;
     }
     for (int i = tid; i < 7 * kSH; i += 256) {
-        int ch = i / kSH, y = i - ch * kSH;
-        if (ch < 6) S[(size_t(ch) * kSH + y) * kSATStride] = 0.0; else Cn[y * kSATStride] = 0;
+        const int ch = i / kSH, y = i - ch * kSH;
+        if (ch < 6) S[ch * cs + y * kSATStride] = 0.0; else Cn[y * kSATStride] = 0;
     }
-    // central differences of the region (initAverage3DGradientMethod): zero on the image border
-    for (int i = tid; i < kRW * kRH; i += 256) {
-        const int ly = i / kRW, lx = i - ly * kRW;
-        const int r = tr - kHaloL + ly, c = tc - kHaloL + lx;
-        float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f, dy0 = 0.f, dy1 = 0.f, dy2 = 0.f;
-        if (r >= 1 && r <= h - 2 && c >= 1 && c <= w - 2) {
-            const int q = r * w + c;
-            dx0 = px[q + 1] - px[q - 1]; dx1 = py[q + 1] - py[q - 1]; dx2 = pz[q + 1] - pz[q - 1];
-            dy0 = px[q + w] - px[q - w]; dy1 = py[q + w] - py[q - w]; dy2 = pz[q + w] - pz[q - w];
-        }
-        const bool finx = isfinite(dx0 + (dx1 + dx2)), finy = isfinite(dy0 + (dy1 + dy2));
-        const size_t o = size_t(ly + 1) * kSATStride + (lx + 1);
-        const size_t cs = size_t(kSH) * kSATStride;
-        S[0 * cs + o] = finx ? double(dx0) : 0.0; S[1 * cs + o] = finx ? double(dx1) : 0.0; S[2 * cs + o] = finx ? double(dx2) : 0.0;
-        S[3 * cs + o] = finy ? double(dy0) : 0.0; S[4 * cs + o] = finy ? double(dy1) : 0.0; S[5 * cs + o] = finy ? double(dy2) : 0.0;
-        // the two images share one count only when both are finite or both are not; keep them packed: lo16 = DX, hi16 = DY
-        Cn[o] = (finx ? 1 : 0) | (finy ? 0x10000 : 0);
-    }
-    __syncthreads();
-    // row prefix sums: one thread per (channel, row)
-    for (int i = tid; i < 7 * kRH; i += 256) {
-        const int ch = i / kRH, y = i - ch * kRH + 1;
-        if (ch < 6) {
-            double *row = S + (size_t(ch) * kSH + y) * kSATStride;
+    const int anynf = __syncthreads_or(nonfinite);
+
+    // ---- 2. row prefix sums of the differences: one thread per (channel, row) ----
+    // difference (ly, lx) sits at image (tr-6+ly, tc-6+lx) = cloud index (ly+1, lx+1)
+    auto interior = [&](int ly, int lx) -> bool {
+        const int r = tr - 6 + ly, c = tc - 6 + lx;
+        return r >= 1 && r <= h - 2 && c >= 1 && c <= w - 2;
+    };
+    if (!anynf) {
+        for (int i = tid; i < 6 * kRH; i += 256) {
+            const int ch = i / kRH, ly = i - ch * kRH;
+            const int k = ch < 3 ? ch : ch - 3;
+            const float *Ck = C + k * ccs;
+            double *row = S + ch * cs + (ly + 1) * kSATStride;
             double run = 0.0;
-            for (int x = 1; x < kSW; ++x) { run += row[x]; row[x] = run; }
-        } else {
-            int *row = Cn + y * kSATStride;
-            int run = 0;
-            for (int x = 1; x < kSW; ++x) { run += row[x]; row[x] = run; }
+            if (ch < 3) {
+                const float *p = Ck + (ly + 1) * kCStride;         // dx = P(r, c+1) - P(r, c-1)
+                for (int lx = 0; lx < kRW; ++lx) {
+                    const float d = interior(ly, lx) ? p[lx + 2] - p[lx] : 0.0f;
+                    run += double(d);
+                    row[lx + 1] = run;
+                }
+            } else {
+                const float *pu = Ck + ly * kCStride + 1, *pd = Ck + (ly + 2) * kCStride + 1;   // dy = P(r+1, c) - P(r-1, c)
+                for (int lx = 0; lx < kRW; ++lx) {
+                    const float d = interior(ly, lx) ? pd[lx] - pu[lx] : 0.0f;
+                    run += double(d);
+                    row[lx + 1] = run;
+                }
+            }
+        }
+    } else {
+        // generic path: a difference enters its image only if isfinite(d0 + (d1 + d2)); finite counts: lo16 = DX, hi16 = DY
+        for (int i = tid; i < 7 * kRH; i += 256) {
+            const int ch = i / kRH, ly = i - ch * kRH;
+            double run = 0.0;
+            int crun = 0;
+            for (int lx = 0; lx < kRW; ++lx) {
+                float dx[3] = {0.f, 0.f, 0.f}, dy[3] = {0.f, 0.f, 0.f};
+                if (interior(ly, lx)) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float *Ck = C + k * ccs;
+                        dx[k] = Ck[(ly + 1) * kCStride + lx + 2] - Ck[(ly + 1) * kCStride + lx];
+                        dy[k] = Ck[(ly + 2) * kCStride + lx + 1] - Ck[ly * kCStride + lx + 1];
+                    }
+                }
+                const bool finx = isfinite(dx[0] + (dx[1] + dx[2])), finy = isfinite(dy[0] + (dy[1] + dy[2]));
+                if (ch < 6) {
+                    const float d = ch < 3 ? dx[ch] : dy[ch - 3];
+                    if (ch < 3 ? finx : finy) run += double(d);
+                    S[ch * cs + (ly + 1) * kSATStride + lx + 1] = run;
+                } else {
+                    crun += (finx ? 1 : 0) | (finy ? 0x10000 : 0);
+                    Cn[(ly + 1) * kSATStride + lx + 1] = crun;
+                }
+            }
         }
     }
     __syncthreads();
-    // column prefix sums: one thread per (channel, column)
-    for (int i = tid; i < 7 * kRW; i += 256) {
+    // ---- column prefix sums: one thread per (channel, column) ----
+    for (int i = tid; i < (anynf ? 7 : 6) * kRW; i += 256) {
         const int ch = i / kRW, x = i - ch * kRW + 1;
         if (ch < 6) {
-            double *col = S + size_t(ch) * kSH * kSATStride + x;
+            double *col = S + ch * cs + x;
             double run = 0.0;
-            for (int y = 1; y < kSH; ++y) { run += col[size_t(y) * kSATStride]; col[size_t(y) * kSATStride] = run; }
+#pragma unroll 2
+            for (int y = 1; y < kSH; ++y) { run += col[y * kSATStride]; col[y * kSATStride] = run; }
         } else {
             int *col = Cn + x;
             int run = 0;
@@ -229,50 +356,109 @@ __global__ void __launch_bounds__(256) k_normals(Params P, Buffers B) {
     }
     __syncthreads();
 
+    // ---- 3. normals of the tile + left column + upper row (kNW x kNH pixels), kept in registers ----
     const float qnan = __int_as_float(0x7fc00000);
     const int border = 10;
-    for (int i = tid; i < kTW * kTH; i += 256) {
-        const int ly = i / kTW, lx = i - ly * kTW;
-        const int r = tr + ly, c = tc + lx;
-        if (r >= h || c >= w) continue;
-        const int q = r * w + c;
-        float nx = qnan, ny = qnan, nz = qnan;
-        const float X = px[q], Y = py[q], Zv = pz[q];
-        if (r >= border && r < h - border && c >= border && c < w - border && isfinite(Zv)) {
-            const float smoothing = fminf(B.dist[fo + q], kDistCap);
-            if (smoothing > 2.0f) {
-                const int k = int(smoothing), half = k / 2;
-                const int x0 = lx + kHaloL - half, y0 = ly + kHaloL - half;   // integral-image coordinates
-                const int x1 = x0 + k, y1 = y0 + k;
-                const size_t ul = size_t(y0) * kSATStride + x0, ur = size_t(y0) * kSATStride + x1;
-                const size_t ll = size_t(y1) * kSATStride + x0, lr = size_t(y1) * kSATStride + x1;
-                const int cn = Cn[lr] + Cn[ul] - Cn[ur] - Cn[ll];
-                if ((cn & 0xffff) != 0 && (cn >> 16) != 0) {
-                    const size_t cs = size_t(kSH) * kSATStride;
-                    double g[6];
+    constexpr int kPer = (kNW * kNH + 255) / 256;
+    float rnx[kPer], rny[kPer], rnz[kPer], rpd[kPer];
 #pragma unroll
-                    for (int ch = 0; ch < 6; ++ch) {
-                        const double *I = S + ch * cs;
-                        g[ch] = ((I[lr] + I[ul]) - I[ur]) - I[ll];
-                    }
-                    // normal_vector = gradient_y.cross(gradient_x)
-                    const double n0 = g[4] * g[2] - g[5] * g[1];
-                    const double n1 = g[5] * g[0] - g[3] * g[2];
-                    const double n2 = g[3] * g[1] - g[4] * g[0];
-                    const double len = (n0 * n0 + n1 * n1) + n2 * n2;
-                    if (len != 0.0) {
-                        const double s = sqrt(len);
-                        nx = float(n0 / s); ny = float(n1 / s); nz = float(n2 / s);
-                        // flipNormalTowardsViewpoint(point, 0, 0, 0, nx, ny, nz)
-                        const float vx = 0.0f - X, vy = 0.0f - Y, vz = 0.0f - Zv;
-                        const float cos_theta = (vx * nx + vy * ny + vz * nz);
-                        if (cos_theta < 0) { nx *= -1; ny *= -1; nz *= -1; }
+    for (int it = 0; it < kPer; ++it) {
+        const int j = tid + it * 256;
+        float nx = qnan, ny = qnan, nz = qnan, pd = qnan;
+        if (j < kNW * kNH) {
+            const int ny_ = j / kNW, nx_ = j - ny_ * kNW;
+            const int r = tr - 1 + ny_, c = tc - 1 + nx_;
+            if (r >= 0 && c >= 0 && r < h && c < w) {
+                const int co = (ny_ + 6) * kCStride + nx_ + 6;
+                const float X = C[co], Y = C[ccs + co], Zv = C[2 * ccs + co];
+                if (r >= border && r < h - border && c >= border && c < w - border && isfinite(Zv)) {
+                    const int k = int(B.kwin[fo + size_t(r) * w + c]);
+                    if (k > 0) {
+                        const int half = k / 2;
+                        const int x0 = nx_ + kHaloL - half, y0 = ny_ + kHaloL - half;   // integral-image coordinates
+                        const int x1 = x0 + k, y1 = y0 + k;
+                        const int ul = y0 * kSATStride + x0, ur = y0 * kSATStride + x1;
+                        const int ll = y1 * kSATStride + x0, lr = y1 * kSATStride + x1;
+                        bool have = true;
+                        if (anynf) {
+                            const int cn = Cn[lr] + Cn[ul] - Cn[ur] - Cn[ll];
+                            have = (cn & 0xffff) != 0 && (cn >> 16) != 0;
+                        }
+                        if (have) {
+                            double g[6];
+#pragma unroll
+                            for (int ch = 0; ch < 6; ++ch) {
+                                const double *I = S + ch * cs;
+                                g[ch] = ((I[lr] + I[ul]) - I[ur]) - I[ll];
+                            }
+                            // normal_vector = gradient_y.cross(gradient_x)
+                            const double n0 = g[4] * g[2] - g[5] * g[1];
+                            const double n1 = g[5] * g[0] - g[3] * g[2];
+                            const double n2 = g[3] * g[1] - g[4] * g[0];
+                            const double len = (n0 * n0 + n1 * n1) + n2 * n2;
+                            if (len != 0.0) {
+                                const double sl = sqrt(len);
+                                nx = float(n0 / sl); ny = float(n1 / sl); nz = float(n2 / sl);
+                                // flipNormalTowardsViewpoint(point, 0, 0, 0, nx, ny, nz)
+                                const float vx = 0.0f - X, vy = 0.0f - Y, vz = 0.0f - Zv;
+                                const float cos_theta = (vx * nx + vy * ny + vz * nz);
+                                if (cos_theta < 0) { nx *= -1; ny *= -1; nz *= -1; }
+                            }
+                        }
                     }
                 }
+                pd = dot3f(X, Y, Zv, nx, ny, nz);
             }
         }
-        B.nx[fo + q] = nx; B.ny[fo + q] = ny; B.nz[fo + q] = nz;
-        B.pd[fo + q] = dot3f(X, Y, Zv, nx, ny, nz);
+        rnx[it] = nx; rny[it] = ny; rnz[it] = nz; rpd[it] = pd;
+    }
+    __syncthreads();   // everybody is done with the integral images: their memory now holds the normals
+    constexpr int ncs = kNH * kNStride;
+#pragma unroll
+    for (int it = 0; it < kPer; ++it) {
+        const int j = tid + it * 256;
+        if (j < kNW * kNH) {
+            const int ny_ = j / kNW, nx_ = j - ny_ * kNW;
+            const int o = ny_ * kNStride + nx_;
+            Nrm[o] = rnx[it]; Nrm[ncs + o] = rny[it]; Nrm[2 * ncs + o] = rnz[it]; Nrm[3 * ncs + o] = rpd[it];
+        }
+    }
+    __syncthreads();
+
+    // ---- 4. comparator links + row runs: warp = one tile row of 32 columns ----
+    const int lane = tid & 31, wy = tid >> 5;
+#pragma unroll
+    for (int yy = 0; yy < kTH / 8; ++yy) {
+        const int ty = wy + yy * 8;
+        const int r = tr + ty, c = tc + lane;
+        if (r >= h) continue;   // warp uniform
+        const bool valid = c < w;
+        bool L = false, U = false;
+        const int q = r * w + c;
+        if (valid) {
+            const int o = (ty + 1) * kNStride + lane + 1;
+            const float d1 = Nrm[3 * ncs + o], n1x = Nrm[o], n1y = Nrm[ncs + o], n1z = Nrm[2 * ncs + o];
+            const int co = (ty + 7) * kCStride + lane + 7;
+            const float X = C[co], Y = C[ccs + co], Zv = C[2 * ccs + co];
+            const float z = X * 0.0f + (Y * 0.0f + Zv * 1.0f);   // vec.dot(z_axis_)
+            float threshold = P.dist_thr;
+            threshold *= z * z;
+            if (c >= 1) {
+                const int ol = o - 1;
+                L = (fabsf(d1 - Nrm[3 * ncs + ol]) < threshold) && (dot3f(n1x, n1y, n1z, Nrm[ol], Nrm[ncs + ol], Nrm[2 * ncs + ol]) > P.ang_cos);
+            }
+            if (r >= 1) {
+                const int ou = o - kNStride;
+                U = (fabsf(d1 - Nrm[3 * ncs + ou]) < threshold) && (dot3f(n1x, n1y, n1z, Nrm[ou], Nrm[ncs + ou], Nrm[2 * ncs + ou]) > P.ang_cos);
+            }
+            B.conn[fo + q] = uint8_t((L ? 1 : 0) | (U ? 2 : 0));
+            B.cnt[fo + q] = 0;
+            if (write_normals) { B.nx[fo + q] = n1x; B.ny[fo + q] = n1y; B.nz[fo + q] = n1z; B.pd[fo + q] = d1; }
+        }
+        const unsigned linked = __ballot_sync(SPX_FULL, valid && L);
+        const unsigned starts = ~linked | 1u;                       // lane 0 always starts a run inside the segment
+        const int s0 = 31 - __clz(starts & (SPX_FULL >> (31 - lane)));
+        if (valid) B.parent[fo + q] = r * w + tc + s0;
     }
 }
 

@@ -96,7 +96,9 @@ struct FrameCtl {
 // all device buffers of a context; per-frame arrays are frame-major (frame f at f * stride)
 struct Buffers {
     float *px, *py, *pz;          // organized cloud, N per frame
-    float *dist;                  // chamfer distance, clamped at 10
+    float *dist;                  // chamfer distance, clamped at 10 (parity tap only)
+    uint8_t *kwin;                // smoothing window size int(min(dist, 10)), 0 where it is <= 2
+    float *cham_tmp;              // forward-pass rows of the chamfer bands
     float *nx, *ny, *nz, *pd;     // normals (NaN = invalid) and plane_d
     uint8_t *conn;                // bit0: comparator edge to the left pixel, bit1: to the upper pixel
     int   *parent;                // union-find forest, then flattened roots
