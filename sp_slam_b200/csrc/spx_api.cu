@@ -53,6 +53,8 @@ struct spx_ctx {
     float *d_depth = nullptr;          // staging for host-side depth (tight pitch)
     int capN = 0, cap_w = 0, cap_h = 0;
     int n_grid = 0;
+    int border_grid = 148 * 8;
+    int lines_grid = 148 * 3;          // persistent CTAs of k_lines: SM count x resident CTAs per SM
     // host results (pinned, grown on demand)
     spx_frame_header *h_frames = nullptr;
     spx_plane *h_planes = nullptr;
@@ -102,6 +104,20 @@ void cloud_dims(int rows, int cols, int dis, int *w, int *h) {
 void mt19937_seeded_state(uint32_t seed, uint32_t s[624]) {
     s[0] = seed;
     for (uint32_t i = 1; i < 624; ++i) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + i;
+}
+
+void mt19937_twist(uint32_t s[624]) {
+    for (int i = 0; i < 624; ++i) {
+        const uint32_t y = (s[i] & 0x80000000u) | (s[(i + 1) % 624] & 0x7fffffffu);
+        s[i] = s[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+}
+uint32_t mt19937_temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
 }
 
 // the values visited by `for(float i = -0.25; i < 0.25;) { ...; i = i + 0.01; }` (src/Frame.cc:1095-1106)
@@ -162,6 +178,8 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given) {
 
     SPX_CK(c, cudaEventRecord(c->ev[0], st));
     SPX_CK(c, cudaMemsetAsync(B.ctl, 0, sizeof(FrameCtl) * size_t(F), st));
+    SPX_CK(c, cudaMemsetAsync(B.work, 0, 2 * sizeof(int), st));
+    SPX_CK(c, cudaMemsetAsync(B.work2, 0, 2 * sizeof(int), st));
     if (!normals_given) {
         const int nb = cdiv(P.h, kBandRows), nch = cdiv(P.w, 32);
         const int dbg = c->debug ? 1 : 0;
@@ -189,7 +207,8 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given) {
     LAUNCH(k_postfilter, cdiv(F, 128), 128, 0, P, B);
     SPX_CK(c, cudaEventRecord(c->ev[1], st));
     if (P.enable_supposed) {
-        LAUNCH(k_lines, dim3(SPX_MAX_MODELS, F), kLineThreads, 0, depth_dev, P, B);
+        LAUNCH(k_lines, c->lines_grid, kLineThreads, kLinesSmem, depth_dev, P, B);
+        LAUNCH(k_border, c->border_grid, kBorderWarps * 32, 0, depth_dev, P, B);
         LAUNCH(k_supposed, cdiv(F, 128), 128, 0, P, B);
     }
     SPX_CK(c, cudaEventRecord(c->ev[2], st));
@@ -373,7 +392,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     const size_t n_cham = F * size_t(cdiv(h, kBandRows)) * size_t(kBandRows + kBandHalo) * size_t(w);
     total += padded<float>(n_cham);
     total += padded<int16_t>(FN) + padded<int8_t>(FN);     // root_model pid
-    total += 3 * padded<int>(FC) + 2 * padded<float4>(FC) + padded<spx_point>(FC);
+    total += 3 * padded<int>(FC) + padded<float4>(FC) + padded<spx_point>(FC) + padded<int>(2 + F * SPX_MAX_MODELS) + padded<int>(2 + F * SPX_MAX_MODELS * SPX_MAX_LINES);
     total += padded<FrameCtl>(F);
     total += padded<spx_frame_header>(F) + padded<spx_plane>(F * SPX_MAX_PLANES);
     total += padded<spx_point>(F * size_t(P.pts_cap)) + padded<spx_point>(F * size_t(P.bnd_cap));
@@ -389,7 +408,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     B.parent = A.take<int>(FN); B.cnt = A.take<int>(FN); B.lab = A.take<int>(FN); B.pos = A.take<int>(FN); B.cand_idx = A.take<int>(FN);
     B.root_model = A.take<int16_t>(FN); B.pid = A.take<int8_t>(FN);
     B.contour_idx = A.take<int>(FC); B.line_sh = A.take<int>(FC); B.line_inl = A.take<int>(FC);
-    B.line_a = A.take<float4>(FC); B.line_b = A.take<float4>(FC); B.line_pts = A.take<spx_point>(FC);
+    B.line_a = A.take<float4>(FC); B.line_pts = A.take<spx_point>(FC); B.work = A.take<int>(2 + F * SPX_MAX_MODELS); B.work2 = A.take<int>(2 + F * SPX_MAX_MODELS * SPX_MAX_LINES);
     B.ctl = A.take<FrameCtl>(F);
     B.out_frames = A.take<spx_frame_header>(F); B.out_planes = A.take<spx_plane>(F * SPX_MAX_PLANES);
     B.out_pts = A.take<spx_point>(F * size_t(P.pts_cap)); B.out_bnd = A.take<spx_point>(F * size_t(P.bnd_cap));
@@ -397,9 +416,20 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     c->d_depth = A.take<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols));
     if (A.used > A.size) { fail(nullptr, SPX_ERR_ARG, "internal: arena accounting"); spx_destroy(c); return SPX_ERR_ARG; }
 
-    uint32_t mt[624];
+    uint32_t mt[624], mt_out[624];
     mt19937_seeded_state(12345u, mt);   // boost::mt19937 rng_alg_ seeded in SampleConsensusModel's ctor (random = false)
-    SPX_CK_CREATE(cudaMemcpyToSymbol(c_mt_init, mt, sizeof(mt)));
+    mt19937_twist(mt);
+    for (int i = 0; i < 624; ++i) mt_out[i] = mt19937_temper(mt[i]);
+    SPX_CK_CREATE(cudaMemcpyToSymbol(c_mt_state1, mt, sizeof(mt)));
+    SPX_CK_CREATE(cudaMemcpyToSymbol(c_mt_out0, mt_out, sizeof(mt_out)));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLinesSmem)));
+    {
+        int per_sm = 0;
+        SPX_CK_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lines, kLineThreads, kLinesSmem));
+        c->lines_grid = prop.multiProcessorCount * (per_sm > 0 ? per_sm : 1);
+        SPX_CK_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_border, kBorderWarps * 32, 0));
+        c->border_grid = prop.multiProcessorCount * (per_sm > 0 ? per_sm : 1);
+    }
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_grid, grid, sizeof(grid)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_link, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kNormalsSmem)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_edge_chamfer<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

@@ -16,37 +16,48 @@
 namespace spx {
 
 constexpr int kLineThreads = 256;
-constexpr int kHyp = 32;                // hypotheses scored per round trip
-constexpr int kShuffleSmem = 6144;      // contours up to this many points keep the shuffled index array in shared memory
+constexpr int kHypMax = 64;             // hypotheses scored per round trip (first trip: 32)
+constexpr int kLineCap = 3072;          // contours up to this many points live in shared memory
 
-__constant__ uint32_t c_mt_init[624];   // mt19937 state after seed(12345u)
+__constant__ uint32_t c_mt_state1[624]; // mt19937 state after seed(12345u) and the first twist
+__constant__ uint32_t c_mt_out0[624];   // its first 624 tempered outputs
 __constant__ float c_grid[64];          // the fp32 values visited by `for(float i=-0.25; i<0.25; i=i+0.01)`
 
-struct Mt {
-    uint32_t s[624];
-    int idx;
-};
-
-__device__ __forceinline__ uint32_t mt_next(Mt &g) {
-    if (g.idx >= 624) {
-        for (int i = 0; i < 624; ++i) {
-            const uint32_t y = (g.s[i] & 0x80000000u) | (g.s[(i + 1) % 624] & 0x7fffffffu);
-            g.s[i] = g.s[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-        }
-        g.idx = 0;
-    }
-    uint32_t y = g.s[g.idx++];
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= (y >> 11);
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
     y ^= (y >> 18);
     return y;
 }
+__device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b, uint32_t m) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+// in-place twist of the 624-word state by the whole CTA: words [0,227) depend on old words only, [227,454) on the
+// new [0,227), [454,623) on the new [227,396), word 623 on the new words 0 and 396.
+__device__ void mt_twist_cta(uint32_t *s) {
+    const int tid = threadIdx.x;
+    uint32_t v = 0;
+    if (tid < 227) v = mt_mix(s[tid], s[tid + 1], s[tid + 397]);
+    __syncthreads();
+    if (tid < 227) s[tid] = v;
+    __syncthreads();
+    if (tid < 227) v = mt_mix(s[tid + 227], s[tid + 228], s[tid]);
+    __syncthreads();
+    if (tid < 227) s[tid + 227] = v;
+    __syncthreads();
+    if (tid < 169) v = mt_mix(s[tid + 454], s[tid + 455], s[tid + 227]);
+    __syncthreads();
+    if (tid < 169) s[tid + 454] = v;
+    __syncthreads();
+    if (tid == 0) s[623] = mt_mix(s[623], s[0], s[396]);
+    __syncthreads();
+}
 
-struct Hyp {            // one RANSAC hypothesis: point + direction after countWithinDistance's second normalisation
-    float c[6];         // model_coefficients as computeModelCoefficients leaves them
-    float dir[3];       // line_dir.normalize() of the Vector4f (w = 0)
-    int   state;        // 0 = valid model, 1 = no samples could be selected (loop ends)
+struct Hyp {            // one RANSAC hypothesis
+    int s0, s1;         // sample indices
+    int state;          // 0 = valid model, 1 = no samples could be selected (the loop ends)
     unsigned skipped;   // skipped_count before this hypothesis' while-condition is evaluated
 };
 
@@ -57,19 +68,35 @@ __device__ __forceinline__ void line_prep_dir(const float c[6], float dir[3]) {
     dir[0] = d[0]; dir[1] = d[1]; dir[2] = d[2];
 }
 
-// (line_pt - p).cross3(line_dir).squaredNorm() on Vector4f, compared in double
-__device__ __forceinline__ bool line_within(const float c[6], const float dir[3], float X, float Y, float Z, double sqr_thr) {
+// computeModelCoefficients from a sample pair (the caller has excluded the degenerate case)
+__device__ __forceinline__ void line_model(const float4 a, const float4 b, float c[6]) {
+    c[0] = a.x; c[1] = a.y; c[2] = a.z;
+    float d0 = b.x - c[0], d1 = b.y - c[1], d2 = b.z - c[2];
+    const float z = dot3f(d0, d1, d2, d0, d1, d2);
+    if (z > 0.0f) { const float s = sqrtf(z); d0 /= s; d1 /= s; d2 /= s; }
+    c[3] = d0; c[4] = d1; c[5] = d2;
+}
+
+// (line_pt - p).cross3(line_dir).squaredNorm() on Vector4f (w = 0), compared with the squared threshold in double.
+// For a float sq and a double T, double(sq) < T  <=>  sq < Tf with Tf the smallest float >= T.
+__device__ __forceinline__ bool line_within(const float c[6], const float dir[3], float X, float Y, float Z, float thr_f) {
     const float a0 = c[0] - X, a1 = c[1] - Y, a2 = c[2] - Z;
     const float x = a1 * dir[2] - a2 * dir[1];
     const float y = a2 * dir[0] - a0 * dir[2];
     const float z = a0 * dir[1] - a1 * dir[0];
-    const float sq = (x * x + z * z) + (y * y + 0.0f);
-    return double(sq) < sqr_thr;
+    const float sq = (x * x + z * z) + y * y;   // Eigen's (a0 + a2) + (a1 + a3) with a3 = +0
+    return sq < thr_f;
+}
+
+__device__ __forceinline__ float float_at_least(double t) {
+    float f = float(t);
+    if (double(f) < t) f = __int_as_float(__float_as_int(f) + 1);   // t > 0
+    return f;
 }
 
 // ordered compaction: out[k] = i for the k-th i in [0, n) with pred(i); returns the count (all threads)
-template <typename Pred>
-__device__ int block_select(int n, int *out, int *s_warp, Pred pred) {
+template <typename IdxT, typename Pred>
+__device__ int block_select(int n, IdxT *out, int *s_warp, Pred pred) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = kLineThreads / 32;
     int total = 0;
@@ -82,76 +109,152 @@ __device__ int block_select(int n, int *out, int *s_warp, Pred pred) {
         int before = 0, chunk = 0;
 #pragma unroll
         for (int k = 0; k < NW; ++k) { const int t = s_warp[k]; if (k < wid) before += t; chunk += t; }
-        if (p) out[total + before + __popc(b & ((1u << lane) - 1u))] = i;
+        if (p) out[total + before + __popc(b & ((1u << lane) - 1u))] = IdxT(i);
         total += chunk;
         __syncthreads();
     }
     return total;
 }
 
-// IsBorderPoint (src/Frame.cc:1026-1056); out-of-buffer samples count as invalid, non-finite projections fail
-__device__ bool is_border_point(const Params &P, const float *img, float PcX, float PcY, float PcZ) {
-    if (PcZ < 0.0f) return false;
-    const float invz = 1.0f / PcZ;
-    const float u = P.fx * PcX * invz + P.cx;
-    const float v = P.fy * PcY * invz + P.cy;
-    if (!isfinite(u) || !isfinite(v)) return false;
-    int num = 0, nan = 0;
-    float res = 0;
+// ---------------------------------------------------------------------------------------------------------------
+// IsBorderLine / IsBorderPoint (src/Frame.cc:1013-1056) for every fitted line that passed LineInRange, after the
+// fits (the border test does not feed back into the RANSAC rounds).  Out-of-buffer samples count as invalid,
+// non-finite projections fail (oracle choice E7).
+// A warp takes 32 points of a line, lane p owns point p.  The 20..21 x 20..21 depth window of a point is summed in
+// the reference's raster order (fp32 running sum), so rows are walked in order: for window row t the warp loads row t
+// of all 32 windows (lanes = window columns, one coalesced segment per point) into shared memory while every lane
+// accumulates its own point's previous row -- the loads of 32 windows are in flight together instead of one
+// dependent row at a time.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBorderWarps = 4;
+
+__global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__restrict__ depth, Params P, Buffers B) {
+    __shared__ float s_win[kBorderWarps][2][32][21];
+    __shared__ int s_fail, s_item;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_items = B.work2[0];
     const int b = 10;
     const long long total = (long long)P.rows * P.cols;
     const int pitch_f = int(P.pitch / sizeof(float));
-    bool bail = false;
-    for (int j = int(v - b); j < v + b && !bail; ++j) {
-        for (int i = int(u - b); i < u + b; ++i) {
-            const long long fidx = (long long)j * P.cols + i;   // flat index on the continuous cv::Mat
-            float d = 0.0f;
-            const bool inside = fidx >= 0 && fidx < total;
-            if (inside) { const int rr = int(fidx / P.cols), cc = int(fidx - (long long)rr * P.cols); d = img[size_t(rr) * pitch_f + cc]; }
-            if (inside && double(d) > 0.05) {
-                res += d;
-                num++;
-            } else {
-                nan++;
-                if (nan > b * b) { bail = true; break; }
+    while (true) {
+        if (tid == 0) { s_item = atomicAdd(&B.work2[1], 1); s_fail = 0; }
+        __syncthreads();
+        const int it = s_item;
+        if (it >= n_items) break;
+        const int code = B.work2[2 + it];
+        const int f = code / (SPX_MAX_MODELS * SPX_MAX_LINES), ls = code - f * (SPX_MAX_MODELS * SPX_MAX_LINES);
+        Line &L = B.ctl[f].lines[ls];
+        const int n_pts = L.n_inliers;
+        const spx_point *pts = B.line_pts + size_t(f) * P.contour_cap + L.pts_off;
+        const float *img = reinterpret_cast<const float *>(reinterpret_cast<const char *>(depth) + size_t(f) * P.frame_stride);
+        int fails = 0;
+        for (int base = wid * 32; base < n_pts; base += kBorderWarps * 32) {
+            const int pi = base + lane;
+            // per-point window geometry (lane = point)
+            bool live = false;   // still needs its window walked
+            bool result = false;
+            float PcZ = 0.f, ue = 0.f, ve = 0.f;
+            int i0 = 0, j0 = 0;
+            if (pi < n_pts) {
+                const spx_point p = pts[pi];
+                PcZ = p.z;
+                if (!(PcZ < 0.0f)) {
+                    const float invz = 1.0f / PcZ;
+                    const float u = P.fx * p.x * invz + P.cx;
+                    const float v = P.fy * p.y * invz + P.cy;
+                    if (isfinite(u) && isfinite(v)) {
+                        live = true;
+                        i0 = int(u - b); j0 = int(v - b);
+                        ue = u + b; ve = v + b;
+                    }
+                }
             }
+            int num = 0, nan = 0;
+            float res = 0.f;
+            // window row t of point q: image row j0_q + t while that is < ve_q (at most 21 rows)
+            auto load_row = [&](int t, int buf) {
+                // 16 loads are issued before the first of them is stored, so their latencies overlap
+#pragma unroll
+                for (int q0 = 0; q0 < 32; q0 += 16) {
+                    float d[16];
+                    bool wr[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const int q = q0 + k;
+                        const int qi0 = __shfl_sync(SPX_FULL, i0, q), qj = __shfl_sync(SPX_FULL, j0, q) + t;
+                        const float que = __shfl_sync(SPX_FULL, ue, q), qve = __shfl_sync(SPX_FULL, ve, q);
+                        const bool qlive = __shfl_sync(SPX_FULL, live ? 1 : 0, q) != 0;
+                        wr[k] = qlive && (qj < qve) && lane < 21;
+                        d[k] = 0.0f;   // invalid sample
+                        const int i = qi0 + lane;
+                        if (wr[k] && i < que) {
+                            const long long fidx = (long long)qj * P.cols + i;   // flat index on the continuous cv::Mat
+                            if (fidx >= 0 && fidx < total) {
+                                int rr = qj, cc = i;
+                                if (i < 0 || i >= P.cols) { rr = int(fidx / P.cols); cc = int(fidx - (long long)rr * P.cols); }
+                                d[k] = img[size_t(rr) * pitch_f + cc];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (wr[k]) s_win[wid][buf][q0 + k][lane] = d[k];
+                }
+            };
+            load_row(0, 0);
+            __syncwarp();
+            for (int t = 0; t < 21; ++t) {
+                if (t + 1 < 21) load_row(t + 1, (t + 1) & 1);
+                if (live && (j0 + t < ve)) {
+                    const float *row = s_win[wid][t & 1][lane];
+#pragma unroll
+                    for (int k = 0; k < 21; ++k) {
+                        if (i0 + k < ue) {
+                            const float d = row[k];
+                            if (double(d) > 0.05) { res += d; num++; }
+                            else { nan++; }
+                        }
+                    }
+                    if (nan > b * b) { live = false; result = false; }   // the reference returns false here
+                }
+                __syncwarp();
+            }
+            if (live) result = !(double(PcZ - res / num) > 0.1);
+            if (pi < n_pts && !result) ++fails;
         }
+        fails = __reduce_add_sync(SPX_FULL, fails);
+        if (lane == 0 && fails) atomicAdd(&s_fail, fails);
+        __syncthreads();
+        // IsBorderLine: fails as soon as more than s/4 points are not border points
+        if (tid == 0) L.is_border = (s_fail > n_pts / 4) ? 0 : 1;
+        __syncthreads();
     }
-    if (bail) return false;
-    if (double(PcZ - res / num) > 0.1) return false;
-    return true;
 }
 
-// one CTA per (model, frame): the <= 4 segLine.segment() rounds on the model's contour (src/Frame.cc:953-997)
-__global__ void __launch_bounds__(kLineThreads) k_lines(const float *__restrict__ depth, Params P, Buffers B) {
-    __shared__ Mt mt;
-    __shared__ Hyp hyp[kHyp];
-    __shared__ int counts[kHyp];
-    __shared__ int s_warp[kLineThreads / 32];
-    __shared__ int sh_smem[kShuffleSmem];
-    __shared__ float s_best[6];
-    __shared__ float s_coef[6];
-    __shared__ float s_dir[3];
-    __shared__ float s_cen[3];
-    __shared__ float s_cov[6];
-    __shared__ int s_stop, s_iter, s_have, s_nhyp, s_fail;
+struct LineShared {
+    uint32_t mt[624];
+    uint16_t J[624];            // draw positions of the current output block (smem path: n <= kLineCap < 65536)
+    int      Jg[624];           // the same for the global-memory path
+    Hyp      hyp[kHypMax];
+    int      counts[kHypMax];
+    int      s_warp[kLineThreads / 32];
+    float    best[6], coef[6], dir[3], cen[3], cov[6];
+    int      stop, iter, have, nhyp, fail, refill, jpos, item;
+};
 
-    const int f = blockIdx.y, m = blockIdx.x;
+// One work item = one kept real plane with a contour of >= 50 points: the <= 4 segLine.segment() rounds on its contour
+// (src/Frame.cc:953-997).  A = the working cloud (boundPoints), sh = RANSAC's shuffled index array, inl = inlier list.
+template <typename IdxT, bool kSmem>
+__device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const float *__restrict__ depth, const Params &P,
+                           const Buffers &B, int f, int m) {
     FrameCtl &ctl = B.ctl[f];
-    if (m >= ctl.n_models) return;
     Model &M = ctl.models[m];
-    if (threadIdx.x == 0) M.n_rounds = 0;
-    if (M.plane < 0 || M.n_contour < 50) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t fo = size_t(f) * P.N;
     const size_t co = size_t(f) * P.contour_cap + M.contour_off;
-    float4 *A = B.line_a + co, *Bb = B.line_b + co;
-    int *inl = B.line_inl + co;
-    int *sh = (M.n_contour <= kShuffleSmem) ? sh_smem : (B.line_sh + co);
     spx_point *lpts = B.line_pts + co;
-    const float *img = reinterpret_cast<const float *>(reinterpret_cast<const char *>(depth) + size_t(f) * P.frame_stride);
     const int boundSize = M.n_contour;
-    const double sqr_thr = P.line_thr * P.line_thr;
+    const float thr_f = float_at_least(P.line_thr * P.line_thr);
 
     // boundPoints->points = mvBoundaryPoints[i].points
     {
@@ -168,82 +271,94 @@ __global__ void __launch_bounds__(kLineThreads) k_lines(const float *__restrict_
     for (int round = 0; round < SPX_MAX_LINES; ++round) {
         Line &L = ctl.lines[m * SPX_MAX_LINES + round];
         // ---- RandomSampleConsensus::computeModel ----
-        for (int i = tid; i < 624; i += kLineThreads) mt.s[i] = c_mt_init[i];
-        for (int i = tid; i < n; i += kLineThreads) sh[i] = i;
-        if (tid == 0) { mt.idx = 624; s_stop = 0; s_iter = 0; s_have = 0; }
+        // a fresh model per segment(): mt19937 seeded with 12345, shuffled = identity
+        for (int i = tid; i < 624; i += kLineThreads) {
+            S.mt[i] = c_mt_state1[i];
+            const unsigned i01 = unsigned(i & 1);
+            const unsigned j = (n >= 2) ? i01 + (c_mt_out0[i] >> 1) % unsigned(n - int(i01)) : 0u;
+            if (kSmem) S.J[i] = uint16_t(j); else S.Jg[i] = int(j);
+        }
+        for (int i = tid; i < n; i += kLineThreads) sh[i] = IdxT(i);
+        if (tid == 0) { S.stop = 0; S.iter = 0; S.have = 0; S.jpos = 0; S.refill = 0; }
         __syncthreads();
         // thread-0 serial state of the RANSAC loop
         int iterations = 0, n_best = -INT_MAX;
         double kk = 1.0;
         unsigned skipped = 0;
+        int v0 = 0, v1 = 1;   // shuffled[0], shuffled[1] live in registers of thread 0
         const unsigned max_skip = unsigned(P.ransac_max_iter) * 10u;
         const double log_probability = log(1.0 - 0.99);
         const double one_over_indices = 1.0 / double(n);
+        int batch = 32;
+        unsigned attempts = 0;   // draws made for the hypothesis under construction (getSamples allows 1000)
         while (true) {
             if (tid == 0) {
-                // draw the next kHyp hypotheses exactly as getSamples / drawIndexSample / isSampleGood /
-                // computeModelCoefficients would, in sequence
-                int nh = 0;
-                while (nh < kHyp) {
-                    Hyp &H = hyp[nh];
-                    H.skipped = skipped;
+                // draw the next `batch` hypotheses exactly as getSamples / drawIndexSample / isSampleGood /
+                // computeModelCoefficients' degeneracy test would, in sequence
+                int nh = 0, jp = S.jpos;
+                bool need_refill = false;
+                while (nh < batch) {
+                    Hyp &H = S.hyp[nh];
+                    if (n < 2) { H.state = 1; H.skipped = skipped; ++nh; break; }
                     bool got = false;
-                    int s0 = 0, s1 = 0;
-                    if (n >= 2) {
-                        for (unsigned it = 0; it < 1000u && !got; ++it) {
-                            for (unsigned i = 0; i < 2u; ++i) {
-                                const unsigned rnd = mt_next(mt) >> 1;
-                                const unsigned j = i + rnd % unsigned(n - int(i));
-                                const int t = sh[i]; sh[i] = sh[j]; sh[j] = t;
-                            }
-                            s0 = sh[0]; s1 = sh[1];
-                            const float4 a = A[s0], b = A[s1];
-                            got = (a.x != b.x) && (a.y != b.y) && (a.z != b.z);
-                        }
+                    while (attempts < 1000u) {
+                        if (jp >= 624) { need_refill = true; break; }
+                        const int j0 = kSmem ? int(S.J[jp]) : S.Jg[jp];
+                        const int j1 = kSmem ? int(S.J[jp + 1]) : S.Jg[jp + 1];
+                        jp += 2;
+                        ++attempts;
+                        // swap(shuffled[0], shuffled[j0]); swap(shuffled[1], shuffled[j1])
+                        if (j0 == 1) { const int t = v0; v0 = v1; v1 = t; }
+                        else if (j0 > 1) { const int t = int(sh[j0]); sh[j0] = IdxT(v0); v0 = t; }
+                        if (j1 > 1) { const int t = int(sh[j1]); sh[j1] = IdxT(v1); v1 = t; }
+                        const float4 a = A[v0], b = A[v1];
+                        if ((a.x != b.x) && (a.y != b.y) && (a.z != b.z)) { got = true; break; }
                     }
+                    if (need_refill) break;
+                    attempts = 0;
+                    H.skipped = skipped;
                     if (!got) { H.state = 1; ++nh; break; }
-                    const float4 a = A[s0], b = A[s1];
+                    const float4 a = A[v0], b = A[v1];
                     if (fabsf(a.x - b.x) <= FLT_EPSILON && fabsf(a.y - b.y) <= FLT_EPSILON && fabsf(a.z - b.z) <= FLT_EPSILON) {
                         ++skipped;
-                        if (skipped >= max_skip) { H.state = 1; ++nh; break; }
+                        if (skipped >= max_skip) { H.state = 1; H.skipped = skipped; ++nh; break; }
                         continue;
                     }
-                    H.c[0] = a.x; H.c[1] = a.y; H.c[2] = a.z;
-                    float d0 = b.x - H.c[0], d1 = b.y - H.c[1], d2 = b.z - H.c[2];
-                    const float z = dot3f(d0, d1, d2, d0, d1, d2);
-                    if (z > 0.0f) { const float s = sqrtf(z); d0 /= s; d1 /= s; d2 /= s; }
-                    H.c[3] = d0; H.c[4] = d1; H.c[5] = d2;
-                    line_prep_dir(H.c, H.dir);
-                    H.state = 0;
+                    H.s0 = v0; H.s1 = v1; H.state = 0;
                     ++nh;
                 }
-                s_nhyp = nh;
+                S.nhyp = nh; S.jpos = jp; S.refill = need_refill ? 1 : 0;
             }
             __syncthreads();
-            const int nh = s_nhyp;
+            const int nh = S.nhyp;
             // score: warp `wid` takes hypotheses wid, wid+8, ...
             for (int hh = wid; hh < nh; hh += kLineThreads / 32) {
-                if (hyp[hh].state != 0) continue;
+                if (S.hyp[hh].state != 0) continue;
+                float c[6], dir[3];
+                line_model(A[S.hyp[hh].s0], A[S.hyp[hh].s1], c);
+                line_prep_dir(c, dir);
                 int cnt = 0;
                 for (int i = lane; i < n; i += 32) {
                     const float4 p = A[i];
-                    cnt += line_within(hyp[hh].c, hyp[hh].dir, p.x, p.y, p.z, sqr_thr) ? 1 : 0;
+                    cnt += line_within(c, dir, p.x, p.y, p.z, thr_f) ? 1 : 0;
                 }
                 cnt = __reduce_add_sync(SPX_FULL, cnt);
-                if (lane == 0) counts[hh] = cnt;
+                if (lane == 0) S.counts[hh] = cnt;
             }
             __syncthreads();
             if (tid == 0) {
                 // replay `while (iterations_ < k && skipped_count < max_skip)` over the scored hypotheses
                 int stop = 0;
                 for (int hh = 0; hh < nh && !stop; ++hh) {
-                    if (!(iterations < kk && hyp[hh].skipped < max_skip)) { stop = 1; break; }
-                    if (hyp[hh].state != 0) { stop = 1; break; }
-                    const int c = counts[hh];
+                    if (!(iterations < kk && S.hyp[hh].skipped < max_skip)) { stop = 1; break; }
+                    if (S.hyp[hh].state != 0) { stop = 1; break; }
+                    const int c = S.counts[hh];
                     if (c > n_best) {
                         n_best = c;
-                        s_have = 1;
-                        for (int q = 0; q < 6; ++q) s_best[q] = hyp[hh].c[q];
+                        S.have = 1;
+                        float mc[6];
+                        line_model(A[S.hyp[hh].s0], A[S.hyp[hh].s1], mc);
+                        for (int q = 0; q < 6; ++q) S.best[q] = mc[q];
                         const double wv = double(n_best) * one_over_indices;
                         double p_no_outliers = 1.0 - wv * wv;
                         p_no_outliers = fmax(DBL_EPSILON, p_no_outliers);
@@ -254,30 +369,45 @@ __global__ void __launch_bounds__(kLineThreads) k_lines(const float *__restrict_
                     if (iterations > P.ransac_max_iter) { stop = 1; break; }
                 }
                 if (!stop && !(iterations < kk && skipped < max_skip)) stop = 1;
-                s_stop = stop; s_iter = iterations;
+                S.stop = stop; S.iter = iterations;
+                // next trip: about as many hypotheses as the adaptive bound still asks for
+                const double left = kk - double(iterations);
+                batch = left >= double(kHypMax) ? kHypMax : (left <= 8.0 ? 8 : int(left) + 1);
             }
             __syncthreads();
-            if (s_stop) break;
+            if (S.stop) break;
+            if (S.refill) {   // the 624 outputs of the block are used up: twist and re-derive the draw positions
+                mt_twist_cta(S.mt);
+                for (int i = tid; i < 624; i += kLineThreads) {
+                    const unsigned i01 = unsigned(i & 1);
+                    const unsigned j = i01 + (mt_temper(S.mt[i]) >> 1) % unsigned(n - int(i01));
+                    if (kSmem) S.J[i] = uint16_t(j); else S.Jg[i] = int(j);
+                }
+                if (tid == 0) S.jpos = 0;
+                __syncthreads();
+            }
         }
-        const bool have = s_have != 0;
+        const bool have = S.have != 0;
         int n_inl = 0;
         if (have) {
             // sac_->getInliers: selectWithinDistance(best)
-            if (tid == 0) { for (int q = 0; q < 6; ++q) s_coef[q] = s_best[q]; line_prep_dir(s_best, s_dir); }
+            if (tid == 0) { for (int q = 0; q < 6; ++q) S.coef[q] = S.best[q]; line_prep_dir(S.best, S.dir); }
             __syncthreads();
-            n_inl = block_select(n, inl, s_warp, [&](int i) { const float4 p = A[i]; return line_within(s_coef, s_dir, p.x, p.y, p.z, sqr_thr); });
+            n_inl = block_select(n, inl, S.s_warp, [&](int i) { const float4 p = A[i]; return line_within(S.coef, S.dir, p.x, p.y, p.z, thr_f); });
             __syncthreads();
             // optimizeModelCoefficients: centroid + principal direction of the inliers (fp32, sequential sums)
             if (n_inl > 2) {
                 if (tid < 3) {
                     float s = 0.0f;
+#pragma unroll 8
                     for (int k = 0; k < n_inl; ++k) { const float4 p = A[inl[k]]; s += (tid == 0 ? p.x : (tid == 1 ? p.y : p.z)); }
-                    s_cen[tid] = s / float(n_inl);
+                    S.cen[tid] = s / float(n_inl);
                 }
                 __syncthreads();
                 if (tid < 6) {
-                    const float c0 = s_cen[0], c1 = s_cen[1], c2 = s_cen[2];
+                    const float c0 = S.cen[0], c1 = S.cen[1], c2 = S.cen[2];
                     float s = 0.0f;
+#pragma unroll 8
                     for (int k = 0; k < n_inl; ++k) {
                         const float4 p = A[inl[k]];
                         const float ptx = p.x - c0, pty = p.y - c1, ptz = p.z - c2;
@@ -292,30 +422,30 @@ __global__ void __launch_bounds__(kLineThreads) k_lines(const float *__restrict_
                         }
                         s += t;
                     }
-                    s_cov[tid] = s;
+                    S.cov[tid] = s;
                 }
                 __syncthreads();
                 if (tid == 0) {
-                    const float cov[9] = {s_cov[0], s_cov[1], s_cov[2], s_cov[1], s_cov[3], s_cov[4], s_cov[2], s_cov[4], s_cov[5]};
+                    const float cov[9] = {S.cov[0], S.cov[1], S.cov[2], S.cov[1], S.cov[3], S.cov[4], S.cov[2], S.cov[4], S.cov[5]};
                     float vec[3];
                     eigen33_largest_vec(cov, vec);
-                    s_coef[0] = s_cen[0]; s_coef[1] = s_cen[1]; s_coef[2] = s_cen[2];
-                    s_coef[3] = vec[0]; s_coef[4] = vec[1]; s_coef[5] = vec[2];
-                    line_prep_dir(s_coef, s_dir);
+                    S.coef[0] = S.cen[0]; S.coef[1] = S.cen[1]; S.coef[2] = S.cen[2];
+                    S.coef[3] = vec[0]; S.coef[4] = vec[1]; S.coef[5] = vec[2];
+                    line_prep_dir(S.coef, S.dir);
                 }
                 __syncthreads();
             }
             // refine inliers with the optimised coefficients
-            n_inl = block_select(n, inl, s_warp, [&](int i) { const float4 p = A[i]; return line_within(s_coef, s_dir, p.x, p.y, p.z, sqr_thr); });
+            n_inl = block_select(n, inl, S.s_warp, [&](int i) { const float4 p = A[i]; return line_within(S.coef, S.dir, p.x, p.y, p.z, thr_f); });
             __syncthreads();
         }
         // record
         const bool stop_round = double(n_inl) < P.line_ratio * double(boundSize);
-        int in_range = 0, is_border = 0;
+        int in_range = 0;
         if (!stop_round) {
             // LineInRange (src/Frame.cc:1058-1074) on the line point (= inlier centroid)
             {
-                const float PcX = s_coef[0], PcY = s_coef[1], PcZ = s_coef[2];
+                const float PcX = S.coef[0], PcY = S.coef[1], PcZ = S.coef[2];
                 if (!(PcZ < 0.0f)) {
                     const float invz = 1.0f / PcZ;
                     const float u = P.fx * PcX * invz + P.cx;
@@ -331,38 +461,60 @@ __global__ void __launch_bounds__(kLineThreads) k_lines(const float *__restrict_
                 spx_point q; q.x = p.x; q.y = p.y; q.z = p.z; q.rgba = pack_rgba(255, 0, 0);
                 lpts[lp_off + k] = q;
             }
-            if (in_range) {
-                // IsBorderLine (src/Frame.cc:1013-1024): fails as soon as more than s/4 points are not border points
-                if (tid == 0) s_fail = 0;
-                __syncthreads();
-                int fails = 0;
-                for (int k = tid; k < n_inl; k += kLineThreads) {
-                    const float4 p = A[inl[k]];
-                    if (!is_border_point(P, img, p.x, p.y, p.z)) ++fails;
-                }
-                if (fails) atomicAdd(&s_fail, fails);
-                __syncthreads();
-                is_border = (s_fail > n_inl / 4) ? 0 : 1;
-            }
         }
         if (tid == 0) {
-            L.model = m; L.round = round; L.n_points = n; L.iterations = s_iter; L.n_inliers = n_inl;
-            L.in_range = in_range; L.is_border = is_border; L.emitted = 0; L.pts_off = M.contour_off + lp_off;
-            for (int q = 0; q < 6; ++q) L.coef[q] = have ? s_coef[q] : 0.0f;
+            L.model = m; L.round = round; L.n_points = n; L.iterations = S.iter; L.n_inliers = n_inl;
+            L.in_range = in_range; L.is_border = 0; L.emitted = 0; L.pts_off = M.contour_off + lp_off;
+            // the border test of an in-range line runs in k_border
+            if (in_range) B.work2[2 + atomicAdd(&B.work2[0], 1)] = (f * SPX_MAX_MODELS + m) * SPX_MAX_LINES + round;
+            for (int q = 0; q < 6; ++q) L.coef[q] = have ? S.coef[q] : 0.0f;
             M.n_rounds = round + 1;
         }
         if (stop_round) break;
-        // ExtractIndices negative: the remaining cloud keeps its order
+        // ExtractIndices negative: the remaining cloud keeps its order (in-place, chunk by chunk: sources never
+        // precede their destination)
         {
-            const int n_rem = block_select(n, inl, s_warp, [&](int i) { const float4 p = A[i]; return !line_within(s_coef, s_dir, p.x, p.y, p.z, sqr_thr); });
+            const int n_rem = block_select(n, inl, S.s_warp, [&](int i) { const float4 p = A[i]; return !line_within(S.coef, S.dir, p.x, p.y, p.z, thr_f); });
             __syncthreads();
-            for (int k = tid; k < n_rem; k += kLineThreads) Bb[k] = A[inl[k]];
-            __syncthreads();
-            float4 *t = A; A = Bb; Bb = t;
+            for (int base = 0; base < n_rem; base += kLineThreads) {
+                const int k = base + tid;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < n_rem) v = A[inl[k]];
+                __syncthreads();
+                if (k < n_rem) A[k] = v;
+            }
             lp_off += n_inl;
             n = n_rem;
         }
         __syncthreads();
+    }
+    __syncthreads();
+}
+
+constexpr size_t kLinesSmem = sizeof(float4) * kLineCap + 2 * sizeof(uint16_t) * kLineCap;
+
+// persistent CTAs pull (frame, model) items from the queue k_postfilter filled
+__global__ void __launch_bounds__(kLineThreads) k_lines(const float *__restrict__ depth, Params P, Buffers B) {
+    extern __shared__ float4 sm_pts[];
+    __shared__ LineShared S;
+    float4 *A = sm_pts;
+    uint16_t *sh = reinterpret_cast<uint16_t *>(A + kLineCap);
+    uint16_t *inl = sh + kLineCap;
+    const int n_items = B.work[0];
+    while (true) {
+        if (threadIdx.x == 0) S.item = atomicAdd(&B.work[1], 1);
+        __syncthreads();
+        const int it = S.item;
+        if (it >= n_items) break;
+        const int code = B.work[2 + it];
+        const int f = code / SPX_MAX_MODELS, m = code - f * SPX_MAX_MODELS;
+        const Model &M = B.ctl[f].models[m];
+        if (M.n_contour <= kLineCap) {
+            lines_item<uint16_t, true>(S, A, sh, inl, depth, P, B, f, m);
+        } else {
+            const size_t co = size_t(f) * P.contour_cap + M.contour_off;
+            lines_item<int, false>(S, B.line_a + co, B.line_sh + co, B.line_inl + co, depth, P, B, f, m);
+        }
     }
 }
 

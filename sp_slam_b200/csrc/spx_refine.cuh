@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(128) k_postfilter(Params P, Buffers B) {
         Model &M = ctl.models[i];
         float coef[4] = {M.coef[0], M.coef[1], M.coef[2], M.coef[3]};
         if (coef[3] < 0) { coef[0] = -coef[0]; coef[1] = -coef[1]; coef[2] = -coef[2]; coef[3] = -coef[3]; }
-        M.plane = -1;
+        M.plane = -1; M.n_rounds = 0;
         if (!plane_not_seen(ctl, np, coef)) continue;
         const int npts = M.n0 + M.n1 + M.n2;
         // an empty contour is replaced by every 20th inlier inside GeneratePlanesFromBoundries (src/Frame.cc:958-959)
@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(128) k_postfilter(Params P, Buffers B) {
         R.n_points = npts; R.n_boundary = nb; R.points_off = poff; R.boundary_off = boff;
         R.src = i; R.is_supposed = 0; R.line = -1; R.pad = 0;
         M.plane = np;
+        if (P.enable_supposed && M.n_contour >= 50) B.work[2 + atomicAdd(&B.work[0], 1)] = f * SPX_MAX_MODELS + i;   // a k_lines item
         poff += npts; boff += nb;
         ++np;
     }

@@ -109,7 +109,9 @@ struct Buffers {
     int   *pos;                   // position of the pixel in its model's inlier list
     int   *cand_idx;              // raster-ordered index lists of the candidates
     int   *contour_idx;           // contour arena, contour_cap per frame
-    float4 *line_a, *line_b;      // RANSAC working clouds (contour_cap per frame)
+    float4 *line_a;               // RANSAC working cloud of contours too long for shared memory (contour_cap per frame)
+    int   *work2;                 // k_border queue: [0] items, [1] pull counter, [2..] (frame * SPX_MAX_MODELS + model) * SPX_MAX_LINES + round
+    int   *work;                  // k_lines queue: [0] items, [1] pull counter, [2..] frame * SPX_MAX_MODELS + model
     int   *line_sh;               // shuffled indices (contour_cap per frame)
     int   *line_inl;              // inlier index scratch (contour_cap per frame)
     spx_point *line_pts;          // accepted line inlier points (contour_cap per frame)
