@@ -53,6 +53,7 @@ typedef struct spx_config {
     int32_t max_frames;                /* frames per batch */
     int32_t max_rows, max_cols;        /* depth image size */
     int32_t device;                    /* CUDA device ordinal */
+    int32_t n_streams;                 /* internal streams a batch's frame groups run on; 0 = default (8) */
 } spx_config;
 
 /* payload of pcl::PointXYZRGB: xyz + rgba packed as (a<<24 | r<<16 | g<<8 | b) */
@@ -148,7 +149,9 @@ int spx_get_times(spx_ctx *ctx, double *t_plane, double *t_splane);
 /* number of kernel launches issued by the last extract call */
 int spx_last_launch_count(const spx_ctx *ctx);
 /* per-kernel device times of the last extract call: with profiling on, every launch is bracketed by CUDA events on
- * the context's stream.  names[k] (static strings) / ms[k] for launch k, k < min(*n, cap). */
+ * the stream it is issued to (a batch is cut into frame groups that run on internal streams, so one kernel appears
+ * once per group and the launches of different groups overlap).  names[k] (static strings) / ms[k] for launch k,
+ * k < min(*n, cap). */
 int spx_set_profile(spx_ctx *ctx, int on);
 int spx_get_kernel_times(spx_ctx *ctx, const char **names, float *ms, int cap, int *n);
 

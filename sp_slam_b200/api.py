@@ -52,6 +52,7 @@ class SpxConfig(C.Structure):
         ("max_depth_change_factor", C.c_float), ("normal_smoothing_size", C.c_float),
         ("ransac_max_iter", C.c_int32), ("enable_supposed", C.c_int32),
         ("max_frames", C.c_int32), ("max_rows", C.c_int32), ("max_cols", C.c_int32), ("device", C.c_int32),
+        ("n_streams", C.c_int32),
     ]
 
 
@@ -276,11 +277,12 @@ class PlaneExtractor:
 
     def kernel_times(self):
         """[(kernel name, device ms)] of the last extract call (needs set_profile(True) before it)."""
-        names = (C.c_char_p * 64)()
-        ms = (C.c_float * 64)()
+        cap = 1024
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
         n = C.c_int()
-        self._ck(lib().spx_get_kernel_times(self._h, names, ms, 64, C.byref(n)))
-        return [(names[k].decode(), float(ms[k])) for k in range(min(n.value, 64))]
+        self._ck(lib().spx_get_kernel_times(self._h, names, ms, cap, C.byref(n)))
+        return [(names[k].decode(), float(ms[k])) for k in range(min(n.value, cap))]
 
     # ---- debug taps (need debug=True) ----
     def _n(self, rows, cols):

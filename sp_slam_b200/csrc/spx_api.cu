@@ -7,6 +7,7 @@
 // There is no CPU fallback: without a usable CUDA device spx_create fails with SPX_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -47,6 +48,11 @@ struct spx_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // frame groups: internal streams + per group events (start, end of the plane section, end of the supposed-plane section)
+    int n_streams = 1, min_group = 32, last_groups = 1;
+    std::vector<cudaStream_t> g_streams;
+    std::vector<cudaEvent_t> g_ev;
+    size_t work_stride = 0, work2_stride = 0;
     Params P;           // geometry of the last call (capacities fixed at create)
     Buffers B;
     DevArena arena;
@@ -146,38 +152,69 @@ int set_geometry(spx_ctx *c, int n_frames, int rows, int cols, size_t pitch, siz
 }
 
 // ---- the kernel schedule -----------------------------------------------------------------------------------
-int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given) {
-    const Params &P = c->P;
-    const Buffers &B = c->B;
-    cudaStream_t st = c->stream;
-    const int F = P.n_frames, N = P.N;
+// Frames are independent, so a batch is cut into groups of consecutive frames and every group runs the whole schedule
+// on its own internal stream: the per-frame serial kernels (one warp or one CTA per frame: chamfer bands, CCL rank,
+// moment chains, refine, contour trace, RANSAC) of one group overlap with the bandwidth/issue bound kernels of the
+// others, a group's working set stays L2 sized, and -- for host input -- group g+1's upload overlaps group g's
+// kernels.  The groups join on the caller-visible stream, where the offsets of every frame's results are scanned and
+// the clouds are packed into the contiguous output buffers.
+struct HostSrc {           // host depth of the batch (null: the depth is already on the device)
+    const float *depth = nullptr;
+    size_t pitch = 0, frame_stride = 0;
+};
+
+int n_groups_for(const spx_ctx *c, int n_frames) {
+    int g = c->n_streams;
+    const int by_size = (n_frames + c->min_group - 1) / c->min_group;
+    if (g > by_size) g = by_size;
+    return g < 1 ? 1 : g;
+}
+
+int prof_slot(spx_ctx *c, const char *name, cudaStream_t st) {
+    const int k = c->prof_n;
+    while (int(c->prof_ev.size()) < 2 * (k + 1)) {
+        cudaEvent_t e;
+        SPX_CK(c, cudaEventCreate(&e));
+        c->prof_ev.push_back(e);
+    }
+    if (int(c->prof_names.size()) <= k) c->prof_names.resize(k + 1);
+    c->prof_names[k] = name;
+    SPX_CK(c, cudaEventRecord(c->prof_ev[2 * k], st));
+    ++c->prof_n;
+    return SPX_OK;
+}
+
+int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int f0, int ng, cudaStream_t st, const HostSrc &src) {
+    Params P = c->P;
+    P.frame0 = f0; P.n_frames = ng;
+    Buffers B = c->B;
+    B.work = c->B.work + size_t(g) * c->work_stride;
+    B.work2 = c->B.work2 + size_t(g) * c->work2_stride;
+    const int F = ng, N = P.N;
     const dim3 gpix(cdiv(N, 256), F);
     int &L = c->launches;
-    L = 0;
-
-    c->prof_n = 0;
     // LAUNCH(kernel, grid, block, smem, args...): counts the launch and, when profiling, brackets it with events
 #define LAUNCH(kern, grid, block, smem, ...)                                                        \
     do {                                                                                            \
-        if (c->profile) {                                                                           \
-            if (int(c->prof_ev.size()) <= c->prof_n + 1) {                                          \
-                cudaEvent_t pe_;                                                                    \
-                SPX_CK(c, cudaEventCreate(&pe_));                                                   \
-                c->prof_ev.push_back(pe_);                                                          \
-                SPX_CK(c, cudaEventCreate(&pe_));                                                   \
-                c->prof_ev.push_back(pe_);                                                          \
-            }                                                                                       \
-            if (int(c->prof_names.size()) <= c->prof_n) c->prof_names.resize(c->prof_n + 1);        \
-            c->prof_names[c->prof_n] = #kern;                                                       \
-            SPX_CK(c, cudaEventRecord(c->prof_ev[c->prof_n], st));                                  \
-            ++c->prof_n;                                                                            \
-        }                                                                                           \
+        if (c->profile) { int rc_ = prof_slot(c, #kern, st); if (rc_ != SPX_OK) return rc_; }       \
         kern<<<grid, block, smem, st>>>(__VA_ARGS__);                                               \
+        if (c->profile) SPX_CK(c, cudaEventRecord(c->prof_ev[2 * (c->prof_n - 1) + 1], st));        \
         ++L;                                                                                        \
     } while (0)
 
-    SPX_CK(c, cudaEventRecord(c->ev[0], st));
-    SPX_CK(c, cudaMemsetAsync(B.ctl, 0, sizeof(FrameCtl) * size_t(F), st));
+    if (src.depth) {   // host depth of this group -> staging buffer (tight pitch)
+        const size_t tight = size_t(P.cols) * sizeof(float);
+        char *dst = reinterpret_cast<char *>(c->d_depth) + tight * P.rows * size_t(f0);
+        const char *hp = reinterpret_cast<const char *>(src.depth) + src.frame_stride * size_t(f0);
+        if (src.pitch == tight && (ng == 1 || src.frame_stride == tight * P.rows)) {
+            SPX_CK(c, cudaMemcpyAsync(dst, hp, tight * P.rows * size_t(ng), cudaMemcpyHostToDevice, st));
+        } else {
+            for (int f = 0; f < ng; ++f)
+                SPX_CK(c, cudaMemcpy2DAsync(dst + tight * P.rows * size_t(f), tight, hp + src.frame_stride * size_t(f), src.pitch, tight,
+                                            size_t(P.rows), cudaMemcpyHostToDevice, st));
+        }
+    }
+    SPX_CK(c, cudaMemsetAsync(B.ctl + f0, 0, sizeof(FrameCtl) * size_t(F), st));
     SPX_CK(c, cudaMemsetAsync(B.work, 0, 2 * sizeof(int), st));
     SPX_CK(c, cudaMemsetAsync(B.work2, 0, 2 * sizeof(int), st));
     if (!normals_given) {
@@ -205,21 +242,50 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given) {
     else LAUNCH(k_refine<16>, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
     LAUNCH(k_contour, F, 32, 0, P, B);
     LAUNCH(k_postfilter, cdiv(F, 128), 128, 0, P, B);
-    SPX_CK(c, cudaEventRecord(c->ev[1], st));
+    SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 1], st));
     if (P.enable_supposed) {
-        LAUNCH(k_lines, c->lines_grid, kLineThreads, kLinesSmem, depth_dev, P, B);
-        LAUNCH(k_border, c->border_grid, kBorderWarps * 32, 0, depth_dev, P, B);
+        const int lg = std::min(c->lines_grid, F * SPX_MAX_MODELS), bg = std::min(c->border_grid, F * SPX_MAX_MODELS * SPX_MAX_LINES);
+        LAUNCH(k_lines, lg, kLineThreads, kLinesSmem, depth_dev, P, B);
+        LAUNCH(k_border, bg, kBorderWarps * 32, 0, depth_dev, P, B);
         LAUNCH(k_supposed, cdiv(F, 128), 128, 0, P, B);
     }
-    SPX_CK(c, cudaEventRecord(c->ev[2], st));
-    LAUNCH(k_scan_frames, 1, 1024, 0, P, B);
-    LAUNCH(k_emit_records, F, 128, 0, P, B);
-    LAUNCH(k_pack_points, gpix, 256, 0, P, B);
-    LAUNCH(k_pack_contours, dim3(SPX_MAX_MODELS, F), 128, 0, P, B);
-    if (P.enable_supposed) LAUNCH(k_pack_supposed, dim3(SPX_MAX_PLANES, F), 128, 0, P, B);
-    SPX_CK(c, cudaEventRecord(c->ev[3], st));
-    if (c->profile) SPX_CK(c, cudaEventRecord(c->prof_ev[c->prof_n], st));
+    SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 2], st));
+    return SPX_OK;
+}
+
+int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given, const HostSrc &src) {
+    cudaStream_t main_st = c->stream;
+    const int F = c->P.n_frames;
+    c->P.frame0 = 0;
+    c->launches = 0;
+    c->prof_n = 0;
+    const int G = normals_given ? 1 : n_groups_for(c, F);
+    c->last_groups = G;
+    SPX_CK(c, cudaEventRecord(c->ev[0], main_st));
+    for (int g = 0; g < G; ++g) {
+        const int f0 = int((long long)F * g / G), f1 = int((long long)F * (g + 1) / G);
+        cudaStream_t st = (G == 1) ? main_st : c->g_streams[g];
+        if (G > 1) SPX_CK(c, cudaStreamWaitEvent(st, c->ev[0], 0));
+        SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 0], st));
+        int rc = run_group(c, depth_dev, normals_given, g, f0, f1 - f0, st, src);
+        if (rc != SPX_OK) return rc;
+        if (G > 1) SPX_CK(c, cudaStreamWaitEvent(main_st, c->g_ev[3 * g + 2], 0));
+    }
+    SPX_CK(c, cudaEventRecord(c->ev[1], main_st));
+    {
+        const Params &P = c->P;
+        const Buffers &B = c->B;
+        cudaStream_t st = main_st;
+        const dim3 gpix(cdiv(P.N, 256), F);
+        int &L = c->launches;
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B);
+        LAUNCH(k_emit_records, F, 128, 0, P, B);
+        LAUNCH(k_pack_points, gpix, 256, 0, P, B);
+        LAUNCH(k_pack_contours, dim3(SPX_MAX_MODELS, F), 128, 0, P, B);
+        if (P.enable_supposed) LAUNCH(k_pack_supposed, dim3(SPX_MAX_PLANES, F), 128, 0, P, B);
+    }
 #undef LAUNCH
+    SPX_CK(c, cudaEventRecord(c->ev[2], main_st));
     SPX_CK(c, cudaGetLastError());
     c->have_run = true;
     c->last_frames = F;
@@ -266,19 +332,6 @@ int fetch(spx_ctx *c, spx_batch_result *out, bool with_clouds) {
         out->planes = c->h_planes;
         out->points = with_clouds ? c->h_pts : nullptr;
         out->boundary = with_clouds ? c->h_bnd : nullptr;
-    }
-    return SPX_OK;
-}
-
-int upload_depth(spx_ctx *c, const float *depth, int n_frames, int rows, int cols, size_t pitch, size_t frame_stride) {
-    const size_t tight = size_t(cols) * sizeof(float);
-    if (pitch == tight && (n_frames == 1 || frame_stride == tight * rows)) {
-        SPX_CK(c, cudaMemcpyAsync(c->d_depth, depth, tight * rows * size_t(n_frames), cudaMemcpyHostToDevice, c->stream));
-    } else {
-        for (int f = 0; f < n_frames; ++f)
-            SPX_CK(c, cudaMemcpy2DAsync(reinterpret_cast<char *>(c->d_depth) + tight * rows * size_t(f), tight,
-                                        reinterpret_cast<const char *>(depth) + frame_stride * size_t(f), pitch, tight, size_t(rows),
-                                        cudaMemcpyHostToDevice, c->stream));
     }
     return SPX_OK;
 }
@@ -384,6 +437,18 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     SPX_CK_CREATE(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (int i = 0; i < 4; ++i) SPX_CK_CREATE(cudaEventCreate(&c->ev[i]));
+    c->n_streams = cfg->n_streams > 0 ? (cfg->n_streams > 32 ? 32 : cfg->n_streams) : 8;
+    c->min_group = 32;
+    for (int g = 0; g < c->n_streams; ++g) {
+        cudaStream_t gs;
+        SPX_CK_CREATE(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+        c->g_streams.push_back(gs);
+        for (int k = 0; k < 3; ++k) {
+            cudaEvent_t e;
+            SPX_CK_CREATE(cudaEventCreate(&e));
+            c->g_ev.push_back(e);
+        }
+    }
 
     const size_t FN = F * N, FC = F * size_t(P.contour_cap);
     size_t total = 0;
@@ -392,7 +457,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     const size_t n_cham = F * size_t(cdiv(h, kBandRows)) * size_t(kBandRows + kBandHalo) * size_t(w);
     total += padded<float>(n_cham);
     total += padded<int16_t>(FN) + padded<int8_t>(FN);     // root_model pid
-    total += 3 * padded<int>(FC) + padded<float4>(FC) + padded<spx_point>(FC) + padded<int>(2 + F * SPX_MAX_MODELS) + padded<int>(2 + F * SPX_MAX_MODELS * SPX_MAX_LINES);
+    total += 3 * padded<int>(FC) + padded<float4>(FC) + padded<spx_point>(FC) + padded<int>(c->n_streams * (2 + F * SPX_MAX_MODELS)) + padded<int>(c->n_streams * (2 + F * SPX_MAX_MODELS * SPX_MAX_LINES));
     total += padded<FrameCtl>(F);
     total += padded<spx_frame_header>(F) + padded<spx_plane>(F * SPX_MAX_PLANES);
     total += padded<spx_point>(F * size_t(P.pts_cap)) + padded<spx_point>(F * size_t(P.bnd_cap));
@@ -408,7 +473,8 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     B.parent = A.take<int>(FN); B.cnt = A.take<int>(FN); B.lab = A.take<int>(FN); B.pos = A.take<int>(FN); B.cand_idx = A.take<int>(FN);
     B.root_model = A.take<int16_t>(FN); B.pid = A.take<int8_t>(FN);
     B.contour_idx = A.take<int>(FC); B.line_sh = A.take<int>(FC); B.line_inl = A.take<int>(FC);
-    B.line_a = A.take<float4>(FC); B.line_pts = A.take<spx_point>(FC); B.work = A.take<int>(2 + F * SPX_MAX_MODELS); B.work2 = A.take<int>(2 + F * SPX_MAX_MODELS * SPX_MAX_LINES);
+    B.line_a = A.take<float4>(FC); B.line_pts = A.take<spx_point>(FC); c->work_stride = 2 + F * SPX_MAX_MODELS; c->work2_stride = 2 + F * SPX_MAX_MODELS * SPX_MAX_LINES;
+    B.work = A.take<int>(c->n_streams * c->work_stride); B.work2 = A.take<int>(c->n_streams * c->work2_stride);
     B.ctl = A.take<FrameCtl>(F);
     B.out_frames = A.take<spx_frame_header>(F); B.out_planes = A.take<spx_plane>(F * SPX_MAX_PLANES);
     B.out_pts = A.take<spx_point>(F * size_t(P.pts_cap)); B.out_bnd = A.take<spx_point>(F * size_t(P.bnd_cap));
@@ -453,6 +519,8 @@ void spx_destroy(spx_ctx *c) {
     if (c->h_bnd) cudaFreeHost(c->h_bnd);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->g_ev) cudaEventDestroy(e);
+    for (cudaStream_t gs : c->g_streams) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -480,7 +548,7 @@ int spx_extract_batch_device(spx_ctx *c, const float *depth_dev, int n_frames, i
     SPX_CK(c, cudaSetDevice(c->device));
     int rc = set_geometry(c, n_frames, rows, cols, pitch_bytes, frame_stride_bytes);
     if (rc != SPX_OK) return rc;
-    return run_pipeline(c, depth_dev, false);
+    return run_pipeline(c, depth_dev, false, HostSrc());
 }
 
 int spx_fetch_results(spx_ctx *c, spx_batch_result *out) {
@@ -513,9 +581,10 @@ int spx_extract_batch(spx_ctx *c, const float *depth, int n_frames, int rows, in
     const size_t tight = size_t(cols) * sizeof(float);
     int rc = set_geometry(c, n_frames, rows, cols, pitch_bytes, frame_stride_bytes);
     if (rc != SPX_OK) return rc;
-    if ((rc = upload_depth(c, depth, n_frames, rows, cols, pitch_bytes, frame_stride_bytes)) != SPX_OK) return rc;
-    c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);
-    if ((rc = run_pipeline(c, c->d_depth, false)) != SPX_OK) return rc;
+    HostSrc src;
+    src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = frame_stride_bytes;
+    c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);   // layout of the staging buffer the kernels read
+    if ((rc = run_pipeline(c, c->d_depth, false, src)) != SPX_OK) return rc;
     return fetch(c, out, true);
 }
 
@@ -531,13 +600,14 @@ int spx_segment_from_normals(spx_ctx *c, const float *depth, int rows, int cols,
     const size_t tight = size_t(cols) * sizeof(float);
     int rc = set_geometry(c, 1, rows, cols, pitch_bytes, pitch_bytes * size_t(rows));
     if (rc != SPX_OK) return rc;
-    if ((rc = upload_depth(c, depth, 1, rows, cols, pitch_bytes, pitch_bytes * size_t(rows))) != SPX_OK) return rc;
+    HostSrc src;
+    src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = pitch_bytes * size_t(rows);
     c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);
     const size_t N = size_t(c->P.N);
     SPX_CK(c, cudaMemcpyAsync(c->B.nx, normals, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     SPX_CK(c, cudaMemcpyAsync(c->B.ny, normals + N, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     SPX_CK(c, cudaMemcpyAsync(c->B.nz, normals + 2 * N, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = run_pipeline(c, c->d_depth, true)) != SPX_OK) return rc;
+    if ((rc = run_pipeline(c, c->d_depth, true, src)) != SPX_OK) return rc;
     return fetch(c, out, true);
 }
 
@@ -551,13 +621,20 @@ int spx_get_times(spx_ctx *c, double *t_plane, double *t_splane) {
     if (!c) return SPX_ERR_ARG;
     if (!c->have_run) return fail(c, SPX_ERR_STATE, "no extract call has been made on this context");
     SPX_CK(c, cudaSetDevice(c->device));
-    SPX_CK(c, cudaEventSynchronize(c->ev[3]));
-    float a = 0, b = 0, d = 0;
-    SPX_CK(c, cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
-    SPX_CK(c, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
-    SPX_CK(c, cudaEventElapsedTime(&d, c->ev[2], c->ev[3]));
-    if (t_plane) *t_plane = (double(a) + double(d)) * 1e-3;   // segmentation + packing of the clouds
-    if (t_splane) *t_splane = double(b) * 1e-3;
+    SPX_CK(c, cudaEventSynchronize(c->ev[2]));
+    float total = 0;
+    SPX_CK(c, cudaEventElapsedTime(&total, c->ev[0], c->ev[2]));
+    // frame groups overlap on the device: the supposed-plane share of the groups' own time is applied to the wall time
+    double sum_all = 0, sum_sp = 0;
+    for (int g = 0; g < c->last_groups; ++g) {
+        float a = 0, b = 0;
+        SPX_CK(c, cudaEventElapsedTime(&a, c->g_ev[3 * g + 0], c->g_ev[3 * g + 2]));
+        SPX_CK(c, cudaEventElapsedTime(&b, c->g_ev[3 * g + 1], c->g_ev[3 * g + 2]));
+        sum_all += a; sum_sp += b;
+    }
+    const double sp = sum_all > 0 ? double(total) * sum_sp / sum_all : 0.0;
+    if (t_plane) *t_plane = (double(total) - sp) * 1e-3;   // segmentation + packing of the clouds
+    if (t_splane) *t_splane = sp * 1e-3;
     return SPX_OK;
 }
 
@@ -573,11 +650,11 @@ int spx_get_kernel_times(spx_ctx *c, const char **names, float *ms, int cap, int
     if (!c || !n) return SPX_ERR_ARG;
     if (!c->have_run || !c->profile || c->prof_n == 0) return fail(c, SPX_ERR_STATE, "no profiled extract call (spx_set_profile) on this context");
     SPX_CK(c, cudaSetDevice(c->device));
-    SPX_CK(c, cudaEventSynchronize(c->prof_ev[c->prof_n]));
+    SPX_CK(c, cudaEventSynchronize(c->ev[2]));
     *n = c->prof_n;
     for (int k = 0; k < c->prof_n && k < cap; ++k) {
         if (names) names[k] = c->prof_names[k];
-        if (ms) SPX_CK(c, cudaEventElapsedTime(&ms[k], c->prof_ev[k], c->prof_ev[k + 1]));
+        if (ms) SPX_CK(c, cudaEventElapsedTime(&ms[k], c->prof_ev[2 * k], c->prof_ev[2 * k + 1]));
     }
     return SPX_OK;
 }

@@ -16,8 +16,7 @@
 namespace spx {
 
 constexpr int kLineThreads = 256;
-constexpr int kHypMax = 64;             // hypotheses scored per round trip (first trip: 32)
-constexpr int kLineCap = 3072;          // contours up to this many points live in shared memory
+constexpr int kLineCap = 2048;          // contours up to this many points live in shared memory
 
 __constant__ uint32_t c_mt_state1[624]; // mt19937 state after seed(12345u) and the first twist
 __constant__ uint32_t c_mt_out0[624];   // its first 624 tempered outputs
@@ -119,7 +118,7 @@ __device__ int block_select(int n, IdxT *out, int *s_warp, Pred pred) {
 // ---------------------------------------------------------------------------------------------------------------
 // IsBorderLine / IsBorderPoint (src/Frame.cc:1013-1056) for every fitted line that passed LineInRange, after the
 // fits (the border test does not feed back into the RANSAC rounds).  Out-of-buffer samples count as invalid,
-// non-finite projections fail (oracle choice E7).
+// non-finite projections fail (arithmetic convention E7).
 // A warp takes 32 points of a line, lane p owns point p.  The 20..21 x 20..21 depth window of a point is summed in
 // the reference's raster order (fp32 running sum), so rows are walked in order: for window row t the warp loads row t
 // of all 32 windows (lanes = window columns, one coalesced segment per point) into shared memory while every lane
@@ -231,15 +230,22 @@ __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__res
     }
 }
 
+constexpr int kTripMax = 64;           // draw attempts per round trip (first trip: 32)
+
 struct LineShared {
     uint32_t mt[624];
     uint16_t J[624];            // draw positions of the current output block (smem path: n <= kLineCap < 65536)
     int      Jg[624];           // the same for the global-memory path
-    Hyp      hyp[kHypMax];
-    int      counts[kHypMax];
+    int      att0[kTripMax], att1[kTripMax];   // shuffled[0], shuffled[1] after each draw attempt of the trip
+    Hyp      hyp[kTripMax];
+    int      counts[kTripMax];
     int      s_warp[kLineThreads / 32];
+    float    stage[32 * 7];     // per-point terms of the centroid / covariance sums, staged for the ordered adds
     float    best[6], coef[6], dir[3], cen[3], cov[6];
-    int      stop, iter, have, nhyp, fail, refill, jpos, item;
+    int      stop, iter, have, nhyp, natt, refill, jpos, item;
+    int      n_best, iterations, best_s0, best_s1;
+    unsigned skipped, run_bad;
+    double   kk;
 };
 
 // One work item = one kept real plane with a contour of >= 50 points: the <= 4 segLine.segment() rounds on its contour
@@ -281,57 +287,77 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
         for (int i = tid; i < n; i += kLineThreads) sh[i] = IdxT(i);
         if (tid == 0) { S.stop = 0; S.iter = 0; S.have = 0; S.jpos = 0; S.refill = 0; }
         __syncthreads();
-        // thread-0 serial state of the RANSAC loop
-        int iterations = 0, n_best = -INT_MAX;
-        double kk = 1.0;
-        unsigned skipped = 0;
+        if (tid == 0) { S.n_best = -INT_MAX; S.iterations = 0; S.kk = 1.0; S.skipped = 0u; S.run_bad = 0u; }
         int v0 = 0, v1 = 1;   // shuffled[0], shuffled[1] live in registers of thread 0
         const unsigned max_skip = unsigned(P.ransac_max_iter) * 10u;
         const double log_probability = log(1.0 - 0.99);
         const double one_over_indices = 1.0 / double(n);
-        int batch = 32;
-        unsigned attempts = 0;   // draws made for the hypothesis under construction (getSamples allows 1000)
+        int trip = 32;        // draw attempts of the next round trip (thread 0)
+        __syncthreads();
         while (true) {
+            // (a) thread 0: the swaps of drawIndexSample for `trip` attempts -- the only inherently serial part
             if (tid == 0) {
-                // draw the next `batch` hypotheses exactly as getSamples / drawIndexSample / isSampleGood /
-                // computeModelCoefficients' degeneracy test would, in sequence
-                int nh = 0, jp = S.jpos;
-                bool need_refill = false;
-                while (nh < batch) {
-                    Hyp &H = S.hyp[nh];
-                    if (n < 2) { H.state = 1; H.skipped = skipped; ++nh; break; }
-                    bool got = false;
-                    while (attempts < 1000u) {
-                        if (jp >= 624) { need_refill = true; break; }
+                int na = 0, jp = S.jpos;
+                if (n >= 2) {
+                    while (na < trip && jp < 624) {
                         const int j0 = kSmem ? int(S.J[jp]) : S.Jg[jp];
                         const int j1 = kSmem ? int(S.J[jp + 1]) : S.Jg[jp + 1];
                         jp += 2;
-                        ++attempts;
                         // swap(shuffled[0], shuffled[j0]); swap(shuffled[1], shuffled[j1])
                         if (j0 == 1) { const int t = v0; v0 = v1; v1 = t; }
                         else if (j0 > 1) { const int t = int(sh[j0]); sh[j0] = IdxT(v0); v0 = t; }
                         if (j1 > 1) { const int t = int(sh[j1]); sh[j1] = IdxT(v1); v1 = t; }
-                        const float4 a = A[v0], b = A[v1];
-                        if ((a.x != b.x) && (a.y != b.y) && (a.z != b.z)) { got = true; break; }
+                        S.att0[na] = v0; S.att1[na] = v1;
+                        ++na;
                     }
-                    if (need_refill) break;
-                    attempts = 0;
-                    H.skipped = skipped;
-                    if (!got) { H.state = 1; ++nh; break; }
-                    const float4 a = A[v0], b = A[v1];
-                    if (fabsf(a.x - b.x) <= FLT_EPSILON && fabsf(a.y - b.y) <= FLT_EPSILON && fabsf(a.z - b.z) <= FLT_EPSILON) {
-                        ++skipped;
-                        if (skipped >= max_skip) { H.state = 1; H.skipped = skipped; ++nh; break; }
-                        continue;
-                    }
-                    H.s0 = v0; H.s1 = v1; H.state = 0;
-                    ++nh;
                 }
-                S.nhyp = nh; S.jpos = jp; S.refill = need_refill ? 1 : 0;
+                S.natt = na; S.jpos = jp; S.refill = (n >= 2 && jp >= 624) ? 1 : 0;
+            }
+            __syncthreads();
+            // (b) warp 0: isSampleGood / the degeneracy test of computeModelCoefficients for every attempt, then the
+            // attempts are folded into hypotheses in order (getSamples gives up after 1000 bad draws in a row)
+            if (wid == 0) {
+                const int na = S.natt;
+                unsigned good[2] = {0u, 0u}, degen[2] = {0u, 0u};
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int t = half * 32 + lane;
+                    bool g = false, dg = false;
+                    if (t < na) {
+                        const float4 a = A[S.att0[t]], b = A[S.att1[t]];
+                        g = (a.x != b.x) && (a.y != b.y) && (a.z != b.z);
+                        dg = fabsf(a.x - b.x) <= FLT_EPSILON && fabsf(a.y - b.y) <= FLT_EPSILON && fabsf(a.z - b.z) <= FLT_EPSILON;
+                    }
+                    good[half] = __ballot_sync(SPX_FULL, g);
+                    degen[half] = __ballot_sync(SPX_FULL, dg);
+                }
+                if (lane == 0) {
+                    int nh = 0;
+                    unsigned skipped = S.skipped, run_bad = S.run_bad;
+                    bool ended = false;
+                    if (n < 2) { S.hyp[0].state = 1; S.hyp[0].skipped = skipped; nh = 1; ended = true; }
+                    for (int t = 0; t < na && !ended; ++t) {
+                        const bool g = (good[t >> 5] >> (t & 31)) & 1u, dg = (degen[t >> 5] >> (t & 31)) & 1u;
+                        if (!g) {
+                            if (++run_bad >= 1000u) { S.hyp[nh].state = 1; S.hyp[nh].skipped = skipped; ++nh; ended = true; }
+                            continue;
+                        }
+                        run_bad = 0u;
+                        if (dg) {
+                            ++skipped;
+                            if (skipped >= max_skip) { S.hyp[nh].state = 1; S.hyp[nh].skipped = skipped; ++nh; ended = true; }
+                            continue;
+                        }
+                        Hyp &H = S.hyp[nh];
+                        H.s0 = S.att0[t]; H.s1 = S.att1[t]; H.state = 0; H.skipped = skipped;
+                        ++nh;
+                    }
+                    S.nhyp = nh; S.skipped = skipped; S.run_bad = run_bad;
+                }
             }
             __syncthreads();
             const int nh = S.nhyp;
-            // score: warp `wid` takes hypotheses wid, wid+8, ...
+            // (c) score: warp `wid` takes hypotheses wid, wid+8, ...
             for (int hh = wid; hh < nh; hh += kLineThreads / 32) {
                 if (S.hyp[hh].state != 0) continue;
                 float c[6], dir[3];
@@ -346,36 +372,65 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
                 if (lane == 0) S.counts[hh] = cnt;
             }
             __syncthreads();
-            if (tid == 0) {
-                // replay `while (iterations_ < k && skipped_count < max_skip)` over the scored hypotheses
-                int stop = 0;
-                for (int hh = 0; hh < nh && !stop; ++hh) {
-                    if (!(iterations < kk && S.hyp[hh].skipped < max_skip)) { stop = 1; break; }
-                    if (S.hyp[hh].state != 0) { stop = 1; break; }
-                    const int c = S.counts[hh];
-                    if (c > n_best) {
-                        n_best = c;
-                        S.have = 1;
-                        float mc[6];
-                        line_model(A[S.hyp[hh].s0], A[S.hyp[hh].s1], mc);
-                        for (int q = 0; q < 6; ++q) S.best[q] = mc[q];
-                        const double wv = double(n_best) * one_over_indices;
+            // (d) warp 0 replays `while (iterations_ < k && skipped_count < max_skip)` over the scored hypotheses:
+            // k only depends on the running maximum of the counts, so prefix maxima give every hypothesis its k
+            if (wid == 0) {
+                int n_best = S.n_best, iterations = S.iterations;
+                double kk = S.kk;
+                int stop = 0, have_new = -1;
+                for (int h0 = 0; h0 < nh && !stop; h0 += 32) {
+                    const int hh = h0 + lane;
+                    const bool valid = hh < nh;
+                    const int st = valid ? S.hyp[hh].state : 1;
+                    const int cnt = (valid && st == 0) ? S.counts[hh] : -INT_MAX;
+                    int run = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(SPX_FULL, run, o); if (lane >= o) run = max(run, t); }
+                    run = max(run, n_best);                                   // n_best after this hypothesis
+                    int prevmax = __shfl_up_sync(SPX_FULL, run, 1);
+                    if (lane == 0) prevmax = n_best;
+                    double k_after = kk;
+                    if (run > n_best) {
+                        const double wv = double(run) * one_over_indices;
                         double p_no_outliers = 1.0 - wv * wv;
                         p_no_outliers = fmax(DBL_EPSILON, p_no_outliers);
                         p_no_outliers = fmin(1.0 - DBL_EPSILON, p_no_outliers);
-                        kk = log_probability / log(p_no_outliers);
+                        k_after = log_probability / log(p_no_outliers);
                     }
-                    ++iterations;
-                    if (iterations > P.ransac_max_iter) { stop = 1; break; }
+                    double k_before = __shfl_up_sync(SPX_FULL, k_after, 1);
+                    if (lane == 0) k_before = kk;
+                    const int it_before = iterations + lane;
+                    const bool enter = valid && (double(it_before) < k_before) && (S.hyp[valid ? hh : 0].skipped < max_skip) && st == 0;
+                    const bool brk_after = enter && (it_before + 1 > P.ransac_max_iter);
+                    const unsigned m_noenter = __ballot_sync(SPX_FULL, valid && !enter);
+                    const unsigned m_brk = __ballot_sync(SPX_FULL, brk_after);
+                    int n_exec = valid ? 32 : 0;
+                    n_exec = __popc(__ballot_sync(SPX_FULL, valid));
+                    if (m_noenter) { n_exec = min(n_exec, __ffs(m_noenter) - 1); }
+                    if (m_brk) { n_exec = min(n_exec, __ffs(m_brk)); }
+                    if (m_noenter || m_brk) stop = 1;
+                    // the last executed hypothesis that raised the maximum carries the best model
+                    const unsigned m_impr = __ballot_sync(SPX_FULL, valid && lane < n_exec && cnt > prevmax);
+                    if (m_impr) have_new = h0 + (31 - __clz(m_impr));
+                    if (n_exec > 0) {
+                        n_best = __shfl_sync(SPX_FULL, run, n_exec - 1);
+                        kk = __shfl_sync(SPX_FULL, k_after, n_exec - 1);
+                        iterations += n_exec;
+                    }
                 }
-                if (!stop && !(iterations < kk && skipped < max_skip)) stop = 1;
-                S.stop = stop; S.iter = iterations;
-                // next trip: about as many hypotheses as the adaptive bound still asks for
-                const double left = kk - double(iterations);
-                batch = left >= double(kHypMax) ? kHypMax : (left <= 8.0 ? 8 : int(left) + 1);
+                if (lane == 0) {
+                    if (!stop && !(double(iterations) < kk && S.skipped < max_skip)) stop = 1;
+                    S.n_best = n_best; S.iterations = iterations; S.kk = kk;
+                    if (have_new >= 0) { S.have = 1; S.best_s0 = S.hyp[have_new].s0; S.best_s1 = S.hyp[have_new].s1; }
+                    S.stop = stop; S.iter = iterations;
+                }
             }
             __syncthreads();
             if (S.stop) break;
+            if (tid == 0) {
+                const double left = S.kk - double(S.iterations);
+                trip = left >= double(kTripMax) ? kTripMax : (left <= 8.0 ? 8 : int(left) + 1);
+            }
             if (S.refill) {   // the 624 outputs of the block are used up: twist and re-derive the draw positions
                 mt_twist_cta(S.mt);
                 for (int i = tid; i < 624; i += kLineThreads) {
@@ -387,6 +442,8 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
                 __syncthreads();
             }
         }
+        if (tid == 0 && S.have) { float mc[6]; line_model(A[S.best_s0], A[S.best_s1], mc); for (int q = 0; q < 6; ++q) S.best[q] = mc[q]; }
+        __syncthreads();
         const bool have = S.have != 0;
         int n_inl = 0;
         if (have) {
@@ -395,43 +452,48 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
             __syncthreads();
             n_inl = block_select(n, inl, S.s_warp, [&](int i) { const float4 p = A[i]; return line_within(S.coef, S.dir, p.x, p.y, p.z, thr_f); });
             __syncthreads();
-            // optimizeModelCoefficients: centroid + principal direction of the inliers (fp32, sequential sums)
+            // optimizeModelCoefficients: centroid + principal direction of the inliers.  compute3DCentroid and
+            // computeCovarianceMatrix add the inliers in list order (fp32): warp 0 gathers 32 inliers at a time
+            // (coalesced), stages their terms in shared memory, and lanes 0..2 / 0..5 carry the ordered sums.
             if (n_inl > 2) {
-                if (tid < 3) {
-                    float s = 0.0f;
-#pragma unroll 8
-                    for (int k = 0; k < n_inl; ++k) { const float4 p = A[inl[k]]; s += (tid == 0 ? p.x : (tid == 1 ? p.y : p.z)); }
-                    S.cen[tid] = s / float(n_inl);
-                }
-                __syncthreads();
-                if (tid < 6) {
-                    const float c0 = S.cen[0], c1 = S.cen[1], c2 = S.cen[2];
-                    float s = 0.0f;
-#pragma unroll 8
-                    for (int k = 0; k < n_inl; ++k) {
-                        const float4 p = A[inl[k]];
-                        const float ptx = p.x - c0, pty = p.y - c1, ptz = p.z - c2;
-                        float t;
-                        switch (tid) {
-                            case 0: t = ptx * ptx; break;   // (0,0)
-                            case 1: t = pty * ptx; break;   // (0,1)
-                            case 2: t = ptz * ptx; break;   // (0,2)
-                            case 3: t = pty * pty; break;   // (1,1)
-                            case 4: t = pty * ptz; break;   // (1,2)
-                            default: t = ptz * ptz; break;  // (2,2)
-                        }
-                        s += t;
+                if (wid == 0) {
+                    float acc = 0.0f;
+                    for (int base = 0; base < n_inl; base += 32) {
+                        const int k = base + lane;
+                        if (k < n_inl) { const float4 p = A[inl[k]]; S.stage[lane * 7 + 0] = p.x; S.stage[lane * 7 + 1] = p.y; S.stage[lane * 7 + 2] = p.z; }
+                        __syncwarp();
+                        const int cnt = min(32, n_inl - base);
+                        if (lane < 3) for (int j = 0; j < cnt; ++j) acc += S.stage[j * 7 + lane];
+                        __syncwarp();
                     }
-                    S.cov[tid] = s;
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    const float cov[9] = {S.cov[0], S.cov[1], S.cov[2], S.cov[1], S.cov[3], S.cov[4], S.cov[2], S.cov[4], S.cov[5]};
-                    float vec[3];
-                    eigen33_largest_vec(cov, vec);
-                    S.coef[0] = S.cen[0]; S.coef[1] = S.cen[1]; S.coef[2] = S.cen[2];
-                    S.coef[3] = vec[0]; S.coef[4] = vec[1]; S.coef[5] = vec[2];
-                    line_prep_dir(S.coef, S.dir);
+                    if (lane < 3) S.cen[lane] = acc / float(n_inl);
+                    __syncwarp();
+                    const float c0 = S.cen[0], c1 = S.cen[1], c2 = S.cen[2];
+                    acc = 0.0f;
+                    for (int base = 0; base < n_inl; base += 32) {
+                        const int k = base + lane;
+                        if (k < n_inl) {
+                            const float4 p = A[inl[k]];
+                            const float ptx = p.x - c0, pty = p.y - c1, ptz = p.z - c2;
+                            float *st = S.stage + lane * 7;
+                            st[0] = ptx * ptx; st[1] = pty * ptx; st[2] = ptz * ptx;   // (0,0) (0,1) (0,2)
+                            st[3] = pty * pty; st[4] = pty * ptz; st[5] = ptz * ptz;   // (1,1) (1,2) (2,2)
+                        }
+                        __syncwarp();
+                        const int cnt = min(32, n_inl - base);
+                        if (lane < 6) for (int j = 0; j < cnt; ++j) acc += S.stage[j * 7 + lane];
+                        __syncwarp();
+                    }
+                    if (lane < 6) S.cov[lane] = acc;
+                    __syncwarp();
+                    if (lane == 0) {
+                        const float cov[9] = {S.cov[0], S.cov[1], S.cov[2], S.cov[1], S.cov[3], S.cov[4], S.cov[2], S.cov[4], S.cov[5]};
+                        float vec[3];
+                        eigen33_largest_vec(cov, vec);
+                        S.coef[0] = S.cen[0]; S.coef[1] = S.cen[1]; S.coef[2] = S.cen[2];
+                        S.coef[3] = vec[0]; S.coef[4] = vec[1]; S.coef[5] = vec[2];
+                        line_prep_dir(S.coef, S.dir);
+                    }
                 }
                 __syncthreads();
             }
@@ -463,7 +525,7 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
             }
         }
         if (tid == 0) {
-            L.model = m; L.round = round; L.n_points = n; L.iterations = S.iter; L.n_inliers = n_inl;
+            L.model = m; L.round = round; L.n_points = n; L.iterations = S.iterations; L.n_inliers = n_inl;
             L.in_range = in_range; L.is_border = 0; L.emitted = 0; L.pts_off = M.contour_off + lp_off;
             // the border test of an in-range line runs in k_border
             if (in_range) B.work2[2 + atomicAdd(&B.work2[0], 1)] = (f * SPX_MAX_MODELS + m) * SPX_MAX_LINES + round;
@@ -520,8 +582,9 @@ __global__ void __launch_bounds__(kLineThreads) k_lines(const float *__restrict_
 
 // CaculatePlanes + the serial control flow of GeneratePlanesFromBoundries: one thread per frame
 __global__ void __launch_bounds__(128) k_supposed(Params P, Buffers B) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= P.n_frames) return;
+    const int fl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fl >= P.n_frames) return;
+    const int f = P.frame0 + fl;
     FrameCtl &ctl = B.ctl[f];
     int np = ctl.n_real, poff = ctl.pts_used, boff = ctl.bnd_used;
     for (int i = ctl.n_real - 1; i >= 0; --i) {
@@ -561,7 +624,7 @@ __global__ void __launch_bounds__(128) k_supposed(Params P, Buffers B) {
 // clouds of the supposed planes (src/Frame.cc:1092-1110, 983-989) and the every-20th-inlier boundary fallback
 // (src/Frame.cc:1001-1011); one CTA per (plane, frame)
 __global__ void __launch_bounds__(128) k_pack_supposed(Params P, Buffers B) {
-    const int f = blockIdx.y, k = blockIdx.x;
+    const int f = P.frame0 + blockIdx.y, k = blockIdx.x;
     const FrameCtl &ctl = B.ctl[f];
     if (k >= ctl.n_planes) return;
     const PlaneRec &R = ctl.planes[k];
@@ -642,7 +705,7 @@ __global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B) {
 
 // frame headers and plane records with batch-global offsets; one CTA per frame
 __global__ void __launch_bounds__(128) k_emit_records(Params P, Buffers B) {
-    const int f = blockIdx.x;
+    const int f = P.frame0 + blockIdx.x;
     const FrameCtl &ctl = B.ctl[f];
     const long long o_pl = B.frame_offs[size_t(f) * 3 + 0], o_pt = B.frame_offs[size_t(f) * 3 + 1], o_bd = B.frame_offs[size_t(f) * 3 + 2];
     if (threadIdx.x == 0) {

@@ -17,7 +17,7 @@ constexpr float kDistCap = 10.0f;   // normal_smoothing_size_: the distance map 
 // z = d; x = (n - cx) * z / fx; y = (m - cy) * z / fy  (src/Frame.cc:861-865).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_backproject(const float *__restrict__ depth, Params P, Buffers B) {
-    const int f = blockIdx.y;
+    const int f = P.frame0 + blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N) return;
     const int r = i / P.w, c = i - r * P.w;
@@ -58,8 +58,9 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_edge_chamfer(const float
     const int w = P.w, h = P.h;
     const int nb = (h + kBandRows - 1) / kBandRows;
     const int g = blockIdx.x * kChamferWarps + warp;
-    const int f = g / nb, band = g - f * nb;
-    if (f >= P.n_frames) return;
+    const int fl = g / nb, band = g - fl * nb;
+    if (fl >= P.n_frames) return;
+    const int f = P.frame0 + fl;
     float *rowA = sm_f + size_t(warp) * (3 * w + kBandSpan * NCH);
     float *rowB = rowA + w;
     float *Bv = rowB + w;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(256) k_normals_link(const float *__restrict__ 
     float *Nrm = reinterpret_cast<float *>(S);                           // [4][kNH][kNStride], aliases S after step 3
     constexpr int cs = kSH * kSATStride;          // channel stride of S
     constexpr int ccs = kCHt * kCStride;          // channel stride of C
-    const int f = blockIdx.z;
+    const int f = P.frame0 + blockIdx.z;
     const int tc = blockIdx.x * kTW, tr = blockIdx.y * kTH;
     const int w = P.w, h = P.h;
     const size_t fo = size_t(f) * P.N;
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(256) k_normals_link(const float *__restrict__ 
 
 // plane_d for caller-supplied normals ("feed the reference's normals")
 __global__ void __launch_bounds__(256) k_plane_d(Params P, Buffers B) {
-    const int f = blockIdx.y;
+    const int f = P.frame0 + blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N) return;
     const size_t o = size_t(f) * P.N + i;

@@ -181,8 +181,9 @@ template <int NCH>
 __global__ void __launch_bounds__(kRefWarps * 32) k_refine(Params P, Buffers B) {
     __shared__ RefineSmem smem[kRefWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int f = blockIdx.x * kRefWarps + warp;
-    if (f >= P.n_frames) return;
+    const int fl = blockIdx.x * kRefWarps + warp;
+    if (fl >= P.n_frames) return;
+    const int f = P.frame0 + fl;
     RefineSmem &S = smem[warp];
     FrameCtl &ctl = B.ctl[f];
     const int nm = ctl.n_models;
@@ -219,7 +220,7 @@ __constant__ int c_ddx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
 __constant__ int c_ddy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
 
 __global__ void __launch_bounds__(32) k_contour(Params P, Buffers B) {
-    const int f = blockIdx.x, lane = threadIdx.x;
+    const int f = P.frame0 + blockIdx.x, lane = threadIdx.x;
     FrameCtl &ctl = B.ctl[f];
     const int nm = ctl.n_models;
     const int w = P.w, h = P.h;
@@ -280,8 +281,9 @@ __device__ __forceinline__ bool plane_not_seen(const FrameCtl &ctl, int n_planes
 
 // real-plane tail of ComputePlanesFromOrganizedPointCloud (src/Frame.cc:912-934): one thread per frame
 __global__ void __launch_bounds__(128) k_postfilter(Params P, Buffers B) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= P.n_frames) return;
+    const int fl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fl >= P.n_frames) return;
+    const int f = P.frame0 + fl;
     FrameCtl &ctl = B.ctl[f];
     int np = 0, poff = 0, boff = 0;
     for (int i = 0; i < ctl.n_models; ++i) {
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(128) k_postfilter(Params P, Buffers B) {
 
 // ExtractIndices(negative = false) of the kept planes: inlier points in inlier_indices order (src/Frame.cc:925-928)
 __global__ void __launch_bounds__(256) k_pack_points(Params P, Buffers B) {
-    const int f = blockIdx.y;
+    const int f = P.frame0 + blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= P.N) return;
     const size_t fo = size_t(f) * P.N;
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(256) k_pack_points(Params P, Buffers B) {
 
 // regions[i].getContour() of the kept planes (src/Frame.cc:930-932); one CTA per (model, frame)
 __global__ void __launch_bounds__(128) k_pack_contours(Params P, Buffers B) {
-    const int f = blockIdx.y, m = blockIdx.x;
+    const int f = P.frame0 + blockIdx.y, m = blockIdx.x;
     const FrameCtl &ctl = B.ctl[f];
     if (m >= ctl.n_models) return;
     const Model &M = ctl.models[m];

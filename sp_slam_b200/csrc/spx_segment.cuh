@@ -38,7 +38,7 @@ __device__ __forceinline__ void uf_unite(int *parent, int a, int b) {
 // PlaneCoefficientComparator::compare(idx1 = current pixel, idx2 = left / upper pixel):
 //   |d1 - d2| < DisTh * z1^2  &&  n1 . n2 > cos(AngTh)          (depth dependent threshold on the CURRENT pixel)
 __global__ void __launch_bounds__(256) k_ccl_link(Params P, Buffers B) {
-    const int f = blockIdx.z, lane = threadIdx.x;
+    const int f = P.frame0 + blockIdx.z, lane = threadIdx.x;
     const int r = blockIdx.y * 8 + threadIdx.y;
     const int c = blockIdx.x * 32 + lane;
     const int w = P.w;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k_ccl_link(Params P, Buffers B) {
 // K4b: merges across the 32-column segment seams and along vertical edges.  A vertical union is skipped when the
 // two pixels are already connected through their left neighbours (L(q) & L(up) & U(left)).
 __global__ void __launch_bounds__(256) k_ccl_merge(Params P, Buffers B) {
-    const int f = blockIdx.y;
+    const int f = P.frame0 + blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= P.N) return;
     const int w = P.w;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) k_ccl_merge(Params P, Buffers B) {
 
 // K4c: path compression to the root + component sizes (warp-aggregated atomics on the root's counter)
 __global__ void __launch_bounds__(256) k_ccl_flatten(Params P, Buffers B) {
-    const int f = blockIdx.y;
+    const int f = P.frame0 + blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = q < P.N;
     const size_t fo = size_t(f) * P.N;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) 
     __shared__ int s_size[SPX_MAX_CAND];
     __shared__ int s_wcnt[SPX_MAX_CAND][32];     // members of candidate c found by warp w in this chunk -> their base
     __shared__ int s_ncand, s_noff;
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int f = P.frame0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t fo = size_t(f) * P.N;
     FrameCtl &ctl = B.ctl[f];
     const int *parent = B.parent + fo;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) 
 
 // K4e: PCL label per pixel (labels.points[i].label before refine); only needed by the parity taps
 __global__ void __launch_bounds__(256) k_ccl_label(Params P, Buffers B) {
-    const int f = blockIdx.y;
+    const int f = P.frame0 + blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= P.N) return;
     const size_t fo = size_t(f) * P.N;
@@ -250,7 +250,7 @@ constexpr int kMomBatch = 128;   // members per iteration (4 per lane)
 
 __global__ void __launch_bounds__(kMomWarps * 32) k_moments_fit(Params P, Buffers B) {
     __shared__ float s_prod[kMomWarps][2][kMomBatch * 9];
-    const int f = blockIdx.y;
+    const int f = P.frame0 + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ci = blockIdx.x * kMomWarps + warp;
     FrameCtl &ctl = B.ctl[f];
@@ -333,8 +333,9 @@ __global__ void __launch_bounds__(kMomWarps * 32) k_moments_fit(Params P, Buffer
 // K5b: one thread per frame replays segment()'s serial tail over the candidates in label order: the viewpoint
 // vector `vp` that is never reset between clusters, the orientation flip, and the curvature acceptance.
 __global__ void __launch_bounds__(128) k_models(Params P, Buffers B) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= P.n_frames) return;
+    const int fl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fl >= P.n_frames) return;
+    const int f = P.frame0 + fl;
     FrameCtl &ctl = B.ctl[f];
     const size_t fo = size_t(f) * P.N;
     float vp[4] = {0.f, 0.f, 0.f, 0.f};
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(128) k_models(Params P, Buffers B) {
 
 // K5c: plane id per pixel = model of its component (or -1)
 __global__ void __launch_bounds__(256) k_pid_init(Params P, Buffers B) {
-    const int f = blockIdx.y;
+    const int f = P.frame0 + blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= P.N) return;
     const size_t fo = size_t(f) * P.N;

@@ -11,7 +11,8 @@ struct Params {
     int rows, cols;
     size_t pitch;          // bytes
     size_t frame_stride;   // bytes
-    int n_frames;
+    int n_frames;          // frames of this launch group
+    int frame0;            // first frame of the group (frames are independent: groups run on separate streams)
     // organized cloud (src/Frame.cc:856-874)
     int dis, w, h, N;
     float fx, fy, cx, cy;

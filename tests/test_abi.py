@@ -85,4 +85,4 @@ def test_product_package_never_touches_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in txt.lower(), os.path.join(dirpath, f)
+                assert "oracle" not in txt.lower(), os.path.join(dirpath, f) + " mentions the oracle"
