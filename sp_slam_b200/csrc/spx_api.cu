@@ -220,7 +220,7 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
     if (!normals_given) {
         const int nb = cdiv(P.h, kBandRows), nch = cdiv(P.w, 32);
         const int dbg = c->debug ? 1 : 0;
-        const size_t csm = size_t(kChamferWarps) * (3 * P.w + kBandSpan * (nch <= 7 ? 7 : (nch <= 14 ? 14 : 16))) * sizeof(float);
+        const size_t csm = size_t(kChamferWarps) * (kBandSpan * (nch <= 7 ? 7 : (nch <= 14 ? 14 : 16))) * sizeof(unsigned);
         if (nch <= 7) LAUNCH(k_edge_chamfer<7>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
         else if (nch <= 14) LAUNCH(k_edge_chamfer<14>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
         else LAUNCH(k_edge_chamfer<16>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
@@ -240,7 +240,7 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
     if (P.w <= 224) LAUNCH(k_refine<7>, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
     else if (P.w <= 448) LAUNCH(k_refine<14>, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
     else LAUNCH(k_refine<16>, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
-    LAUNCH(k_contour, F, 32, 0, P, B);
+    LAUNCH(k_contour, F, kContourThreads, size_t(P.w + 2) * (P.h + 2), P, B);
     LAUNCH(k_postfilter, cdiv(F, 128), 128, 0, P, B);
     SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 1], st));
     if (P.enable_supposed) {
@@ -385,6 +385,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     cloud_dims(cfg->max_rows, cfg->max_cols, cfg->cloud_dis, &w, &h);
     if (w > kMaxW) return fail(nullptr, SPX_ERR_ARG, "organized cloud wider than %d columns", kMaxW);
     if (size_t(w) * h >= (1u << 20)) return fail(nullptr, SPX_ERR_ARG, "organized cloud larger than 2^20 points");
+    if (size_t(w + 2) * (h + 2) > 200u * 1024u) return fail(nullptr, SPX_ERR_ARG, "organized cloud too large for the shared-memory plane-id map of the contour trace");
 
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -489,6 +490,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_mt_state1, mt, sizeof(mt)));
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_mt_out0, mt_out, sizeof(mt_out)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLinesSmem)));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_contour, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(w + 2) * (h + 2))));
     {
         int per_sm = 0;
         SPX_CK_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lines, kLineThreads, kLinesSmem));

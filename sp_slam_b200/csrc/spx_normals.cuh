@@ -46,6 +46,56 @@ __global__ void __launch_bounds__(256) k_backproject(const float *__restrict__ d
 // The reference's row wrap-around (previous_row[w] aliases current_row[0]; next_row[-1] aliases current_row[w-1])
 // is reproduced.  Output: kwin = int(min(dist, 10)) if that is > 2 else 0 (all the normal estimation consumes).
 // ---------------------------------------------------------------------------------------------------------------
+// One row of a chamfer pass for the CW contiguous columns [c0, c0 + CW) a lane owns (k_edge_chamfer).
+// kFwd: left-to-right chain, `prev` = the row above; else right-to-left, `prev` = the row below.  `wrapv` is the
+// reference's aliased neighbour (forward: current row's column 0; backward: its column w-1).
+template <int CW, bool kFwd>
+__device__ __forceinline__ void chamfer_row_step(const float (&prev)[CW], float (&cur)[CW], float wrapv, int c0, int w, int lane) {
+    const float kInf = 3.0e38f;
+    // neighbours of the own columns in the previous row
+    float pl = __shfl_up_sync(SPX_FULL, prev[CW - 1], 1);     // prev[c0 - 1]
+    float pr = __shfl_down_sync(SPX_FULL, prev[0], 1);        // prev[c0 + CW]
+    if (lane == 0) pl = kInf;
+    if (lane == 31) pr = kInf;
+    float Bv[CW];
+#pragma unroll
+    for (int k = 0; k < CW; ++k) {
+        const int c = c0 + k;
+        float a = (k == 0) ? pl : prev[k == 0 ? 0 : k - 1];                  // prev[c - 1]
+        float d = (k == CW - 1) ? pr : prev[k == CW - 1 ? k : k + 1];        // prev[c + 1]
+        if (kFwd) { if (c == w - 1) d = wrapv; } else { if (c == 0) a = wrapv; }
+        float v = cur[k];
+        const bool upd = kFwd ? (c >= 1 && c < w) : (c <= w - 2);
+        if (upd) v = fminf(v, fminf(fminf(a + 1.4f, prev[k] + 1.0f), d + 1.4f));
+        Bv[k] = (c < w) ? fminf(v, kDistCap) : kInf;
+    }
+    // local chain in visiting order, then two carry rounds from the neighbouring lane
+    // (column 0 in the forward pass and column w-1 in the backward pass are not updated by the row at all)
+    if (kFwd) {
+        float run = kInf;
+#pragma unroll
+        for (int k = 0; k < CW; ++k) { const int c = c0 + k; run = (c >= 1) ? fminf(Bv[k], run + 1.0f) : Bv[k]; cur[k] = fminf(run, kDistCap); }
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+            float carry = __shfl_up_sync(SPX_FULL, cur[CW - 1], 1);
+            if (lane == 0) carry = kInf;
+#pragma unroll
+            for (int k = 0; k < CW; ++k) { const int c = c0 + k; carry = carry + 1.0f; if (c >= 1 && c < w) cur[k] = fminf(cur[k], fminf(carry, kDistCap)); }
+        }
+    } else {
+        float run = kInf;
+#pragma unroll
+        for (int k = CW - 1; k >= 0; --k) { const int c = c0 + k; run = (c <= w - 2) ? fminf(Bv[k], run + 1.0f) : Bv[k]; cur[k] = fminf(run, kDistCap); }
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+            float carry = __shfl_down_sync(SPX_FULL, cur[0], 1);
+            if (lane == 31) carry = kInf;
+#pragma unroll
+            for (int k = CW - 1; k >= 0; --k) { const int c = c0 + k; carry = carry + 1.0f; if (c <= w - 2) cur[k] = fminf(cur[k], fminf(carry, kDistCap)); }
+        }
+    }
+}
+
 constexpr int kChamferWarps = 4;
 constexpr int kBandRows = 32;
 constexpr int kBandHalo = 10;
@@ -61,10 +111,7 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_edge_chamfer(const float
     const int fl = g / nb, band = g - fl * nb;
     if (fl >= P.n_frames) return;
     const int f = P.frame0 + fl;
-    float *rowA = sm_f + size_t(warp) * (3 * w + kBandSpan * NCH);
-    float *rowB = rowA + w;
-    float *Bv = rowB + w;
-    unsigned *mbits = reinterpret_cast<unsigned *>(Bv + w);   // [kBandSpan][NCH]
+    unsigned *mbits = reinterpret_cast<unsigned *>(sm_f) + size_t(warp) * (kBandSpan * NCH);   // [kBandSpan][NCH]
     const size_t fo = size_t(f) * P.N;
     const int r0 = band * kBandRows, r1 = min(r0 + kBandRows, h);
     const int ra = max(r0 - kBandHalo, 0), rb = min(r1 + kBandHalo, h);
@@ -128,84 +175,68 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_edge_chamfer(const float
             for (int c = lane; c < w; c += 32) { kwin[r * w + c] = kk; if (write_dist) dist[r * w + c] = initv; }
         return;
     }
-    auto init_of = [&](int r, int c) -> float { return ((mbits[(r - ra) * NCH + (c >> 5)] >> (c & 31)) & 1u) ? 0.0f : initv; };
+    // ---- phase 2: the two raster passes, rows in registers ----
+    // lane l owns the CW contiguous columns [l*CW, l*CW + CW); neighbours across lanes come from shuffles.  Within a
+    // row the recurrence cur[c] = min(B[c], cur[c-1] (+) 1.0f) only reaches 10 columns back under the cap (< 2 lanes),
+    // so a local scan plus two rounds of carry from the neighbouring lane reproduce the sequential scan exactly.
+    constexpr int CW = NCH;   // 32 * NCH columns over 32 lanes
+    const int c0 = lane * CW;
     float *scratch = B.cham_tmp + (size_t(f) * nb + band) * size_t(kBandRows + kBandHalo) * w;   // forward rows [r0, rb)
-    const int CH = (w + 31) / 32;
-    const int c0 = lane * CH;
-    const int c1 = min(c0 + CH, w);
-
-    float *prev = rowA, *cur = rowB;
-    for (int c = lane; c < w; c += 32) {
-        const float v = init_of(ra, c);
-        prev[c] = v;
-        if (ra >= r0) scratch[(ra - r0) * w + c] = v;
-    }
-    __syncwarp();
-    // forward pass: rows ra+1 .. rb-1, columns 1..w-1
-    for (int r = ra + 1; r < rb; ++r) {
-        for (int c = lane; c < w; c += 32) cur[c] = init_of(r, c);
-        __syncwarp();
-        const float cur0 = cur[0];
-        for (int c = lane; c < w; c += 32) {
-            float v = cur[c];
-            if (c >= 1) {
-                const float upLeft = prev[c - 1] + 1.4f;
-                const float up = prev[c] + 1.0f;
-                const float upRight = (c + 1 < w ? prev[c + 1] : cur0) + 1.4f;
-                v = fminf(v, fminf(fminf(upLeft, up), upRight));
-            }
-            Bv[c] = fminf(v, kDistCap);
-        }
-        __syncwarp();
-        if (c0 < w) {
-            int start = max(c0 - 10, 0);
-            float run = Bv[start];
-            if (start >= c0) cur[start] = run;
-            for (int c = start + 1; c < c1; ++c) {
-                run = fminf(Bv[c], run + 1.0f);
-                if (c >= c0) cur[c] = fminf(run, kDistCap);
-            }
-        }
-        __syncwarp();
-        if (r >= r0) for (int c = lane; c < w; c += 32) scratch[(r - r0) * w + c] = cur[c];
-        float *t = prev; prev = cur; cur = t;
-    }
-    // backward pass: rows rb-2 .. r0, columns w-2..0; `prev` holds the finished row below (row rb-1: forward values)
-    auto emit = [&](int r, const float *row) {
-        for (int c = lane; c < w; c += 32) {
-            const float s = fminf(row[c], kDistCap);
-            kwin[r * w + c] = s > 2.0f ? uint8_t(int(s)) : uint8_t(0);
-            if (write_dist) dist[r * w + c] = s;
+    const float kInf = 3.0e38f;
+    auto init_row = [&](int r, float (&v)[CW]) {
+#pragma unroll
+        for (int k = 0; k < CW; ++k) {
+            const int c = c0 + k;
+            v[k] = (c < w) ? (((mbits[(r - ra) * NCH + (c >> 5)] >> (c & 31)) & 1u) ? 0.0f : initv) : kInf;
         }
     };
+    auto store_row = [&](float *dst, const float (&v)[CW]) {
+#pragma unroll
+        for (int k = 0; k < CW; ++k) if (c0 + k < w) dst[c0 + k] = v[k];
+    };
+    auto load_row_f = [&](const float *src, float (&v)[CW]) {
+#pragma unroll
+        for (int k = 0; k < CW; ++k) v[k] = (c0 + k < w) ? src[c0 + k] : kInf;
+    };
+    auto emit = [&](int r, const float (&v)[CW]) {
+#pragma unroll
+        for (int k = 0; k < CW; ++k) {
+            const int c = c0 + k;
+            if (c < w) {
+                const float sv = fminf(v[k], kDistCap);
+                kwin[r * w + c] = sv > 2.0f ? uint8_t(int(sv)) : uint8_t(0);
+                if (write_dist) dist[r * w + c] = sv;
+            }
+        }
+    };
+
+    float prev[CW], cur[CW];
+    init_row(ra, prev);
+    if (ra >= r0) store_row(scratch + (ra - r0) * w, prev);
+    // forward pass: rows ra+1 .. rb-1, columns 1..w-1; previous_row[w] aliases current_row[0]
+    for (int r = ra + 1; r < rb; ++r) {
+        init_row(r, cur);
+        const float cur0 = __shfl_sync(SPX_FULL, cur[0], 0);
+        chamfer_row_step<CW, true>(prev, cur, cur0, c0, w, lane);
+        if (r >= r0) store_row(scratch + (r - r0) * w, cur);
+#pragma unroll
+        for (int k = 0; k < CW; ++k) prev[k] = cur[k];
+    }
+    // backward pass: rows rb-2 .. r0, columns w-2..0; `prev` holds the finished row below (row rb-1: forward values);
+    // next_row[-1] aliases current_row[w-1]
     if (rb - 1 < r1) emit(rb - 1, prev);   // the frame's last row is never touched by the backward pass
+    __syncwarp();
+    const int lane_last = (w - 1) / CW, k_last = (w - 1) - lane_last * CW;
     for (int r = rb - 2; r >= r0; --r) {
-        for (int c = lane; c < w; c += 32) cur[c] = scratch[(r - r0) * w + c];
-        __syncwarp();
-        const float curLast = cur[w - 1];
-        for (int c = lane; c < w; c += 32) {
-            float v = cur[c];
-            if (c <= w - 2) {
-                const float lowerLeft = (c >= 1 ? prev[c - 1] : curLast) + 1.4f;
-                const float lower = prev[c] + 1.0f;
-                const float lowerRight = prev[c + 1] + 1.4f;
-                v = fminf(v, fminf(fminf(lowerLeft, lower), lowerRight));
-            }
-            Bv[c] = fminf(v, kDistCap);
-        }
-        __syncwarp();
-        if (c0 < w) {
-            int start = min(c1 - 1 + 10, w - 1);
-            float run = Bv[start];
-            if (start < c1) cur[start] = run;
-            for (int c = start - 1; c >= c0; --c) {
-                run = fminf(Bv[c], run + 1.0f);
-                if (c < c1) cur[c] = fminf(run, kDistCap);
-            }
-        }
-        __syncwarp();
+        load_row_f(scratch + (r - r0) * w, cur);
+        float lastv = 0.f;
+#pragma unroll
+        for (int k = 0; k < CW; ++k) if (k == k_last) lastv = cur[k];
+        const float curLast = __shfl_sync(SPX_FULL, lastv, lane_last);
+        chamfer_row_step<CW, false>(prev, cur, curLast, c0, w, lane);
         if (r < r1) emit(r, cur);
-        float *t = prev; prev = cur; cur = t;
+#pragma unroll
+        for (int k = 0; k < CW; ++k) prev[k] = cur[k];
     }
 }
 

@@ -215,19 +215,35 @@ __global__ void __launch_bounds__(kRefWarps * 32) k_refine(Params P, Buffers B) 
     }
 }
 
-// K7: findLabeledRegionBoundary from inlier_indices[i].back(); one thread per model (the walk is serial).
+// K7: findLabeledRegionBoundary from inlier_indices[i].back().  The Moore walk is serial per model, so it is made
+// short instead: one CTA per frame stages the plane-id map in shared memory with a one-pixel sentinel frame (no bounds
+// tests), thread m walks model m, and every step reads the 8 neighbours at once (independent loads) and picks the
+// next direction from an 8-bit "same label" mask with a rotate + find-first-set.
 __constant__ int c_ddx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
 __constant__ int c_ddy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+constexpr int kContourThreads = 128;
+constexpr int kPidOutside = 0x7f;   // sentinel of the frame around the image: neither "same" nor an in-image "different"
 
-__global__ void __launch_bounds__(32) k_contour(Params P, Buffers B) {
-    const int f = P.frame0 + blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(kContourThreads) k_contour(Params P, Buffers B) {
+    extern __shared__ int8_t sm_pid[];   // (h + 2) x (w + 2)
+    const int f = P.frame0 + blockIdx.x, tid = threadIdx.x;
     FrameCtl &ctl = B.ctl[f];
     const int nm = ctl.n_models;
-    const int w = P.w, h = P.h;
+    if (nm == 0) return;
+    const int w = P.w, h = P.h, sw = w + 2;
     const size_t fo = size_t(f) * P.N;
     const int8_t *pid = B.pid + fo;
+    for (int i = tid; i < (h + 2) * sw; i += kContourThreads) {
+        const int y = i / sw - 1, x = i - (y + 1) * sw - 1;
+        sm_pid[i] = (x >= 0 && x < w && y >= 0 && y < h) ? pid[y * w + x] : int8_t(kPidOutside);
+    }
+    __syncthreads();
     int *arena = B.contour_idx + size_t(f) * P.contour_cap;
-    for (int m = lane; m < nm; m += 32) {
+    // offsets of the neighbours in the padded map, in the reference's direction order
+    int noff[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) noff[d] = c_ddy[d] * sw + c_ddx[d];
+    for (int m = tid; m < nm; m += kContourThreads) {
         Model &M = ctl.models[m];
         int off = 0;
         for (int k = 0; k < m; ++k) { const Model &K = ctl.models[k]; off += 2 * (K.n0 + K.n1 + K.n2) + 16; }
@@ -235,31 +251,38 @@ __global__ void __launch_bounds__(32) k_contour(Params P, Buffers B) {
         M.contour_off = off;
         int *out = arena + off;
         const int start = M.last_inlier;
-        int cx = start % w, cy = start / w, cidx = start;
-        int direction = -1;
-        for (int d = 0; d < 8; ++d) {
-            const int x = cx + c_ddx[d], y = cy + c_ddy[d];
-            if (x >= 0 && x < w && y >= 0 && y < h && pid[y * w + x] != m) { direction = d; break; }
-        }
+        int cx = start % w, cy = start / w;
+        int sp = (cy + 1) * sw + cx + 1;           // position in the padded map
+        const int sp_start = sp;
+        auto masks = [&](int p, unsigned &same, unsigned &diff) {
+            same = 0u; diff = 0u;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const int v = sm_pid[p + noff[d]];
+                same |= (v == m ? 1u : 0u) << d;
+                diff |= ((v != m && v != kPidOutside) ? 1u : 0u) << d;
+            }
+        };
+        unsigned same, diff;
+        masks(sp, same, diff);
         int n = 0;
-        if (direction != -1) {
+        if (diff != 0u) {                          // first direction whose in-image neighbour carries another label
+            int direction = __ffs(diff) - 1;
             out[n++] = start;
             const long long guard = 8ll * P.N + 8;
             long long steps = 0;
             bool overflow = false;
             do {
-                int nIdx = direction;
-                for (int d = 1; d <= 8; ++d) {
-                    nIdx = (direction + d) & 7;
-                    const int x = cx + c_ddx[nIdx], y = cy + c_ddy[nIdx];
-                    if (x >= 0 && x < w && y >= 0 && y < h && pid[y * w + x] == m) break;
-                }
+                // for d = 1..8: nIdx = (direction + d) & 7, stop at the first neighbour with the same label
+                const unsigned rot = ((same | (same << 8)) >> ((direction + 1) & 7)) & 0xffu;
+                const int nIdx = rot ? ((direction + 1 + (__ffs(rot) - 1)) & 7) : direction;
                 direction = (nIdx + 4) & 7;
+                sp += noff[nIdx];
                 cx += c_ddx[nIdx]; cy += c_ddy[nIdx];
-                cidx = cy * w + cx;
-                if (n < cap) out[n++] = cidx; else overflow = true;
                 if (++steps > guard || cx < 0 || cx >= w || cy < 0 || cy >= h) { overflow = true; break; }
-            } while (cidx != start);
+                if (n < cap) out[n++] = cy * w + cx; else overflow = true;
+                masks(sp, same, diff);
+            } while (sp != sp_start);
             if (overflow) atomicOr(&ctl.flags, unsigned(SPX_FRAME_OVERFLOW));
         }
         M.n_contour = n;

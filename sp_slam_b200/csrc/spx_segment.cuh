@@ -130,14 +130,24 @@ __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) 
     int *pos = B.pos + fo;
     if (tid == 0) { running_s = 0; s_ncand = 0; s_noff = 0; }
     __syncthreads();
+    // software pipeline: the next chunk's forest entries and sizes are loaded while this chunk is processed, and the
+    // candidate id of a pixel whose root lies in an EARLIER chunk (final by then) is fetched ahead as well
+    int root_n = (tid < P.N) ? parent[tid] : -1;
+    int cnt_n = (tid < P.N) ? B.cnt[fo + tid] : 0;
+    int cand_n = -1;
     for (int base = 0; base < P.N; base += kRankThreads) {
         const int q = base + tid;
+        const int root = root_n, sz_q = cnt_n, cand_pre = cand_n;
+        {
+            const int qn = q + kRankThreads;
+            root_n = (qn < P.N) ? parent[qn] : -1;
+            cnt_n = (qn < P.N) ? B.cnt[fo + qn] : 0;
+        }
         bool isroot = false, iscand = false;
-        int sz = 0, root = -1;
+        int sz = 0;
         if (q < P.N) {
-            root = parent[q];
             isroot = root == q;
-            if (isroot) { sz = B.cnt[fo + q]; iscand = unsigned(sz) > unsigned(P.min_size); }
+            if (isroot) { sz = sz_q; iscand = unsigned(sz) > unsigned(P.min_size); }
         }
         // roots are counted in bits 0..19 (N < 2^20), candidates in bits 20..31
         const unsigned v = (isroot ? 1u : 0u) | (iscand ? (1u << 20) : 0u);
@@ -190,8 +200,11 @@ __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) 
         }
         for (int i = tid; i < nc_now * 32; i += kRankThreads) s_wcnt[i >> 5][i & 31] = 0;
         __syncthreads();
+        // every root below base + kRankThreads has its candidate id in memory now
+        cand_n = (root_n >= 0 && root_n < base + kRankThreads) ? int(root_cand[root_n]) : -1;
         if (nc_now > 0) {   // uniform over the CTA
-            const int c = (q < P.N) ? int(root_cand[root]) : -1;
+            // roots of earlier chunks were ranked before their id was prefetched; same-chunk roots are read now
+            const int c = (q < P.N) ? ((root < base) ? cand_pre : int(root_cand[root])) : -1;
             const unsigned peers = __match_any_sync(SPX_FULL, c);
             const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
             if (c >= 0 && rank_in_warp == 0) s_wcnt[c][wid] = __popc(peers);
@@ -261,16 +274,18 @@ __global__ void __launch_bounds__(kMomWarps * 32) k_moments_fit(Params P, Buffer
     const float *px = B.px + fo, *py = B.py + fo, *pz = B.pz + fo;
     const int *idx = B.cand_idx + fo + cd.idx_off;
     float accu = 0.0f;
-    // software pipeline: indices two batches ahead, coordinates one batch ahead of the dependent chain
-    float x[4], y[4], z[4];
+    // software pipeline: indices three batches ahead, coordinates two batches ahead of the dependent chain
+    float x[4], y[4], z[4], x2[4], y2[4], z2[4];
     int pnext[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int m = j * 32 + lane;
-        x[j] = y[j] = z[j] = 0.f;
+        x[j] = y[j] = z[j] = 0.f; x2[j] = y2[j] = z2[j] = 0.f;
         if (m < size) { const int p = idx[m]; x[j] = px[p]; y[j] = py[p]; z[j] = pz[p]; }
         const int m2 = kMomBatch + m;
-        pnext[j] = m2 < size ? idx[m2] : -1;
+        if (m2 < size) { const int p = idx[m2]; x2[j] = px[p]; y2[j] = py[p]; z2[j] = pz[p]; }
+        const int m3 = 2 * kMomBatch + m;
+        pnext[j] = m3 < size ? idx[m3] : -1;
     }
     int buf = 0;
     for (int base = 0; base < size; base += kMomBatch, buf ^= 1) {
@@ -283,11 +298,12 @@ __global__ void __launch_bounds__(kMomWarps * 32) k_moments_fit(Params P, Buffer
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            x[j] = x2[j]; y[j] = y2[j]; z[j] = z2[j];
             const int p = pnext[j];
-            x[j] = y[j] = z[j] = 0.f;
-            if (p >= 0) { x[j] = px[p]; y[j] = py[p]; z[j] = pz[p]; }
-            const int m2 = base + 2 * kMomBatch + j * 32 + lane;
-            pnext[j] = m2 < size ? idx[m2] : -1;
+            x2[j] = y2[j] = z2[j] = 0.f;
+            if (p >= 0) { x2[j] = px[p]; y2[j] = py[p]; z2[j] = pz[p]; }
+            const int m3 = base + 3 * kMomBatch + j * 32 + lane;
+            pnext[j] = m3 < size ? idx[m3] : -1;
         }
         __syncwarp();
         const int cnt = min(kMomBatch, size - base);
