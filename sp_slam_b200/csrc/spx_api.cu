@@ -53,6 +53,11 @@ struct spx_ctx {
     std::vector<cudaStream_t> g_streams;
     std::vector<cudaEvent_t> g_ev;
     size_t work_stride = 0, work2_stride = 0;
+    // host path: every group compacts its own results (at the device offset of its first frame) and ships them itself
+    bool group_pack = false;
+    std::vector<cudaEvent_t> g_tot_ev;
+    struct GroupOut { int f0 = 0, f1 = 0; long long dev_pl = 0, dev_pt = 0, dev_bd = 0; };
+    std::vector<GroupOut> g_out;
     Params P;           // geometry of the last call (capacities fixed at create)
     Buffers B;
     DevArena arena;
@@ -249,12 +254,26 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
         LAUNCH(k_border, bg, kBorderWarps * 32, 0, depth_dev, P, B);
         LAUNCH(k_supposed, cdiv(F, 128), 128, 0, P, B);
     }
+    if (c->group_pack) {
+        spx_ctx::GroupOut &go = c->g_out[g];
+        go.f0 = f0; go.f1 = f0 + ng;
+        go.dev_pl = (long long)f0 * SPX_MAX_PLANES; go.dev_pt = (long long)f0 * P.pts_cap; go.dev_bd = (long long)f0 * P.bnd_cap;
+        long long *tot = B.out_totals + 4 * (g + 1);
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, go.dev_pl, go.dev_pt, go.dev_bd, tot);
+        LAUNCH(k_emit_records, F, 128, 0, P, B);
+        LAUNCH(k_pack_points, gpix, 256, 0, P, B);
+        LAUNCH(k_pack_contours, dim3(SPX_MAX_MODELS, F), 128, 0, P, B);
+        if (P.enable_supposed) LAUNCH(k_pack_supposed, dim3(SPX_MAX_PLANES, F), 128, 0, P, B);
+        SPX_CK(c, cudaMemcpyAsync(c->h_totals + 4 * (g + 1), tot, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        SPX_CK(c, cudaEventRecord(c->g_tot_ev[g], st));
+    }
     SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 2], st));
     return SPX_OK;
 }
 
-int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given, const HostSrc &src) {
+int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given, const HostSrc &src, bool group_pack) {
     cudaStream_t main_st = c->stream;
+    c->group_pack = group_pack;
     const int F = c->P.n_frames;
     c->P.frame0 = 0;
     c->launches = 0;
@@ -272,13 +291,13 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given, const H
         if (G > 1) SPX_CK(c, cudaStreamWaitEvent(main_st, c->g_ev[3 * g + 2], 0));
     }
     SPX_CK(c, cudaEventRecord(c->ev[1], main_st));
-    {
+    if (!group_pack) {
         const Params &P = c->P;
         const Buffers &B = c->B;
         cudaStream_t st = main_st;
         const dim3 gpix(cdiv(P.N, 256), F);
         int &L = c->launches;
-        LAUNCH(k_scan_frames, 1, 1024, 0, P, B);
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 0ll, 0ll, 0ll, B.out_totals);
         LAUNCH(k_emit_records, F, 128, 0, P, B);
         LAUNCH(k_pack_points, gpix, 256, 0, P, B);
         LAUNCH(k_pack_contours, dim3(SPX_MAX_MODELS, F), 128, 0, P, B);
@@ -307,6 +326,7 @@ int grow_pinned(spx_ctx *c, T **p, size_t *cap, size_t need) {
 
 int fetch(spx_ctx *c, spx_batch_result *out, bool with_clouds) {
     if (!c->have_run) return fail(c, SPX_ERR_STATE, "no extract call has been made on this context");
+    if (c->group_pack) return fail(c, SPX_ERR_STATE, "the last extract already delivered its results to the host; fetch follows spx_extract_batch_device");
     cudaStream_t st = c->stream;
     const int F = c->last_frames;
     SPX_CK(c, cudaMemcpyAsync(c->h_totals, c->B.out_totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -333,6 +353,67 @@ int fetch(spx_ctx *c, spx_batch_result *out, bool with_clouds) {
         out->points = with_clouds ? c->h_pts : nullptr;
         out->boundary = with_clouds ? c->h_bnd : nullptr;
     }
+    return SPX_OK;
+}
+
+// pinned buffer growth that keeps the first `used` elements (other groups' copies may already have landed there)
+template <typename T>
+int grow_pinned_keep(spx_ctx *c, T **p, size_t *cap, size_t need, size_t used) {
+    if (need <= *cap) return SPX_OK;
+    for (int g = 0; g < c->last_groups; ++g) SPX_CK(c, cudaStreamSynchronize(c->last_groups == 1 ? c->stream : c->g_streams[g]));
+    size_t ncap = *cap ? *cap : 1024;
+    while (ncap < need) ncap *= 2;
+    T *np = nullptr;
+    SPX_CK(c, cudaHostAlloc(reinterpret_cast<void **>(&np), ncap * sizeof(T), cudaHostAllocDefault));
+    if (*p && used) std::memcpy(np, *p, used * sizeof(T));
+    if (*p) SPX_CK(c, cudaFreeHost(*p));
+    *p = np; *cap = ncap;
+    return SPX_OK;
+}
+
+// host path: as soon as a group's totals are known its frame headers, plane records and clouds are copied to where
+// they belong in the contiguous host arrays (on the group's own stream, overlapping the other groups' work); the
+// offsets inside the records are rebased from the device layout to the host layout at the end.
+int fetch_groups(spx_ctx *c, spx_batch_result *out) {
+    const int F = c->last_frames, G = c->last_groups;
+    long long run_pl = 0, run_pt = 0, run_bd = 0;
+    std::vector<long long> host_pl(G), host_pt(G), host_bd(G), n_pls(G);
+    int rc;
+    for (int g = 0; g < G; ++g) {
+        cudaStream_t st = (G == 1) ? c->stream : c->g_streams[g];
+        SPX_CK(c, cudaEventSynchronize(c->g_tot_ev[g]));
+        const long long *t = c->h_totals + 4 * (g + 1);
+        const long long n_pl = t[0], n_pt = t[1], n_bd = t[2];
+        const spx_ctx::GroupOut &go = c->g_out[g];
+        if ((rc = grow_pinned_keep(c, &c->h_planes, &c->h_planes_cap, size_t(run_pl + n_pl), size_t(run_pl))) != SPX_OK) return rc;
+        if ((rc = grow_pinned_keep(c, &c->h_pts, &c->h_pts_cap, size_t(run_pt + n_pt), size_t(run_pt))) != SPX_OK) return rc;
+        if ((rc = grow_pinned_keep(c, &c->h_bnd, &c->h_bnd_cap, size_t(run_bd + n_bd), size_t(run_bd))) != SPX_OK) return rc;
+        SPX_CK(c, cudaMemcpyAsync(c->h_frames + go.f0, c->B.out_frames + go.f0, sizeof(spx_frame_header) * size_t(go.f1 - go.f0), cudaMemcpyDeviceToHost, st));
+        if (n_pl) SPX_CK(c, cudaMemcpyAsync(c->h_planes + run_pl, c->B.out_planes + go.dev_pl, sizeof(spx_plane) * size_t(n_pl), cudaMemcpyDeviceToHost, st));
+        if (n_pt) SPX_CK(c, cudaMemcpyAsync(c->h_pts + run_pt, c->B.out_pts + go.dev_pt, sizeof(spx_point) * size_t(n_pt), cudaMemcpyDeviceToHost, st));
+        if (n_bd) SPX_CK(c, cudaMemcpyAsync(c->h_bnd + run_bd, c->B.out_bnd + go.dev_bd, sizeof(spx_point) * size_t(n_bd), cudaMemcpyDeviceToHost, st));
+        host_pl[g] = run_pl; host_pt[g] = run_pt; host_bd[g] = run_bd; n_pls[g] = n_pl;
+        run_pl += n_pl; run_pt += n_pt; run_bd += n_bd;
+    }
+    for (int g = 0; g < G; ++g) SPX_CK(c, cudaStreamSynchronize((G == 1) ? c->stream : c->g_streams[g]));
+    SPX_CK(c, cudaStreamSynchronize(c->stream));
+    for (int g = 0; g < G; ++g) {
+        const spx_ctx::GroupOut &go = c->g_out[g];
+        const long long d_pl = host_pl[g] - go.dev_pl, d_pt = host_pt[g] - go.dev_pt, d_bd = host_bd[g] - go.dev_bd;
+        for (int f = go.f0; f < go.f1; ++f) c->h_frames[f].first_plane += int(d_pl);
+        for (long long k = 0; k < n_pls[g]; ++k) {
+            spx_plane &pl = c->h_planes[host_pl[g] + k];
+            pl.points_off += d_pt; pl.boundary_off += d_bd;
+        }
+    }
+    out->n_frames = F;
+    out->n_planes_total = int(run_pl);
+    out->n_points_total = run_pt;
+    out->n_boundary_total = run_bd;
+    out->frames = c->h_frames;
+    out->planes = c->h_planes;
+    out->points = c->h_pts;
+    out->boundary = c->h_bnd;
     return SPX_OK;
 }
 
@@ -449,6 +530,10 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
             SPX_CK_CREATE(cudaEventCreate(&e));
             c->g_ev.push_back(e);
         }
+        cudaEvent_t te;
+        SPX_CK_CREATE(cudaEventCreateWithFlags(&te, cudaEventDisableTiming));
+        c->g_tot_ev.push_back(te);
+        c->g_out.push_back(spx_ctx::GroupOut());
     }
 
     const size_t FN = F * N, FC = F * size_t(P.contour_cap);
@@ -462,7 +547,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     total += padded<FrameCtl>(F);
     total += padded<spx_frame_header>(F) + padded<spx_plane>(F * SPX_MAX_PLANES);
     total += padded<spx_point>(F * size_t(P.pts_cap)) + padded<spx_point>(F * size_t(P.bnd_cap));
-    total += padded<long long>(4) + padded<long long>(3 * F);
+    total += padded<long long>(4 * size_t(c->n_streams + 1)) + padded<long long>(3 * F);
     total += padded<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols));
     SPX_CK_CREATE(cudaMalloc(reinterpret_cast<void **>(&c->arena.base), total));
     c->arena.size = total;
@@ -479,7 +564,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     B.ctl = A.take<FrameCtl>(F);
     B.out_frames = A.take<spx_frame_header>(F); B.out_planes = A.take<spx_plane>(F * SPX_MAX_PLANES);
     B.out_pts = A.take<spx_point>(F * size_t(P.pts_cap)); B.out_bnd = A.take<spx_point>(F * size_t(P.bnd_cap));
-    B.out_totals = A.take<long long>(4); B.frame_offs = A.take<long long>(3 * F);
+    B.out_totals = A.take<long long>(4 * size_t(c->n_streams + 1)); B.frame_offs = A.take<long long>(3 * F);
     c->d_depth = A.take<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols));
     if (A.used > A.size) { fail(nullptr, SPX_ERR_ARG, "internal: arena accounting"); spx_destroy(c); return SPX_ERR_ARG; }
 
@@ -502,7 +587,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_link, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kNormalsSmem)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_edge_chamfer<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_edge_chamfer<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_totals), 4 * sizeof(long long), cudaHostAllocDefault));
+    SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_totals), 4 * size_t(c->n_streams + 1) * sizeof(long long), cudaHostAllocDefault));
     SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_frames), F * sizeof(spx_frame_header), cudaHostAllocDefault));
 #undef SPX_CK_CREATE
     *out = c;
@@ -522,6 +607,7 @@ void spx_destroy(spx_ctx *c) {
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->g_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->g_tot_ev) cudaEventDestroy(e);
     for (cudaStream_t gs : c->g_streams) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -550,7 +636,7 @@ int spx_extract_batch_device(spx_ctx *c, const float *depth_dev, int n_frames, i
     SPX_CK(c, cudaSetDevice(c->device));
     int rc = set_geometry(c, n_frames, rows, cols, pitch_bytes, frame_stride_bytes);
     if (rc != SPX_OK) return rc;
-    return run_pipeline(c, depth_dev, false, HostSrc());
+    return run_pipeline(c, depth_dev, false, HostSrc(), false);
 }
 
 int spx_fetch_results(spx_ctx *c, spx_batch_result *out) {
@@ -567,7 +653,7 @@ int spx_fetch_planes(spx_ctx *c, spx_batch_result *out) {
 
 int spx_get_device_results(spx_ctx *c, spx_device_result *out) {
     if (!c || !out) return SPX_ERR_ARG;
-    if (!c->have_run) return fail(c, SPX_ERR_STATE, "no extract call has been made on this context");
+    if (!c->have_run || c->group_pack) return fail(c, SPX_ERR_STATE, "device results follow spx_extract_batch_device");
     out->n_frames = c->last_frames;
     out->frames = c->B.out_frames; out->planes = c->B.out_planes; out->points = c->B.out_pts; out->boundary = c->B.out_bnd;
     out->totals = c->B.out_totals;
@@ -586,8 +672,8 @@ int spx_extract_batch(spx_ctx *c, const float *depth, int n_frames, int rows, in
     HostSrc src;
     src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = frame_stride_bytes;
     c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);   // layout of the staging buffer the kernels read
-    if ((rc = run_pipeline(c, c->d_depth, false, src)) != SPX_OK) return rc;
-    return fetch(c, out, true);
+    if ((rc = run_pipeline(c, c->d_depth, false, src, true)) != SPX_OK) return rc;
+    return fetch_groups(c, out);
 }
 
 int spx_extract(spx_ctx *c, const float *depth, int rows, int cols, size_t pitch_bytes, spx_batch_result *out) {
@@ -609,7 +695,7 @@ int spx_segment_from_normals(spx_ctx *c, const float *depth, int rows, int cols,
     SPX_CK(c, cudaMemcpyAsync(c->B.nx, normals, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     SPX_CK(c, cudaMemcpyAsync(c->B.ny, normals + N, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     SPX_CK(c, cudaMemcpyAsync(c->B.nz, normals + 2 * N, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = run_pipeline(c, c->d_depth, true, src)) != SPX_OK) return rc;
+    if ((rc = run_pipeline(c, c->d_depth, true, src, false)) != SPX_OK) return rc;
     return fetch(c, out, true);
 }
 

@@ -661,9 +661,10 @@ __global__ void __launch_bounds__(128) k_pack_supposed(Params P, Buffers B) {
     }
 }
 
-// exclusive scan of the per-frame totals (one CTA): where each frame's planes / points / boundary points start in the
-// contiguous output buffers the pack kernels write to
-__global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B) {
+// exclusive scan of the per-frame totals of a frame range (one CTA): where each frame's planes / points / boundary
+// points start in the output buffers the pack kernels write to (base_* = where the range's results start)
+__global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B, long long base_pl, long long base_pt, long long base_bd,
+                                                        long long *totals) {
     __shared__ long long s_run[3];
     __shared__ long long s_w[3][32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -672,7 +673,7 @@ __global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B) {
     for (int base = 0; base < P.n_frames; base += 1024) {
         const int f = base + tid;
         long long v[3] = {0, 0, 0};
-        if (f < P.n_frames) { v[0] = B.ctl[f].n_planes; v[1] = B.ctl[f].pts_used; v[2] = B.ctl[f].bnd_used; }
+        if (f < P.n_frames) { const FrameCtl &K = B.ctl[P.frame0 + f]; v[0] = K.n_planes; v[1] = K.pts_used; v[2] = K.bnd_used; }
         long long inc[3];
         for (int k = 0; k < 3; ++k) {
             long long x = v[k];
@@ -693,14 +694,15 @@ __global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B) {
         long long tot[3];
         for (int k = 0; k < 3; ++k) {
             const long long excl = s_run[k] + s_w[k][wid] + inc[k] - v[k];
-            if (f < P.n_frames) B.frame_offs[size_t(f) * 3 + k] = excl;
+            const long long gb = k == 0 ? base_pl : (k == 1 ? base_pt : base_bd);
+            if (f < P.n_frames) B.frame_offs[size_t(P.frame0 + f) * 3 + k] = gb + excl;
             tot[k] = excl + v[k];
         }
         __syncthreads();
         if (tid == 1023) for (int k = 0; k < 3; ++k) s_run[k] = tot[k];
         __syncthreads();
     }
-    if (tid < 3) B.out_totals[tid] = s_run[tid];
+    if (tid < 3) totals[tid] = s_run[tid];
 }
 
 // frame headers and plane records with batch-global offsets; one CTA per frame

@@ -92,8 +92,9 @@ __device__ __forceinline__ void refine_pass(RefineSmem &S, const Params &P, cons
             for (int ch = 0; ch < NCH; ++ch) {
                 mV[ch] = -1;
                 const int m = prev[ch];
-                if (a[ch] == -1 && m >= 0 && (kReverse || col(ch) <= w - 2) && refine_dist_ok(S.coef[m], x[ch], y[ch], z[ch])) {
-                    a[ch] = m; mV[ch] = m;
+                const bool cand = a[ch] == -1 && m >= 0 && (kReverse || col(ch) <= w - 2);
+                if (__any_sync(SPX_FULL, cand)) {   // most chunks lie inside a plane or inside nothing
+                    if (cand && refine_dist_ok(S.coef[m], x[ch], y[ch], z[ch])) { a[ch] = m; mV[ch] = m; }
                 }
             }
             // W) wrap claim of (r+1, 0) on (r, w-1): visiting index w-1 of the previous row claims visiting index 0
@@ -147,6 +148,12 @@ __device__ __forceinline__ void refine_pass(RefineSmem &S, const Params &P, cons
                 const bool valid = ch * 32 + lane < w;
                 const int cur = a[ch];
                 const unsigned labelled = __ballot_sync(SPX_FULL, cur >= 0);
+                const unsigned freem = __ballot_sync(SPX_FULL, valid && cur == -1);
+                if (freem == 0u || (labelled == 0u && carry < 0)) {   // nothing to claim / nobody to claim it
+                    carry = __shfl_sync(SPX_FULL, cur, 31);
+                    if (carry < 0) carry = -1;
+                    continue;
+                }
                 const unsigned below = labelled & ((1u << lane) - 1u);
                 const int src_lane = below ? (31 - __clz(below)) : -1;
                 const int m_lane = __shfl_sync(SPX_FULL, cur, src_lane < 0 ? 0 : src_lane);

@@ -274,21 +274,24 @@ __global__ void __launch_bounds__(kMomWarps * 32) k_moments_fit(Params P, Buffer
     const float *px = B.px + fo, *py = B.py + fo, *pz = B.pz + fo;
     const int *idx = B.cand_idx + fo + cd.idx_off;
     float accu = 0.0f;
-    // software pipeline: indices three batches ahead, coordinates two batches ahead of the dependent chain
-    float x[4], y[4], z[4], x2[4], y2[4], z2[4];
-    int pnext[4];
+    // software pipeline, two register stages (A: even batches, B: odd batches): a stage's coordinates are reloaded
+    // for the batch two ahead right after its products are staged, so a gather has two chains of time to land and
+    // no register is moved while a load is pending; indices run two batches further ahead.
+    float xa[4], ya[4], za[4], xb[4], yb[4], zb[4];
+    int ia[4], ib[4];   // indices of the batches the stages will load next
+    auto gather = [&](int m, float &x, float &y, float &z) {
+        x = y = z = 0.f;
+        if (m < size) { const int p = idx[m]; x = px[p]; y = py[p]; z = pz[p]; }
+    };
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int m = j * 32 + lane;
-        x[j] = y[j] = z[j] = 0.f; x2[j] = y2[j] = z2[j] = 0.f;
-        if (m < size) { const int p = idx[m]; x[j] = px[p]; y[j] = py[p]; z[j] = pz[p]; }
-        const int m2 = kMomBatch + m;
-        if (m2 < size) { const int p = idx[m2]; x2[j] = px[p]; y2[j] = py[p]; z2[j] = pz[p]; }
-        const int m3 = 2 * kMomBatch + m;
-        pnext[j] = m3 < size ? idx[m3] : -1;
+        gather(m, xa[j], ya[j], za[j]);
+        gather(kMomBatch + m, xb[j], yb[j], zb[j]);
+        ia[j] = (2 * kMomBatch + m < size) ? idx[2 * kMomBatch + m] : -1;
+        ib[j] = (3 * kMomBatch + m < size) ? idx[3 * kMomBatch + m] : -1;
     }
-    int buf = 0;
-    for (int base = 0; base < size; base += kMomBatch, buf ^= 1) {
+    auto stage = [&](int base, int buf, float (&x)[4], float (&y)[4], float (&z)[4], int (&inext)[4]) {
         float *pr = s_prod[warp][buf];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -297,13 +300,12 @@ __global__ void __launch_bounds__(kMomWarps * 32) k_moments_fit(Params P, Buffer
             q[6] = x[j]; q[7] = y[j]; q[8] = z[j];
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            x[j] = x2[j]; y[j] = y2[j]; z[j] = z2[j];
-            const int p = pnext[j];
-            x2[j] = y2[j] = z2[j] = 0.f;
-            if (p >= 0) { x2[j] = px[p]; y2[j] = py[p]; z2[j] = pz[p]; }
-            const int m3 = base + 3 * kMomBatch + j * 32 + lane;
-            pnext[j] = m3 < size ? idx[m3] : -1;
+        for (int j = 0; j < 4; ++j) {   // this stage's next batch is base + 2 batches; its indices were fetched earlier
+            const int p = inext[j];
+            x[j] = y[j] = z[j] = 0.f;
+            if (p >= 0) { x[j] = px[p]; y[j] = py[p]; z[j] = pz[p]; }
+            const int m4 = base + 4 * kMomBatch + j * 32 + lane;
+            inext[j] = m4 < size ? idx[m4] : -1;
         }
         __syncwarp();
         const int cnt = min(kMomBatch, size - base);
@@ -316,6 +318,10 @@ __global__ void __launch_bounds__(kMomWarps * 32) k_moments_fit(Params P, Buffer
                 for (int j = 0; j < cnt; ++j) accu += src[j * 9];
             }
         }
+    };
+    for (int base = 0; base < size; base += 2 * kMomBatch) {
+        stage(base, 0, xa, ya, za, ia);
+        if (base + kMomBatch < size) stage(base + kMomBatch, 1, xb, yb, zb, ib);
     }
     float acc[9];
 #pragma unroll

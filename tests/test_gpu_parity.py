@@ -86,3 +86,33 @@ def test_cpp_host_adapter_fills_frame_fields(ext, seq, tmp_path):
         p = fp.mvPlanePoints[i]
         sx = float(np.sum(p["x"].astype(np.float64) + 2.0 * p["y"].astype(np.float64) + 3.0 * p["z"].astype(np.float64)))
         assert abs(float(t[8]) - sx) <= 1e-9 * max(1.0, abs(sx))
+
+
+def test_frame_groups_host_and_device_paths_agree():
+    """A batch large enough to be cut into several frame groups (internal streams, per-group compaction and
+    download on the host path; batch-wide compaction on the device path) returns what the one-frame call returns."""
+    import torch
+    n = 100
+    d = scenes.boxroom_sequence(n, start=170)
+    ext = api.PlaneExtractor(max_frames=n, n_streams=4)
+    host = ext.extract_batch(d)
+    dev = torch.from_numpy(d).cuda()
+    ext.extract_device(dev.data_ptr(), n, 480, 640)
+    devres = ext.fetch()
+    one = api.PlaneExtractor()
+    assert len(host) == len(devres) == n
+    assert int(host.frames["n_planes"].sum()) == len(host.planes) == len(devres.planes)
+    for k in range(n):
+        a, b = host.frame(k), devres.frame(k)
+        ref = one.extract(d[k]) if k % 9 == 0 else None
+        for other in (b, ref):
+            if other is None:
+                continue
+            assert a.mnPlaneNum == other.mnPlaneNum and a.mnRealPlaneNum == other.mnRealPlaneNum
+            assert np.array_equal(a.mvPlaneCoefficients.view(np.uint32), other.mvPlaneCoefficients.view(np.uint32))
+            for p, q in zip(a.mvPlanePoints, other.mvPlanePoints):
+                assert np.array_equal(p, q)
+            for p, q in zip(a.mvBoundaryPoints, other.mvBoundaryPoints):
+                assert np.array_equal(p, q)
+    ext.close()
+    one.close()
