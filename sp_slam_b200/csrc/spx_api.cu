@@ -229,7 +229,7 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
         if (nch <= 7) LAUNCH(k_edge_chamfer<7>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
         else if (nch <= 14) LAUNCH(k_edge_chamfer<14>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
         else LAUNCH(k_edge_chamfer<16>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
-        LAUNCH(k_normals_link, dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), 256, kNormalsSmem, depth_dev, P, B, dbg);
+        LAUNCH(k_normals_link, dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), kNormThreads, kNormalsSmem, depth_dev, P, B, dbg);
     } else {
         LAUNCH(k_backproject, gpix, 256, 0, depth_dev, P, B);
         LAUNCH(k_plane_d, gpix, 256, 0, P, B);

@@ -266,13 +266,14 @@ constexpr int kCStride = kCW + 1;
 constexpr int kSW = kRW + 1, kSH = kRH + 1;      // 43 x 27 integral-image nodes
 constexpr int kSATStride = kSW;                  // 43, odd
 constexpr int kNStride = kNW + 1;
-constexpr size_t kNormalsSmem = size_t(6) * kSH * kSATStride * sizeof(double) + size_t(3) * kCHt * kCStride * sizeof(float) +
+constexpr int kNormThreads = 288;                // 9 warps: the 33 x 17 = 561 normals take exactly two rounds
+constexpr size_t kNormalsSmem = size_t(3) * kSH * kSATStride * sizeof(double) + size_t(3) * kCHt * kCStride * sizeof(float) +
                                 size_t(kSH) * kSATStride * sizeof(int);
 
-__global__ void __launch_bounds__(256) k_normals_link(const float *__restrict__ depth, Params P, Buffers B, int write_normals) {
+__global__ void __launch_bounds__(kNormThreads) k_normals_link(const float *__restrict__ depth, Params P, Buffers B, int write_normals) {
     extern __shared__ double sm_d[];
-    double *S = sm_d;                                                    // [6][kSH][kSATStride]
-    float *C = reinterpret_cast<float *>(S + 6 * kSH * kSATStride);      // [3][kCHt][kCStride]
+    double *S = sm_d;                                                    // [3][kSH][kSATStride]: DX, then DY
+    float *C = reinterpret_cast<float *>(S + 3 * kSH * kSATStride);      // [3][kCHt][kCStride]
     int *Cn = reinterpret_cast<int *>(C + 3 * kCHt * kCStride);          // [kSH][kSATStride], only with non-finite depth
     float *Nrm = reinterpret_cast<float *>(S);                           // [4][kNH][kNStride], aliases S after step 3
     constexpr int cs = kSH * kSATStride;          // channel stride of S
@@ -284,171 +285,222 @@ __global__ void __launch_bounds__(256) k_normals_link(const float *__restrict__ 
     const int tid = threadIdx.x;
     const char *img = reinterpret_cast<const char *>(depth) + size_t(f) * P.frame_stride;
 
-    // ---- 1. cloud region ----
+    // ---- 1. cloud region: thread = one region column, 5 region rows per sweep (all loads of a thread in flight) ----
     int nonfinite = 0;
-    for (int i = tid; i < kCW * kCHt; i += 256) {
-        const int ly = i / kCW, lx = i - ly * kCW;
-        const int r = tr - 7 + ly, c = tc - 7 + lx;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (r >= 0 && r < h && c >= 0 && c < w) {
-            z = *reinterpret_cast<const float *>(img + size_t(r) * P.dis * P.pitch + size_t(c) * P.dis * sizeof(float));
-            x = (float(c * P.dis) - P.cx) * z / P.fx;
-            y = (float(r * P.dis) - P.cy) * z / P.fy;
-            if (!isfinite(z)) nonfinite = 1;
-            if (ly >= 7 && ly < 7 + kTH && lx >= 7 && lx < 7 + kTW) {
-                const size_t o = fo + size_t(r) * w + c;
-                B.px[o] = x; B.py[o] = y; B.pz[o] = z;
+    if (tid < 5 * kCW) {
+        const int lx = tid % kCW, ly0 = tid / kCW;
+        const int c = tc - 7 + lx;
+        const bool cin = c >= 0 && c < w;
+        const float xfac = float(c * P.dis) - P.cx;
+        const char *colp = img + size_t(cin ? c : 0) * P.dis * sizeof(float);
+        const size_t rstep = size_t(P.dis) * P.pitch;
+        const bool cown = lx >= 7 && lx < 7 + kTW;
+        float zz[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int ly = ly0 + 5 * i, r = tr - 7 + ly;
+            zz[i] = 0.f;
+            if (ly < kCHt && cin && r >= 0 && r < h) zz[i] = *reinterpret_cast<const float *>(colp + size_t(r) * rstep);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int ly = ly0 + 5 * i, r = tr - 7 + ly;
+            if (ly < kCHt) {
+                float x = 0.f, y = 0.f;
+                const float z = zz[i];
+                if (cin && r >= 0 && r < h) {
+                    x = xfac * z / P.fx;
+                    y = (float(r * P.dis) - P.cy) * z / P.fy;
+                    if (!isfinite(z)) nonfinite = 1;
+                    if (cown && ly >= 7 && ly < 7 + kTH) {
+                        const size_t o = fo + size_t(r * w + c);
+                        B.px[o] = x; B.py[o] = y; B.pz[o] = z;
+                    }
+                }
+                const int o = ly * kCStride + lx;
+                C[o] = x; C[ccs + o] = y; C[2 * ccs + o] = z;
             }
         }
-        const int o = ly * kCStride + lx;
-        C[o] = x; C[ccs + o] = y; C[2 * ccs + o] = z;
-    }
-    // zero row 0 and column 0 of every integral image
-    for (int i = tid; i < 7 * kSW; i += 256) {
-        const int ch = i / kSW, x = i - ch * kSW;
-        if (ch < 6) S[ch * cs + x] = 0.0; else Cn[x] = 0;
-    }
-    for (int i = tid; i < 7 * kSH; i += 256) {
-        const int ch = i / kSH, y = i - ch * kSH;
-        if (ch < 6) S[ch * cs + y * kSATStride] = 0.0; else Cn[y * kSATStride] = 0;
     }
     const int anynf = __syncthreads_or(nonfinite);
 
-    // ---- 2. row prefix sums of the differences: one thread per (channel, row) ----
-    // difference (ly, lx) sits at image (tr-6+ly, tc-6+lx) = cloud index (ly+1, lx+1)
-    auto interior = [&](int ly, int lx) -> bool {
-        const int r = tr - 6 + ly, c = tc - 6 + lx;
-        return r >= 1 && r <= h - 2 && c >= 1 && c <= w - 2;
-    };
-    if (!anynf) {
-        for (int i = tid; i < 6 * kRH; i += 256) {
-            const int ch = i / kRH, ly = i - ch * kRH;
-            const int k = ch < 3 ? ch : ch - 3;
-            const float *Ck = C + k * ccs;
-            double *row = S + ch * cs + (ly + 1) * kSATStride;
-            double run = 0.0;
-            if (ch < 3) {
-                const float *p = Ck + (ly + 1) * kCStride;         // dx = P(r, c+1) - P(r, c-1)
-                for (int lx = 0; lx < kRW; ++lx) {
-                    const float d = interior(ly, lx) ? p[lx + 2] - p[lx] : 0.0f;
-                    run += double(d);
-                    row[lx + 1] = run;
-                }
-            } else {
-                const float *pu = Ck + ly * kCStride + 1, *pd = Ck + (ly + 2) * kCStride + 1;   // dy = P(r+1, c) - P(r-1, c)
-                for (int lx = 0; lx < kRW; ++lx) {
-                    const float d = interior(ly, lx) ? pd[lx] - pu[lx] : 0.0f;
-                    run += double(d);
-                    row[lx + 1] = run;
-                }
-            }
-        }
-    } else {
-        // generic path: a difference enters its image only if isfinite(d0 + (d1 + d2)); finite counts: lo16 = DX, hi16 = DY
-        for (int i = tid; i < 7 * kRH; i += 256) {
-            const int ch = i / kRH, ly = i - ch * kRH;
-            double run = 0.0;
-            int crun = 0;
-            for (int lx = 0; lx < kRW; ++lx) {
-                float dx[3] = {0.f, 0.f, 0.f}, dy[3] = {0.f, 0.f, 0.f};
-                if (interior(ly, lx)) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const float *Ck = C + k * ccs;
-                        dx[k] = Ck[(ly + 1) * kCStride + lx + 2] - Ck[(ly + 1) * kCStride + lx];
-                        dy[k] = Ck[(ly + 2) * kCStride + lx + 1] - Ck[ly * kCStride + lx + 1];
-                    }
-                }
-                const bool finx = isfinite(dx[0] + (dx[1] + dx[2])), finy = isfinite(dy[0] + (dy[1] + dy[2]));
-                if (ch < 6) {
-                    const float d = ch < 3 ? dx[ch] : dy[ch - 3];
-                    if (ch < 3 ? finx : finy) run += double(d);
-                    S[ch * cs + (ly + 1) * kSATStride + lx + 1] = run;
-                } else {
-                    crun += (finx ? 1 : 0) | (finy ? 0x10000 : 0);
-                    Cn[(ly + 1) * kSATStride + lx + 1] = crun;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    // ---- column prefix sums: one thread per (channel, column) ----
-    for (int i = tid; i < (anynf ? 7 : 6) * kRW; i += 256) {
-        const int ch = i / kRW, x = i - ch * kRW + 1;
-        if (ch < 6) {
-            double *col = S + ch * cs + x;
-            double run = 0.0;
-#pragma unroll 2
-            for (int y = 1; y < kSH; ++y) { run += col[y * kSATStride]; col[y * kSATStride] = run; }
-        } else {
-            int *col = Cn + x;
-            int run = 0;
-            for (int y = 1; y < kSH; ++y) { run += col[y * kSATStride]; col[y * kSATStride] = run; }
-        }
-    }
-    __syncthreads();
-
-    // ---- 3. normals of the tile + left column + upper row (kNW x kNH pixels), kept in registers ----
+    // ---- per-pixel window geometry of the kNW x kNH pixels that get a normal (two per thread) ----
     const float qnan = __int_as_float(0x7fc00000);
+    const uint8_t *kwin = B.kwin + fo;
     const int border = 10;
-    constexpr int kPer = (kNW * kNH + 255) / 256;
-    float rnx[kPer], rny[kPer], rnz[kPer], rpd[kPer];
+    constexpr int kPer = (kNW * kNH + kNormThreads - 1) / kNormThreads;
+    int w_ul[kPer], w_k[kPer];          // upper-left integral-image node of the window, window size (0 = no window)
+    bool inimg[kPer];
+    float PX[kPer], PY[kPer], PZ[kPer];
 #pragma unroll
     for (int it = 0; it < kPer; ++it) {
-        const int j = tid + it * 256;
-        float nx = qnan, ny = qnan, nz = qnan, pd = qnan;
+        const int j = tid + it * kNormThreads;
+        w_ul[it] = 0; w_k[it] = 0; inimg[it] = false; PX[it] = PY[it] = PZ[it] = 0.f;
         if (j < kNW * kNH) {
             const int ny_ = j / kNW, nx_ = j - ny_ * kNW;
             const int r = tr - 1 + ny_, c = tc - 1 + nx_;
             if (r >= 0 && c >= 0 && r < h && c < w) {
+                inimg[it] = true;
                 const int co = (ny_ + 6) * kCStride + nx_ + 6;
-                const float X = C[co], Y = C[ccs + co], Zv = C[2 * ccs + co];
-                if (r >= border && r < h - border && c >= border && c < w - border && isfinite(Zv)) {
-                    const int k = int(B.kwin[fo + size_t(r) * w + c]);
+                PX[it] = C[co]; PY[it] = C[ccs + co]; PZ[it] = C[2 * ccs + co];
+                if (r >= border && r < h - border && c >= border && c < w - border && isfinite(PZ[it])) {
+                    const int k = int(kwin[r * w + c]);
                     if (k > 0) {
                         const int half = k / 2;
-                        const int x0 = nx_ + kHaloL - half, y0 = ny_ + kHaloL - half;   // integral-image coordinates
-                        const int x1 = x0 + k, y1 = y0 + k;
-                        const int ul = y0 * kSATStride + x0, ur = y0 * kSATStride + x1;
-                        const int ll = y1 * kSATStride + x0, lr = y1 * kSATStride + x1;
-                        bool have = true;
-                        if (anynf) {
-                            const int cn = Cn[lr] + Cn[ul] - Cn[ur] - Cn[ll];
-                            have = (cn & 0xffff) != 0 && (cn >> 16) != 0;
-                        }
-                        if (have) {
-                            double g[6];
-#pragma unroll
-                            for (int ch = 0; ch < 6; ++ch) {
-                                const double *I = S + ch * cs;
-                                g[ch] = ((I[lr] + I[ul]) - I[ur]) - I[ll];
-                            }
-                            // normal_vector = gradient_y.cross(gradient_x)
-                            const double n0 = g[4] * g[2] - g[5] * g[1];
-                            const double n1 = g[5] * g[0] - g[3] * g[2];
-                            const double n2 = g[3] * g[1] - g[4] * g[0];
-                            const double len = (n0 * n0 + n1 * n1) + n2 * n2;
-                            if (len != 0.0) {
-                                const double sl = sqrt(len);
-                                nx = float(n0 / sl); ny = float(n1 / sl); nz = float(n2 / sl);
-                                // flipNormalTowardsViewpoint(point, 0, 0, 0, nx, ny, nz)
-                                const float vx = 0.0f - X, vy = 0.0f - Y, vz = 0.0f - Zv;
-                                const float cos_theta = (vx * nx + vy * ny + vz * nz);
-                                if (cos_theta < 0) { nx *= -1; ny *= -1; nz *= -1; }
-                            }
-                        }
+                        w_k[it] = k;
+                        w_ul[it] = (ny_ + kHaloL - half) * kSATStride + (nx_ + kHaloL - half);   // integral-image coordinates
                     }
                 }
-                pd = dot3f(X, Y, Zv, nx, ny, nz);
             }
+        }
+    }
+
+    // ---- 2. the two gradient images one after the other in the same 3-channel buffer: DX (pass 0), DY (pass 1).
+    // difference (ly, lx) sits at image (tr-6+ly, tc-6+lx) = cloud index (ly+1, lx+1); differences are zero on the
+    // image border: non-zero only for lx in [lo, hi) of rows with 1 <= r <= h-2
+    double g[kPer][6];
+    bool have[kPer];
+#pragma unroll
+    for (int it = 0; it < kPer; ++it) {
+        have[it] = w_k[it] > 0;
+#pragma unroll
+        for (int ch = 0; ch < 6; ++ch) g[it][ch] = 0.0;
+    }
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        // zero row 0 and column 0 of the integral images
+        for (int i = tid; i < 4 * kSW; i += kNormThreads) {
+            const int ch = i / kSW, x = i - ch * kSW;
+            if (ch < 3) S[ch * cs + x] = 0.0; else Cn[x] = 0;
+        }
+        for (int i = tid; i < 4 * kSH; i += kNormThreads) {
+            const int ch = i / kSH, y = i - ch * kSH;
+            if (ch < 3) S[ch * cs + y * kSATStride] = 0.0; else Cn[y * kSATStride] = 0;
+        }
+        // row prefix sums: one thread per (channel, row)
+        if (!anynf) {
+            if (tid < 3 * kRH) {
+                const int ch = tid / kRH, ly = tid - ch * kRH;
+                const float *Ck = C + ch * ccs;
+                double *row = S + ch * cs + (ly + 1) * kSATStride;
+                const int r = tr - 6 + ly;
+                const bool rowok = r >= 1 && r <= h - 2;
+                const int lo = rowok ? max(0, 7 - tc) : 0, hi = rowok ? min(kRW, w + 5 - tc) : 0;
+                double run = 0.0;
+                if (pass == 0) {
+                    const float *p = Ck + (ly + 1) * kCStride;         // dx = P(r, c+1) - P(r, c-1)
+                    float pa = p[0], pb = p[1];
+#pragma unroll
+                    for (int lx = 0; lx < kRW; ++lx) {
+                        const float pc = p[lx + 2];
+                        const float d = (lx >= lo && lx < hi) ? pc - pa : 0.0f;
+                        pa = pb; pb = pc;
+                        run += double(d);
+                        row[lx + 1] = run;
+                    }
+                } else {
+                    const float *pu = Ck + ly * kCStride + 1, *pd = Ck + (ly + 2) * kCStride + 1;   // dy = P(r+1, c) - P(r-1, c)
+#pragma unroll
+                    for (int lx = 0; lx < kRW; ++lx) {
+                        const float d = (lx >= lo && lx < hi) ? pd[lx] - pu[lx] : 0.0f;
+                        run += double(d);
+                        row[lx + 1] = run;
+                    }
+                }
+            }
+        } else {
+            // generic path: a difference enters its image only if isfinite(d0 + (d1 + d2)); Cn counts the finite ones
+            for (int i = tid; i < 4 * kRH; i += kNormThreads) {
+                const int ch = i / kRH, ly = i - ch * kRH;
+                const int r = tr - 6 + ly;
+                double run = 0.0;
+                int crun = 0;
+                for (int lx = 0; lx < kRW; ++lx) {
+                    const int c = tc - 6 + lx;
+                    float d[3] = {0.f, 0.f, 0.f};
+                    if (r >= 1 && r <= h - 2 && c >= 1 && c <= w - 2) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const float *Ck = C + k * ccs;
+                            d[k] = pass == 0 ? Ck[(ly + 1) * kCStride + lx + 2] - Ck[(ly + 1) * kCStride + lx]
+                                             : Ck[(ly + 2) * kCStride + lx + 1] - Ck[ly * kCStride + lx + 1];
+                        }
+                    }
+                    const bool fin = isfinite(d[0] + (d[1] + d[2]));
+                    if (ch < 3) {
+                        if (fin) run += double(d[ch]);
+                        S[ch * cs + (ly + 1) * kSATStride + lx + 1] = run;
+                    } else {
+                        crun += fin ? 1 : 0;
+                        Cn[(ly + 1) * kSATStride + lx + 1] = crun;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // column prefix sums: one thread per (channel, column)
+        for (int i = tid; i < (anynf ? 4 : 3) * kRW; i += kNormThreads) {
+            const int ch = i / kRW, x = i - ch * kRW + 1;
+            if (ch < 3) {
+                double *col = S + ch * cs + x;
+                double run = 0.0;
+#pragma unroll
+                for (int y = 1; y < kSH; ++y) { run += col[y * kSATStride]; col[y * kSATStride] = run; }
+            } else {
+                int *col = Cn + x;
+                int run = 0;
+                for (int y = 1; y < kSH; ++y) { run += col[y * kSATStride]; col[y * kSATStride] = run; }
+            }
+        }
+        __syncthreads();
+        // window sums of this gradient image: ((I[y1][x1] + I[y0][x0]) - I[y0][x1]) - I[y1][x0]
+#pragma unroll
+        for (int it = 0; it < kPer; ++it) {
+            if (w_k[it] > 0) {
+                const int k = w_k[it];
+                const int ul = w_ul[it], ur = ul + k, ll = ul + k * kSATStride, lr = ll + k;
+                if (anynf) { if (Cn[lr] + Cn[ul] - Cn[ur] - Cn[ll] == 0) have[it] = false; }
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const double *I = S + ch * cs;
+                    g[it][pass * 3 + ch] = ((I[lr] + I[ul]) - I[ur]) - I[ll];
+                }
+            }
+        }
+        __syncthreads();   // the buffer is rebuilt by the next pass / re-used for the normals
+    }
+
+    // ---- 3. normals of the tile + left column + upper row (kNW x kNH pixels), kept in registers ----
+    float rnx[kPer], rny[kPer], rnz[kPer], rpd[kPer];
+#pragma unroll
+    for (int it = 0; it < kPer; ++it) {
+        float nx = qnan, ny = qnan, nz = qnan, pd = qnan;
+        if (inimg[it]) {
+            const float X = PX[it], Y = PY[it], Zv = PZ[it];
+            if (have[it]) {
+                // normal_vector = gradient_y.cross(gradient_x)
+                const double n0 = g[it][4] * g[it][2] - g[it][5] * g[it][1];
+                const double n1 = g[it][5] * g[it][0] - g[it][3] * g[it][2];
+                const double n2 = g[it][3] * g[it][1] - g[it][4] * g[it][0];
+                const double len = (n0 * n0 + n1 * n1) + n2 * n2;
+                if (len != 0.0) {
+                    const double sl = sqrt(len);
+                    nx = float(n0 / sl); ny = float(n1 / sl); nz = float(n2 / sl);
+                    // flipNormalTowardsViewpoint(point, 0, 0, 0, nx, ny, nz)
+                    const float vx = 0.0f - X, vy = 0.0f - Y, vz = 0.0f - Zv;
+                    const float cos_theta = (vx * nx + vy * ny + vz * nz);
+                    if (cos_theta < 0) { nx *= -1; ny *= -1; nz *= -1; }
+                }
+            }
+            pd = dot3f(X, Y, Zv, nx, ny, nz);
         }
         rnx[it] = nx; rny[it] = ny; rnz[it] = nz; rpd[it] = pd;
     }
-    __syncthreads();   // everybody is done with the integral images: their memory now holds the normals
+    // (the barrier closing the second pass: everybody is done with the integral images, their memory now holds the normals)
     constexpr int ncs = kNH * kNStride;
 #pragma unroll
     for (int it = 0; it < kPer; ++it) {
-        const int j = tid + it * 256;
+        const int j = tid + it * kNormThreads;
         if (j < kNW * kNH) {
             const int ny_ = j / kNW, nx_ = j - ny_ * kNW;
             const int o = ny_ * kNStride + nx_;
@@ -463,7 +515,7 @@ __global__ void __launch_bounds__(256) k_normals_link(const float *__restrict__ 
     for (int yy = 0; yy < kTH / 8; ++yy) {
         const int ty = wy + yy * 8;
         const int r = tr + ty, c = tc + lane;
-        if (r >= h) continue;   // warp uniform
+        if (wy >= 8 || r >= h) continue;   // warp uniform (the ninth warp only helps with the normals)
         const bool valid = c < w;
         bool L = false, U = false;
         const int q = r * w + c;
