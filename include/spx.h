@@ -154,6 +154,8 @@ int spx_last_launch_count(const spx_ctx *ctx);
  * k < min(*n, cap). */
 int spx_set_profile(spx_ctx *ctx, int on);
 int spx_get_kernel_times(spx_ctx *ctx, const char **names, float *ms, int cap, int *n);
+/* the same launches as a timeline: start / end of launch k in ms after the beginning of the extract call */
+int spx_get_kernel_timeline(spx_ctx *ctx, const char **names, float *start_ms, float *end_ms, int cap, int *n);
 
 /* ---- debug taps for the parity tests: intermediates of frame `frame` of the last extract call, copied to host.
  * They need spx_set_debug(ctx, 1) BEFORE the extract call (it adds the per-pixel label kernel to the schedule). ---- */

@@ -37,7 +37,7 @@ EXPORTS = (
     "spx_default_config", "spx_create", "spx_destroy", "spx_last_error", "spx_set_stream", "spx_extract",
     "spx_extract_batch", "spx_extract_batch_device", "spx_fetch_results", "spx_fetch_planes",
     "spx_segment_from_normals", "spx_cloud_dims", "spx_get_times", "spx_last_launch_count", "spx_set_debug",
-    "spx_set_profile", "spx_get_kernel_times", "spx_get_device_results",
+    "spx_set_profile", "spx_get_kernel_times", "spx_get_kernel_timeline", "spx_get_device_results",
     "spx_get_cloud", "spx_get_distance_map", "spx_get_normals", "spx_get_labels_raw", "spx_get_plane_ids",
     "spx_get_models", "spx_get_model_inliers", "spx_get_model_contour", "spx_get_lines",
 )
@@ -110,6 +110,7 @@ def lib():
         L.spx_get_device_results.argtypes = [vp, C.POINTER(SpxDeviceResult)]
         L.spx_set_profile.argtypes = [vp, i32]
         L.spx_get_kernel_times.argtypes = [vp, vp, vp, i32, C.POINTER(i32)]
+        L.spx_get_kernel_timeline.argtypes = [vp, vp, vp, vp, i32, C.POINTER(i32)]
         L.spx_get_cloud.argtypes = [vp, i32, vp, vp, vp]
         L.spx_get_distance_map.argtypes = [vp, i32, vp]
         L.spx_get_normals.argtypes = [vp, i32, vp, vp, vp, vp]
@@ -283,6 +284,16 @@ class PlaneExtractor:
         n = C.c_int()
         self._ck(lib().spx_get_kernel_times(self._h, names, ms, cap, C.byref(n)))
         return [(names[k].decode(), float(ms[k])) for k in range(min(n.value, cap))]
+
+    def kernel_timeline(self):
+        """[(kernel name, start ms, end ms)] of the last extract call, relative to its beginning."""
+        cap = 1024
+        names = (C.c_char_p * cap)()
+        t0 = (C.c_float * cap)()
+        t1 = (C.c_float * cap)()
+        n = C.c_int()
+        self._ck(lib().spx_get_kernel_timeline(self._h, names, t0, t1, cap, C.byref(n)))
+        return [(names[k].decode(), float(t0[k]), float(t1[k])) for k in range(min(n.value, cap))]
 
     # ---- debug taps (need debug=True) ----
     def _n(self, rows, cols):

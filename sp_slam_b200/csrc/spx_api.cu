@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -235,7 +236,7 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
         LAUNCH(k_plane_d, gpix, 256, 0, P, B);
         LAUNCH(k_ccl_link, dim3(cdiv(P.w, 32), cdiv(P.h, 8), F), dim3(32, 8), 0, P, B);
     }
-    LAUNCH(k_ccl_merge, gpix, 256, 0, P, B);
+    LAUNCH(k_ccl_merge, gpix, 256, 0, P, B, 1);
     LAUNCH(k_ccl_flatten, gpix, 256, 0, P, B);
     LAUNCH(k_ccl_rank, F, kRankThreads, 0, P, B);
     if (c->debug) LAUNCH(k_ccl_label, gpix, 256, 0, P, B);
@@ -521,6 +522,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     for (int i = 0; i < 4; ++i) SPX_CK_CREATE(cudaEventCreate(&c->ev[i]));
     c->n_streams = cfg->n_streams > 0 ? (cfg->n_streams > 32 ? 32 : cfg->n_streams) : 8;
     c->min_group = 32;
+    if (const char *e = std::getenv("SPX_MIN_GROUP")) { const int v = std::atoi(e); if (v > 0) c->min_group = v; }   // tuning knob
     for (int g = 0; g < c->n_streams; ++g) {
         cudaStream_t gs;
         SPX_CK_CREATE(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
@@ -743,6 +745,20 @@ int spx_get_kernel_times(spx_ctx *c, const char **names, float *ms, int cap, int
     for (int k = 0; k < c->prof_n && k < cap; ++k) {
         if (names) names[k] = c->prof_names[k];
         if (ms) SPX_CK(c, cudaEventElapsedTime(&ms[k], c->prof_ev[2 * k], c->prof_ev[2 * k + 1]));
+    }
+    return SPX_OK;
+}
+
+int spx_get_kernel_timeline(spx_ctx *c, const char **names, float *start_ms, float *end_ms, int cap, int *n) {
+    if (!c || !n) return SPX_ERR_ARG;
+    if (!c->have_run || !c->profile || c->prof_n == 0) return fail(c, SPX_ERR_STATE, "no profiled extract call (spx_set_profile) on this context");
+    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_CK(c, cudaEventSynchronize(c->ev[2]));
+    *n = c->prof_n;
+    for (int k = 0; k < c->prof_n && k < cap; ++k) {
+        if (names) names[k] = c->prof_names[k];
+        if (start_ms) SPX_CK(c, cudaEventElapsedTime(&start_ms[k], c->ev[0], c->prof_ev[2 * k]));
+        if (end_ms) SPX_CK(c, cudaEventElapsedTime(&end_ms[k], c->ev[0], c->prof_ev[2 * k + 1]));
     }
     return SPX_OK;
 }

@@ -22,10 +22,23 @@ __device__ __forceinline__ int uf_find(int *parent, int x) {
         x = p;
     }
 }
+// find with path halving: every visited node is re-pointed at its grandparent.  Only non-roots are written here and
+// only roots are written by uf_unite's atomicMin (a non-root never becomes a root again), so the plain stores cannot
+// undo a union; they only ever move a pointer further up its own tree.
+__device__ __forceinline__ int uf_find_halving(int *parent, int x) {
+    while (true) {
+        const int p = __ldcg(parent + x);
+        if (p == x) return x;
+        const int gp = __ldcg(parent + p);
+        if (gp == p) return p;
+        __stcg(parent + x, gp);
+        x = gp;
+    }
+}
 __device__ __forceinline__ void uf_unite(int *parent, int a, int b) {
     while (true) {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
+        a = uf_find_halving(parent, a);
+        b = uf_find_halving(parent, b);
         if (a == b) return;
         if (a < b) { const int t = a; a = b; b = t; }
         const int old = atomicMin(parent + a, b);
@@ -72,9 +85,11 @@ __global__ void __launch_bounds__(256) k_ccl_link(Params P, Buffers B) {
     if (valid) B.parent[fo + q] = r * w + blockIdx.x * 32 + s;
 }
 
-// K4b: merges across the 32-column segment seams and along vertical edges.  A vertical union is skipped when the
-// two pixels are already connected through their left neighbours (L(q) & L(up) & U(left)).
-__global__ void __launch_bounds__(256) k_ccl_merge(Params P, Buffers B) {
+// K4b: joins the tile-local forests of k_normals_link across tile borders: left links on the first column of a
+// tile, upper links on its first row (tile_w x tile_h = 32 x 16).  With tile_h = 1 (the feed-normals path, where
+// k_ccl_link only forms row runs) every upper link is a border.  A vertical union is skipped when the two pixels are
+// already connected through their left neighbours (L(q) & L(up) & U(left)).
+__global__ void __launch_bounds__(256) k_ccl_merge(Params P, Buffers B, int tile_h) {
     const int f = P.frame0 + blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= P.N) return;
@@ -83,9 +98,13 @@ __global__ void __launch_bounds__(256) k_ccl_merge(Params P, Buffers B) {
     const int r = q / w, c = q - r * w;
     const unsigned cb = B.conn[fo + q];
     int *parent = B.parent + fo;
-    if ((cb & 1u) && (c & 31) == 0) uf_unite(parent, q, q - 1);
-    if (cb & 2u) {
-        const bool skip = c > 0 && (cb & 1u) && (B.conn[fo + q - w] & 1u) && (B.conn[fo + q - 1] & 2u);
+    if ((cb & 1u) && (c & 31) == 0) {
+        // redundant when the pair is already joined through the row above: U(q) & U(left) & L(up)
+        const bool skip = r > 0 && (cb & 2u) && (B.conn[fo + q - 1] & 2u) && (B.conn[fo + q - w] & 1u);
+        if (!skip) uf_unite(parent, q, q - 1);
+    }
+    if ((cb & 2u) && (r % tile_h) == 0) {
+        const bool skip = (c & 31) != 0 && (cb & 1u) && (B.conn[fo + q - w] & 1u) && (B.conn[fo + q - 1] & 2u);
         if (!skip) uf_unite(parent, q, q - w);
     }
 }
