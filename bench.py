@@ -283,13 +283,40 @@ def main():
             launches_e2e = ext.launches
         barrier()
         e2e_s = time.perf_counter() - t0
+    # the same end to end from the raw 16-bit depth image (the convertTo of Tracking::GrabImageRGBD fused in)
+    e2e16_s = None
+    if (rows * cols) % 4 == 0:
+        factor = float(np.float32(1.0) / np.float32(5000.0))
+        host16 = torch.from_numpy(np.round(np.clip(depth_np, 0, 13.0).astype(np.float64) * 5000.0).astype(np.uint16)).pin_memory()
+        for _ in range(2):
+            ext.extract_batch_u16_ptr(host16.data_ptr(), F, rows, cols, factor)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ext.extract_batch_u16_ptr(host16.data_ptr(), F, rows, cols, factor)
+        barrier()
+        e2e16_s = time.perf_counter() - t0
+    # BASELINE configs[4] (tracking loop): one frame at a time through the host-buffer call, as Frame's constructor would
+    lat_ms = None
+    if rank == 0:
+        one = api.PlaneExtractor(max_frames=1, max_rows=rows, max_cols=cols, device=local_rank, fx=it.fx, fy=it.fy, cx=it.cx,
+                                 cy=it.cy, max_x=float(it.width), max_y=float(it.height))
+        ts = []
+        for k in range(min(F, 60)):
+            t1 = time.perf_counter()
+            one.extract_batch_ptr(host[k].data_ptr(), 1, rows, cols)
+            ts.append((time.perf_counter() - t1) * 1e3)
+        ts = np.array(ts[10:])
+        lat_ms = {"median": float(np.median(ts)), "p95": float(np.percentile(ts, 95)), "max": float(ts.max()),
+                  "frames": len(ts), "budget_ms": 33.3}
+        one.close()
     planes_per_frame = float(res.frames["n_planes"].mean())
     overflow = int((res.frames["flags"] != 0).sum())
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_s * 1e3, (e2e16_s or 0.0) * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, e2e16_ms = float(t[0]), float(t[1]), float(t[2])
     value = world * F * args.steps / (ms * 1e-3)
     e2e_val = world * F * args.steps / (e2e_ms * 1e-3)
 
@@ -335,8 +362,13 @@ def main():
                        "planes_per_frame": planes_per_frame, "overflow_frames": overflow},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": F * rows * cols * 4,
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps},
+            "e2e_u16": None if not e2e16_ms else {
+                "value": world * F * args.steps / (e2e16_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": F * rows * cols * 2,
+                "ms_per_step": e2e16_ms / args.steps,
+                "note": "host input = the raw CV_16U depth image, DepthMapFactor conversion on the device (spx_extract_batch_u16)"},
             "gpu_launches": launches,
             "latency_ms_per_frame_in_batch": ms / args.steps / F,
+            "single_frame_latency_ms": lat_ms,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clk.summary(),

@@ -113,6 +113,12 @@ int spx_extract(spx_ctx *ctx, const float *depth, int rows, int cols, size_t pit
 int spx_extract_batch(spx_ctx *ctx, const float *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
                       size_t frame_stride_bytes, spx_batch_result *out);
 
+/* The same from the raw 16-bit depth image (CV_16U, e.g. a TUM PNG): replaces, in addition, the conversion
+ * imDepth.convertTo(imDepth, CV_32F, mDepthMapFactor) of Tracking::GrabImageRGBD (src/Tracking.cc:230-231; the factor
+ * is 1.0f / DepthMapFactor, src/Tracking.cc:142-146).  Half the upload; depth = float(d) * depth_map_factor on the device. */
+int spx_extract_batch_u16(spx_ctx *ctx, const uint16_t *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
+                          size_t frame_stride_bytes, float depth_map_factor, spx_batch_result *out);
+
 /* device-resident variant: `depth_dev` is DEVICE memory; only kernels run (asynchronously on the context's stream),
  * results stay on the device until spx_fetch_results (which synchronises and copies them to the host). */
 int spx_extract_batch_device(spx_ctx *ctx, const float *depth_dev, int n_frames, int rows, int cols,

@@ -35,7 +35,7 @@ LINE_DTYPE = np.dtype([("plane", "<i4"), ("round", "<i4"), ("n_points", "<i4"), 
 # every symbol include/spx.h declares (tests check the built library exports exactly these)
 EXPORTS = (
     "spx_default_config", "spx_create", "spx_destroy", "spx_last_error", "spx_set_stream", "spx_extract",
-    "spx_extract_batch", "spx_extract_batch_device", "spx_fetch_results", "spx_fetch_planes",
+    "spx_extract_batch", "spx_extract_batch_u16", "spx_extract_batch_device", "spx_fetch_results", "spx_fetch_planes",
     "spx_segment_from_normals", "spx_cloud_dims", "spx_get_times", "spx_last_launch_count", "spx_set_debug",
     "spx_set_profile", "spx_get_kernel_times", "spx_get_kernel_timeline", "spx_get_device_results",
     "spx_get_cloud", "spx_get_distance_map", "spx_get_normals", "spx_get_labels_raw", "spx_get_plane_ids",
@@ -100,6 +100,7 @@ def lib():
         L.spx_set_debug.argtypes = [vp, i32]
         L.spx_extract.argtypes = [vp, vp, i32, i32, sz, C.POINTER(SpxBatchResult)]
         L.spx_extract_batch.argtypes = [vp, vp, i32, i32, i32, sz, sz, C.POINTER(SpxBatchResult)]
+        L.spx_extract_batch_u16.argtypes = [vp, vp, i32, i32, i32, sz, sz, C.c_float, C.POINTER(SpxBatchResult)]
         L.spx_extract_batch_device.argtypes = [vp, vp, i32, i32, i32, sz, sz]
         L.spx_fetch_results.argtypes = [vp, C.POINTER(SpxBatchResult)]
         L.spx_fetch_planes.argtypes = [vp, C.POINTER(SpxBatchResult)]
@@ -228,6 +229,24 @@ class PlaneExtractor:
         """Same, from a raw host pointer (e.g. a pinned torch tensor's data_ptr()); tight row-major layout."""
         r = SpxBatchResult()
         self._ck(lib().spx_extract_batch(self._h, host_ptr, n, rows, cols, cols * 4, rows * cols * 4, C.byref(r)))
+        return BatchResult(r, copy=copy)
+
+    def extract_batch_u16(self, depth_u16: np.ndarray, depth_map_factor: float = float(np.float32(1.0) / np.float32(5000.0)),
+                          copy: bool = True) -> BatchResult:
+        """(n_frames, rows, cols) uint16 host array (e.g. TUM PNG depth); depth = float(d) * depth_map_factor on the device
+        (Tracking::GrabImageRGBD's convertTo, src/Tracking.cc:230-231)."""
+        if depth_u16.dtype != np.uint16 or depth_u16.ndim != 3 or depth_u16.strides[2] != 2:
+            depth_u16 = np.ascontiguousarray(depth_u16, dtype=np.uint16)
+        n, rows, cols = depth_u16.shape
+        r = SpxBatchResult()
+        self._ck(lib().spx_extract_batch_u16(self._h, depth_u16.ctypes.data, n, rows, cols, depth_u16.strides[1],
+                                             depth_u16.strides[0], C.c_float(depth_map_factor), C.byref(r)))
+        return BatchResult(r, copy=copy)
+
+    def extract_batch_u16_ptr(self, host_ptr: int, n: int, rows: int, cols: int, depth_map_factor: float, copy: bool = False):
+        r = SpxBatchResult()
+        self._ck(lib().spx_extract_batch_u16(self._h, host_ptr, n, rows, cols, cols * 2, rows * cols * 2,
+                                             C.c_float(depth_map_factor), C.byref(r)))
         return BatchResult(r, copy=copy)
 
     def extract_device(self, dev_ptr: int, n: int, rows: int, cols: int, pitch: int | None = None,

@@ -63,6 +63,7 @@ struct spx_ctx {
     Buffers B;
     DevArena arena;
     float *d_depth = nullptr;          // staging for host-side depth (tight pitch)
+    uint16_t *d_depth16 = nullptr;     // staging for CV_16U host depth
     int capN = 0, cap_w = 0, cap_h = 0;
     int n_grid = 0;
     int border_grid = 148 * 8;
@@ -165,8 +166,10 @@ int set_geometry(spx_ctx *c, int n_frames, int rows, int cols, size_t pitch, siz
 // kernels.  The groups join on the caller-visible stream, where the offsets of every frame's results are scanned and
 // the clouds are packed into the contiguous output buffers.
 struct HostSrc {           // host depth of the batch (null: the depth is already on the device)
-    const float *depth = nullptr;
+    const void *depth = nullptr;
     size_t pitch = 0, frame_stride = 0;
+    bool u16 = false;      // CV_16U source: uploaded as is and converted on the device
+    float alpha = 1.0f;    // mDepthMapFactor
 };
 
 int n_groups_for(const spx_ctx *c, int n_frames) {
@@ -209,8 +212,9 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
     } while (0)
 
     if (src.depth) {   // host depth of this group -> staging buffer (tight pitch)
-        const size_t tight = size_t(P.cols) * sizeof(float);
-        char *dst = reinterpret_cast<char *>(c->d_depth) + tight * P.rows * size_t(f0);
+        const size_t esz = src.u16 ? sizeof(uint16_t) : sizeof(float);
+        const size_t tight = size_t(P.cols) * esz;
+        char *dst = (src.u16 ? reinterpret_cast<char *>(c->d_depth16) : reinterpret_cast<char *>(c->d_depth)) + tight * P.rows * size_t(f0);
         const char *hp = reinterpret_cast<const char *>(src.depth) + src.frame_stride * size_t(f0);
         if (src.pitch == tight && (ng == 1 || src.frame_stride == tight * P.rows)) {
             SPX_CK(c, cudaMemcpyAsync(dst, hp, tight * P.rows * size_t(ng), cudaMemcpyHostToDevice, st));
@@ -218,6 +222,12 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
             for (int f = 0; f < ng; ++f)
                 SPX_CK(c, cudaMemcpy2DAsync(dst + tight * P.rows * size_t(f), tight, hp + src.frame_stride * size_t(f), src.pitch, tight,
                                             size_t(P.rows), cudaMemcpyHostToDevice, st));
+        }
+        if (src.u16) {
+            const size_t n = size_t(P.rows) * P.cols * size_t(ng);   // a multiple of 4 is not guaranteed: pad handled by capacity
+            const size_t n4 = (n + 3) / 4;
+            LAUNCH(k_convert_u16, unsigned((n4 + 255) / 256), 256, 0, c->d_depth16 + size_t(P.rows) * P.cols * size_t(f0),
+                   c->d_depth + size_t(P.rows) * P.cols * size_t(f0), n4, src.alpha);
         }
     }
     SPX_CK(c, cudaMemsetAsync(B.ctl + f0, 0, sizeof(FrameCtl) * size_t(F), st));
@@ -550,7 +560,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     total += padded<spx_frame_header>(F) + padded<spx_plane>(F * SPX_MAX_PLANES);
     total += padded<spx_point>(F * size_t(P.pts_cap)) + padded<spx_point>(F * size_t(P.bnd_cap));
     total += padded<long long>(4 * size_t(c->n_streams + 1)) + padded<long long>(3 * F);
-    total += padded<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols));
+    total += padded<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4) + padded<uint16_t>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     SPX_CK_CREATE(cudaMalloc(reinterpret_cast<void **>(&c->arena.base), total));
     c->arena.size = total;
     DevArena &A = c->arena;
@@ -567,7 +577,8 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     B.out_frames = A.take<spx_frame_header>(F); B.out_planes = A.take<spx_plane>(F * SPX_MAX_PLANES);
     B.out_pts = A.take<spx_point>(F * size_t(P.pts_cap)); B.out_bnd = A.take<spx_point>(F * size_t(P.bnd_cap));
     B.out_totals = A.take<long long>(4 * size_t(c->n_streams + 1)); B.frame_offs = A.take<long long>(3 * F);
-    c->d_depth = A.take<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols));
+    c->d_depth = A.take<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
+    c->d_depth16 = A.take<uint16_t>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     if (A.used > A.size) { fail(nullptr, SPX_ERR_ARG, "internal: arena accounting"); spx_destroy(c); return SPX_ERR_ARG; }
 
     uint32_t mt[624], mt_out[624];
@@ -674,6 +685,24 @@ int spx_extract_batch(spx_ctx *c, const float *depth, int n_frames, int rows, in
     HostSrc src;
     src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = frame_stride_bytes;
     c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);   // layout of the staging buffer the kernels read
+    if ((rc = run_pipeline(c, c->d_depth, false, src, true)) != SPX_OK) return rc;
+    return fetch_groups(c, out);
+}
+
+int spx_extract_batch_u16(spx_ctx *c, const uint16_t *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
+                          size_t frame_stride_bytes, float depth_map_factor, spx_batch_result *out) {
+    if (!c) return SPX_ERR_ARG;
+    if (!depth || !out) return fail(c, SPX_ERR_ARG, "null argument");
+    SPX_CK(c, cudaSetDevice(c->device));
+    const size_t tight = size_t(cols) * sizeof(float);
+    // geometry checks are stated for the float image; the 16-bit pitch / stride are validated here
+    if (pitch_bytes < size_t(cols) * sizeof(uint16_t) || pitch_bytes % sizeof(uint16_t)) return fail(c, SPX_ERR_ARG, "bad pitch");
+    if (n_frames > 1 && frame_stride_bytes < pitch_bytes * size_t(rows > 0 ? rows : 0)) return fail(c, SPX_ERR_ARG, "bad frame stride");
+    if ((size_t(rows) * size_t(cols)) % 4 != 0 && n_frames > 1) return fail(c, SPX_ERR_ARG, "16-bit batches need rows * cols to be a multiple of 4");
+    int rc = set_geometry(c, n_frames, rows, cols, tight, tight * size_t(rows));
+    if (rc != SPX_OK) return rc;
+    HostSrc src;
+    src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = frame_stride_bytes; src.u16 = true; src.alpha = depth_map_factor;
     if ((rc = run_pipeline(c, c->d_depth, false, src, true)) != SPX_OK) return rc;
     return fetch_groups(c, out);
 }

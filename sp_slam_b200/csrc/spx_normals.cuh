@@ -546,6 +546,17 @@ __global__ void __launch_bounds__(kNormThreads) k_normals_link(const float *__re
     }
 }
 
+// cv::Mat::convertTo(CV_32F, alpha) of a CV_16U depth image (src/Tracking.cc:230-231): dst = float(src) * alpha, one
+// rounding.  Four pixels per thread; the 16-bit image is tightly packed on the device.
+__global__ void __launch_bounds__(256) k_convert_u16(const uint16_t *__restrict__ src, float *__restrict__ dst, size_t n4, float alpha) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const ushort4 v = reinterpret_cast<const ushort4 *>(src)[i];
+    float4 o;
+    o.x = float(v.x) * alpha; o.y = float(v.y) * alpha; o.z = float(v.z) * alpha; o.w = float(v.w) * alpha;
+    reinterpret_cast<float4 *>(dst)[i] = o;
+}
+
 // plane_d for caller-supplied normals ("feed the reference's normals")
 __global__ void __launch_bounds__(256) k_plane_d(Params P, Buffers B) {
     const int f = P.frame0 + blockIdx.y;

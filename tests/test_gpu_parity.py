@@ -116,3 +116,84 @@ def test_frame_groups_host_and_device_paths_agree():
                 assert np.array_equal(p, q)
     ext.close()
     one.close()
+
+
+@pytest.fixture(scope="module")
+def realsense_frames():
+    return scenes.realsense_sequence(3, start=100)
+
+
+@pytest.mark.parametrize("k,noisy", [(0, False), (1, True), (2, True)])
+def test_realsense_1280x720(oracle_lib, realsense_frames, k, noisy):
+    """BASELINE configs[3]: 1280x720 RealSense-shaped depth with small tilted patches (427 x 240 organized cloud:
+    the 14-chunk variants of the chamfer / refine kernels, the large contour map)."""
+    it = scenes.REALSENSE
+    d = realsense_frames[k]
+    if noisy:
+        d = scenes.add_noise(d, 100 + k, "realsense")
+    kw = dict(fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy, max_x=float(it.width), max_y=float(it.height))
+    ext = api.PlaneExtractor(debug=True, max_rows=720, max_cols=1280, **kw)
+    fp = ext.extract(d)
+    orc = oracle_lib.Oracle(**kw).run(d)
+    assert (orc.width, orc.height) == (427, 240)
+    rep = compare_frame(ext, orc, d, fp)
+    assert rep["normals_bit_exact"] and rep["labels_bit_exact"] and rep.get("models_bit_exact", True), rep
+    ext.close()
+
+
+def test_min_size_1000_icl_config(ext, seq, oracle_lib):
+    """Plane.MinSize 1000 (Examples/RGB-D/ICL.yaml:81) instead of TUM1's 500."""
+    e2 = api.PlaneExtractor(debug=True, min_size=1000)
+    d = seq[2]
+    fp = e2.extract(d)
+    orc = oracle_lib.Oracle(min_size=1000).run(d)
+    compare_frame(e2, orc, d, fp)
+    e2.close()
+
+
+def test_degenerate_inputs(ext, oracle_lib):
+    """zero depth (slam_zero_run's frames), constant depth, and white noise: no crash, same plane lists as the oracle"""
+    rng = np.random.default_rng(5)
+    for d in (np.zeros((480, 640), np.float32), np.full((480, 640), 2.0, np.float32),
+              rng.uniform(0.3, 5.0, (480, 640)).astype(np.float32)):
+        fp = ext.extract(d)
+        orc = oracle_lib.Oracle().run(d)
+        assert (fp.mnRealPlaneNum, fp.mnPlaneNum) == (orc.n_real, orc.n_planes)
+        compare_frame(ext, orc, d, fp)
+
+
+def test_pitched_and_small_images(oracle_lib):
+    """row pitch larger than the row (a cv::Mat ROI) and an image size that is not a multiple of Cloud.Dis"""
+    big = scenes.render(scenes.boxroom_rects(), scenes.poses(1000)[[200]], scenes.TUM1)[0]
+    padded = np.zeros((480, 700), np.float32)
+    padded[:, :640] = big
+    view = padded[:, :640]          # strides (2800, 4)
+    e = api.PlaneExtractor(debug=True)
+    a = e.extract_batch(view[None]).frame(0)
+    b = e.extract(big)
+    assert a.mnPlaneNum == b.mnPlaneNum and np.array_equal(a.mvPlaneCoefficients.view(np.uint32), b.mvPlaneCoefficients.view(np.uint32))
+    small = np.ascontiguousarray(big[:401, :500])
+    it = scenes.TUM1
+    e2 = api.PlaneExtractor(debug=True, max_rows=401, max_cols=500, max_x=500.0, max_y=401.0)
+    fp = e2.extract(small)
+    orc = oracle_lib.Oracle(max_x=500.0, max_y=401.0).run(small)
+    assert (orc.width, orc.height) == (167, 134)
+    compare_frame(e2, orc, small, fp)
+    e.close(); e2.close()
+
+
+def test_u16_depth_ingest_equals_converted_float(seq):
+    """spx_extract_batch_u16 (CV_16U + DepthMapFactor, src/Tracking.cc:230-231) against the float path fed with the
+    host-side convertTo result, on several frame groups."""
+    n = 70
+    d = scenes.boxroom_sequence(n, start=400)
+    u16 = np.round(np.clip(d, 0, 13.0).astype(np.float64) * 5000.0).astype(np.uint16)
+    factor = np.float32(1.0) / np.float32(5000.0)                       # mDepthMapFactor = 1.0f / DepthMapFactor
+    as_float = (u16.astype(np.float32) * factor).astype(np.float32)     # cv::Mat::convertTo(CV_32F, factor)
+    ext = api.PlaneExtractor(max_frames=n, n_streams=2)
+    a = ext.extract_batch_u16(u16, float(factor))
+    b = ext.extract_batch(as_float)
+    assert np.array_equal(a.frames, b.frames) and np.array_equal(a.planes, b.planes)
+    assert np.array_equal(a.points, b.points) and np.array_equal(a.boundary, b.boundary)
+    assert int(a.frames["n_planes"].sum()) > 50
+    ext.close()
