@@ -196,6 +196,7 @@ int prof_slot(spx_ctx *c, const char *name, cudaStream_t st) {
 int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int f0, int ng, cudaStream_t st, const HostSrc &src) {
     Params P = c->P;
     P.frame0 = f0; P.n_frames = ng;
+    P.refine_fast = (ng <= 64 && P.h <= kRefMaxH) ? 1 : 0;   // small launches are latency bound: parallelism inside the frame
     Buffers B = c->B;
     B.work = c->B.work + size_t(g) * c->work_stride;
     B.work2 = c->B.work2 + size_t(g) * c->work2_stride;
@@ -253,6 +254,13 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
     LAUNCH(k_moments_fit, dim3(SPX_MAX_CAND / kMomWarps, F), kMomWarps * 32, 0, P, B);
     LAUNCH(k_models, cdiv(F, 128), 128, 0, P, B);
     LAUNCH(k_pid_init, gpix, 256, 0, P, B);
+    {
+        if (P.refine_fast) {
+            if (P.w <= 224) LAUNCH(k_refine2<7>, F, 7 * 32, size_t(2) * P.h * 7 * 4 + kRefTableCap * 4, P, B);
+            else if (P.w <= 448) LAUNCH(k_refine2<14>, F, 14 * 32, size_t(2) * P.h * 14 * 4 + kRefTableCap * 4, P, B);
+            else LAUNCH(k_refine2<16>, F, 16 * 32, size_t(2) * P.h * 16 * 4 + kRefTableCap * 4, P, B);
+        }
+    }
     if (P.w <= 224) LAUNCH(k_refine<7>, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
     else if (P.w <= 448) LAUNCH(k_refine<14>, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
     else LAUNCH(k_refine<16>, cdiv(F, kRefWarps), kRefWarps * 32, 0, P, B);
@@ -554,7 +562,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     total += 2 * padded<uint8_t>(FN) + 5 * padded<int>(FN);    // conn kwin | parent cnt lab pos cand_idx
     const size_t n_cham = F * size_t(cdiv(h, kBandRows)) * size_t(kBandRows + kBandHalo) * size_t(w);
     total += padded<float>(n_cham);
-    total += padded<int16_t>(FN) + padded<int8_t>(FN);     // root_model pid
+    total += padded<int16_t>(FN) + 2 * padded<int8_t>(FN + 16 * F);     // root_model pid pid_bak
     total += 3 * padded<int>(FC) + padded<float4>(FC) + padded<spx_point>(FC) + padded<int>(c->n_streams * (2 + F * SPX_MAX_MODELS)) + padded<int>(c->n_streams * (2 + F * SPX_MAX_MODELS * SPX_MAX_LINES));
     total += padded<FrameCtl>(F);
     total += padded<spx_frame_header>(F) + padded<spx_plane>(F * SPX_MAX_PLANES);
@@ -569,7 +577,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     B.nx = A.take<float>(FN); B.ny = A.take<float>(FN); B.nz = A.take<float>(FN); B.pd = A.take<float>(FN);
     B.conn = A.take<uint8_t>(FN); B.kwin = A.take<uint8_t>(FN); B.cham_tmp = A.take<float>(n_cham);
     B.parent = A.take<int>(FN); B.cnt = A.take<int>(FN); B.lab = A.take<int>(FN); B.pos = A.take<int>(FN); B.cand_idx = A.take<int>(FN);
-    B.root_model = A.take<int16_t>(FN); B.pid = A.take<int8_t>(FN);
+    B.root_model = A.take<int16_t>(FN); B.pid = A.take<int8_t>(FN + 16 * F); B.pid_bak = A.take<int8_t>(FN + 16 * F);
     B.contour_idx = A.take<int>(FC); B.line_sh = A.take<int>(FC); B.line_inl = A.take<int>(FC);
     B.line_a = A.take<float4>(FC); B.line_pts = A.take<spx_point>(FC); c->work_stride = 2 + F * SPX_MAX_MODELS; c->work2_stride = 2 + F * SPX_MAX_MODELS * SPX_MAX_LINES;
     B.work = A.take<int>(c->n_streams * c->work_stride); B.work2 = A.take<int>(c->n_streams * c->work2_stride);
@@ -588,6 +596,9 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_mt_state1, mt, sizeof(mt)));
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_mt_out0, mt_out, sizeof(mt_out)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLinesSmem)));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_refine2<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kRefMaxH * 7 * 4 + kRefTableCap * 4));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_refine2<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kRefMaxH * 14 * 4 + kRefTableCap * 4));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_refine2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kRefMaxH * 16 * 4 + kRefTableCap * 4));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_contour, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(w + 2) * (h + 2))));
     {
         int per_sm = 0;

@@ -15,6 +15,12 @@ namespace spx {
 constexpr int kRefWarps = 2;
 constexpr int kMaxW = 512;           // widest organized cloud the row buffers hold (1280/3 = 427)
 constexpr float kRefineThr = 0.02f;  // PlaneCoefficientComparator's default distance_threshold_
+// frames handled by the multi-warp kernel k_refine2 (its per-(row, model) count table must fit); the rest: k_refine
+constexpr int kRefMaxH = 512;
+constexpr int kRefTableCap = 4096;   // entries of the per-(row, model) count table
+
+__host__ __device__ __forceinline__ bool refine_fast_ok(int h, int nm) { return h <= kRefMaxH && h * nm <= kRefTableCap; }
+
 
 struct RefineSmem {
     float  coef[SPX_MAX_MODELS][4];
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(kRefWarps * 32) k_refine(Params P, Buffers B) 
     RefineSmem &S = smem[warp];
     FrameCtl &ctl = B.ctl[f];
     const int nm = ctl.n_models;
-    if (nm == 0) return;
+    if (nm == 0 || (P.refine_fast && refine_fast_ok(P.h, nm))) return;   // k_refine2 takes the frames whose count table fits
     const size_t fo = size_t(f) * P.N;
     const float *px = B.px + fo, *py = B.py + fo, *pz = B.pz + fo;
     int8_t *pid = B.pid + fo;
@@ -219,6 +225,298 @@ __global__ void __launch_bounds__(kRefWarps * 32) k_refine(Params P, Buffers B) 
         M.n1 = S.cnt1[m]; M.n2 = S.cnt2[m];
         if (S.cnt2[m] > 0) M.last_inlier = S.last2[m];
         else if (S.cnt1[m] > 0) M.last_inlier = S.last1[m];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K6 (fast path): the same two raster passes with the parallelism INSIDE a frame.  One CTA per frame, one warp per
+// 32-column chunk.  A pass is split in two:
+//  (1) label propagation on a skewed (systolic) schedule: warp k handles chunk k of the row at step T(row) + k, so
+//      the vertical claim (same chunk, previous row) and the chain carry (previous chunk, same row) it depends on
+//      were produced one step earlier.  Which pixels were claimed sideways / vertically is kept as bit rows.
+//      In the reverse pass the "left neighbour" of (r, 0) is the last pixel of the row above, i.e. the chain runs on
+//      through the flattened image: a row whose first visited pixel could take such a wrap claim (it is free and
+//      within 0.02 m of some model plane) starts only after the row below is complete (T advances by NW for it).
+//  (2) emission, parallel over rows: per (claimer row, model) claim counts, an exclusive prefix over the rows, then
+//      every claimed pixel gets its position in inlier_indices[model] -- claimers in visiting order, the sideways
+//      claim of a claimer before its vertical claim, exactly the order in which the reference appends them.
+// Frames whose (rows x models) table does not fit are left to the one-warp kernel k_refine.  The multi-warp kernel
+// executes more instructions per frame (every warp pays the per-step overhead), so it is the choice for small launches
+// (latency: the tracking loop), while large batches keep one warp per frame (throughput) -- Params::refine_fast.
+// ---------------------------------------------------------------------------------------------------------------
+struct Refine2Smem {
+    float    coef[SPX_MAX_MODELS][4];
+    int      n0[SPX_MAX_MODELS];
+    int      cnt[2][SPX_MAX_MODELS];
+    unsigned long long lastkey[2][SPX_MAX_MODELS];
+    int      carry[2][16];
+    int      rowlast[2];              // final label of the last visited pixel of a row (reverse pass: column 0)
+    uint16_t T[kRefMaxH];             // start step of every row of the reverse pass
+    uint8_t  wrapflag[kRefMaxH];      // rows that wait for the row below (wrap claim possible)
+    uint8_t  wrapcand[kRefMaxH];      // rows whose first visited pixel is free and close to some model plane
+    int      total_steps;
+};
+
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+template <int NW, bool kReverse>
+__device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, unsigned *Vb, const Params &P, const float *__restrict__ px,
+                                                  const float *__restrict__ py, const float *__restrict__ pz, int8_t *pid) {
+    const int w = P.w, h = P.h;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int v = k * 32 + lane;                  // visiting index inside a row
+    const bool valid = v < w;
+    const int c = kReverse ? (w - 1 - v) : v;
+    auto row_of = [&](int i) { return kReverse ? (h - 1 - i) : i; };
+    const int total_steps = kReverse ? S.total_steps : (h + NW - 1);
+    const int k_last = (w - 1) >> 5, lane_last = (w - 1) & 31;   // where the last visited pixel of a row lives
+    // statically rotated prefetch registers: plane ids 8 rows ahead, xyz of the free pixels 4 rows ahead -- a load has
+    // at least four steps to land and no register holding a pending load is ever moved
+    int pr[8];
+    float xr[4], yr[4], zr[4];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) pr[u] = (valid && u < h) ? int(pid[row_of(u) * w + c]) : -2;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        xr[u] = yr[u] = zr[u] = 0.f;
+        if (u < h && pr[u] == -1) { const int q = row_of(u) * w + c; xr[u] = px[q]; yr[u] = py[q]; zr[u] = pz[q]; }
+    }
+    int prev = -2;
+    int s = 0;   // barriers passed = current step
+    for (int ib = 0; ib < h; ib += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = ib + u;
+            if (i >= h) break;
+            const int Ti = kReverse ? int(S.T[i]) : i;
+            while (s < Ti + k) { cta_bar(); ++s; }
+            const int r = row_of(i);
+            int a = pr[u];
+            const float x = xr[u & 3], y = yr[u & 3], z = zr[u & 3];
+            // A) vertical claim by the previous row (same column)
+            bool cV = false;
+            {
+                const bool cand = i >= 1 && a == -1 && prev >= 0 && (kReverse || c <= w - 2);
+                if (__any_sync(SPX_FULL, cand)) {
+                    if (cand && refine_dist_ok(S.coef[prev], x, y, z)) { a = prev; cV = true; }
+                }
+            }
+            // B) chain along the row: claimers are rows <= h-2 (forward) / rows >= 1 (reverse); in the reverse pass the
+            // carry into the first chunk is the wrap claim of the row below
+            bool cH = false;
+            int carry = -1;
+            if (k > 0) carry = S.carry[i & 1][k - 1];
+            else if (kReverse && i >= 1 && S.wrapflag[r]) carry = S.rowlast[(i - 1) & 1];
+            const bool chain_on = kReverse ? (r >= 1) : (r <= h - 2);
+            const unsigned labelled = __ballot_sync(SPX_FULL, a >= 0);
+            const unsigned freem = __ballot_sync(SPX_FULL, valid && a == -1);
+            if (freem != 0u && (chain_on ? (labelled != 0u || carry >= 0) : (k == 0 && carry >= 0))) {
+                const unsigned below = chain_on ? (labelled & ((1u << lane) - 1u)) : 0u;
+                const int src_lane = below ? (31 - __clz(below)) : -1;
+                const int m_lane = __shfl_sync(SPX_FULL, a, src_lane < 0 ? 0 : src_lane);
+                const int m_src = src_lane < 0 ? carry : m_lane;
+                const bool isfree = valid && a == -1;
+                const bool ok = isfree && m_src >= 0 && refine_dist_ok(S.coef[m_src], x, y, z);
+                const unsigned blocked = __ballot_sync(SPX_FULL, !valid || (a == -1 && !ok));
+                const unsigned le_src = src_lane < 0 ? 0u : ((2u << src_lane) - 1u);
+                const unsigned mask = ((1u << lane) - 1u) & ~le_src;
+                bool claimed = ok && (blocked & mask) == 0u;
+                if (!chain_on) claimed = claimed && lane == 0;   // row 0 of the reverse pass: only the wrap claim itself
+                if (claimed) { a = m_src; cH = true; }
+            }
+            const unsigned hb = __ballot_sync(SPX_FULL, cH), vb = __ballot_sync(SPX_FULL, cV);
+            const int last_lbl = __shfl_sync(SPX_FULL, a, (k == k_last) ? lane_last : 31);
+            if (lane == 0) {
+                Hb[i * NW + k] = hb; Vb[i * NW + k] = vb;
+                S.carry[i & 1][k] = chain_on ? (last_lbl < 0 ? -1 : last_lbl) : -1;
+                if (k == k_last) S.rowlast[i & 1] = last_lbl < 0 ? -1 : last_lbl;
+            }
+            if (valid && (cH || cV)) pid[r * w + c] = int8_t(a);
+            prev = a;
+            // refill the slots just consumed: plane ids of row i+8, xyz of row i+4 (its plane ids arrived long ago)
+            pr[u] = (valid && i + 8 < h) ? int(pid[row_of(i + 8) * w + c]) : -2;
+            if (i + 4 < h && pr[(u + 4) & 7] == -1) { const int q = row_of(i + 4) * w + c; xr[u & 3] = px[q]; yr[u & 3] = py[q]; zr[u & 3] = pz[q]; }
+        }
+    }
+    while (s < total_steps) { cta_bar(); ++s; }
+}
+
+// emission of one pass; kCount: accumulate the per-(row, model) counts, else assign positions from the prefixed table
+template <int NW, bool kReverse, bool kCount>
+__device__ __forceinline__ void refine2_emit(Refine2Smem &S, const unsigned *Hb, const unsigned *Vb, unsigned *table, int nm, const Params &P,
+                                             const int8_t *pid, int *pos, const int *pos_base, int pass) {
+    const int w = P.w, h = P.h;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k_last = (w - 1) >> 5, lane_last = (w - 1) & 31;
+    for (int i = wid; i < h; i += NW) {           // claimer row i (pass order)
+        const int r = kReverse ? (h - 1 - i) : i;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            // sideways targets of the claimers of chunk k: visiting index v + 1 (the wrap target is bit 0 of the next row)
+            unsigned sm = Hb[i * NW + k] >> 1;
+            if (k + 1 < NW) sm |= Hb[i * NW + k + 1] << 31;
+            if (kReverse && k == k_last && i + 1 < h) sm |= (Hb[(i + 1) * NW] & 1u) << lane_last;
+            const unsigned vm = (i + 1 < h) ? Vb[(i + 1) * NW + k] : 0u;
+            if ((sm | vm) == 0u) continue;        // warp uniform
+            const int v = k * 32 + lane;
+            const int c = kReverse ? (w - 1 - v) : v;
+            const int qS = kReverse ? (r * w + c - 1) : (r * w + c + 1);      // (wraps at c == 0 in the reverse pass)
+            const int qV = kReverse ? ((r - 1) * w + c) : ((r + 1) * w + c);
+            const int mS = ((sm >> lane) & 1u) ? int(pid[qS]) : -1;
+            const int mv = ((vm >> lane) & 1u) ? int(pid[qV]) : -1;
+            unsigned todoS = sm, todoV = vm;
+            while (todoS | todoV) {
+                const int src = __ffs(todoS | todoV) - 1;
+                const int mine = mS >= 0 ? mS : mv;
+                const int mm = __shfl_sync(SPX_FULL, mine, src);
+                const unsigned bS = __ballot_sync(SPX_FULL, mS == mm), bV = __ballot_sync(SPX_FULL, mv == mm);
+                const int n_here = __popc(bS) + __popc(bV);
+                if (kCount) {
+                    if (lane == 0) table[i * nm + mm] += unsigned(n_here);
+                } else {
+                    const unsigned lt = (1u << lane) - 1u;
+                    const int before = __popc(bS & lt) + __popc(bV & lt);
+                    const int b0 = int(table[i * nm + mm]);      // claims of this model before this chunk (whole pass)
+                    if (mS == mm) pos[qS] = pos_base[mm] + b0 + before;
+                    if (mv == mm) pos[qV] = pos_base[mm] + b0 + before + (mS == mm ? 1 : 0);
+                    const int hl = 31 - __clz(bS | bV);
+                    __syncwarp();
+                    if (lane == hl) {
+                        table[i * nm + mm] = unsigned(b0 + n_here);
+                        // the last claim of the pass: largest (row, visiting index, vertical-after-sideways) key
+                        const unsigned key = unsigned(i) * unsigned(2 * w + 2) + unsigned(2 * v + (mv == mm ? 1 : 0));
+                        const int tgt = (mv == mm) ? qV : qS;
+                        atomicMax(&S.lastkey[pass][mm], (static_cast<unsigned long long>(key) << 32) | unsigned(tgt));
+                    }
+                    __syncwarp();
+                }
+                todoS &= ~bS; todoV &= ~bV;
+            }
+        }
+    }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
+    extern __shared__ unsigned sm_ref[];
+    __shared__ Refine2Smem S;
+    const int f = P.frame0 + blockIdx.x;
+    FrameCtl &ctl = B.ctl[f];
+    const int nm = ctl.n_models;
+    const int w = P.w, h = P.h;
+    if (nm == 0 || !P.refine_fast || !refine_fast_ok(h, nm)) return;
+    unsigned *Hb = sm_ref, *Vb = Hb + h * NW;
+    unsigned *table = Vb + h * NW;
+    const int tid = threadIdx.x;
+    const size_t fo = size_t(f) * P.N;
+    const float *px = B.px + fo, *py = B.py + fo, *pz = B.pz + fo;
+    int8_t *pid = B.pid + fo;
+    int *pos = B.pos + fo;
+    for (int m = tid; m < nm; m += NW * 32) {
+        const Model &M = ctl.models[m];
+        S.coef[m][0] = M.coef[0]; S.coef[m][1] = M.coef[1]; S.coef[m][2] = M.coef[2]; S.coef[m][3] = M.coef[3];
+        S.n0[m] = M.n0; S.cnt[0][m] = 0; S.cnt[1][m] = 0; S.lastkey[0][m] = 0ull; S.lastkey[1][m] = 0ull;
+    }
+    for (int i = tid; i < h * nm; i += NW * 32) table[i] = 0;
+    __syncthreads();
+
+    // ---------------- pass 1 ----------------
+    refine2_propagate<NW, false>(S, Hb, Vb, P, px, py, pz, pid);
+    __threadfence_block();
+    __syncthreads();
+    refine2_emit<NW, false, true>(S, Hb, Vb, table, nm, P, pid, pos, S.n0, 0);
+    __syncthreads();
+    for (int m = tid; m < nm; m += NW * 32) {     // exclusive prefix over the rows
+        int run = 0;
+        for (int i = 0; i < h; ++i) { const int t = int(table[i * nm + m]); table[i * nm + m] = unsigned(run); run += t; }
+        S.cnt[0][m] = run;
+    }
+    __syncthreads();
+    refine2_emit<NW, false, false>(S, Hb, Vb, table, nm, P, pid, pos, S.n0, 0);
+    __syncthreads();
+
+    // ---------------- pass 2 ----------------
+    // positions of pass-2 claims start after the originals and the pass-1 claims
+    for (int m = tid; m < nm; m += NW * 32) S.n0[m] += S.cnt[0][m];
+    for (int i = tid; i < h * nm; i += NW * 32) table[i] = 0;
+    // rows whose first visited pixel (column w-1) could take the wrap claim of the row below: it is free and within
+    // 0.02 m of some model plane.  Such rows are common (a free pixel on the right image border that is coplanar with
+    // any model), real wrap claims are rare (the model must also end up at column 0 of the row below), so the pass
+    // runs SPECULATIVELY on the plain skewed schedule; afterwards every candidate row is checked with the final
+    // labels, and only if a wrap claim would have fired the labels are restored and the pass is redone with the
+    // candidate rows waiting for the row below to complete.
+    int8_t *bak = B.pid_bak + fo;
+    int n_cand_local = 0;
+    for (int r = tid; r < h; r += NW * 32) {
+        bool fl = false;
+        const int q = r * w + w - 1;
+        if (r <= h - 2 && pid[q] == -1) {
+            const float x = px[q], y = py[q], z = pz[q];
+            for (int m = 0; m < nm && !fl; ++m) fl = refine_dist_ok(S.coef[m], x, y, z);
+        }
+        S.wrapcand[r] = fl ? 1 : 0;
+        S.wrapflag[r] = 0;
+        n_cand_local += fl ? 1 : 0;
+    }
+    const int any_cand = __syncthreads_or(n_cand_local);
+    if (any_cand) {
+        if ((P.N & 15) == 0) { for (int i = tid; i < P.N / 16; i += NW * 32) reinterpret_cast<uint4 *>(bak)[i] = reinterpret_cast<const uint4 *>(pid)[i]; }
+        else { for (int i = tid; i < P.N; i += NW * 32) bak[i] = pid[i]; }
+    }
+    if (tid == 0) {
+        for (int i = 0; i < h; ++i) S.T[i] = uint16_t(i);
+        S.total_steps = h + NW - 1;
+    }
+    __syncthreads();
+    refine2_propagate<NW, true>(S, Hb, Vb, P, px, py, pz, pid);
+    __threadfence_block();
+    __syncthreads();
+    if (any_cand) {
+        // a wrap claim fires at row r iff (r, w-1) stayed free and the final label m of (r+1, 0) is a model with
+        // |n.p + d| < 0.02 at (r, w-1).  Rows below the first such row are correct as computed, so the test is exact.
+        int viol = 0;
+        for (int r = tid; r < h - 1; r += NW * 32) {
+            if (S.wrapcand[r]) {
+                const int q = r * w + w - 1;
+                const int m0 = int(pid[(r + 1) * w]);
+                if (pid[q] == -1 && m0 >= 0 && refine_dist_ok(S.coef[m0], px[q], py[q], pz[q])) viol = 1;
+            }
+        }
+        if (__syncthreads_or(viol)) {
+            if ((P.N & 15) == 0) { for (int i = tid; i < P.N / 16; i += NW * 32) reinterpret_cast<uint4 *>(pid)[i] = reinterpret_cast<const uint4 *>(bak)[i]; }
+            else { for (int i = tid; i < P.N; i += NW * 32) pid[i] = bak[i]; }
+            for (int r = tid; r < h; r += NW * 32) S.wrapflag[r] = S.wrapcand[r];
+            __threadfence_block();
+            __syncthreads();
+            if (tid == 0) {
+                int t = 0;
+                for (int i = 0; i < h; ++i) {
+                    if (i > 0) t += S.wrapflag[h - 1 - i] ? NW : 1;
+                    S.T[i] = uint16_t(t);
+                }
+                S.total_steps = t + NW;
+            }
+            __syncthreads();
+            refine2_propagate<NW, true>(S, Hb, Vb, P, px, py, pz, pid);
+            __threadfence_block();
+            __syncthreads();
+        }
+    }
+    refine2_emit<NW, true, true>(S, Hb, Vb, table, nm, P, pid, pos, S.n0, 1);
+    __syncthreads();
+    for (int m = tid; m < nm; m += NW * 32) {
+        int run = 0;
+        for (int i = 0; i < h; ++i) { const int t = int(table[i * nm + m]); table[i * nm + m] = unsigned(run); run += t; }
+        S.cnt[1][m] = run;
+    }
+    __syncthreads();
+    refine2_emit<NW, true, false>(S, Hb, Vb, table, nm, P, pid, pos, S.n0, 1);
+    __syncthreads();
+    for (int m = tid; m < nm; m += NW * 32) {
+        Model &M = ctl.models[m];
+        M.n1 = S.cnt[0][m]; M.n2 = S.cnt[1][m];
+        if (S.cnt[1][m] > 0) M.last_inlier = int(S.lastkey[1][m] & 0xffffffffull);
+        else if (S.cnt[0][m] > 0) M.last_inlier = int(S.lastkey[0][m] & 0xffffffffull);
     }
 }
 

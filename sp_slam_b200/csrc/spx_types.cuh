@@ -12,6 +12,7 @@ struct Params {
     size_t pitch;          // bytes
     size_t frame_stride;   // bytes
     int n_frames;          // frames of this launch group
+    int refine_fast;       // 1: k_refine2 (a CTA per frame) where its table fits; 0: k_refine (a warp per frame) for all
     int frame0;            // first frame of the group (frames are independent: groups run on separate streams)
     // organized cloud (src/Frame.cc:856-874)
     int dis, w, h, N;
@@ -107,6 +108,7 @@ struct Buffers {
     int   *lab;                   // PCL labels (rank of the component)
     int16_t *root_model;          // model index at component roots, -1 otherwise
     int8_t *pid;                  // plane (model) id per pixel, -1 = none
+    int8_t *pid_bak;              // plane ids after the first refine pass (restored if the speculative second pass fails)
     int   *pos;                   // position of the pixel in its model's inlier list
     int   *cand_idx;              // raster-ordered index lists of the candidates
     int   *contour_idx;           // contour arena, contour_cap per frame
