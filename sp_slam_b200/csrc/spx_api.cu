@@ -51,7 +51,10 @@ struct spx_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // frame groups: internal streams + per group events (start, end of the plane section, end of the supposed-plane section)
     int n_streams = 1, min_group = 32, last_groups = 1;
-    std::vector<cudaStream_t> g_streams;
+    bool use_prio = false;   // back stream with higher priority: measured slower (co-running kernels slow each other), kept as a knob
+    std::vector<cudaStream_t> g_streams;      // front: upload, chamfer, normals (low priority)
+    std::vector<cudaStream_t> g_back;         // back: everything after the normals (high priority: it is what frees a group)
+    std::vector<cudaEvent_t> g_link;          // front -> back hand-over
     std::vector<cudaEvent_t> g_ev;
     size_t work_stride = 0, work2_stride = 0;
     // host path: every group compacts its own results (at the device offset of its first frame) and ships them itself
@@ -193,7 +196,8 @@ int prof_slot(spx_ctx *c, const char *name, cudaStream_t st) {
     return SPX_OK;
 }
 
-int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int f0, int ng, cudaStream_t st, const HostSrc &src) {
+int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int f0, int ng, cudaStream_t st, cudaStream_t st_back,
+              const HostSrc &src) {
     Params P = c->P;
     P.frame0 = f0; P.n_frames = ng;
     P.refine_fast = (ng <= 64 && P.h <= kRefMaxH) ? 1 : 0;   // small launches are latency bound: parallelism inside the frame
@@ -246,6 +250,11 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
         LAUNCH(k_backproject, gpix, 256, 0, depth_dev, P, B);
         LAUNCH(k_plane_d, gpix, 256, 0, P, B);
         LAUNCH(k_ccl_link, dim3(cdiv(P.w, 32), cdiv(P.h, 8), F), dim3(32, 8), 0, P, B);
+    }
+    if (st_back != st) {   // the rest of the group's chain runs on its high-priority stream
+        SPX_CK(c, cudaEventRecord(c->g_link[g], st));
+        SPX_CK(c, cudaStreamWaitEvent(st_back, c->g_link[g], 0));
+        st = st_back;
     }
     LAUNCH(k_ccl_merge, gpix, 256, 0, P, B, 1);
     LAUNCH(k_ccl_flatten, gpix, 256, 0, P, B);
@@ -303,9 +312,10 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given, const H
     for (int g = 0; g < G; ++g) {
         const int f0 = int((long long)F * g / G), f1 = int((long long)F * (g + 1) / G);
         cudaStream_t st = (G == 1) ? main_st : c->g_streams[g];
+        cudaStream_t st_back = (G == 1) ? main_st : (c->use_prio ? c->g_back[g] : c->g_streams[g]);
         if (G > 1) SPX_CK(c, cudaStreamWaitEvent(st, c->ev[0], 0));
         SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 0], st));
-        int rc = run_group(c, depth_dev, normals_given, g, f0, f1 - f0, st, src);
+        int rc = run_group(c, depth_dev, normals_given, g, f0, f1 - f0, st, st_back, src);
         if (rc != SPX_OK) return rc;
         if (G > 1) SPX_CK(c, cudaStreamWaitEvent(main_st, c->g_ev[3 * g + 2], 0));
     }
@@ -379,7 +389,7 @@ int fetch(spx_ctx *c, spx_batch_result *out, bool with_clouds) {
 template <typename T>
 int grow_pinned_keep(spx_ctx *c, T **p, size_t *cap, size_t need, size_t used) {
     if (need <= *cap) return SPX_OK;
-    for (int g = 0; g < c->last_groups; ++g) SPX_CK(c, cudaStreamSynchronize(c->last_groups == 1 ? c->stream : c->g_streams[g]));
+    for (int g = 0; g < c->last_groups; ++g) SPX_CK(c, cudaStreamSynchronize(c->last_groups == 1 ? c->stream : (c->use_prio ? c->g_back[g] : c->g_streams[g])));
     size_t ncap = *cap ? *cap : 1024;
     while (ncap < need) ncap *= 2;
     T *np = nullptr;
@@ -399,7 +409,7 @@ int fetch_groups(spx_ctx *c, spx_batch_result *out) {
     std::vector<long long> host_pl(G), host_pt(G), host_bd(G), n_pls(G);
     int rc;
     for (int g = 0; g < G; ++g) {
-        cudaStream_t st = (G == 1) ? c->stream : c->g_streams[g];
+        cudaStream_t st = (G == 1) ? c->stream : (c->use_prio ? c->g_back[g] : c->g_streams[g]);
         SPX_CK(c, cudaEventSynchronize(c->g_tot_ev[g]));
         const long long *t = c->h_totals + 4 * (g + 1);
         const long long n_pl = t[0], n_pt = t[1], n_bd = t[2];
@@ -414,7 +424,7 @@ int fetch_groups(spx_ctx *c, spx_batch_result *out) {
         host_pl[g] = run_pl; host_pt[g] = run_pt; host_bd[g] = run_bd; n_pls[g] = n_pl;
         run_pl += n_pl; run_pt += n_pt; run_bd += n_bd;
     }
-    for (int g = 0; g < G; ++g) SPX_CK(c, cudaStreamSynchronize((G == 1) ? c->stream : c->g_streams[g]));
+    for (int g = 0; g < G; ++g) SPX_CK(c, cudaStreamSynchronize((G == 1) ? c->stream : (c->use_prio ? c->g_back[g] : c->g_streams[g])));
     SPX_CK(c, cudaStreamSynchronize(c->stream));
     for (int g = 0; g < G; ++g) {
         const spx_ctx::GroupOut &go = c->g_out[g];
@@ -540,11 +550,19 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     for (int i = 0; i < 4; ++i) SPX_CK_CREATE(cudaEventCreate(&c->ev[i]));
     c->n_streams = cfg->n_streams > 0 ? (cfg->n_streams > 32 ? 32 : cfg->n_streams) : 8;
     c->min_group = 32;
+    if (const char *e = std::getenv("SPX_PRIO")) c->use_prio = std::atoi(e) != 0;   // tuning knob
     if (const char *e = std::getenv("SPX_MIN_GROUP")) { const int v = std::atoi(e); if (v > 0) c->min_group = v; }   // tuning knob
+    int prio_lo = 0, prio_hi = 0;
+    SPX_CK_CREATE(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // numerically lower = higher priority
     for (int g = 0; g < c->n_streams; ++g) {
         cudaStream_t gs;
-        SPX_CK_CREATE(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+        SPX_CK_CREATE(cudaStreamCreateWithPriority(&gs, cudaStreamNonBlocking, prio_lo));
         c->g_streams.push_back(gs);
+        SPX_CK_CREATE(cudaStreamCreateWithPriority(&gs, cudaStreamNonBlocking, prio_hi));
+        c->g_back.push_back(gs);
+        cudaEvent_t le;
+        SPX_CK_CREATE(cudaEventCreateWithFlags(&le, cudaEventDisableTiming));
+        c->g_link.push_back(le);
         for (int k = 0; k < 3; ++k) {
             cudaEvent_t e;
             SPX_CK_CREATE(cudaEventCreate(&e));
@@ -633,6 +651,8 @@ void spx_destroy(spx_ctx *c) {
     for (cudaEvent_t e : c->g_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->g_tot_ev) cudaEventDestroy(e);
     for (cudaStream_t gs : c->g_streams) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
+    for (cudaStream_t gs : c->g_back) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
+    for (cudaEvent_t e : c->g_link) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
