@@ -42,27 +42,28 @@ def algorithmic_bytes_per_frame(rows=ROWS, cols=COLS, dis=3):
     n = w * h
     path = rows * cols * 4 + n * 4 + n * 4 + n * 16 + 65536
     k = {
-        "k_backproject": n * 4 + n * 16,                 # 1 depth sample in, x y z dist out
-        "k_chamfer": 2 * (n * 4 + n * 4),                # two passes over the distance map
-        "k_normals": n * 16 + n * 16,                    # x y z dist in, nx ny nz plane_d out
-        "k_ccl_link": n * 28 + n * 9,                    # x y z n d in, conn parent cnt out
-        "k_ccl_merge": n * 1 + n * 4,                    # conn in, parent forest touched
-        "k_ccl_flatten": n * 4 + n * 4 + n * 4,          # parent in/out, counts
-        "k_ccl_rank": n * 8 + n * 4,                     # parent + cnt in, root labels out
+        "k_edge_chamfer": n * 4 + n * 1,                 # one depth sample per organized pixel in, window size out
+        "k_normals_link": n * 4 + n * 1 + n * 12 + n * 9, # depth sample + window size in; x y z, link bits, forest, counts out
+        "k_ccl_merge": n * 1 + n * 4,                    # link bits in, forest touched
+        "k_ccl_flatten": n * 4 + n * 4 + n * 4,          # forest in/out, counts
+        "k_ccl_rank": n * 8 + n * 2 + n * 8,             # forest + sizes in, index lists + positions out (upper bound)
         "k_ccl_label": n * 8,
-        "k_moments_fit": n * 4 + n * 12 + n * 8,         # parent + xyz of members in, index list + positions out
+        "k_moments_fit": n * 4 + n * 12,                 # index list + xyz of the members in
         "k_models": 8192,
         "k_pid_init": n * 4 + n * 1,
         "k_refine": 2 * 2 * n + n * 12 + n * 4,          # plane ids in/out twice, xyz of free pixels, positions
+        "k_refine2": 2 * 2 * n + n * 12 + n * 4,
         "k_contour": n * 1 + 16384,                      # plane-id map in, contour indices out
         "k_postfilter": 8192,
-        "k_lines": 4 * 4096 * 16 + 2 * 160000,           # <=4 rounds over a ~4k point contour + 20x20 depth windows
+        "k_lines": 4 * 4096 * 16,                        # <= 4 rounds over a contour of a few thousand points
+        "k_border": 2 * 160000,                          # 20x20 full-resolution depth windows of the line points
         "k_supposed": 8192,
         "k_scan_frames": 64,
         "k_emit_records": 8192,
         "k_pack_points": n * 17 + n * 16,                # pid pos xyz in, 16-byte points out
         "k_pack_contours": 4096 * (4 + 12 + 16),
         "k_pack_supposed": 2 * 2500 * 16,
+        "k_convert_u16": rows * cols * 6,
     }
     return path, k, n
 
@@ -197,6 +198,7 @@ def main():
     ap.add_argument("--noise", default="none", choices=["none", "sensor"])
     ap.add_argument("--res", default="480p", choices=["480p", "720p"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-groups", action="store_true", help="take the kernel table from the multi-group timed steps")
     ap.add_argument("--streams", type=int, default=0, help="internal streams (frame groups) per context; 0 = library default")
     args = ap.parse_args()
 
@@ -228,11 +230,21 @@ def main():
     dev = host.cuda(non_blocking=False)
     ext = api.PlaneExtractor(max_frames=F, max_rows=rows, max_cols=cols, device=local_rank, fx=it.fx, fy=it.fy, cx=it.cx,
                              cy=it.cy, max_x=float(it.width), max_y=float(it.height), n_streams=args.streams)
+    if not args.profile_groups and (args.streams == 0 or args.streams > 1):
+        # the per-kernel table comes from one extra profiled step in which the batch runs as ONE group (kernels back to
+        # back on one stream, so their CUDA-event times add up to the step and can be compared with an ncu launch list)
+        ext1 = api.PlaneExtractor(max_frames=F, max_rows=rows, max_cols=cols, device=local_rank, fx=it.fx, fy=it.fy,
+                                  cx=it.cx, cy=it.cy, max_x=float(it.width), max_y=float(it.height), n_streams=1)
+    else:
+        ext1 = None
     # a real (non-default) stream shared by torch and the library, so torch.cuda.Event brackets the kernels
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
     ext.set_stream(stream.cuda_stream)
-    ext.set_profile(os.environ.get("SPX_BENCH_PROFILE", "1") != "0")
+    ext.set_profile(ext1 is None)
+    if ext1 is not None:
+        ext1.set_stream(stream.cuda_stream)
+        ext1.set_profile(True)
 
     def gather_planes():
         """the one collective of the path: plane lists (frame headers + plane records) to every rank over NCCL"""
@@ -266,7 +278,18 @@ def main():
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
-        for name, t in (ext.kernel_times() if os.environ.get("SPX_BENCH_PROFILE", "1") != "0" else [("unprofiled", ms / args.steps)]):   # events of the last timed step
+        ms_one = None
+        if ext1 is not None:
+            for _ in range(2):
+                ext1.extract_device(dev.data_ptr(), F, rows, cols)
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(stream)
+            ext1.extract_device(dev.data_ptr(), F, rows, cols)
+            p1.record(stream)
+            barrier()
+            ms_one = p0.elapsed_time(p1)
+        for name, t in (ext1 or ext).kernel_times():   # CUDA events around every launch of the profiled step
             name = name.split("<")[0]
             ktimes[name] = ktimes.get(name, 0.0) + t
             kcount[name] = kcount.get(name, 0) + 1
@@ -330,13 +353,20 @@ def main():
         top = max(ktimes, key=ktimes.get)
         step_kernel_ms = sum(ktimes.values())
         achieved = kbytes.get(top, 0) * F / (ktimes[top] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, scaled to this launch
+            tj = json.load(open(tpath)).get(top)
+            if tj and rows == ROWS and cols == COLS:
+                traffic = tj["dram_bytes_per_frame"] * F / max(kcount[top], 1)
         roofline = {
             "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": traffic, "peak_source": peak_src,
             "kernel_ms_per_step": ktimes[top], "kernel_launches_per_step": kcount[top],
             "kernel_ms_per_launch": ktimes[top] / kcount[top], "kernel_share_of_step": ktimes[top] / step_kernel_ms,
-            "note": "a step's frames run as frame groups on internal streams, so one kernel is launched once per group and "
-                    "launches of different groups overlap; durations are CUDA events around each launch on its stream",
+            "profiled_step_ms": ms_one,
+            "note": "kernel durations: CUDA events around every launch of one extra step run as a single frame group (kernels "
+                    "back to back on one stream); `value` is timed with the batch cut into frame groups on internal streams",
             "algorithmic_bytes_per_frame": kbytes.get(top, 0),
             "path": {"algorithmic_bytes_per_frame": path_bytes,
                      "achieved": (value / world) * path_bytes / 1e9, "frac": (value / world) * path_bytes / 1e9 / peak},
@@ -375,6 +405,8 @@ def main():
         }
         print(json.dumps(line), flush=True)
     ext.close()
+    if ext1 is not None:
+        ext1.close()
     if world > 1:
         dist.destroy_process_group()
 
