@@ -99,6 +99,12 @@ def test_frame_groups_host_and_device_paths_agree():
     dev = torch.from_numpy(d).cuda()
     ext.extract_device(dev.data_ptr(), n, 480, 640)
     devres = ext.fetch()
+    # one group of 100 frames: the large-launch variants (one-warp refine with the plane ids taken from the forest)
+    big = api.PlaneExtractor(max_frames=n, n_streams=1)
+    bigres = big.extract_batch(d)
+    assert np.array_equal(bigres.frames, host.frames) and np.array_equal(bigres.planes, host.planes)
+    assert np.array_equal(bigres.points, host.points) and np.array_equal(bigres.boundary, host.boundary)
+    big.close()
     one = api.PlaneExtractor()
     assert len(host) == len(devres) == n
     assert int(host.frames["n_planes"].sum()) == len(host.planes) == len(devres.planes)
