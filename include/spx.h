@@ -32,7 +32,10 @@ enum {
     SPX_ERR_STATE = 3      /* call order violated (e.g. results fetched before an extract)         */
 };
 
-enum { SPX_FRAME_OVERFLOW = 1u };
+enum {
+    SPX_FRAME_OVERFLOW = 1u,    /* a per-frame capacity above was exceeded; the frame's plane list is truncated */
+    SPX_FRAME_NONFINITE = 2u    /* the depth image held NaN / Inf samples (such points stay unlabelled, as in PCL) */
+};
 
 /* Thresholds the reference reads from YAML through Config::Get (Examples/RGB-D/TUM1.yaml:73-78,99-100), the Frame
  * statics (src/Frame.cc:169-177,536-564) and the constants hard-coded in src/Frame.cc:881-882,945. */

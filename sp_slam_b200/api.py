@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libspx.so")
 
 SPX_OK, SPX_ERR_ARG, SPX_ERR_CUDA, SPX_ERR_STATE = 0, 1, 2, 3
 SPX_FRAME_OVERFLOW = 1
+SPX_FRAME_NONFINITE = 2
 SPX_MAX_CAND, SPX_MAX_MODELS, SPX_MAX_PLANES, SPX_MAX_LINES = 96, 64, 128, 4
 
 POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgba", "<u4")])

@@ -54,7 +54,7 @@ __device__ __forceinline__ bool refine_dist_ok(const float *cf, float x, float y
 template <int NCH, bool kReverse>
 __device__ __forceinline__ void refine_pass(RefineSmem &S, const Params &P, const float *__restrict__ px, const float *__restrict__ py,
                                             const float *__restrict__ pz, int8_t *pid, int *pos, int *cnt, int *last,
-                                            const int *pos_base, int lane) {
+                                            const int *pos_base, int lane, bool has_invalid) {
     const int w = P.w, h = P.h;
     int a[NCH], prev[NCH], pn[NCH], pn2[NCH], mV[NCH];
     float x[NCH], y[NCH], z[NCH], xn[NCH], yn[NCH], zn[NCH];
@@ -98,7 +98,13 @@ __device__ __forceinline__ void refine_pass(RefineSmem &S, const Params &P, cons
             for (int ch = 0; ch < NCH; ++ch) {
                 mV[ch] = -1;
                 const int m = prev[ch];
-                const bool cand = a[ch] == -1 && m >= 0 && (kReverse || col(ch) <= w - 2);
+                bool cand = a[ch] == -1 && m >= 0 && (kReverse || col(ch) <= w - 2);
+                // PCL: `if (current_label < 0 || right_label < 0) continue;` also drops the claimer's vertical claim when
+                // its sideways neighbour (flat index +-1) is an unlabelled point; only frames with non-finite depth have those
+                if (has_invalid && cand) {
+                    const int cr = kReverse ? r + 1 : r - 1;
+                    if (pid[cr * w + col(ch) + (kReverse ? -1 : 1)] == -2) cand = false;
+                }
                 if (__any_sync(SPX_FULL, cand)) {   // most chunks lie inside a plane or inside nothing
                     if (cand && refine_dist_ok(S.coef[m], x[ch], y[ch], z[ch])) { a[ch] = m; mV[ch] = m; }
                 }
@@ -212,13 +218,14 @@ __global__ void __launch_bounds__(kRefWarps * 32) k_refine(Params P, Buffers B) 
         S.n0[m] = M.n0; S.cnt1[m] = 0; S.cnt2[m] = 0; S.last1[m] = -1; S.last2[m] = -1;
     }
     __syncwarp();
-    refine_pass<NCH, false>(S, P, px, py, pz, pid, pos, S.cnt1, S.last1, S.n0, lane);
+    const bool has_invalid = (ctl.flags & unsigned(SPX_FRAME_NONFINITE)) != 0u;
+    refine_pass<NCH, false>(S, P, px, py, pz, pid, pos, S.cnt1, S.last1, S.n0, lane, has_invalid);
     __threadfence_block();
     __syncwarp();
     // positions of pass-2 claims start after the originals and the pass-1 claims
     for (int m = lane; m < nm; m += 32) S.n0[m] += S.cnt1[m];
     __syncwarp();
-    refine_pass<NCH, true>(S, P, px, py, pz, pid, pos, S.cnt2, S.last2, S.n0, lane);
+    refine_pass<NCH, true>(S, P, px, py, pz, pid, pos, S.cnt2, S.last2, S.n0, lane, has_invalid);
     __syncwarp();
     for (int m = lane; m < nm; m += 32) {
         Model &M = ctl.models[m];
@@ -261,7 +268,7 @@ __device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memo
 
 template <int NW, bool kReverse>
 __device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, unsigned *Vb, const Params &P, const float *__restrict__ px,
-                                                  const float *__restrict__ py, const float *__restrict__ pz, int8_t *pid) {
+                                                  const float *__restrict__ py, const float *__restrict__ pz, int8_t *pid, bool has_invalid) {
     const int w = P.w, h = P.h;
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int v = k * 32 + lane;                  // visiting index inside a row
@@ -296,7 +303,11 @@ __device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, 
             // A) vertical claim by the previous row (same column)
             bool cV = false;
             {
-                const bool cand = i >= 1 && a == -1 && prev >= 0 && (kReverse || c <= w - 2);
+                bool cand = i >= 1 && a == -1 && prev >= 0 && (kReverse || c <= w - 2);
+                if (has_invalid && cand) {   // (see k_refine: an unlabelled sideways neighbour of the claimer cancels its vertical claim)
+                    const int cr = kReverse ? r + 1 : r - 1;
+                    if (pid[cr * w + c + (kReverse ? -1 : 1)] == -2) cand = false;
+                }
                 if (__any_sync(SPX_FULL, cand)) {
                     if (cand && refine_dist_ok(S.coef[prev], x, y, z)) { a = prev; cV = true; }
                 }
@@ -406,6 +417,7 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
     const int w = P.w, h = P.h;
     if (nm == 0 || !P.refine_fast || !refine_fast_ok(h, nm)) return;
     unsigned *Hb = sm_ref, *Vb = Hb + h * NW;
+    const bool has_invalid = (ctl.flags & unsigned(SPX_FRAME_NONFINITE)) != 0u;
     unsigned *table = Vb + h * NW;
     const int tid = threadIdx.x;
     const size_t fo = size_t(f) * P.N;
@@ -421,7 +433,7 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
     __syncthreads();
 
     // ---------------- pass 1 ----------------
-    refine2_propagate<NW, false>(S, Hb, Vb, P, px, py, pz, pid);
+    refine2_propagate<NW, false>(S, Hb, Vb, P, px, py, pz, pid, has_invalid);
     __threadfence_block();
     __syncthreads();
     refine2_emit<NW, false, true>(S, Hb, Vb, table, nm, P, pid, pos, S.n0, 0);
@@ -468,7 +480,7 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
         S.total_steps = h + NW - 1;
     }
     __syncthreads();
-    refine2_propagate<NW, true>(S, Hb, Vb, P, px, py, pz, pid);
+    refine2_propagate<NW, true>(S, Hb, Vb, P, px, py, pz, pid, has_invalid);
     __threadfence_block();
     __syncthreads();
     if (any_cand) {
@@ -497,7 +509,7 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
                 S.total_steps = t + NW;
             }
             __syncthreads();
-            refine2_propagate<NW, true>(S, Hb, Vb, P, px, py, pz, pid);
+            refine2_propagate<NW, true>(S, Hb, Vb, P, px, py, pz, pid, has_invalid);
             __threadfence_block();
             __syncthreads();
         }

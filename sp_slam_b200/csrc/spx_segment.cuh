@@ -164,9 +164,13 @@ __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) 
         }
         bool isroot = false, iscand = false;
         int sz = 0;
+        bool nolabel = false;
         if (q < P.N) {
             isroot = root == q;
             if (isroot) { sz = sz_q; iscand = unsigned(sz) > unsigned(P.min_size); }
+            // PCL skips points with a non-finite x: they get no label at all (they are singletons of the forest here,
+            // since every comparison with a NaN fails)
+            if (isroot && !isfinite(B.px[fo + q])) { nolabel = true; isroot = false; iscand = false; }
         }
         // roots are counted in bits 0..19 (N < 2^20), candidates in bits 20..31
         const unsigned v = (isroot ? 1u : 0u) | (iscand ? (1u << 20) : 0u);
@@ -193,6 +197,7 @@ __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) 
         const unsigned run_before = running_s;   // thread 0 advances it after the next barrier
         const unsigned chunk_tot = block_tot;
         const unsigned excl = run_before + warp_tot[wid] + incl - v;
+        if (nolabel) { B.lab[fo + q] = -1; root_cand[q] = -1; atomicOr(&ctl.flags, unsigned(SPX_FRAME_NONFINITE)); }
         if (isroot) {
             B.lab[fo + q] = int(excl & 0xFFFFFu);
             int16_t rc = -1;
@@ -425,7 +430,8 @@ __global__ void __launch_bounds__(256) k_pid_init(Params P, Buffers B) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= P.N) return;
     const size_t fo = size_t(f) * P.N;
-    B.pid[fo + q] = int8_t(B.root_model[fo + B.parent[fo + q]]);
+    // -1: labelled but not part of a plane (refine may claim it); -2: a point PCL left unlabelled (non-finite)
+    B.pid[fo + q] = isfinite(B.px[fo + q]) ? int8_t(B.root_model[fo + B.parent[fo + q]]) : int8_t(-2);
 }
 
 }  // namespace spx

@@ -203,3 +203,34 @@ def test_u16_depth_ingest_equals_converted_float(seq):
     assert np.array_equal(a.points, b.points) and np.array_equal(a.boundary, b.boundary)
     assert int(a.frames["n_planes"].sum()) > 50
     ext.close()
+
+
+def test_non_finite_depth(oracle_lib, seq):
+    """NaN / Inf depth (never produced by a 16-bit sensor image, but legal in a CV_32F Mat): PCL leaves such points
+    unlabelled, they take part in no plane, no claim and no window sum."""
+    d = seq[2].copy()
+    d[100:140, 200:260] = np.nan
+    d[300:330, 400:520] = np.inf
+    d[50, 50] = np.nan
+    d[240:243, :] = np.nan            # a full stripe: splits the frame
+    ext = api.PlaneExtractor(debug=True)
+    fp = ext.extract(d)
+    orc = oracle_lib.Oracle().run(d)
+    lab_ref, _ = orc.labels_raw()
+    assert (lab_ref == 0xFFFFFFFF).sum() > 500
+    rep = compare_frame(ext, orc, d, fp)
+    assert rep["labels_bit_exact"], rep
+    assert fp.mnRealPlaneNum == orc.n_real >= 1
+    assert fp.flags & api.SPX_FRAME_NONFINITE
+    # the same frame inside one large launch (one-warp refine kernel)
+    batch = np.repeat(seq[1][None], 70, axis=0)
+    batch[3] = d
+    big = api.PlaneExtractor(max_frames=70, n_streams=1)
+    res = big.extract_batch(batch)
+    b = res.frame(3)
+    assert b.mnPlaneNum == fp.mnPlaneNum and np.array_equal(b.mvPlaneCoefficients.view(np.uint32), fp.mvPlaneCoefficients.view(np.uint32))
+    for p_, q_ in zip(b.mvPlanePoints + b.mvBoundaryPoints, fp.mvPlanePoints + fp.mvBoundaryPoints):
+        assert np.array_equal(p_, q_)
+    assert not (res.frame(2).flags & api.SPX_FRAME_NONFINITE)
+    big.close()
+    ext.close()
