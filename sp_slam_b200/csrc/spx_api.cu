@@ -260,7 +260,7 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
     LAUNCH(k_ccl_flatten, gpix, 256, 0, P, B);
     LAUNCH(k_ccl_rank, F, kRankThreads, 0, P, B);
     if (c->debug) LAUNCH(k_ccl_label, gpix, 256, 0, P, B);
-    LAUNCH(k_moments_fit, dim3(SPX_MAX_CAND / kMomWarps, F), kMomWarps * 32, 0, P, B);
+    LAUNCH(k_moments_fit, dim3(kMomCands, F), 96, 0, P, B);
     LAUNCH(k_models, cdiv(F, 128), 128, 0, P, B);
     LAUNCH(k_pid_init, gpix, 256, 0, P, B);
     {

@@ -5,6 +5,7 @@
 // PCL 1.8.0 features/impl/integral_image_normal.hpp (initAverage3DGradientMethod, computeFeature,
 // computeFeatureFull, computePointNormal), features/impl/integral_image2D.hpp (IntegralImage2D<float,3>).
 #pragma once
+#include <climits>
 #include "spx_math.cuh"
 #include "spx_types.cuh"
 
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(kNormThreads) k_normals_link(const float *__re
                 U = (fabsf(d1 - Nrm[3 * ncs + ou]) < threshold) && (dot3f(n1x, n1y, n1z, Nrm[ou], Nrm[ncs + ou], Nrm[2 * ncs + ou]) > P.ang_cos);
             }
             B.conn[fo + q] = uint8_t((L ? 1 : 0) | (U ? 2 : 0));
-            B.cnt[fo + q] = 0;
+            B.cnt[fo + q] = isfinite(Zv) ? 0 : INT_MIN;   // a non-finite point: its (singleton) component size stays negative
             if (write_normals) { B.nx[fo + q] = n1x; B.ny[fo + q] = n1y; B.nz[fo + q] = n1z; B.pd[fo + q] = d1; }
         }
         const unsigned linked = __ballot_sync(SPX_FULL, valid && L);

@@ -6,6 +6,7 @@
 // (compare), segmentation/impl/organized_connected_component_segmentation.hpp (segment),
 // common/impl/centroid.hpp (computeMeanAndCovarianceMatrix), common/impl/eigen.hpp (eigen33).
 #pragma once
+#include <climits>
 #include "spx_math.cuh"
 #include "spx_types.cuh"
 
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) k_ccl_link(Params P, Buffers B) {
                 (dot3f(n1x, n1y, n1z, B.nx[fo + o], B.ny[fo + o], B.nz[fo + o]) > P.ang_cos);
         }
         B.conn[fo + q] = uint8_t((L ? 1 : 0) | (U ? 2 : 0));
-        B.cnt[fo + q] = 0;
+        B.cnt[fo + q] = isfinite(X) ? 0 : INT_MIN;
     }
     const unsigned linked = __ballot_sync(SPX_FULL, valid && L);
     const unsigned starts = ~linked | 1u;                       // lane 0 always starts a run inside the segment
@@ -168,9 +169,9 @@ __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) 
         if (q < P.N) {
             isroot = root == q;
             if (isroot) { sz = sz_q; iscand = unsigned(sz) > unsigned(P.min_size); }
-            // PCL skips points with a non-finite x: they get no label at all (they are singletons of the forest here,
-            // since every comparison with a NaN fails)
-            if (isroot && !isfinite(B.px[fo + q])) { nolabel = true; isroot = false; iscand = false; }
+            // PCL skips points with a non-finite x: they get no label at all.  They are singletons of the forest (every
+            // comparison with a NaN fails) whose size counter was preset to INT_MIN by the link kernel
+            if (isroot && sz < 0) { nolabel = true; isroot = false; iscand = false; }
         }
         // roots are counted in bits 0..19 (N < 2^20), candidates in bits 20..31
         const unsigned v = (isroot ? 1u : 0u) | (iscand ? (1u << 20) : 0u);
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) 
         const unsigned run_before = running_s;   // thread 0 advances it after the next barrier
         const unsigned chunk_tot = block_tot;
         const unsigned excl = run_before + warp_tot[wid] + incl - v;
-        if (nolabel) { B.lab[fo + q] = -1; root_cand[q] = -1; atomicOr(&ctl.flags, unsigned(SPX_FRAME_NONFINITE)); }
+        if (nolabel) { B.lab[fo + q] = -1; root_cand[q] = -2; atomicOr(&ctl.flags, unsigned(SPX_FRAME_NONFINITE)); }
         if (isroot) {
             B.lab[fo + q] = int(excl & 0xFFFFFu);
             int16_t rc = -1;
@@ -282,97 +283,110 @@ __global__ void __launch_bounds__(256) k_ccl_label(Params P, Buffers B) {
 // memory, and lanes 0..8 each carry one accumulator through the 32 staged products in order.  Lane 0 then solves
 // the 3x3 eigenproblem.  The time of the kernel is the longest chain: size x one dependent fp32 add.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kMomWarps = 4;
-constexpr int kMomBatch = 128;   // members per iteration (4 per lane)
+constexpr int kMomBatch = 128;   // members per batch (4 per producer lane)
+constexpr int kMomCands = 8;     // CTAs per frame; CTA c takes candidates c, c + kMomCands, ...
 
-__global__ void __launch_bounds__(kMomWarps * 32) k_moments_fit(Params P, Buffers B) {
-    __shared__ float s_prod[kMomWarps][2][kMomBatch * 9];
+// three warps per candidate: warps 1 and 2 (producers, even / odd batches) gather 128 members at a time -- coalesced
+// index loads, gathered xyz, each producer two of its own batches ahead -- and stage their nine products in shared
+// memory; warp 0 (consumer) does nothing but the ordered chain (one LDS + one dependent FADD per member on lanes
+// 0..8), so the chain runs at the latency of the add.
+__global__ void __launch_bounds__(96) k_moments_fit(Params P, Buffers B) {
+    __shared__ float s_prod[2][kMomBatch * 9];
     const int f = P.frame0 + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ci = blockIdx.x * kMomWarps + warp;
     FrameCtl &ctl = B.ctl[f];
-    if (ci >= ctl.n_cand) return;
-    Cand &cd = ctl.cand[ci];
-    const int size = cd.size;
+    const int n_cand = ctl.n_cand;
     const size_t fo = size_t(f) * P.N;
     const float *px = B.px + fo, *py = B.py + fo, *pz = B.pz + fo;
-    const int *idx = B.cand_idx + fo + cd.idx_off;
-    float accu = 0.0f;
-    // software pipeline, two register stages (A: even batches, B: odd batches): a stage's coordinates are reloaded
-    // for the batch two ahead right after its products are staged, so a gather has two chains of time to land and
-    // no register is moved while a load is pending; indices run two batches further ahead.
-    float xa[4], ya[4], za[4], xb[4], yb[4], zb[4];
-    int ia[4], ib[4];   // indices of the batches the stages will load next
-    auto gather = [&](int m, float &x, float &y, float &z) {
-        x = y = z = 0.f;
-        if (m < size) { const int p = idx[m]; x = px[p]; y = py[p]; z = pz[p]; }
-    };
+    for (int ci = blockIdx.x; ci < n_cand; ci += kMomCands) {
+        Cand &cd = ctl.cand[ci];
+        const int size = cd.size;
+        const int *idx = B.cand_idx + fo + cd.idx_off;
+        const int n_batches = (size + kMomBatch - 1) / kMomBatch;
+        float accu = 0.0f;
+        // producer state: two register stages (A: even batches, B: odd batches), indices two batches further ahead
+        float xa[4], ya[4], za[4], xb[4], yb[4], zb[4];
+        int ia[4], ib[4];
+        const int par = warp - 1;   // producer: parity of its batches
+        if (warp >= 1) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int m = j * 32 + lane;
-        gather(m, xa[j], ya[j], za[j]);
-        gather(kMomBatch + m, xb[j], yb[j], zb[j]);
-        ia[j] = (2 * kMomBatch + m < size) ? idx[2 * kMomBatch + m] : -1;
-        ib[j] = (3 * kMomBatch + m < size) ? idx[3 * kMomBatch + m] : -1;
-    }
-    auto stage = [&](int base, int buf, float (&x)[4], float (&y)[4], float (&z)[4], int (&inext)[4]) {
-        float *pr = s_prod[warp][buf];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float *q = pr + (j * 32 + lane) * 9;
-            q[0] = x[j] * x[j]; q[1] = x[j] * y[j]; q[2] = x[j] * z[j]; q[3] = y[j] * y[j]; q[4] = y[j] * z[j]; q[5] = z[j] * z[j];
-            q[6] = x[j]; q[7] = y[j]; q[8] = z[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {   // this stage's next batch is base + 2 batches; its indices were fetched earlier
-            const int p = inext[j];
-            x[j] = y[j] = z[j] = 0.f;
-            if (p >= 0) { x[j] = px[p]; y[j] = py[p]; z[j] = pz[p]; }
-            const int m4 = base + 4 * kMomBatch + j * 32 + lane;
-            inext[j] = m4 < size ? idx[m4] : -1;
-        }
-        __syncwarp();
-        const int cnt = min(kMomBatch, size - base);
-        if (lane < 9) {
-            const float *src = pr + lane;
-            if (cnt == kMomBatch) {
-#pragma unroll 32
-                for (int j = 0; j < kMomBatch; ++j) accu += src[j * 9];
-            } else {
-                for (int j = 0; j < cnt; ++j) accu += src[j * 9];
+            for (int j = 0; j < 4; ++j) {
+                const int m0 = par * kMomBatch + j * 32 + lane;        // its 1st batch
+                const int m1 = m0 + 2 * kMomBatch;                     // its 2nd batch
+                xa[j] = ya[j] = za[j] = xb[j] = yb[j] = zb[j] = 0.f;
+                if (m0 < size) { const int p = idx[m0]; xa[j] = px[p]; ya[j] = py[p]; za[j] = pz[p]; }
+                if (m1 < size) { const int p = idx[m1]; xb[j] = px[p]; yb[j] = py[p]; zb[j] = pz[p]; }
+                ia[j] = (m0 + 4 * kMomBatch < size) ? idx[m0 + 4 * kMomBatch] : -1;
+                ib[j] = (m1 + 4 * kMomBatch < size) ? idx[m1 + 4 * kMomBatch] : -1;
             }
         }
-    };
-    for (int base = 0; base < size; base += 2 * kMomBatch) {
-        stage(base, 0, xa, ya, za, ia);
-        if (base + kMomBatch < size) stage(base + kMomBatch, 1, xb, yb, zb, ib);
-    }
-    float acc[9];
+        auto produce = [&](int bt, float (&x)[4], float (&y)[4], float (&z)[4], int (&inext)[4]) {
+            float *pr = s_prod[bt & 1];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = __shfl_sync(SPX_FULL, accu, k);
-    if (lane == 0) {
-        const float cnt = float(size);
+            for (int j = 0; j < 4; ++j) {
+                float *q = pr + (j * 32 + lane) * 9;
+                q[0] = x[j] * x[j]; q[1] = x[j] * y[j]; q[2] = x[j] * z[j]; q[3] = y[j] * y[j]; q[4] = y[j] * z[j]; q[5] = z[j] * z[j];
+                q[6] = x[j]; q[7] = y[j]; q[8] = z[j];
+            }
 #pragma unroll
-        for (int k = 0; k < 9; ++k) acc[k] /= cnt;
-        float cov[9];
-        cov[0] = acc[0] - acc[6] * acc[6];
-        cov[1] = acc[1] - acc[6] * acc[7];
-        cov[2] = acc[2] - acc[6] * acc[8];
-        cov[4] = acc[3] - acc[7] * acc[7];
-        cov[5] = acc[4] - acc[7] * acc[8];
-        cov[8] = acc[5] - acc[8] * acc[8];
-        cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
-        float ev, vec[3];
-        eigen33_smallest(cov, ev, vec);
-        const float eig_sum = cov[0] + cov[4] + cov[8];
-        float curvature;
-        if (eig_sum != 0) curvature = fabsf(ev / eig_sum); else curvature = 0;
-        cd.vec[0] = vec[0]; cd.vec[1] = vec[1]; cd.vec[2] = vec[2];
-        cd.eigenvalue = ev;
-        cd.centroid[0] = acc[6]; cd.centroid[1] = acc[7]; cd.centroid[2] = acc[8];
-        cd.curvature = curvature;
+            for (int j = 0; j < 4; ++j) {   // reload this stage for batch bt + 4 (this producer's batch after next); indices of bt + 8
+                const int p = inext[j];
+                x[j] = y[j] = z[j] = 0.f;
+                if (p >= 0) { x[j] = px[p]; y[j] = py[p]; z[j] = pz[p]; }
+                const int m8 = (bt + 8) * kMomBatch + j * 32 + lane;
+                inext[j] = m8 < size ? idx[m8] : -1;
+            }
+        };
+        // batch bt is produced while batch bt - 1 is consumed
+        if (warp == 1) produce(0, xa, ya, za, ia);
+        __syncthreads();
+        for (int bt = 0; bt < n_batches; ++bt) {
+            if (warp >= 1) {
+                // batch bt + 1 belongs to the producer of its parity; that producer alternates its stages A, B
+                const int nb = bt + 1;
+                if (nb < n_batches && (nb & 1) == par) { if ((nb >> 1) & 1) produce(nb, xb, yb, zb, ib); else produce(nb, xa, ya, za, ia); }
+            } else if (lane < 9) {
+                const float *src = s_prod[bt & 1] + lane;
+                const int cnt = min(kMomBatch, size - bt * kMomBatch);
+                if (cnt == kMomBatch) {
+#pragma unroll 32
+                    for (int j = 0; j < kMomBatch; ++j) accu += src[j * 9];
+                } else {
+                    for (int j = 0; j < cnt; ++j) accu += src[j * 9];
+                }
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+            float acc[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) cd.cov[k] = cov[k];
+            for (int k = 0; k < 9; ++k) acc[k] = __shfl_sync(SPX_FULL, accu, k);
+            if (lane == 0) {
+                const float cnt = float(size);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc[k] /= cnt;
+                float cov[9];
+                cov[0] = acc[0] - acc[6] * acc[6];
+                cov[1] = acc[1] - acc[6] * acc[7];
+                cov[2] = acc[2] - acc[6] * acc[8];
+                cov[4] = acc[3] - acc[7] * acc[7];
+                cov[5] = acc[4] - acc[7] * acc[8];
+                cov[8] = acc[5] - acc[8] * acc[8];
+                cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+                float ev, vec[3];
+                eigen33_smallest(cov, ev, vec);
+                const float eig_sum = cov[0] + cov[4] + cov[8];
+                float curvature;
+                if (eig_sum != 0) curvature = fabsf(ev / eig_sum); else curvature = 0;
+                cd.vec[0] = vec[0]; cd.vec[1] = vec[1]; cd.vec[2] = vec[2];
+                cd.eigenvalue = ev;
+                cd.centroid[0] = acc[6]; cd.centroid[1] = acc[7]; cd.centroid[2] = acc[8];
+                cd.curvature = curvature;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) cd.cov[k] = cov[k];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -431,7 +445,7 @@ __global__ void __launch_bounds__(256) k_pid_init(Params P, Buffers B) {
     if (q >= P.N) return;
     const size_t fo = size_t(f) * P.N;
     // -1: labelled but not part of a plane (refine may claim it); -2: a point PCL left unlabelled (non-finite)
-    B.pid[fo + q] = isfinite(B.px[fo + q]) ? int8_t(B.root_model[fo + B.parent[fo + q]]) : int8_t(-2);
+    B.pid[fo + q] = int8_t(B.root_model[fo + B.parent[fo + q]]);   // k_ccl_rank left -2 at the roots of unlabelled points
 }
 
 }  // namespace spx
