@@ -129,6 +129,7 @@ constexpr int kBorderWarps = 4;
 
 __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__restrict__ depth, Params P, Buffers B) {
     __shared__ float s_win[kBorderWarps][2][32][21];
+    __shared__ int4 s_geo[kBorderWarps][32];
     __shared__ int s_fail, s_item;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n_items = B.work2[0];
@@ -171,6 +172,16 @@ __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__res
             int num = 0, nan = 0;
             float res = 0.f;
             // window row t of point q: image row j0_q + t while that is < ve_q (at most 21 rows)
+            // window geometry of the warp's 32 points, staged once: (i0, j0, columns, rows) of every window
+            __syncwarp();
+            {
+                int ncol = 0, nrow = 0;
+                if (live) {
+                    for (int k = 0; k < 21; ++k) { if (i0 + k < ue) ++ncol; if (j0 + k < ve) ++nrow; }
+                }
+                s_geo[wid][lane] = make_int4(i0, j0, ncol, nrow);   // a dead point has an empty window
+            }
+            __syncwarp();
             auto load_row = [&](int t, int buf) {
                 // 16 loads are issued before the first of them is stored, so their latencies overlap
 #pragma unroll
@@ -179,19 +190,19 @@ __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__res
                     bool wr[16];
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
-                        const int q = q0 + k;
-                        const int qi0 = __shfl_sync(SPX_FULL, i0, q), qj = __shfl_sync(SPX_FULL, j0, q) + t;
-                        const float que = __shfl_sync(SPX_FULL, ue, q), qve = __shfl_sync(SPX_FULL, ve, q);
-                        const bool qlive = __shfl_sync(SPX_FULL, live ? 1 : 0, q) != 0;
-                        wr[k] = qlive && (qj < qve) && lane < 21;
+                        const int4 gq = s_geo[wid][q0 + k];
+                        const int qj = gq.y + t, i = gq.x + lane;
+                        wr[k] = t < gq.w && lane < 21;
                         d[k] = 0.0f;   // invalid sample
-                        const int i = qi0 + lane;
-                        if (wr[k] && i < que) {
-                            const long long fidx = (long long)qj * P.cols + i;   // flat index on the continuous cv::Mat
-                            if (fidx >= 0 && fidx < total) {
-                                int rr = qj, cc = i;
-                                if (i < 0 || i >= P.cols) { rr = int(fidx / P.cols); cc = int(fidx - (long long)rr * P.cols); }
-                                d[k] = img[size_t(rr) * pitch_f + cc];
+                        if (wr[k] && lane < gq.z) {
+                            if (qj >= 0 && qj < P.rows && i >= 0 && i < P.cols) {
+                                d[k] = img[qj * pitch_f + i];
+                            } else {
+                                const long long fidx = (long long)qj * P.cols + i;   // flat index on the continuous cv::Mat
+                                if (fidx >= 0 && fidx < total) {
+                                    const int rr = int(fidx / P.cols), cc = int(fidx - (long long)rr * P.cols);
+                                    d[k] = img[size_t(rr) * pitch_f + cc];
+                                }
                             }
                         }
                     }
