@@ -51,6 +51,7 @@ struct spx_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // frame groups: internal streams + per group events (start, end of the plane section, end of the supposed-plane section)
     int n_streams = 1, min_group = 32, last_groups = 1;
+    int refine_fast_max = 700;  // batches of at most this many frames use k_refine2
     bool use_prio = false;   // back stream with higher priority: measured slower (co-running kernels slow each other), kept as a knob
     std::vector<cudaStream_t> g_streams;      // front: upload, chamfer, normals (low priority)
     std::vector<cudaStream_t> g_back;         // back: everything after the normals (high priority: it is what frees a group)
@@ -200,7 +201,9 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
               const HostSrc &src) {
     Params P = c->P;
     P.frame0 = f0; P.n_frames = ng;
-    P.refine_fast = (ng <= 64 && P.h <= kRefMaxH) ? 1 : 0;   // small launches are latency bound: parallelism inside the frame
+    // k_refine2 (a CTA per frame) has the shorter critical path but executes ~1.8x the instructions of k_refine (a warp per
+    // frame): it wins while the whole batch fits the machine in about one wave (measured cross-over ~700 frames)
+    P.refine_fast = (c->P.n_frames <= c->refine_fast_max && P.h <= kRefMaxH) ? 1 : 0;   // small launches are latency bound: parallelism inside the frame
     Buffers B = c->B;
     B.work = c->B.work + size_t(g) * c->work_stride;
     B.work2 = c->B.work2 + size_t(g) * c->work2_stride;
@@ -550,6 +553,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     for (int i = 0; i < 4; ++i) SPX_CK_CREATE(cudaEventCreate(&c->ev[i]));
     c->n_streams = cfg->n_streams > 0 ? (cfg->n_streams > 32 ? 32 : cfg->n_streams) : 8;
     c->min_group = 32;
+    if (const char *e = std::getenv("SPX_REFINE_FAST_MAX")) c->refine_fast_max = std::atoi(e);   // tuning knob
     if (const char *e = std::getenv("SPX_PRIO")) c->use_prio = std::atoi(e) != 0;   // tuning knob
     if (const char *e = std::getenv("SPX_MIN_GROUP")) { const int v = std::atoi(e); if (v > 0) c->min_group = v; }   // tuning knob
     int prio_lo = 0, prio_hi = 0;
