@@ -30,6 +30,8 @@ struct RefineSmem {
     int8_t cmA[kMaxW];                 // model claimed sideways by claimer column c  (pass 1: right, pass 2: left)
 };
 
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
+
 // point-to-plane test of PlaneRefinementComparator::compare (fp32 products and sums, no contraction)
 __device__ __forceinline__ bool refine_dist_ok(const float *cf, float x, float y, float z) {
     const float v = cf[0] * x + cf[1] * y + cf[2] * z + cf[3];
@@ -263,8 +265,6 @@ struct Refine2Smem {
     uint8_t  wrapcand[kRefMaxH];      // rows whose first visited pixel is free and close to some model plane
     int      total_steps;
 };
-
-__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 template <int NW, bool kReverse>
 __device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, unsigned *Vb, const Params &P, const float *__restrict__ px,

@@ -7,6 +7,20 @@ from tests.parity import compare_frame
 
 pytestmark = pytest.mark.gpu
 
+
+def large_batch_extractor(**kw):
+    """A context that uses the large-batch kernel variants (one-warp-per-frame refine) regardless of the batch size."""
+    import os
+    old = os.environ.get("SPX_REFINE_FAST_MAX")
+    os.environ["SPX_REFINE_FAST_MAX"] = "0"
+    try:
+        return api.PlaneExtractor(**kw)
+    finally:
+        if old is None:
+            del os.environ["SPX_REFINE_FAST_MAX"]
+        else:
+            os.environ["SPX_REFINE_FAST_MAX"] = old
+
 FRAMES = [0, 80, 200, 240, 280, 600, 800, 880]
 
 
@@ -100,7 +114,7 @@ def test_frame_groups_host_and_device_paths_agree():
     ext.extract_device(dev.data_ptr(), n, 480, 640)
     devres = ext.fetch()
     # one group of 100 frames: the large-launch variants (one-warp refine with the plane ids taken from the forest)
-    big = api.PlaneExtractor(max_frames=n, n_streams=1)
+    big = large_batch_extractor(max_frames=n, n_streams=1)
     bigres = big.extract_batch(d)
     assert np.array_equal(bigres.frames, host.frames) and np.array_equal(bigres.planes, host.planes)
     assert np.array_equal(bigres.points, host.points) and np.array_equal(bigres.boundary, host.boundary)
@@ -155,6 +169,29 @@ def test_min_size_1000_icl_config(ext, seq, oracle_lib):
     orc = oracle_lib.Oracle(min_size=1000).run(d)
     compare_frame(e2, orc, d, fp)
     e2.close()
+
+
+@pytest.mark.parametrize("k", [1, 2, 4, 7])
+def test_large_batch_kernels_against_oracle(seq, oracle_lib, k):
+    """the kernel variants a 1000-frame batch uses (one-warp-per-frame refine), with the parity taps on"""
+    e = large_batch_extractor(debug=True)
+    d = scenes.add_noise(seq[k], FRAMES[k]) if k == 4 else seq[k]
+    fp = e.extract(d)
+    orc = oracle_lib.Oracle().run(d)
+    rep = compare_frame(e, orc, d, fp)
+    assert rep["labels_bit_exact"] and rep.get("models_bit_exact", True), rep
+    e.close()
+
+
+def test_large_batch_kernels_720p(oracle_lib, realsense_frames):
+    it = scenes.REALSENSE
+    d = scenes.add_noise(realsense_frames[1], 101, "realsense")
+    kw = dict(fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy, max_x=float(it.width), max_y=float(it.height))
+    e = large_batch_extractor(debug=True, max_rows=720, max_cols=1280, **kw)
+    fp = e.extract(d)
+    orc = oracle_lib.Oracle(**kw).run(d)
+    compare_frame(e, orc, d, fp)
+    e.close()
 
 
 def test_degenerate_inputs(ext, oracle_lib):
@@ -225,7 +262,7 @@ def test_non_finite_depth(oracle_lib, seq):
     # the same frame inside one large launch (one-warp refine kernel)
     batch = np.repeat(seq[1][None], 70, axis=0)
     batch[3] = d
-    big = api.PlaneExtractor(max_frames=70, n_streams=1)
+    big = large_batch_extractor(max_frames=70, n_streams=1)
     res = big.extract_batch(batch)
     b = res.frame(3)
     assert b.mnPlaneNum == fp.mnPlaneNum and np.array_equal(b.mvPlaneCoefficients.view(np.uint32), fp.mvPlaneCoefficients.view(np.uint32))
