@@ -125,57 +125,73 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(Params P, Buffers B) {
     if (valid && (__ffs(peers) - 1) == int(threadIdx.x & 31)) atomicAdd(B.cnt + fo + root, __popc(peers));
 }
 
-// K4d: one CTA per frame, one pass over the frame in 1024-pixel chunks (raster order).
+// K4d: one CTA per frame, one pass over the frame in 2048-pixel chunks (raster order).
 //  (1) exclusive prefix count of roots = PCL's dense label of each component; components with size > Plane.MinSize
 //      become plane candidates, in label order, and get the offset of their index list;
 //  (2) order-preserving multi-way compaction: every pixel of a candidate component is appended to that candidate's
 //      raster-ordered index list (label_indices[l] of PCL) and learns its position in it.  A component's root is its
 //      first raster pixel, so the candidate is always known before (or in the same chunk as) its members.
-constexpr int kRankThreads = 1024;
+// Every thread owns 4 consecutive pixels of a 2048-pixel chunk, so one block scan and one set of barriers serve four
+// pixels, and the ranking of a candidate's members inside a warp is a small-count scan per candidate present.
+constexpr int kRankThreads = 512;
+constexpr int kRankPer = 4;
+constexpr int kRankChunk = kRankThreads * kRankPer;
+constexpr int kRankWarps = kRankThreads / 32;
 
 __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) {
-    __shared__ unsigned warp_tot[32];
+    __shared__ unsigned warp_tot[kRankWarps];
     __shared__ unsigned running_s, block_tot;
     __shared__ int s_off[SPX_MAX_CAND];          // start of the candidate's index list
     __shared__ int s_cnt[SPX_MAX_CAND];          // members emitted so far
     __shared__ int s_size[SPX_MAX_CAND];
-    __shared__ int s_wcnt[SPX_MAX_CAND][32];     // members of candidate c found by warp w in this chunk -> their base
+    __shared__ int s_wcnt[SPX_MAX_CAND][kRankWarps];   // members of candidate c found by warp w in this chunk -> their base
     __shared__ int s_ncand, s_noff;
     const int f = P.frame0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t fo = size_t(f) * P.N;
     FrameCtl &ctl = B.ctl[f];
     const int *parent = B.parent + fo;
-    int16_t *root_cand = B.root_model + fo;      // at roots: candidate index or -1 (re-used for model ids by k_models)
+    const int *cntp = B.cnt + fo;
+    int16_t *root_cand = B.root_model + fo;      // at roots: candidate index, -1, or -2 for an unlabelled point (re-used for model ids by k_models)
     int *cand_idx = B.cand_idx + fo;
     int *pos = B.pos + fo;
     if (tid == 0) { running_s = 0; s_ncand = 0; s_noff = 0; }
     __syncthreads();
     // software pipeline: the next chunk's forest entries and sizes are loaded while this chunk is processed, and the
     // candidate id of a pixel whose root lies in an EARLIER chunk (final by then) is fetched ahead as well
-    int root_n = (tid < P.N) ? parent[tid] : -1;
-    int cnt_n = (tid < P.N) ? B.cnt[fo + tid] : 0;
-    int cand_n = -1;
-    for (int base = 0; base < P.N; base += kRankThreads) {
-        const int q = base + tid;
-        const int root = root_n, sz_q = cnt_n, cand_pre = cand_n;
-        {
-            const int qn = q + kRankThreads;
-            root_n = (qn < P.N) ? parent[qn] : -1;
-            cnt_n = (qn < P.N) ? B.cnt[fo + qn] : 0;
-        }
-        bool isroot = false, iscand = false;
-        int sz = 0;
-        bool nolabel = false;
-        if (q < P.N) {
-            isroot = root == q;
-            if (isroot) { sz = sz_q; iscand = unsigned(sz) > unsigned(P.min_size); }
-            // PCL skips points with a non-finite x: they get no label at all.  They are singletons of the forest (every
-            // comparison with a NaN fails) whose size counter was preset to INT_MIN by the link kernel
-            if (isroot && sz < 0) { nolabel = true; isroot = false; iscand = false; }
+    int root_n[kRankPer], cnt_n[kRankPer], cand_n[kRankPer];
+#pragma unroll
+    for (int j = 0; j < kRankPer; ++j) {
+        const int q = tid * kRankPer + j;
+        root_n[j] = q < P.N ? parent[q] : -1;
+        cnt_n[j] = q < P.N ? cntp[q] : 0;
+        cand_n[j] = -1;
+    }
+    for (int base = 0; base < P.N; base += kRankChunk) {
+        const int q0 = base + tid * kRankPer;
+        int root[kRankPer], sz[kRankPer], cand_pre[kRankPer];
+#pragma unroll
+        for (int j = 0; j < kRankPer; ++j) {
+            root[j] = root_n[j]; sz[j] = cnt_n[j]; cand_pre[j] = cand_n[j];
+            const int qn = q0 + kRankChunk + j;
+            root_n[j] = qn < P.N ? parent[qn] : -1;
+            cnt_n[j] = qn < P.N ? cntp[qn] : 0;
         }
         // roots are counted in bits 0..19 (N < 2^20), candidates in bits 20..31
-        const unsigned v = (isroot ? 1u : 0u) | (iscand ? (1u << 20) : 0u);
-        unsigned incl = v;
+        unsigned v[kRankPer], vt = 0u;
+        bool nolabel[kRankPer];
+#pragma unroll
+        for (int j = 0; j < kRankPer; ++j) {
+            const int q = q0 + j;
+            bool isroot = q < P.N && root[j] == q;
+            // PCL skips points with a non-finite x: they get no label at all.  They are singletons of the forest (every
+            // comparison with a NaN fails) whose size counter was preset to INT_MIN by the link kernel
+            nolabel[j] = isroot && sz[j] < 0;
+            if (nolabel[j]) isroot = false;
+            const bool iscand = isroot && unsigned(sz[j]) > unsigned(P.min_size);
+            v[j] = (isroot ? 1u : 0u) | (iscand ? (1u << 20) : 0u);
+            vt += v[j];
+        }
+        unsigned incl = vt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned t = __shfl_up_sync(SPX_FULL, incl, o);
@@ -184,35 +200,40 @@ __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) 
         if (lane == 31) warp_tot[wid] = incl;
         __syncthreads();
         if (wid == 0) {
-            const unsigned t = warp_tot[lane];
-            unsigned s = t;
+            const unsigned t = lane < kRankWarps ? warp_tot[lane] : 0u;
+            unsigned sc = t;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const unsigned u = __shfl_up_sync(SPX_FULL, s, o);
-                if (lane >= o) s += u;
+                const unsigned u = __shfl_up_sync(SPX_FULL, sc, o);
+                if (lane >= o) sc += u;
             }
-            warp_tot[lane] = s - t;   // exclusive prefix of the warp totals
-            if (lane == 31) block_tot = s;
+            if (lane < kRankWarps) warp_tot[lane] = sc - t;   // exclusive prefix of the warp totals
+            if (lane == 31) block_tot = sc;
         }
         __syncthreads();
         const unsigned run_before = running_s;   // thread 0 advances it after the next barrier
         const unsigned chunk_tot = block_tot;
-        const unsigned excl = run_before + warp_tot[wid] + incl - v;
-        if (nolabel) { B.lab[fo + q] = -1; root_cand[q] = -2; atomicOr(&ctl.flags, unsigned(SPX_FRAME_NONFINITE)); }
-        if (isroot) {
-            B.lab[fo + q] = int(excl & 0xFFFFFu);
-            int16_t rc = -1;
-            if (iscand) {
-                const unsigned k = excl >> 20;
-                if (k < SPX_MAX_CAND) {
-                    ctl.cand[k].root = q; ctl.cand[k].label = int(excl & 0xFFFFFu); ctl.cand[k].size = sz;
-                    s_size[k] = sz;
-                    rc = int16_t(k);
-                } else {
-                    atomicOr(&ctl.flags, unsigned(SPX_FRAME_OVERFLOW));
+        unsigned excl = run_before + warp_tot[wid] + incl - vt;
+#pragma unroll
+        for (int j = 0; j < kRankPer; ++j) {
+            const int q = q0 + j;
+            if (nolabel[j]) { B.lab[fo + q] = -1; root_cand[q] = -2; atomicOr(&ctl.flags, unsigned(SPX_FRAME_NONFINITE)); }
+            if (v[j] & 1u) {
+                B.lab[fo + q] = int(excl & 0xFFFFFu);
+                int16_t rc = -1;
+                if (v[j] >> 20) {
+                    const unsigned k = excl >> 20;
+                    if (k < SPX_MAX_CAND) {
+                        ctl.cand[k].root = q; ctl.cand[k].label = int(excl & 0xFFFFFu); ctl.cand[k].size = sz[j];
+                        s_size[k] = sz[j];
+                        rc = int16_t(k);
+                    } else {
+                        atomicOr(&ctl.flags, unsigned(SPX_FRAME_OVERFLOW));
+                    }
                 }
+                root_cand[q] = rc;
             }
-            root_cand[q] = rc;
+            excl += v[j];
         }
         __syncthreads();
         int nc_now = int((run_before + chunk_tot) >> 20);
@@ -223,19 +244,45 @@ __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) 
             s_noff = off; s_ncand = nc_now;
             running_s = run_before + chunk_tot;
         }
-        for (int i = tid; i < nc_now * 32; i += kRankThreads) s_wcnt[i >> 5][i & 31] = 0;
+        for (int i = tid; i < nc_now * kRankWarps; i += kRankThreads) s_wcnt[i / kRankWarps][i % kRankWarps] = 0;
         __syncthreads();
-        // every root below base + kRankThreads has its candidate id in memory now
-        cand_n = (root_n >= 0 && root_n < base + kRankThreads) ? int(root_cand[root_n]) : -1;
+        // every root below base + kRankChunk has its candidate id in memory now
+#pragma unroll
+        for (int j = 0; j < kRankPer; ++j)
+            cand_n[j] = (root_n[j] >= 0 && root_n[j] < base + kRankChunk) ? int(root_cand[root_n[j]]) : -1;
         if (nc_now > 0) {   // uniform over the CTA
             // roots of earlier chunks were ranked before their id was prefetched; same-chunk roots are read now
-            const int c = (q < P.N) ? ((root < base) ? cand_pre : int(root_cand[root])) : -1;
-            const unsigned peers = __match_any_sync(SPX_FULL, c);
-            const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
-            if (c >= 0 && rank_in_warp == 0) s_wcnt[c][wid] = __popc(peers);
+            int c[kRankPer], rk[kRankPer];
+#pragma unroll
+            for (int j = 0; j < kRankPer; ++j) {
+                c[j] = (q0 + j < P.N) ? ((root[j] < base) ? cand_pre[j] : int(root_cand[root[j]])) : -1;
+                rk[j] = 0;
+            }
+            // rank inside the warp, one candidate value at a time (ascending): lane counts of 0..4, prefix over the lanes
+            int donebelow = -1;   // candidates <= donebelow are ranked
+            while (true) {
+                int cmin = INT_MAX;
+#pragma unroll
+                for (int j = 0; j < kRankPer; ++j) if (c[j] > donebelow && c[j] < cmin) cmin = c[j];
+                const int wmin = __reduce_min_sync(SPX_FULL, cmin);
+                if (wmin == INT_MAX) break;
+                int n_me = 0;
+#pragma unroll
+                for (int j = 0; j < kRankPer; ++j) { if (c[j] == wmin) { rk[j] = n_me; ++n_me; } }
+                int sc = n_me;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(SPX_FULL, sc, o);
+                    if (lane >= o) sc += u;
+                }
+#pragma unroll
+                for (int j = 0; j < kRankPer; ++j) if (c[j] == wmin) rk[j] += sc - n_me;
+                if (lane == 31) s_wcnt[wmin][wid] = sc;
+                donebelow = wmin;
+            }
             __syncthreads();
-            for (int cc = wid; cc < nc_now; cc += 32) {
-                const int t = s_wcnt[cc][lane];
+            for (int cc = wid; cc < nc_now; cc += kRankWarps) {
+                const int t = lane < kRankWarps ? s_wcnt[cc][lane] : 0;
                 int sc = t;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -243,15 +290,18 @@ __global__ void __launch_bounds__(kRankThreads) k_ccl_rank(Params P, Buffers B) 
                     if (lane >= o) sc += u;
                 }
                 const int b0 = s_cnt[cc];
-                s_wcnt[cc][lane] = b0 + sc - t;
+                if (lane < kRankWarps) s_wcnt[cc][lane] = b0 + sc - t;
                 __syncwarp();
                 if (lane == 31) s_cnt[cc] = b0 + sc;
             }
             __syncthreads();
-            if (c >= 0) {
-                const int k = s_wcnt[c][wid] + rank_in_warp;
-                cand_idx[s_off[c] + k] = q;
-                pos[q] = k;
+#pragma unroll
+            for (int j = 0; j < kRankPer; ++j) {
+                if (c[j] >= 0) {
+                    const int k = s_wcnt[c[j]][wid] + rk[j];
+                    cand_idx[s_off[c[j]] + k] = q0 + j;
+                    pos[q0 + j] = k;
+                }
             }
             __syncthreads();
         }

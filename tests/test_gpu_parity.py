@@ -271,3 +271,25 @@ def test_non_finite_depth(oracle_lib, seq):
     assert not (res.frame(2).flags & api.SPX_FRAME_NONFINITE)
     big.close()
     ext.close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_clutter_scenes(oracle_lib, seed):
+    """Randomised sweep: the box room plus a random clutter field (tilted patches -> many small planes, depth edges,
+    supposed planes), random pose, every third case with sensor noise; alternating small-/large-batch kernel variants.
+    Everything must be bit-identical to the oracle, down to the order of the inlier lists."""
+    rng = np.random.default_rng(1000 + seed)
+    rects = np.concatenate([scenes.boxroom_rects(), scenes.clutter_rects(n=int(rng.integers(5, 40)), seed=int(rng.integers(1 << 30)))])
+    pose = scenes.poses(1000, seed=int(rng.integers(1 << 30)))[[int(rng.integers(1000))]]
+    d = scenes.render(rects, pose, scenes.TUM1)[0]
+    if seed % 3 == 2:
+        d = scenes.add_noise(d, seed)
+    if seed % 4 == 1:
+        d[rng.integers(0, 480, 40), rng.integers(0, 640, 40)] = 0.0       # isolated dropouts
+    make = large_batch_extractor if seed % 2 else api.PlaneExtractor
+    e = make(debug=True)
+    fp = e.extract(d)
+    orc = oracle_lib.Oracle().run(d)
+    rep = compare_frame(e, orc, d, fp)
+    assert rep["normals_bit_exact"] and rep["labels_bit_exact"] and rep.get("models_bit_exact", True), rep
+    e.close()
