@@ -148,7 +148,7 @@ def oracle_config(res):
     return pyoracle.default_config(fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy, max_x=float(it.width), max_y=float(it.height))
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """CPU arm: the oracle port of the reference's PCL path, all host threads, bounded sample per step."""
     if rank != 0:
         return
@@ -177,7 +177,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "planes_per_frame": planes / (args.steps * n),
     }
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
 
 
 def workload_name(args):
@@ -186,7 +186,32 @@ def workload_name(args):
     return f"{args.frames}-frame synthetic 640x480 box-room orbit (BASELINE configs[1]), batched plane extraction"
 
 
+class _StdoutToStderr:
+    """Everything libraries print on fd 1 (NCCL's version banner, ...) goes to stderr; the JSON line is the only thing
+    that reaches the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self._saved, (line + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 def main():
+    with _StdoutToStderr() as out:
+        _main(out)
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -206,7 +231,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -371,6 +396,10 @@ def main():
             "path": {"algorithmic_bytes_per_frame": path_bytes,
                      "achieved": (value / world) * path_bytes / 1e9, "frac": (value / world) * path_bytes / 1e9 / peak},
             "kernels_ms": {k: round(v, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1])},
+            "kernels": [{"kernel": k, "ms": round(v, 4), "algorithmic_bytes_per_frame": kbytes.get(k, 0),
+                         "achieved_gbs": round(kbytes.get(k, 0) * F / (v * 1e-3) / 1e9, 1) if v > 0 else None,
+                         "frac": round(kbytes.get(k, 0) * F / (v * 1e-3) / 1e9 / peak, 4) if v > 0 else None}
+                        for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1])],
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -403,7 +432,7 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
         }
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     ext.close()
     if ext1 is not None:
         ext1.close()
