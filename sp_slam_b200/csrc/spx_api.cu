@@ -556,6 +556,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     c->n_streams = cfg->n_streams > 0 ? (cfg->n_streams > 32 ? 32 : cfg->n_streams) : 8;
     c->min_group = 32;
     if (const char *e = std::getenv("SPX_REFINE_FAST_MAX")) c->refine_fast_max = std::atoi(e);   // tuning knob
+    if (const char *e = std::getenv("SPX_LINES_GLOBAL")) c->P.lines_in_global = std::atoi(e) != 0 ? 1 : 0;   // test knob
     if (const char *e = std::getenv("SPX_PRIO")) c->use_prio = std::atoi(e) != 0;   // tuning knob
     if (const char *e = std::getenv("SPX_MIN_GROUP")) { const int v = std::atoi(e); if (v > 0) c->min_group = v; }   // tuning knob
     int prio_lo = 0, prio_hi = 0;

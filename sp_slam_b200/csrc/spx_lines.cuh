@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kLineThreads) k_lines(const float *__restrict_
         const int code = B.work[2 + it];
         const int f = code / SPX_MAX_MODELS, m = code - f * SPX_MAX_MODELS;
         const Model &M = B.ctl[f].models[m];
-        if (M.n_contour <= kLineCap) {
+        if (M.n_contour <= kLineCap && !P.lines_in_global) {
             lines_item<uint16_t, true>(S, A, sh, inl, depth, P, B, f, m);
         } else {
             const size_t co = size_t(f) * P.contour_cap + M.contour_off;

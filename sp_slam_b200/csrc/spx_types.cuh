@@ -12,6 +12,7 @@ struct Params {
     size_t pitch;          // bytes
     size_t frame_stride;   // bytes
     int n_frames;          // frames of this launch group
+    int lines_in_global;   // test knob: run every k_lines item on the global-memory path (contours beyond the smem buffer use it)
     int refine_fast;       // 1: k_refine2 (a CTA per frame) where its table fits; 0: k_refine (a warp per frame) for all
     int frame0;            // first frame of the group (frames are independent: groups run on separate streams)
     // organized cloud (src/Frame.cc:856-874)

@@ -8,6 +8,20 @@ from tests.parity import compare_frame
 pytestmark = pytest.mark.gpu
 
 
+def extractor_with_env(env: dict, **kw):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return api.PlaneExtractor(**kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
 def large_batch_extractor(**kw):
     """A context that uses the large-batch kernel variants (one-warp-per-frame refine) regardless of the batch size."""
     import os
@@ -292,4 +306,15 @@ def test_random_clutter_scenes(oracle_lib, seed):
     orc = oracle_lib.Oracle().run(d)
     rep = compare_frame(e, orc, d, fp)
     assert rep["normals_bit_exact"] and rep["labels_bit_exact"] and rep.get("models_bit_exact", True), rep
+    e.close()
+
+
+@pytest.mark.parametrize("k", [2, 3, 7])
+def test_line_fits_on_the_global_memory_path(seq, oracle_lib, k):
+    """contours longer than the shared-memory buffer of k_lines are fitted from global memory; force that path"""
+    e = extractor_with_env({"SPX_LINES_GLOBAL": "1"}, debug=True)
+    fp = e.extract(seq[k])
+    orc = oracle_lib.Oracle().run(seq[k])
+    rep = compare_frame(e, orc, seq[k], fp)
+    assert rep.get("models_bit_exact", True) and len(orc.line_recs()) > 0
     e.close()
