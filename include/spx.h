@@ -116,6 +116,20 @@ int spx_extract(spx_ctx *ctx, const float *depth, int rows, int cols, size_t pit
 int spx_extract_batch(spx_ctx *ctx, const float *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
                       size_t frame_stride_bytes, spx_batch_result *out);
 
+/* Host input, how the depth gets to the device.  The organized cloud samples every Cloud.Dis-th row and column
+ * (src/Frame.cc:857-872); full-resolution depth is read only by IsBorderPoint's 21x21 windows around line points
+ * (src/Frame.cc:1038-1052).  When the caller's image is page-locked (cudaHostAlloc, cudaHostRegister or
+ * spx_host_register below) the library uploads only the sampled rows (1/Cloud.Dis of the bytes, one strided copy) and the
+ * border tests read their windows in place over PCIe; a pageable image is uploaded whole.  Results are identical.
+ * mode 0 = automatic (default), 1 = always upload the whole image, 2 = sparse whenever the image is page-locked. */
+int spx_set_upload_mode(spx_ctx *ctx, int mode);
+/* page-lock / release a caller-owned host buffer (e.g. the cv::Mat data of the depth images a loader recycles) */
+int spx_host_register(void *ptr, size_t bytes);
+int spx_host_unregister(void *ptr);
+/* bytes moved by the last host-input extract: uploaded by copies, read in place by the border tests, results copied back */
+int spx_get_transfer_bytes(const spx_ctx *ctx, unsigned long long *h2d_copied, unsigned long long *h2d_in_place,
+                           unsigned long long *d2h);
+
 /* The same from the raw 16-bit depth image (CV_16U, e.g. a TUM PNG): replaces, in addition, the conversion
  * imDepth.convertTo(imDepth, CV_32F, mDepthMapFactor) of Tracking::GrabImageRGBD (src/Tracking.cc:230-231; the factor
  * is 1.0f / DepthMapFactor, src/Tracking.cc:142-146).  Half the upload; depth = float(d) * depth_map_factor on the device. */
@@ -165,6 +179,12 @@ int spx_set_profile(spx_ctx *ctx, int on);
 int spx_get_kernel_times(spx_ctx *ctx, const char **names, float *ms, int cap, int *n);
 /* the same launches as a timeline: start / end of launch k in ms after the beginning of the extract call */
 int spx_get_kernel_timeline(spx_ctx *ctx, const char **names, float *start_ms, float *end_ms, int cap, int *n);
+
+/* host-input calls (spx_extract_batch / _u16): when each frame group of the last call reached five points, in ms after
+ * the call began: [7g+0] group started, [7g+1] its depth is on the device, [7g+2] real planes final (post-filter),
+ * [7g+3] its last kernel ended, [7g+4] its results are on the host (device clock); [7g+5] the host began to enqueue the
+ * group, [7g+6] the host saw the group's totals (host clock) */
+int spx_get_group_timeline(spx_ctx *ctx, float *t_ms, int cap_groups, int *n_groups);
 
 /* ---- debug taps for the parity tests: intermediates of frame `frame` of the last extract call, copied to host.
  * They need spx_set_debug(ctx, 1) BEFORE the extract call (it adds the per-pixel label kernel to the schedule). ---- */

@@ -15,6 +15,11 @@ from dataclasses import dataclass
 
 import numpy as np
 
+# The library runs a batch as frame groups on their own CUDA streams plus an upload and a download stream; streams beyond
+# the driver's hardware-queue count (default 8) share a queue and serialise.  The variable is read when the CUDA context
+# is created (spx_create sets it too, for processes in which the library is the first CUDA user).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspx.so")
 
@@ -41,6 +46,8 @@ EXPORTS = (
     "spx_set_profile", "spx_get_kernel_times", "spx_get_kernel_timeline", "spx_get_device_results",
     "spx_get_cloud", "spx_get_distance_map", "spx_get_normals", "spx_get_labels_raw", "spx_get_plane_ids",
     "spx_get_models", "spx_get_model_inliers", "spx_get_model_contour", "spx_get_lines",
+    "spx_set_upload_mode", "spx_host_register", "spx_host_unregister", "spx_get_transfer_bytes",
+    "spx_get_group_timeline",
 )
 
 
@@ -122,10 +129,29 @@ def lib():
         L.spx_get_model_inliers.argtypes = [vp, i32, i32, vp]
         L.spx_get_model_contour.argtypes = [vp, i32, i32, vp]
         L.spx_get_lines.argtypes = [vp, i32, vp, C.POINTER(i32)]
+        L.spx_get_group_timeline.argtypes = [vp, vp, i32, C.POINTER(i32)]
+        L.spx_set_upload_mode.argtypes = [vp, i32]
+        L.spx_host_register.argtypes = [vp, sz]
+        L.spx_host_unregister.argtypes = [vp]
+        u64p = C.POINTER(C.c_ulonglong)
+        L.spx_get_transfer_bytes.argtypes = [vp, u64p, u64p, u64p]
         for name in EXPORTS:
             getattr(L, name)   # AttributeError here = the library is stale
         _lib = L
     return _lib
+
+
+def host_register(arr: np.ndarray):
+    """Page-lock a host array in place (spx_host_register); pair with host_unregister."""
+    rc = lib().spx_host_register(arr.ctypes.data, arr.nbytes)
+    if rc != SPX_OK:
+        raise SpxError(rc, (lib().spx_last_error(None) or b"").decode())
+
+
+def host_unregister(arr: np.ndarray):
+    rc = lib().spx_host_unregister(arr.ctypes.data)
+    if rc != SPX_OK:
+        raise SpxError(rc, (lib().spx_last_error(None) or b"").decode())
 
 
 def default_config(**overrides) -> SpxConfig:
@@ -292,6 +318,25 @@ class PlaneExtractor:
     @property
     def launches(self) -> int:
         return lib().spx_last_launch_count(self._h)
+
+    def set_upload_mode(self, mode: int):
+        """0 automatic, 1 whole image, 2 sparse (sampled rows uploaded, border windows read in place) when page-locked."""
+        self._ck(lib().spx_set_upload_mode(self._h, mode))
+
+    def transfer_bytes(self):
+        """(bytes uploaded by copies, bytes read in place from the caller's pinned image, bytes copied back) of the last
+        host-input extract."""
+        a, b, d = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
+        self._ck(lib().spx_get_transfer_bytes(self._h, C.byref(a), C.byref(b), C.byref(d)))
+        return a.value, b.value, d.value
+
+    def group_timeline(self) -> np.ndarray:
+        """(groups, 7) ms after the start of the last host-input call: started, depth on the device, real planes final,
+        last kernel ended, results on the host (device clock); enqueue began, totals seen (host clock)."""
+        t = np.zeros((64, 7), np.float32)
+        n = C.c_int()
+        self._ck(lib().spx_get_group_timeline(self._h, t.ctypes.data, 64, C.byref(n)))
+        return t[:n.value].copy()
 
     def set_profile(self, on: bool):
         self._ck(lib().spx_set_profile(self._h, 1 if on else 0))

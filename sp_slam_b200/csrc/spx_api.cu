@@ -7,6 +7,8 @@
 // There is no CPU fallback: without a usable CUDA device spx_create fails with SPX_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <chrono>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -48,15 +50,28 @@ struct spx_ctx {
     spx_config cfg;
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // host path with several frame groups: all uploads go through one stream in group order and all downloads through
+    // another, so a group's copies never queue behind another group's kernels (the device has few hardware queues:
+    // streams beyond CUDA_DEVICE_MAX_CONNECTIONS share one and serialise)
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // frame groups: internal streams + per group events (start, end of the plane section, end of the supposed-plane section)
     int n_streams = 1, min_group = 32, last_groups = 1;
     int refine_fast_max = 700;  // batches of at most this many frames use k_refine2
+    bool refine_per_group = true;
+    int group_prio = 0;      // 1: group g's stream gets a priority that falls with g (earlier groups finish first)
+    int border_grid_cap = 0;
+    int upload_mode = 0;     // host input: 0 auto (sparse upload for pinned images of batches >= sparse_min_frames), 1 whole image, 2 sparse whenever possible
+    int sparse_min_frames = 1;
     bool use_prio = false;   // back stream with higher priority: measured slower (co-running kernels slow each other), kept as a knob
     std::vector<cudaStream_t> g_streams;      // front: upload, chamfer, normals (low priority)
     std::vector<cudaStream_t> g_back;         // back: everything after the normals (high priority: it is what frees a group)
-    std::vector<cudaEvent_t> g_link;          // front -> back hand-over
+    std::vector<cudaEvent_t> g_link;          // fork of the group's side stream
+    std::vector<cudaEvent_t> g_side;          // side stream done (real clouds packed)
     std::vector<cudaEvent_t> g_ev;
+    std::vector<float> g_host_ms;             // host clock, 2 per group: enqueue began / totals seen, ms after the call began
+    std::chrono::steady_clock::time_point t_call;
+    std::vector<cudaEvent_t> g_xev;           // host path: 2 per group, upload done / results on the host (spx_get_group_timeline)
     size_t work_stride = 0, work2_stride = 0;
     // host path: every group compacts its own results (at the device offset of its first frame) and ships them itself
     bool group_pack = false;
@@ -71,6 +86,7 @@ struct spx_ctx {
     int capN = 0, cap_w = 0, cap_h = 0;
     int n_grid = 0;
     int border_grid = 148 * 8;
+    int fetch_grid = 148 * 4;
     int lines_grid = 148 * 3;          // persistent CTAs of k_lines: SM count x resident CTAs per SM
     // host results (pinned, grown on demand)
     spx_frame_header *h_frames = nullptr;
@@ -84,6 +100,10 @@ struct spx_ctx {
     int last_frames = 0;
     const float *last_depth_dev = nullptr;
     int launches = 0;
+    // bytes the last host-input extract moved: explicit uploads, in-place reads of the caller's pinned image by the border
+    // tests (sparse upload), results copied back
+    unsigned long long xfer_h2d = 0, xfer_inplace = 0, xfer_d2h = 0;
+    size_t inplace_esz = 0;
     // optional per-kernel timing (spx_set_profile): event k is recorded before launch k, one more after the last
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -156,6 +176,7 @@ int set_geometry(spx_ctx *c, int n_frames, int rows, int cols, size_t pitch, siz
     if (n_frames > 1 && frame_stride < pitch * size_t(rows)) return fail(c, SPX_ERR_ARG, "bad frame stride");
     Params &P = c->P;
     P.rows = rows; P.cols = cols; P.pitch = pitch; P.frame_stride = frame_stride; P.n_frames = n_frames;
+    P.samp_rstep = size_t(P.dis) * pitch; P.samp_fstride = frame_stride; P.full_alpha = 1.0f;
     cloud_dims(rows, cols, P.dis, &P.w, &P.h);
     P.N = P.w * P.h;
     if (P.N > c->capN) return fail(c, SPX_ERR_ARG, "organized cloud exceeds the context capacity");
@@ -174,6 +195,11 @@ struct HostSrc {           // host depth of the batch (null: the depth is alread
     size_t pitch = 0, frame_stride = 0;
     bool u16 = false;      // CV_16U source: uploaded as is and converted on the device
     float alpha = 1.0f;    // mDepthMapFactor
+    // sparse upload: only the rows the organized cloud samples (every Cloud.Dis-th) are copied to the device; the border
+    // tests of GeneratePlanesFromBoundries, the one consumer of full-resolution depth, read their 21x21 windows in place
+    // from the caller's pinned image (`mapped` = its device-visible address)
+    bool sparse = false;
+    const void *mapped = nullptr;
 };
 
 int n_groups_for(const spx_ctx *c, int n_frames) {
@@ -197,13 +223,15 @@ int prof_slot(spx_ctx *c, const char *name, cudaStream_t st) {
     return SPX_OK;
 }
 
-int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int f0, int ng, cudaStream_t st, cudaStream_t st_back,
-              const HostSrc &src) {
+int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool normals_given, int g, int f0, int ng, cudaStream_t st,
+              cudaStream_t st_back, const HostSrc &src) {
     Params P = c->P;
     P.frame0 = f0; P.n_frames = ng;
     // k_refine2 (a CTA per frame) has the shorter critical path but executes ~1.8x the instructions of k_refine (a warp per
     // frame): it wins while the whole batch fits the machine in about one wave (measured cross-over ~700 frames)
-    P.refine_fast = (c->P.n_frames <= c->refine_fast_max && P.h <= kRefMaxH) ? 1 : 0;   // small launches are latency bound: parallelism inside the frame
+    // On the host path the groups start one upload apart instead of together, so the decision is made per group there.
+    const int refine_load = (c->group_pack && c->refine_per_group) ? ng : c->P.n_frames;
+    P.refine_fast = (refine_load <= c->refine_fast_max && P.h <= kRefMaxH) ? 1 : 0;   // small launches are latency bound: parallelism inside the frame
     Buffers B = c->B;
     B.work = c->B.work + size_t(g) * c->work_stride;
     B.work2 = c->B.work2 + size_t(g) * c->work2_stride;
@@ -219,9 +247,32 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
         ++L;                                                                                        \
     } while (0)
 
-    if (src.depth) {   // host depth of this group -> staging buffer (tight pitch)
+    cudaStream_t compute_st = st;
+    if (src.depth && c->group_pack && c->last_groups > 1) st = c->up_stream;   // copies: the upload stream
+    if (src.depth && src.sparse) {   // host depth of this group: the sampled rows only, at their place in the device image
         const size_t esz = src.u16 ? sizeof(uint16_t) : sizeof(float);
         const size_t tight = size_t(P.cols) * esz;
+        c->xfer_h2d += tight * size_t(P.h) * size_t(ng);
+        char *dst = (src.u16 ? reinterpret_cast<char *>(c->d_depth16) : reinterpret_cast<char *>(c->d_depth)) + tight * P.rows * size_t(f0);
+        const char *hp = reinterpret_cast<const char *>(src.depth) + src.frame_stride * size_t(f0);
+        if (ng == 1 || (P.rows % P.dis == 0 && src.frame_stride == src.pitch * size_t(P.rows))) {
+            // the sampled rows of consecutive frames are equally spaced: one strided copy for the whole group
+            SPX_CK(c, cudaMemcpy2DAsync(dst, tight * size_t(P.dis), hp, src.pitch * size_t(P.dis), tight, size_t(P.h) * size_t(ng), cudaMemcpyHostToDevice, st));
+        } else {
+            for (int f = 0; f < ng; ++f)
+                SPX_CK(c, cudaMemcpy2DAsync(dst + tight * P.rows * size_t(f), tight * size_t(P.dis), hp + src.frame_stride * size_t(f),
+                                            src.pitch * size_t(P.dis), tight, size_t(P.h), cudaMemcpyHostToDevice, st));
+        }
+        if (src.u16) {
+            if (st != compute_st) { SPX_CK(c, cudaEventRecord(c->g_xev[2 * g + 0], st)); SPX_CK(c, cudaStreamWaitEvent(compute_st, c->g_xev[2 * g + 0], 0)); st = compute_st; }
+            const size_t per = size_t(P.rows) * P.cols;   // cols % 4 == 0 on this path
+            LAUNCH(k_convert_u16_rows, dim3(cdiv(P.cols / 4, 128), P.h * ng), 128, 0, c->d_depth16 + per * size_t(f0), c->d_depth + per * size_t(f0),
+                   P.cols, P.rows, P.h, P.dis, src.alpha);
+        }
+    } else if (src.depth) {   // host depth of this group -> staging buffer (tight pitch)
+        const size_t esz = src.u16 ? sizeof(uint16_t) : sizeof(float);
+        const size_t tight = size_t(P.cols) * esz;
+        c->xfer_h2d += tight * size_t(P.rows) * size_t(ng);
         char *dst = (src.u16 ? reinterpret_cast<char *>(c->d_depth16) : reinterpret_cast<char *>(c->d_depth)) + tight * P.rows * size_t(f0);
         const char *hp = reinterpret_cast<const char *>(src.depth) + src.frame_stride * size_t(f0);
         if (src.pitch == tight && (ng == 1 || src.frame_stride == tight * P.rows)) {
@@ -234,13 +285,26 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
         if (src.u16) {
             const size_t n = size_t(P.rows) * P.cols * size_t(ng);   // a multiple of 4 is not guaranteed: pad handled by capacity
             const size_t n4 = (n + 3) / 4;
+            if (st != compute_st) { SPX_CK(c, cudaEventRecord(c->g_xev[2 * g + 0], st)); SPX_CK(c, cudaStreamWaitEvent(compute_st, c->g_xev[2 * g + 0], 0)); st = compute_st; }
             LAUNCH(k_convert_u16, unsigned((n4 + 255) / 256), 256, 0, c->d_depth16 + size_t(P.rows) * P.cols * size_t(f0),
                    c->d_depth + size_t(P.rows) * P.cols * size_t(f0), n4, src.alpha);
         }
     }
+    if (src.depth && st != compute_st) {   // (float input) hand over from the upload stream
+        SPX_CK(c, cudaEventRecord(c->g_xev[2 * g + 0], st));
+        SPX_CK(c, cudaStreamWaitEvent(compute_st, c->g_xev[2 * g + 0], 0));
+        st = compute_st;
+    } else if (src.depth && !(src.u16 && c->group_pack && c->last_groups > 1)) {
+        SPX_CK(c, cudaEventRecord(c->g_xev[2 * g + 0], st));
+    }
     SPX_CK(c, cudaMemsetAsync(B.ctl + f0, 0, sizeof(FrameCtl) * size_t(F), st));
     SPX_CK(c, cudaMemsetAsync(B.work, 0, 2 * sizeof(int), st));
     SPX_CK(c, cudaMemsetAsync(B.work2, 0, 2 * sizeof(int), st));
+    if (src.sparse && P.enable_supposed) {
+        const size_t words = size_t(P.rows) * size_t(((P.cols + 7) / 8 + 31) / 32);
+        SPX_CK(c, cudaMemsetAsync(B.fetch_bits + words * size_t(f0), 0, words * sizeof(unsigned) * size_t(F), st));
+        SPX_CK(c, cudaMemsetAsync(B.out_totals + 8 * (c->group_pack ? g + 1 : 0) + 3, 0, sizeof(long long), st));
+    }
     if (!normals_given) {
         const int nb = cdiv(P.h, kBandRows), nch = cdiv(P.w, 32);
         const int dbg = c->debug ? 1 : 0;
@@ -281,61 +345,110 @@ int run_group(spx_ctx *c, const float *depth_dev, bool normals_given, int g, int
     LAUNCH(k_contour, F, kContourThreads, size_t(P.w + 2) * (P.h + 2), P, B);
     LAUNCH(k_postfilter, cdiv(F, 128), 128, 0, P, B);
     SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 1], st));
+    // The clouds of the real planes are final now.  When this group compacts its own results (host path, or a batch
+    // that is one group) their packing runs on a side stream while the line fits / border tests (latency bound, the
+    // GPU is mostly idle) continue here; the supposed planes' clouds follow once k_supposed has run.
+    const bool own_pack = c->group_pack || c->last_groups == 1;
+    long long *tot = B.out_totals + 8 * (c->group_pack ? g + 1 : 0);
+    long long base_pl = 0, base_pt = 0, base_bd = 0;
+    if (own_pack) {
+        if (c->group_pack) {
+            spx_ctx::GroupOut &go = c->g_out[g];
+            go.f0 = f0; go.f1 = f0 + ng;
+            go.dev_pl = (long long)f0 * SPX_MAX_PLANES; go.dev_pt = (long long)f0 * P.pts_cap; go.dev_bd = (long long)f0 * P.bnd_cap;
+            base_pl = go.dev_pl; base_pt = go.dev_pt; base_bd = go.dev_bd;
+        }
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 0, base_pl, base_pt, base_bd, tot);
+        const bool use_side = c->last_groups == 1;   // with several groups in flight the other groups fill the gaps already
+        cudaStream_t side = use_side ? c->g_back[g] : st, keep = st;
+        if (use_side) {
+            SPX_CK(c, cudaEventRecord(c->g_link[g], st));
+            SPX_CK(c, cudaStreamWaitEvent(side, c->g_link[g], 0));
+        }
+        st = side;
+        LAUNCH(k_pack_points, gpix, 256, 0, P, B);
+        LAUNCH(k_pack_contours, dim3(SPX_MAX_MODELS, F), 128, 0, P, B);
+        if (use_side) SPX_CK(c, cudaEventRecord(c->g_side[g], side));
+        st = keep;
+    }
     if (P.enable_supposed) {
         const int lg = std::min(c->lines_grid, F * SPX_MAX_MODELS), bg = std::min(c->border_grid, F * SPX_MAX_MODELS * SPX_MAX_LINES);
         LAUNCH(k_lines, lg, kLineThreads, kLinesSmem, depth_dev, P, B);
-        LAUNCH(k_border, bg, kBorderWarps * 32, 0, depth_dev, P, B);
+        if (src.sparse) {
+            // bring in the window sectors the border tests will read (counted in out_totals slot [3] of the group)
+            unsigned long long *n_sectors = reinterpret_cast<unsigned long long *>(tot + 3);
+            const int fg = std::min(c->fetch_grid, F * SPX_MAX_MODELS * SPX_MAX_LINES);
+            if (src.u16) LAUNCH(k_border_fetch<uint16_t>, fg, 256, 0, static_cast<const uint16_t *>(src.mapped), c->d_depth, P, B, n_sectors);
+            else LAUNCH(k_border_fetch<float>, fg, 256, 0, static_cast<const float *>(src.mapped), c->d_depth, P, B, n_sectors);
+        }
+        LAUNCH(k_border, bg, kBorderWarps * 32, 0, static_cast<const float *>(depth_full), P, B);
         LAUNCH(k_supposed, cdiv(F, 128), 128, 0, P, B);
     }
-    if (c->group_pack) {
-        spx_ctx::GroupOut &go = c->g_out[g];
-        go.f0 = f0; go.f1 = f0 + ng;
-        go.dev_pl = (long long)f0 * SPX_MAX_PLANES; go.dev_pt = (long long)f0 * P.pts_cap; go.dev_bd = (long long)f0 * P.bnd_cap;
-        long long *tot = B.out_totals + 4 * (g + 1);
-        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, go.dev_pl, go.dev_pt, go.dev_bd, tot);
+    if (own_pack) {
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 1, base_pl, base_pt, base_bd, tot);
         LAUNCH(k_emit_records, F, 128, 0, P, B);
-        LAUNCH(k_pack_points, gpix, 256, 0, P, B);
-        LAUNCH(k_pack_contours, dim3(SPX_MAX_MODELS, F), 128, 0, P, B);
+        if (c->last_groups == 1) SPX_CK(c, cudaStreamWaitEvent(st, c->g_side[g], 0));   // the fallback boundaries read the packed real clouds
         if (P.enable_supposed) LAUNCH(k_pack_supposed, dim3(SPX_MAX_PLANES, F), 128, 0, P, B);
-        SPX_CK(c, cudaMemcpyAsync(c->h_totals + 4 * (g + 1), tot, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-        SPX_CK(c, cudaEventRecord(c->g_tot_ev[g], st));
+        if (c->group_pack) {
+            SPX_CK(c, cudaMemcpyAsync(c->h_totals + 8 * (g + 1), tot, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+            SPX_CK(c, cudaEventRecord(c->g_tot_ev[g], st));
+        }
     }
     SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 2], st));
     return SPX_OK;
 }
 
-int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given, const HostSrc &src, bool group_pack) {
+// depth_dev: what the sampling kernels read (layout P.samp_*); depth_full: the full-resolution image of the border tests
+// (layout P.pitch / P.frame_stride; device memory, or the caller's mapped host image on the sparse-upload path)
+int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, bool normals_given, const HostSrc &src, bool group_pack) {
     cudaStream_t main_st = c->stream;
     c->group_pack = group_pack;
     const int F = c->P.n_frames;
     c->P.frame0 = 0;
     c->launches = 0;
     c->prof_n = 0;
+    c->xfer_h2d = c->xfer_inplace = c->xfer_d2h = 0;
+    c->inplace_esz = src.sparse ? (src.u16 ? sizeof(uint16_t) : sizeof(float)) : 0;
     const int G = normals_given ? 1 : n_groups_for(c, F);
     c->last_groups = G;
     SPX_CK(c, cudaEventRecord(c->ev[0], main_st));
+    c->t_call = std::chrono::steady_clock::now();
+    c->g_host_ms.assign(size_t(2 * G), 0.f);
+    if (group_pack && G > 1) SPX_CK(c, cudaStreamWaitEvent(c->up_stream, c->ev[0], 0));
     for (int g = 0; g < G; ++g) {
         const int f0 = int((long long)F * g / G), f1 = int((long long)F * (g + 1) / G);
         cudaStream_t st = (G == 1) ? main_st : c->g_streams[g];
         cudaStream_t st_back = (G == 1) ? main_st : (c->use_prio ? c->g_back[g] : c->g_streams[g]);
         if (G > 1) SPX_CK(c, cudaStreamWaitEvent(st, c->ev[0], 0));
         SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 0], st));
-        int rc = run_group(c, depth_dev, normals_given, g, f0, f1 - f0, st, st_back, src);
+        c->g_host_ms[2 * g] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - c->t_call).count();
+        int rc = run_group(c, depth_dev, depth_full, normals_given, g, f0, f1 - f0, st, st_back, src);
         if (rc != SPX_OK) return rc;
-        if (G > 1) SPX_CK(c, cudaStreamWaitEvent(main_st, c->g_ev[3 * g + 2], 0));
+        if (G > 1 && group_pack) SPX_CK(c, cudaStreamWaitEvent(main_st, c->g_ev[3 * g + 2], 0));
     }
-    SPX_CK(c, cudaEventRecord(c->ev[1], main_st));
-    if (!group_pack) {
+    if (!group_pack && G > 1) {
+        // several groups, one contiguous device result: the real planes' clouds are packed on a side stream as soon as
+        // every group has passed its post-filter; the rest follows when the groups are done
         const Params &P = c->P;
         const Buffers &B = c->B;
-        cudaStream_t st = main_st;
         const dim3 gpix(cdiv(P.N, 256), F);
         int &L = c->launches;
-        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 0ll, 0ll, 0ll, B.out_totals);
-        LAUNCH(k_emit_records, F, 128, 0, P, B);
+        cudaStream_t side = c->g_back[0];
+        cudaStream_t st = side;
+        for (int g = 0; g < G; ++g) SPX_CK(c, cudaStreamWaitEvent(side, c->g_ev[3 * g + 1], 0));
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 0, 0ll, 0ll, 0ll, B.out_totals);
         LAUNCH(k_pack_points, gpix, 256, 0, P, B);
         LAUNCH(k_pack_contours, dim3(SPX_MAX_MODELS, F), 128, 0, P, B);
+        SPX_CK(c, cudaEventRecord(c->g_side[0], side));
+        st = main_st;
+        for (int g = 0; g < G; ++g) SPX_CK(c, cudaStreamWaitEvent(main_st, c->g_ev[3 * g + 2], 0));
+        SPX_CK(c, cudaStreamWaitEvent(main_st, c->g_side[0], 0));
+        SPX_CK(c, cudaEventRecord(c->ev[1], main_st));
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 1, 0ll, 0ll, 0ll, B.out_totals);
+        LAUNCH(k_emit_records, F, 128, 0, P, B);
         if (P.enable_supposed) LAUNCH(k_pack_supposed, dim3(SPX_MAX_PLANES, F), 128, 0, P, B);
+    } else {
+        SPX_CK(c, cudaEventRecord(c->ev[1], main_st));
     }
 #undef LAUNCH
     SPX_CK(c, cudaEventRecord(c->ev[2], main_st));
@@ -344,6 +457,21 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, bool normals_given, const H
     c->last_frames = F;
     c->last_depth_dev = depth_dev;
     return SPX_OK;
+}
+
+// Host input: may only the sampled rows be uploaded?  Yes when nothing reads full-resolution depth (supposed planes off),
+// or when the caller's image is page-locked (cudaHostAlloc / cudaHostRegister / spx_host_register): then the border tests
+// read their windows in place through the image's device-visible address.  A pageable image is uploaded whole.
+bool sparse_upload(spx_ctx *c, const void *host, int n_frames, HostSrc *src) {
+    src->sparse = false; src->mapped = nullptr;
+    if (c->upload_mode == 1) return false;
+    if (c->upload_mode == 0 && n_frames < c->sparse_min_frames) return false;
+    if (!c->P.enable_supposed) { src->sparse = true; return true; }
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    src->sparse = true; src->mapped = at.devicePointer;
+    return true;
 }
 
 template <typename T>
@@ -394,7 +522,7 @@ int fetch(spx_ctx *c, spx_batch_result *out, bool with_clouds) {
 template <typename T>
 int grow_pinned_keep(spx_ctx *c, T **p, size_t *cap, size_t need, size_t used) {
     if (need <= *cap) return SPX_OK;
-    for (int g = 0; g < c->last_groups; ++g) SPX_CK(c, cudaStreamSynchronize(c->last_groups == 1 ? c->stream : (c->use_prio ? c->g_back[g] : c->g_streams[g])));
+    SPX_CK(c, cudaStreamSynchronize(c->last_groups == 1 ? c->stream : c->down_stream));
     size_t ncap = *cap ? *cap : 1024;
     while (ncap < need) ncap *= 2;
     T *np = nullptr;
@@ -414,10 +542,13 @@ int fetch_groups(spx_ctx *c, spx_batch_result *out) {
     std::vector<long long> host_pl(G), host_pt(G), host_bd(G), n_pls(G);
     int rc;
     for (int g = 0; g < G; ++g) {
-        cudaStream_t st = (G == 1) ? c->stream : (c->use_prio ? c->g_back[g] : c->g_streams[g]);
+        cudaStream_t st = (G == 1) ? c->stream : c->down_stream;   // the group's kernels are done once its totals have arrived
         SPX_CK(c, cudaEventSynchronize(c->g_tot_ev[g]));
-        const long long *t = c->h_totals + 4 * (g + 1);
+        c->g_host_ms[2 * g + 1] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - c->t_call).count();
+        const long long *t = c->h_totals + 8 * (g + 1);
         const long long n_pl = t[0], n_pt = t[1], n_bd = t[2];
+        c->xfer_inplace += (unsigned long long)t[3] * 8ull * c->inplace_esz;   // sectors of 8 pixels
+        c->xfer_d2h += sizeof(spx_frame_header) * size_t(c->g_out[g].f1 - c->g_out[g].f0) + sizeof(spx_plane) * size_t(n_pl) + sizeof(spx_point) * size_t(n_pt + n_bd) + 4 * sizeof(long long);
         const spx_ctx::GroupOut &go = c->g_out[g];
         if ((rc = grow_pinned_keep(c, &c->h_planes, &c->h_planes_cap, size_t(run_pl + n_pl), size_t(run_pl))) != SPX_OK) return rc;
         if ((rc = grow_pinned_keep(c, &c->h_pts, &c->h_pts_cap, size_t(run_pt + n_pt), size_t(run_pt))) != SPX_OK) return rc;
@@ -426,10 +557,11 @@ int fetch_groups(spx_ctx *c, spx_batch_result *out) {
         if (n_pl) SPX_CK(c, cudaMemcpyAsync(c->h_planes + run_pl, c->B.out_planes + go.dev_pl, sizeof(spx_plane) * size_t(n_pl), cudaMemcpyDeviceToHost, st));
         if (n_pt) SPX_CK(c, cudaMemcpyAsync(c->h_pts + run_pt, c->B.out_pts + go.dev_pt, sizeof(spx_point) * size_t(n_pt), cudaMemcpyDeviceToHost, st));
         if (n_bd) SPX_CK(c, cudaMemcpyAsync(c->h_bnd + run_bd, c->B.out_bnd + go.dev_bd, sizeof(spx_point) * size_t(n_bd), cudaMemcpyDeviceToHost, st));
+        SPX_CK(c, cudaEventRecord(c->g_xev[2 * g + 1], st));
         host_pl[g] = run_pl; host_pt[g] = run_pt; host_bd[g] = run_bd; n_pls[g] = n_pl;
         run_pl += n_pl; run_pt += n_pt; run_bd += n_bd;
     }
-    for (int g = 0; g < G; ++g) SPX_CK(c, cudaStreamSynchronize((G == 1) ? c->stream : (c->use_prio ? c->g_back[g] : c->g_streams[g])));
+    if (G > 1) SPX_CK(c, cudaStreamSynchronize(c->down_stream));
     SPX_CK(c, cudaStreamSynchronize(c->stream));
     for (int g = 0; g < G; ++g) {
         const spx_ctx::GroupOut &go = c->g_out[g];
@@ -502,6 +634,11 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (size_t(w) * h >= (1u << 20)) return fail(nullptr, SPX_ERR_ARG, "organized cloud larger than 2^20 points");
     if (size_t(w + 2) * (h + 2) > 200u * 1024u) return fail(nullptr, SPX_ERR_ARG, "organized cloud too large for the shared-memory plane-id map of the contour trace");
 
+    // A batch runs as several frame groups on their own streams plus an upload and a download stream.  The driver maps
+    // streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue serialise, which
+    // costs the host path ~20 %.  The variable is read when the CUDA context is created: if this library is the first CUDA
+    // user of the process (SP-SLAM itself has no other), ask for the maximum unless the caller has chosen a value.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
@@ -552,28 +689,47 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
 
     SPX_CK_CREATE(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    SPX_CK_CREATE(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+    SPX_CK_CREATE(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) SPX_CK_CREATE(cudaEventCreate(&c->ev[i]));
     c->n_streams = cfg->n_streams > 0 ? (cfg->n_streams > 32 ? 32 : cfg->n_streams) : 8;
     c->min_group = 32;
     if (const char *e = std::getenv("SPX_REFINE_FAST_MAX")) c->refine_fast_max = std::atoi(e);   // tuning knob
     if (const char *e = std::getenv("SPX_LINES_GLOBAL")) c->P.lines_in_global = std::atoi(e) != 0 ? 1 : 0;   // test knob
+    if (const char *e = std::getenv("SPX_UPLOAD")) c->upload_mode = std::atoi(e);   // test / tuning knob (see spx_ctx::upload_mode)
+    if (const char *e = std::getenv("SPX_SPARSE_MIN_FRAMES")) c->sparse_min_frames = std::atoi(e);   // tuning knob
+    if (const char *e = std::getenv("SPX_REFINE_PER_GROUP")) c->refine_per_group = std::atoi(e) != 0;   // tuning knob
+    if (const char *e = std::getenv("SPX_GROUP_PRIO")) c->group_prio = std::atoi(e);   // tuning knob
+    if (const char *e = std::getenv("SPX_BORDER_GRID")) c->border_grid_cap = std::atoi(e);   // tuning knob
     if (const char *e = std::getenv("SPX_PRIO")) c->use_prio = std::atoi(e) != 0;   // tuning knob
     if (const char *e = std::getenv("SPX_MIN_GROUP")) { const int v = std::atoi(e); if (v > 0) c->min_group = v; }   // tuning knob
     int prio_lo = 0, prio_hi = 0;
     SPX_CK_CREATE(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // numerically lower = higher priority
     for (int g = 0; g < c->n_streams; ++g) {
         cudaStream_t gs;
-        SPX_CK_CREATE(cudaStreamCreateWithPriority(&gs, cudaStreamNonBlocking, prio_lo));
+        int pr = prio_lo;
+        if (c->group_prio) {   // prio_hi (numerically lowest) for group 0, falling to prio_lo for the last group
+            const int levels = prio_lo - prio_hi + 1;
+            pr = prio_hi + std::min(levels - 1, g * levels / c->n_streams);
+        }
+        SPX_CK_CREATE(cudaStreamCreateWithPriority(&gs, cudaStreamNonBlocking, pr));
         c->g_streams.push_back(gs);
         SPX_CK_CREATE(cudaStreamCreateWithPriority(&gs, cudaStreamNonBlocking, prio_hi));
         c->g_back.push_back(gs);
         cudaEvent_t le;
         SPX_CK_CREATE(cudaEventCreateWithFlags(&le, cudaEventDisableTiming));
         c->g_link.push_back(le);
+        SPX_CK_CREATE(cudaEventCreateWithFlags(&le, cudaEventDisableTiming));
+        c->g_side.push_back(le);
         for (int k = 0; k < 3; ++k) {
             cudaEvent_t e;
             SPX_CK_CREATE(cudaEventCreate(&e));
             c->g_ev.push_back(e);
+        }
+        for (int k = 0; k < 2; ++k) {
+            cudaEvent_t e;
+            SPX_CK_CREATE(cudaEventCreate(&e));
+            c->g_xev.push_back(e);
         }
         cudaEvent_t te;
         SPX_CK_CREATE(cudaEventCreateWithFlags(&te, cudaEventDisableTiming));
@@ -590,9 +746,11 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     total += padded<int16_t>(FN) + 2 * padded<int8_t>(FN + 16 * F);     // root_model pid pid_bak
     total += 3 * padded<int>(FC) + padded<float4>(FC) + padded<spx_point>(FC) + padded<int>(c->n_streams * (2 + F * SPX_MAX_MODELS)) + padded<int>(c->n_streams * (2 + F * SPX_MAX_MODELS * SPX_MAX_LINES));
     total += padded<FrameCtl>(F);
+    const size_t fetch_words = F * size_t(cfg->max_rows) * size_t(((cfg->max_cols + 7) / 8 + 31) / 32);
+    total += padded<unsigned>(fetch_words);
     total += padded<spx_frame_header>(F) + padded<spx_plane>(F * SPX_MAX_PLANES);
     total += padded<spx_point>(F * size_t(P.pts_cap)) + padded<spx_point>(F * size_t(P.bnd_cap));
-    total += padded<long long>(4 * size_t(c->n_streams + 1)) + padded<long long>(3 * F);
+    total += padded<long long>(8 * size_t(c->n_streams + 1)) + padded<long long>(5 * F);
     total += padded<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4) + padded<uint16_t>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     SPX_CK_CREATE(cudaMalloc(reinterpret_cast<void **>(&c->arena.base), total));
     c->arena.size = total;
@@ -607,9 +765,10 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     B.line_a = A.take<float4>(FC); B.line_pts = A.take<spx_point>(FC); c->work_stride = 2 + F * SPX_MAX_MODELS; c->work2_stride = 2 + F * SPX_MAX_MODELS * SPX_MAX_LINES;
     B.work = A.take<int>(c->n_streams * c->work_stride); B.work2 = A.take<int>(c->n_streams * c->work2_stride);
     B.ctl = A.take<FrameCtl>(F);
+    B.fetch_bits = A.take<unsigned>(fetch_words);
     B.out_frames = A.take<spx_frame_header>(F); B.out_planes = A.take<spx_plane>(F * SPX_MAX_PLANES);
     B.out_pts = A.take<spx_point>(F * size_t(P.pts_cap)); B.out_bnd = A.take<spx_point>(F * size_t(P.bnd_cap));
-    B.out_totals = A.take<long long>(4 * size_t(c->n_streams + 1)); B.frame_offs = A.take<long long>(3 * F);
+    B.out_totals = A.take<long long>(8 * size_t(c->n_streams + 1)); B.frame_offs = A.take<long long>(5 * F);
     c->d_depth = A.take<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     c->d_depth16 = A.take<uint16_t>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     if (A.used > A.size) { fail(nullptr, SPX_ERR_ARG, "internal: arena accounting"); spx_destroy(c); return SPX_ERR_ARG; }
@@ -631,12 +790,13 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
         c->lines_grid = prop.multiProcessorCount * (per_sm > 0 ? per_sm : 1);
         SPX_CK_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_border, kBorderWarps * 32, 0));
         c->border_grid = prop.multiProcessorCount * (per_sm > 0 ? per_sm : 1);
+        if (c->border_grid_cap > 0) c->border_grid = std::min(c->border_grid, prop.multiProcessorCount * c->border_grid_cap);
     }
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_grid, grid, sizeof(grid)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_link, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kNormalsSmem)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_edge_chamfer<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_edge_chamfer<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_totals), 4 * size_t(c->n_streams + 1) * sizeof(long long), cudaHostAllocDefault));
+    SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_totals), 8 * size_t(c->n_streams + 1) * sizeof(long long), cudaHostAllocDefault));
     SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_frames), F * sizeof(spx_frame_header), cudaHostAllocDefault));
 #undef SPX_CK_CREATE
     *out = c;
@@ -657,9 +817,13 @@ void spx_destroy(spx_ctx *c) {
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->g_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->g_tot_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->g_xev) cudaEventDestroy(e);
     for (cudaStream_t gs : c->g_streams) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
     for (cudaStream_t gs : c->g_back) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
     for (cudaEvent_t e : c->g_link) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->g_side) cudaEventDestroy(e);
+    if (c->up_stream) { cudaStreamSynchronize(c->up_stream); cudaStreamDestroy(c->up_stream); }
+    if (c->down_stream) { cudaStreamSynchronize(c->down_stream); cudaStreamDestroy(c->down_stream); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -687,7 +851,7 @@ int spx_extract_batch_device(spx_ctx *c, const float *depth_dev, int n_frames, i
     SPX_CK(c, cudaSetDevice(c->device));
     int rc = set_geometry(c, n_frames, rows, cols, pitch_bytes, frame_stride_bytes);
     if (rc != SPX_OK) return rc;
-    return run_pipeline(c, depth_dev, false, HostSrc(), false);
+    return run_pipeline(c, depth_dev, depth_dev, false, HostSrc(), false);
 }
 
 int spx_fetch_results(spx_ctx *c, spx_batch_result *out) {
@@ -722,8 +886,15 @@ int spx_extract_batch(spx_ctx *c, const float *depth, int n_frames, int rows, in
     if (rc != SPX_OK) return rc;
     HostSrc src;
     src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = frame_stride_bytes;
-    c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);   // layout of the staging buffer the kernels read
-    if ((rc = run_pipeline(c, c->d_depth, false, src, true)) != SPX_OK) return rc;
+    const void *full = c->d_depth;
+    c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);   // layout of the device image the kernels read
+    c->P.samp_rstep = tight * size_t(c->P.dis); c->P.samp_fstride = c->P.frame_stride;
+    if (sparse_upload(c, depth, n_frames, &src)) {
+        // only the sampled rows are uploaded (to their place in the device image); k_border_fetch adds the window sectors
+        c->P.host_pitch = pitch_bytes; c->P.host_fstride = frame_stride_bytes; c->P.fetch_skip_sampled = 1;
+        c->P.fetch_vec = (reinterpret_cast<uintptr_t>(src.mapped) % 16 == 0 && pitch_bytes % 16 == 0 && frame_stride_bytes % 16 == 0 && cols % 8 == 0) ? 1 : 0;
+    }
+    if ((rc = run_pipeline(c, c->d_depth, full, false, src, true)) != SPX_OK) return rc;
     return fetch_groups(c, out);
 }
 
@@ -741,7 +912,14 @@ int spx_extract_batch_u16(spx_ctx *c, const uint16_t *depth, int n_frames, int r
     if (rc != SPX_OK) return rc;
     HostSrc src;
     src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = frame_stride_bytes; src.u16 = true; src.alpha = depth_map_factor;
-    if ((rc = run_pipeline(c, c->d_depth, false, src, true)) != SPX_OK) return rc;
+    const void *full = c->d_depth;
+    if (cols % 4 == 0 && sparse_upload(c, depth, n_frames, &src)) {
+        c->P.host_pitch = pitch_bytes; c->P.host_fstride = frame_stride_bytes; c->P.fetch_skip_sampled = 1; c->P.full_alpha = depth_map_factor;
+        c->P.fetch_vec = (reinterpret_cast<uintptr_t>(src.mapped) % 16 == 0 && pitch_bytes % 16 == 0 && frame_stride_bytes % 16 == 0 && cols % 8 == 0) ? 1 : 0;
+    } else {
+        src.sparse = false;
+    }
+    if ((rc = run_pipeline(c, c->d_depth, full, false, src, true)) != SPX_OK) return rc;
     return fetch_groups(c, out);
 }
 
@@ -760,11 +938,12 @@ int spx_segment_from_normals(spx_ctx *c, const float *depth, int rows, int cols,
     HostSrc src;
     src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = pitch_bytes * size_t(rows);
     c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);
+    c->P.samp_rstep = tight * size_t(c->P.dis); c->P.samp_fstride = c->P.frame_stride;
     const size_t N = size_t(c->P.N);
     SPX_CK(c, cudaMemcpyAsync(c->B.nx, normals, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     SPX_CK(c, cudaMemcpyAsync(c->B.ny, normals + N, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     SPX_CK(c, cudaMemcpyAsync(c->B.nz, normals + 2 * N, N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = run_pipeline(c, c->d_depth, true, src, false)) != SPX_OK) return rc;
+    if ((rc = run_pipeline(c, c->d_depth, c->d_depth, true, src, false)) != SPX_OK) return rc;
     return fetch(c, out, true);
 }
 
@@ -795,7 +974,48 @@ int spx_get_times(spx_ctx *c, double *t_plane, double *t_splane) {
     return SPX_OK;
 }
 
+int spx_get_group_timeline(spx_ctx *c, float *t_ms, int cap_groups, int *n_groups) {
+    if (!c || !n_groups) return SPX_ERR_ARG;
+    if (!c->have_run || !c->group_pack) return fail(c, SPX_ERR_STATE, "the group timeline follows a host-input extract");
+    SPX_CK(c, cudaSetDevice(c->device));
+    *n_groups = c->last_groups;
+    for (int g = 0; g < c->last_groups && g < cap_groups && t_ms; ++g) {
+        cudaEvent_t evs[5] = {c->g_ev[3 * g + 0], c->g_xev[2 * g + 0], c->g_ev[3 * g + 1], c->g_ev[3 * g + 2], c->g_xev[2 * g + 1]};
+        for (int k = 0; k < 5; ++k) SPX_CK(c, cudaEventElapsedTime(&t_ms[7 * g + k], c->ev[0], evs[k]));
+        t_ms[7 * g + 5] = c->g_host_ms[2 * g]; t_ms[7 * g + 6] = c->g_host_ms[2 * g + 1];
+    }
+    return SPX_OK;
+}
+
 int spx_last_launch_count(const spx_ctx *c) { return c ? c->launches : 0; }
+
+int spx_get_transfer_bytes(const spx_ctx *c, unsigned long long *h2d_copied, unsigned long long *h2d_in_place, unsigned long long *d2h) {
+    if (!c) return SPX_ERR_ARG;
+    if (h2d_copied) *h2d_copied = c->xfer_h2d;
+    if (h2d_in_place) *h2d_in_place = c->xfer_inplace;
+    if (d2h) *d2h = c->xfer_d2h;
+    return SPX_OK;
+}
+
+int spx_set_upload_mode(spx_ctx *c, int mode) {
+    if (!c || mode < 0 || mode > 2) return SPX_ERR_ARG;
+    c->upload_mode = mode;
+    return SPX_OK;
+}
+
+int spx_host_register(void *ptr, size_t bytes) {
+    if (!ptr || !bytes) return SPX_ERR_ARG;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) { cudaGetLastError(); fail(nullptr, SPX_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); return SPX_ERR_CUDA; }
+    return SPX_OK;
+}
+
+int spx_host_unregister(void *ptr) {
+    if (!ptr) return SPX_ERR_ARG;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); fail(nullptr, SPX_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); return SPX_ERR_CUDA; }
+    return SPX_OK;
+}
 
 int spx_set_profile(spx_ctx *c, int on) {
     if (!c) return SPX_ERR_ARG;

@@ -127,6 +127,136 @@ __device__ int block_select(int n, IdxT *out, int *s_warp, Pred pred) {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kBorderWarps = 4;
 
+// window of IsBorderPoint around a line point (src/Frame.cc:1030-1037): columns i0 .. while < u + 10, rows j0 .. while < v + 10
+struct BorderWin { int i0, j0; float ue, ve; bool live; };
+__device__ __forceinline__ BorderWin border_window(const Params &P, const spx_point &p) {
+    BorderWin W;
+    W.i0 = 0; W.j0 = 0; W.ue = 0.f; W.ve = 0.f; W.live = false;
+    const int b = 10;
+    const float PcZ = p.z;
+    if (!(PcZ < 0.0f)) {
+        const float invz = 1.0f / PcZ;
+        const float u = P.fx * p.x * invz + P.cx;
+        const float v = P.fy * p.y * invz + P.cy;
+        if (isfinite(u) && isfinite(v)) {
+            W.live = true;
+            W.i0 = int(u - b); W.j0 = int(v - b);
+            W.ue = u + b; W.ve = v + b;
+        }
+    }
+    return W;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sparse upload (host input, page-locked image): only the rows the organized cloud samples are copied to the device
+// image (at their natural position).  This kernel brings in the rest of what the border tests will read: for every
+// window row of every line point, the 8-pixel sectors it touches are claimed in a per-frame bitmap (atomicOr) and the
+// claimer copies the sector from the caller's image (mapped host memory, read over PCIe) to the same place of the
+// device image -- every sector crosses the bus once, all reads are independent (one round trip of latency), and
+// k_border below then works on device memory.  DepthT = uint16_t: the raw CV_16U image, converted on the way
+// (float(d) * mDepthMapFactor, as Tracking::GrabImageRGBD's convertTo).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fetch_convert8(const float *src, float *dst, int n, bool vec, float) {
+    if (vec) {
+        const float4 a = reinterpret_cast<const float4 *>(src)[0], b = reinterpret_cast<const float4 *>(src)[1];
+        reinterpret_cast<float4 *>(dst)[0] = a; reinterpret_cast<float4 *>(dst)[1] = b;
+    } else {
+        for (int k = 0; k < n; ++k) dst[k] = src[k];
+    }
+}
+__device__ __forceinline__ void fetch_convert8(const uint16_t *src, float *dst, int n, bool vec, float alpha) {
+    if (vec) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(src);
+        float4 a, b;
+        a.x = float(v.x & 0xffffu) * alpha; a.y = float(v.x >> 16) * alpha; a.z = float(v.y & 0xffffu) * alpha; a.w = float(v.y >> 16) * alpha;
+        b.x = float(v.z & 0xffffu) * alpha; b.y = float(v.z >> 16) * alpha; b.z = float(v.w & 0xffffu) * alpha; b.w = float(v.w >> 16) * alpha;
+        reinterpret_cast<float4 *>(dst)[0] = a; reinterpret_cast<float4 *>(dst)[1] = b;
+    } else {
+        for (int k = 0; k < n; ++k) dst[k] = float(src[k]) * alpha;
+    }
+}
+
+template <typename DepthT>
+__global__ void __launch_bounds__(256) k_border_fetch(const DepthT *__restrict__ host_img, float *__restrict__ dev_img, Params P, Buffers B,
+                                                      unsigned long long *n_sectors) {
+    const int tid = threadIdx.x;
+    const int n_items = B.work2[0];
+    const long long total = (long long)P.rows * P.cols;
+    const int dev_pitch = int(P.pitch / sizeof(float));
+    const int spr = (P.cols + 7) >> 3;                 // sectors per row
+    const int wpr = (spr + 31) >> 5;                   // bitmap words per row
+    const bool vec = P.fetch_vec != 0;
+    unsigned mine_total = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int code = B.work2[2 + it];
+        const int f = code / (SPX_MAX_MODELS * SPX_MAX_LINES), ls = code - f * (SPX_MAX_MODELS * SPX_MAX_LINES);
+        const Line &L = B.ctl[f].lines[ls];
+        const int n_pts = L.n_inliers;
+        const spx_point *pts = B.line_pts + size_t(f) * P.contour_cap + L.pts_off;
+        const DepthT *himg = reinterpret_cast<const DepthT *>(reinterpret_cast<const char *>(host_img) + size_t(f) * P.host_fstride);
+        float *dimg = reinterpret_cast<float *>(reinterpret_cast<char *>(dev_img) + size_t(f) * P.frame_stride);
+        unsigned *bits = B.fetch_bits + size_t(f) * size_t(P.rows) * wpr;
+        // one (point, window row) per thread
+        for (int idx = tid; idx < n_pts * 21; idx += blockDim.x) {
+            const int pi = idx / 21, t = idx - pi * 21;
+            const BorderWin W = border_window(P, pts[pi]);
+            if (!W.live) continue;
+            const int qj = W.j0 + t;
+            if (!(qj < W.ve)) continue;
+            int ncol = 0;
+#pragma unroll
+            for (int k = 0; k < 21; ++k) if (W.i0 + k < W.ue) ++ncol;
+            // sectors [s0, s1] of image row r, columns [c_lo, c_hi): claim, then copy the claimed ones (loads first)
+            auto fetch_row = [&](int r, int c_lo, int c_hi) {
+                if (c_lo >= c_hi) return;
+                if (P.fetch_skip_sampled && r % P.dis == 0) return;        // uploaded with the sampled rows
+                const int s0 = c_lo >> 3, s1 = (c_hi - 1) >> 3;
+                unsigned *brow = bits + size_t(r) * wpr;
+                const DepthT *hrow = reinterpret_cast<const DepthT *>(reinterpret_cast<const char *>(himg) + size_t(r) * P.host_pitch);
+                float *drow = dimg + size_t(r) * dev_pitch;
+                for (int sb = s0; sb <= s1; sb += 4) {
+                    bool mine[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int sct = sb + k;
+                        mine[k] = false;
+                        if (sct <= s1) {
+                            const unsigned bit = 1u << (sct & 31);
+                            mine[k] = (atomicOr(&brow[sct >> 5], bit) & bit) == 0u;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (mine[k]) {
+                            const int c0 = (sb + k) << 3;
+                            const int n = min(8, P.cols - c0);
+                            fetch_convert8(hrow + c0, drow + c0, n, vec && n == 8, P.full_alpha);
+                            ++mine_total;
+                        }
+                    }
+                }
+            };
+            if (qj >= 0 && qj < P.rows) fetch_row(qj, max(W.i0, 0), min(W.i0 + ncol, P.cols));
+            if (W.i0 < 0 || W.i0 + ncol > P.cols || qj < 0 || qj >= P.rows) {
+                // samples outside the image are read through the flat index of the continuous cv::Mat (convention E7)
+                for (int k = 0; k < ncol; ++k) {
+                    const int i = W.i0 + k;
+                    if (qj >= 0 && qj < P.rows && i >= 0 && i < P.cols) continue;
+                    const long long fidx = (long long)qj * P.cols + i;
+                    if (fidx >= 0 && fidx < total) {
+                        const int rr = int(fidx / P.cols), cc = int(fidx - (long long)rr * P.cols);
+                        fetch_row(rr, cc, cc + 1);
+                    }
+                }
+            }
+        }
+    }
+    if (n_sectors) {
+        mine_total = __reduce_add_sync(SPX_FULL, mine_total);
+        if ((tid & 31) == 0 && mine_total) atomicAdd(n_sectors, (unsigned long long)mine_total);
+    }
+}
+
 __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__restrict__ depth, Params P, Buffers B) {
     __shared__ float s_win[kBorderWarps][2][32][21];
     __shared__ int4 s_geo[kBorderWarps][32];
@@ -158,16 +288,8 @@ __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__res
             if (pi < n_pts) {
                 const spx_point p = pts[pi];
                 PcZ = p.z;
-                if (!(PcZ < 0.0f)) {
-                    const float invz = 1.0f / PcZ;
-                    const float u = P.fx * p.x * invz + P.cx;
-                    const float v = P.fy * p.y * invz + P.cy;
-                    if (isfinite(u) && isfinite(v)) {
-                        live = true;
-                        i0 = int(u - b); j0 = int(v - b);
-                        ue = u + b; ve = v + b;
-                    }
-                }
+                const BorderWin W = border_window(P, p);
+                live = W.live; i0 = W.i0; j0 = W.j0; ue = W.ue; ve = W.ve;
             }
             int num = 0, nan = 0;
             float res = 0.f;
@@ -597,7 +719,9 @@ __global__ void __launch_bounds__(128) k_supposed(Params P, Buffers B) {
     if (fl >= P.n_frames) return;
     const int f = P.frame0 + fl;
     FrameCtl &ctl = B.ctl[f];
-    int np = ctl.n_real, poff = ctl.pts_used, boff = ctl.bnd_used;
+    // offsets of a supposed plane's clouds are relative to the frame's supposed-plane region of the arenas
+    int np = ctl.n_real, poff = 0, boff = 0;
+    const int preal = ctl.pts_used, breal = ctl.bnd_used;
     for (int i = ctl.n_real - 1; i >= 0; --i) {
         const int m = ctl.planes[i].src;
         const Model &M = ctl.models[m];
@@ -619,7 +743,7 @@ __global__ void __launch_bounds__(128) k_supposed(Params P, Buffers B) {
             if (coef[3] < 0) { coef[0] = -coef[0]; coef[1] = -coef[1]; coef[2] = -coef[2]; coef[3] = -coef[3]; }
             if (!plane_not_seen(ctl, np, coef)) continue;
             const int npts = P.n_grid * P.n_grid + L.n_inliers;
-            if (np >= SPX_MAX_PLANES || poff + npts > P.pts_cap || boff + L.n_inliers > P.bnd_cap) { ctl.flags |= unsigned(SPX_FRAME_OVERFLOW); continue; }
+            if (np >= SPX_MAX_PLANES || preal + poff + npts > P.pts_cap || breal + boff + L.n_inliers > P.bnd_cap) { ctl.flags |= unsigned(SPX_FRAME_OVERFLOW); continue; }
             PlaneRec &R = ctl.planes[np];
             R.coef[0] = coef[0]; R.coef[1] = coef[1]; R.coef[2] = coef[2]; R.coef[3] = coef[3];
             R.n_points = npts; R.n_boundary = L.n_inliers; R.points_off = poff; R.boundary_off = boff;
@@ -629,7 +753,7 @@ __global__ void __launch_bounds__(128) k_supposed(Params P, Buffers B) {
             ++np;
         }
     }
-    ctl.n_planes = np; ctl.pts_used = poff; ctl.bnd_used = boff;
+    ctl.n_planes = np; ctl.pts_sup = poff; ctl.bnd_sup = boff;
 }
 
 // clouds of the supposed planes (src/Frame.cc:1092-1110, 983-989) and the every-20th-inlier boundary fallback
@@ -639,8 +763,8 @@ __global__ void __launch_bounds__(128) k_pack_supposed(Params P, Buffers B) {
     const FrameCtl &ctl = B.ctl[f];
     if (k >= ctl.n_planes) return;
     const PlaneRec &R = ctl.planes[k];
-    spx_point *pts = B.out_pts + B.frame_offs[size_t(f) * 3 + 1] + R.points_off;
-    spx_point *bnd = B.out_bnd + B.frame_offs[size_t(f) * 3 + 2] + R.boundary_off;
+    spx_point *pts = B.out_pts + B.frame_offs[size_t(f) * 5 + (R.is_supposed ? 3 : 1)] + R.points_off;
+    spx_point *bnd = B.out_bnd + B.frame_offs[size_t(f) * 5 + (R.is_supposed ? 4 : 2)] + R.boundary_off;
     if (!R.is_supposed) {
         if (ctl.models[R.src].n_contour == 0 && P.enable_supposed) {
             for (int j = threadIdx.x; j < R.n_boundary; j += blockDim.x) {
@@ -672,19 +796,27 @@ __global__ void __launch_bounds__(128) k_pack_supposed(Params P, Buffers B) {
     }
 }
 
-// exclusive scan of the per-frame totals of a frame range (one CTA): where each frame's planes / points / boundary
-// points start in the output buffers the pack kernels write to (base_* = where the range's results start)
-__global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B, long long base_pl, long long base_pt, long long base_bd,
-                                                        long long *totals) {
+// exclusive scan of the per-frame totals of a frame range (one CTA): where each frame's plane records and clouds
+// start in the output buffers (base_* = where the range's results start).  stage 0, right after k_postfilter: the
+// real planes' points / boundary points (their packing then overlaps the line fits); stage 1, after k_supposed: the
+// plane records and the supposed planes' clouds, which follow the real part of the range.
+// tot: 8 values, [0..2] final totals (planes, points, boundary points), [5], [6] the real part of [1], [2].
+__global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B, int stage, long long base_pl, long long base_pt, long long base_bd,
+                                                        long long *tot) {
     __shared__ long long s_run[3];
     __shared__ long long s_w[3][32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long real_pt = stage ? tot[5] : 0, real_bd = stage ? tot[6] : 0;
     if (tid < 3) s_run[tid] = 0;
     __syncthreads();
     for (int base = 0; base < P.n_frames; base += 1024) {
         const int f = base + tid;
         long long v[3] = {0, 0, 0};
-        if (f < P.n_frames) { const FrameCtl &K = B.ctl[P.frame0 + f]; v[0] = K.n_planes; v[1] = K.pts_used; v[2] = K.bnd_used; }
+        if (f < P.n_frames) {
+            const FrameCtl &K = B.ctl[P.frame0 + f];
+            if (stage == 0) { v[1] = K.pts_used; v[2] = K.bnd_used; }
+            else { v[0] = K.n_planes; v[1] = K.pts_sup; v[2] = K.bnd_sup; }
+        }
         long long inc[3];
         for (int k = 0; k < 3; ++k) {
             long long x = v[k];
@@ -702,25 +834,32 @@ __global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B, long 
             }
         }
         __syncthreads();
-        long long tot[3];
+        long long totl[3];
         for (int k = 0; k < 3; ++k) {
             const long long excl = s_run[k] + s_w[k][wid] + inc[k] - v[k];
-            const long long gb = k == 0 ? base_pl : (k == 1 ? base_pt : base_bd);
-            if (f < P.n_frames) B.frame_offs[size_t(P.frame0 + f) * 3 + k] = gb + excl;
-            tot[k] = excl + v[k];
+            if (f < P.n_frames) {
+                long long *fo = B.frame_offs + size_t(P.frame0 + f) * 5;
+                if (stage == 0) { if (k == 1) fo[1] = base_pt + excl; if (k == 2) fo[2] = base_bd + excl; }
+                else { if (k == 0) fo[0] = base_pl + excl; if (k == 1) fo[3] = base_pt + real_pt + excl; if (k == 2) fo[4] = base_bd + real_bd + excl; }
+            }
+            totl[k] = excl + v[k];
         }
         __syncthreads();
-        if (tid == 1023) for (int k = 0; k < 3; ++k) s_run[k] = tot[k];
+        if (tid == 1023) for (int k = 0; k < 3; ++k) s_run[k] = totl[k];
         __syncthreads();
     }
-    if (tid < 3) totals[tid] = s_run[tid];
+    if (tid == 0) {
+        if (stage == 0) { tot[5] = s_run[1]; tot[6] = s_run[2]; }
+        else { tot[0] = s_run[0]; tot[1] = real_pt + s_run[1]; tot[2] = real_bd + s_run[2]; }
+    }
 }
 
 // frame headers and plane records with batch-global offsets; one CTA per frame
 __global__ void __launch_bounds__(128) k_emit_records(Params P, Buffers B) {
     const int f = P.frame0 + blockIdx.x;
     const FrameCtl &ctl = B.ctl[f];
-    const long long o_pl = B.frame_offs[size_t(f) * 3 + 0], o_pt = B.frame_offs[size_t(f) * 3 + 1], o_bd = B.frame_offs[size_t(f) * 3 + 2];
+    const long long *fo5 = B.frame_offs + size_t(f) * 5;
+    const long long o_pl = fo5[0];
     if (threadIdx.x == 0) {
         spx_frame_header h;
         h.n_real = ctl.n_real; h.n_planes = ctl.n_planes; h.first_plane = int(o_pl); h.flags = ctl.flags;
@@ -731,7 +870,7 @@ __global__ void __launch_bounds__(128) k_emit_records(Params P, Buffers B) {
         spx_plane o;
         o.coef[0] = R.coef[0]; o.coef[1] = R.coef[1]; o.coef[2] = R.coef[2]; o.coef[3] = R.coef[3];
         o.n_points = R.n_points; o.n_boundary = R.n_boundary;
-        o.points_off = o_pt + R.points_off; o.boundary_off = o_bd + R.boundary_off;
+        o.points_off = fo5[R.is_supposed ? 3 : 1] + R.points_off; o.boundary_off = fo5[R.is_supposed ? 4 : 2] + R.boundary_off;
         o.src = R.src; o.is_supposed = R.is_supposed;
         B.out_planes[o_pl + k] = o;
     }

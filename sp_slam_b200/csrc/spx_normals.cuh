@@ -22,8 +22,8 @@ __global__ void __launch_bounds__(256) k_backproject(const float *__restrict__ d
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.N) return;
     const int r = i / P.w, c = i - r * P.w;
-    const char *img = reinterpret_cast<const char *>(depth) + size_t(f) * P.frame_stride;
-    const float z = *reinterpret_cast<const float *>(img + size_t(r) * P.dis * P.pitch + size_t(c) * P.dis * sizeof(float));
+    const char *img = reinterpret_cast<const char *>(depth) + size_t(f) * P.samp_fstride;
+    const float z = *reinterpret_cast<const float *>(img + size_t(r) * P.samp_rstep + size_t(c) * P.dis * sizeof(float));
     const float x = (float(c * P.dis) - P.cx) * z / P.fx;
     const float y = (float(r * P.dis) - P.cy) * z / P.fy;
     const size_t o = size_t(f) * P.N + i;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_edge_chamfer(const float
     const size_t fo = size_t(f) * P.N;
     const int r0 = band * kBandRows, r1 = min(r0 + kBandRows, h);
     const int ra = max(r0 - kBandHalo, 0), rb = min(r1 + kBandHalo, h);
-    const char *img = reinterpret_cast<const char *>(depth) + size_t(f) * P.frame_stride;
+    const char *img = reinterpret_cast<const char *>(depth) + size_t(f) * P.samp_fstride;
     const float initv = fminf(float(w + h), kDistCap);
 
     // ---- phase 1: mask bits of rows [ra, rb) ----
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_edge_chamfer(const float
             for (int ch = 0; ch < NCH; ++ch) {
                 const int c = ch * 32 + lane;
                 dst[ch] = (r >= 0 && r < h && c < w)
-                              ? *reinterpret_cast<const float *>(img + size_t(r) * P.dis * P.pitch + size_t(c) * P.dis * sizeof(float))
+                              ? *reinterpret_cast<const float *>(img + size_t(r) * P.samp_rstep + size_t(c) * P.dis * sizeof(float))
                               : 0.0f;
             }
         };
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kNormThreads) k_normals_link(const float *__re
     const int w = P.w, h = P.h;
     const size_t fo = size_t(f) * P.N;
     const int tid = threadIdx.x;
-    const char *img = reinterpret_cast<const char *>(depth) + size_t(f) * P.frame_stride;
+    const char *img = reinterpret_cast<const char *>(depth) + size_t(f) * P.samp_fstride;
 
     // ---- 1. cloud region: thread = one region column, 5 region rows per sweep (all loads of a thread in flight) ----
     int nonfinite = 0;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kNormThreads) k_normals_link(const float *__re
         const bool cin = c >= 0 && c < w;
         const float xfac = float(c * P.dis) - P.cx;
         const char *colp = img + size_t(cin ? c : 0) * P.dis * sizeof(float);
-        const size_t rstep = size_t(P.dis) * P.pitch;
+        const size_t rstep = P.samp_rstep;
         const bool cown = lx >= 7 && lx < 7 + kTW;
         float zz[6];
 #pragma unroll
@@ -556,6 +556,19 @@ __global__ void __launch_bounds__(256) k_convert_u16(const uint16_t *__restrict_
     float4 o;
     o.x = float(v.x) * alpha; o.y = float(v.y) * alpha; o.z = float(v.z) * alpha; o.w = float(v.w) * alpha;
     reinterpret_cast<float4 *>(dst)[i] = o;
+}
+
+// the same for the sampled rows only (sparse upload): row m of frame f sits at its place in the full image, (f * rows + m * dis) * cols
+__global__ void __launch_bounds__(128) k_convert_u16_rows(const uint16_t *__restrict__ src, float *__restrict__ dst, int cols, int rows, int h,
+                                                          int dis, float alpha) {
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x4 >= cols / 4) return;
+    const int f = blockIdx.y / h, m = blockIdx.y - f * h;
+    const size_t off = (size_t(f) * rows + size_t(m) * dis) * cols;
+    const ushort4 v = reinterpret_cast<const ushort4 *>(src + off)[x4];
+    float4 o;
+    o.x = float(v.x) * alpha; o.y = float(v.y) * alpha; o.z = float(v.z) * alpha; o.w = float(v.w) * alpha;
+    reinterpret_cast<float4 *>(dst + off)[x4] = o;
 }
 
 // plane_d for caller-supplied normals ("feed the reference's normals")

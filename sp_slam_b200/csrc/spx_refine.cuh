@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(128) k_postfilter(Params P, Buffers B) {
         poff += npts; boff += nb;
         ++np;
     }
-    ctl.n_real = np; ctl.n_planes = np; ctl.pts_used = poff; ctl.bnd_used = boff; ctl.n_lines = 0;
+    ctl.n_real = np; ctl.n_planes = np; ctl.pts_used = poff; ctl.bnd_used = boff; ctl.pts_sup = 0; ctl.bnd_sup = 0; ctl.n_lines = 0;
 }
 
 // ExtractIndices(negative = false) of the kept planes: inlier points in inlier_indices order (src/Frame.cc:925-928)
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(256) k_pack_points(Params P, Buffers B) {
     if (k < 0) return;
     spx_point pt;
     pt.x = B.px[fo + q]; pt.y = B.py[fo + q]; pt.z = B.pz[fo + q]; pt.rgba = pack_rgba(0, 0, 250);
-    B.out_pts[B.frame_offs[size_t(f) * 3 + 1] + ctl.planes[k].points_off + B.pos[fo + q]] = pt;
+    B.out_pts[B.frame_offs[size_t(f) * 5 + 1] + ctl.planes[k].points_off + B.pos[fo + q]] = pt;
 }
 
 // regions[i].getContour() of the kept planes (src/Frame.cc:930-932); one CTA per (model, frame)
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(128) k_pack_contours(Params P, Buffers B) {
     if (M.plane < 0 || M.n_contour == 0) return;
     const size_t fo = size_t(f) * P.N;
     const int *src = B.contour_idx + size_t(f) * P.contour_cap + M.contour_off;
-    spx_point *dst = B.out_bnd + B.frame_offs[size_t(f) * 3 + 2] + ctl.planes[M.plane].boundary_off;
+    spx_point *dst = B.out_bnd + B.frame_offs[size_t(f) * 5 + 2] + ctl.planes[M.plane].boundary_off;
     for (int j = threadIdx.x; j < M.n_contour; j += blockDim.x) {
         const int q = src[j];
         spx_point pt;

@@ -11,6 +11,15 @@ struct Params {
     int rows, cols;
     size_t pitch;          // bytes
     size_t frame_stride;   // bytes
+    // where the kernels that only need the organized cloud's samples (every Cloud.Dis-th row and column) read them:
+    // bytes between consecutive SAMPLED rows / between frames.  The full image: dis * pitch, frame_stride; a staging
+    // buffer that holds only the sampled rows (host input, sparse upload): its row pitch, h * pitch.
+    size_t samp_rstep, samp_fstride;
+    // sparse upload (k_border_fetch): the caller's page-locked image the missing window sectors are fetched from
+    size_t host_pitch, host_fstride;   // bytes
+    float  full_alpha;     // 16-bit host image: depth = float(d) * full_alpha (mDepthMapFactor)
+    int    fetch_vec;      // 16-byte aligned host rows and cols % 8 == 0: whole sectors move as vectors
+    int    fetch_skip_sampled;   // the rows at multiples of Cloud.Dis are on the device already
     int n_frames;          // frames of this launch group
     int lines_in_global;   // test knob: run every k_lines item on the global-memory path (contours beyond the smem buffer use it)
     int refine_fast;       // 1: k_refine2 (a CTA per frame) where its table fits; 0: k_refine (a warp per frame) for all
@@ -87,9 +96,10 @@ struct FrameCtl {
     int n_models;
     int n_real, n_planes;
     unsigned flags;
-    int pts_used, bnd_used;
+    int pts_used, bnd_used;   // points / boundary points of the REAL planes (set by k_postfilter)
+    int pts_sup, bnd_sup;     // ... of the supposed planes (set by k_supposed)
     int n_lines;
-    int pad[3];
+    int pad[1];
     Cand     cand[SPX_MAX_CAND];
     Model    models[SPX_MAX_MODELS];
     PlaneRec planes[SPX_MAX_PLANES];
@@ -120,13 +130,16 @@ struct Buffers {
     int   *line_inl;              // inlier index scratch (contour_cap per frame)
     spx_point *line_pts;          // accepted line inlier points (contour_cap per frame)
     FrameCtl *ctl;
-    // compacted outputs: frame f's planes / points / boundary points start at frame_offs[3f + 0/1/2]
+    unsigned *fetch_bits;         // sparse upload: claimed 8-pixel sectors, rows x ceil(ceil(cols/8)/32) words per frame
+    // compacted outputs.  The point / boundary arenas hold the clouds of all REAL planes first and those of all supposed
+    // planes behind them, so the real part can be packed while the line fits still run.  frame_offs[5f + k]: k = 0 plane
+    // records, 1 / 2 points / boundary points of the frame's real planes, 3 / 4 of its supposed planes (all absolute).
     spx_frame_header *out_frames;
     spx_plane *out_planes;
     spx_point *out_pts;
     spx_point *out_bnd;
-    long long *out_totals;        // [0] planes, [1] points, [2] boundary
-    long long *frame_offs;        // per frame: plane, point, boundary offsets (3 per frame)
+    long long *out_totals;        // slots of 8: [0] planes, [1] points, [2] boundary points; [5], [6] the real-plane part of [1], [2]
+    long long *frame_offs;        // 5 per frame
 };
 
 }  // namespace spx
