@@ -216,6 +216,38 @@ typedef struct spx_line_info {
 /* one record per SACSegmentation::segment call of GeneratePlanesFromBoundries, in the reference's call order */
 int spx_get_lines(spx_ctx *ctx, int frame, spx_line_info *lines /* SPX_MAX_MODELS*SPX_MAX_LINES */, int *n_lines);
 
+/* ================= the steps either side of the path ================= */
+
+/* N4.  replaces: pcl::VoxelGrid<pcl::PointXYZRGB> voxel; voxel.setLeafSize(lx, ly, lz); voxel.setInputCloud(c); voxel.filter(out)
+ * (src/MapDrawer.cc:91-92,115-116, src/PointCloudMapping.cc:117-118,172-173; dead path src/Frame.cc:810-814) for
+ * `n_clouds` independent clouds in one call.  Cloud s = points[cloud_off[s] .. cloud_off[s+1]) (HOST memory); its
+ * downsampled points land in out[out_off[s] .. out_off[s+1]) in PCL's order (ascending voxel index); `out` must hold
+ * as many points as the input, `out_off` n_clouds + 1 entries.  A cloud whose voxel indices would overflow an int comes
+ * back unchanged, as PCL does after its "leaf size is too small" warning. */
+int spx_voxel_grid(spx_ctx *ctx, const spx_point *points, const int64_t *cloud_off, int n_clouds, const float leaf[3],
+                   spx_point *out, int64_t *out_off);
+/* the same on the device for the clouds of the last spx_extract_batch_device, before spx_fetch_results:
+ * which = 0 every plane's mvPlanePoints, which = 1 every plane's mvBoundaryPoints (the contours); the plane records'
+ * counts / offsets and the totals are rewritten.  Off by default: the reference stores both raw (src/Frame.cc:925-932). */
+int spx_voxel_downsample_results(spx_ctx *ctx, float leaf, int which);
+
+/* N1.  replaces: Map::AssociatePlanesByBoundary + Map::PointDistanceFromPlane (src/Map.cc:196-283,345-361) for the planes
+ * of one frame against a device-resident copy of the map planes.  spx_map_upload mirrors the map whenever it changes
+ * (new MapPlane, MapPlane::UpdateBoundary, src/Tracking.cc:434-441,1288-1291): world coefficients (4 per plane) and
+ * world-frame boundary clouds, map planes in the VISITING order of the reference's loops -- the first n_seen are
+ * mspMapPlanes, the rest mspNotSeenMapPlanes (the reference iterates std::set<MapPlane*>, i.e. in pointer order).
+ * spx_map_associate takes the frame planes' world coefficients (Frame::ComputePlaneWorldCoeff, src/Frame.cc:1146-1150)
+ * and the thresholds Map reads from YAML (Plane.AssociationDisRef, AssociationAngRef, VerticalThreshold,
+ * ParallelThreshold; src/Map.cc:30-37) and returns, per frame plane, the index of the associated / vertical / parallel
+ * map plane in that order (or -1: mvpMapPlanes[i] / mvpVerticalPlanes[i] / mvpParallelPlanes[i] stay null) and the
+ * final ldTh. */
+typedef struct spx_map spx_map;
+int  spx_map_create(spx_ctx *ctx, spx_map **out);
+void spx_map_destroy(spx_map *map);
+int  spx_map_upload(spx_map *map, const float *map_w, const spx_point *boundary, const int64_t *boundary_off, int n_seen, int n_map);
+int  spx_map_associate(spx_map *map, const float *plane_w, int n_planes, float dis_th, float ang_th, float ver_th, float par_th,
+                       int32_t *assoc, int32_t *vertical, int32_t *parallel, float *assoc_dist);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,10 @@ def lib():
         L.orc_sac_line.argtypes = [vp, i32, C.c_double, i32, vp, vp, C.POINTER(i32)]
         L.orc_sac_line.restype = i32
         L.orc_ransac_draws.argtypes = [i32, i32, vp]
+        L.orc_voxel_grid.argtypes = [vp, i32, vp, vp, vp]
+        L.orc_voxel_grid.restype = i32
+        L.orc_associate_planes.argtypes = [vp, i32, vp, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
+        L.orc_associate_planes.restype = None
         _lib = L
     return _lib
 
@@ -272,3 +276,29 @@ def ransac_draws(n: int, n_draws: int) -> np.ndarray:
     out = np.empty((n_draws, 2), np.int32)
     lib().orc_ransac_draws(int(n), int(n_draws), out.ctypes.data)
     return out
+
+
+def voxel_grid(points: np.ndarray, leaf):
+    """pcl::VoxelGrid<PointXYZRGB> (PCL 1.8.0) on one cloud; returns (downsampled cloud, voxel index per output point)."""
+    pts = np.ascontiguousarray(points, dtype=POINT_DTYPE)
+    leaf3 = np.broadcast_to(np.asarray(leaf, np.float32), (3,)).copy()
+    out = np.empty(max(len(pts), 1), POINT_DTYPE)
+    idx = np.empty(max(len(pts), 1), np.int32)
+    n = lib().orc_voxel_grid(pts.ctypes.data, len(pts), leaf3.ctypes.data, out.ctypes.data, idx.ctypes.data)
+    return out[:n].copy(), idx[:n].copy()
+
+
+def associate_planes(plane_w, map_w, boundaries, n_seen=None, dis_th=0.2, ang_th=0.8, ver_th=0.08716, par_th=0.9962):
+    """Map::AssociatePlanesByBoundary (src/Map.cc:196-283) for one frame; returns (assoc, vertical, parallel, dist)."""
+    plane_w = np.ascontiguousarray(plane_w, np.float32).reshape(-1, 4)
+    map_w = np.ascontiguousarray(map_w, np.float32).reshape(-1, 4)
+    n, n_map = len(plane_w), len(map_w)
+    off = np.zeros(n_map + 1, np.int64)
+    off[1:] = np.cumsum([len(b) for b in boundaries])
+    pts = np.ascontiguousarray(np.concatenate([np.asarray(b, POINT_DTYPE) for b in boundaries]) if n_map else np.empty(0, POINT_DTYPE))
+    a, v, p = (np.full(max(n, 1), -1, np.int32) for _ in range(3))
+    d = np.zeros(max(n, 1), np.float32)
+    lib().orc_associate_planes(plane_w.ctypes.data, n, map_w.ctypes.data, pts.ctypes.data, off.ctypes.data,
+                               n_map if n_seen is None else n_seen, n_map, dis_th, ang_th, ver_th, par_th,
+                               a.ctypes.data, v.ctypes.data, p.ctypes.data, d.ctypes.data)
+    return a[:n], v[:n], p[:n], d[:n]

@@ -1036,4 +1036,122 @@ void orc_ransac_draws(int n, int n_draws, int32_t *pairs) {
     for (int i = 0; i < n_draws; ++i) { int s[2]; sac.draw(s); pairs[2 * i] = s[0]; pairs[2 * i + 1] = s[1]; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// N4: pcl::VoxelGrid<pcl::PointXYZRGB>::applyFilter, PCL 1.8.0 filters/impl/voxel_grid.hpp, as SP-SLAM
+// configures it: setLeafSize(l, l, l), everything else default (downsample_all_data_ = true, min_points_per_voxel_ = 0,
+// no filter field).  Call sites: src/MapDrawer.cc:91-92,115-116, src/PointCloudMapping.cc:117-118,172-173 and the dead
+// path src/Frame.cc:810-814.
+//   1. getMinMax3D over the finite points; 2. if the voxel index range overflows an int the filter warns and returns
+//   the input unchanged; 3. min_b = int(floor(min * inverse_leaf)), div_b = max_b - min_b + 1; 4. every finite point gets
+//   idx = ijk . (1, div_b.x, div_b.x * div_b.y) with ijk = int(floor(p * inverse_leaf) - float(min_b));
+//   5. std::sort of (idx, point) by idx -- NOT stable: the order of points inside a voxel is libstdc++'s introsort order;
+//   6. one output point per run of equal idx, in ascending idx order: CentroidPoint<PointXYZRGB> = fp32 running sums of
+//   x, y, z and of r, g, b, a (as floats) in that order, divided by float(n); colours truncated to uint32.
+// Returns the number of output points (out must hold n).
+// ---------------------------------------------------------------------------------------------------------------
+int orc_voxel_grid(const orc_point *pts, int n, const float leaf[3], orc_point *out, int32_t *out_idx) {
+    if (n <= 0) return 0;
+    const float inv[3] = {1.0f / leaf[0], 1.0f / leaf[1], 1.0f / leaf[2]};   // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = 0; i < n; ++i) {
+        const float v[3] = {pts[i].x, pts[i].y, pts[i].z};
+        if (!std::isfinite(v[0]) || !std::isfinite(v[1]) || !std::isfinite(v[2])) continue;
+        for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], v[k]); mx[k] = std::max(mx[k], v[k]); }
+    }
+    const int64_t dx = static_cast<int64_t>((mx[0] - mn[0]) * inv[0]) + 1;
+    const int64_t dy = static_cast<int64_t>((mx[1] - mn[1]) * inv[1]) + 1;
+    const int64_t dz = static_cast<int64_t>((mx[2] - mn[2]) * inv[2]) + 1;
+    if ((dx * dy * dz) > static_cast<int64_t>(std::numeric_limits<int32_t>::max())) {
+        for (int i = 0; i < n; ++i) { out[i] = pts[i]; if (out_idx) out_idx[i] = -1; }   // "Leaf size is too small": output = *input_
+        return n;
+    }
+    int min_b[3], max_b[3], div_b[3];
+    for (int k = 0; k < 3; ++k) {
+        min_b[k] = static_cast<int>(std::floor(mn[k] * inv[k]));
+        max_b[k] = static_cast<int>(std::floor(mx[k] * inv[k]));
+        div_b[k] = max_b[k] - min_b[k] + 1;
+    }
+    const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+    struct Item { unsigned idx; unsigned pt; bool operator<(const Item &o) const { return idx < o.idx; } };   // cloud_point_index_idx
+    std::vector<Item> iv;
+    iv.reserve(size_t(n));
+    for (int i = 0; i < n; ++i) {
+        const float v[3] = {pts[i].x, pts[i].y, pts[i].z};
+        if (!std::isfinite(v[0]) || !std::isfinite(v[1]) || !std::isfinite(v[2])) continue;
+        const int i0 = static_cast<int>(std::floor(v[0] * inv[0]) - static_cast<float>(min_b[0]));
+        const int i1 = static_cast<int>(std::floor(v[1] * inv[1]) - static_cast<float>(min_b[1]));
+        const int i2 = static_cast<int>(std::floor(v[2] * inv[2]) - static_cast<float>(min_b[2]));
+        iv.push_back({static_cast<unsigned>(i0 * mul[0] + i1 * mul[1] + i2 * mul[2]), static_cast<unsigned>(i)});
+    }
+    std::sort(iv.begin(), iv.end(), std::less<Item>());
+    int n_out = 0;
+    for (size_t a = 0; a < iv.size();) {
+        size_t b = a + 1;
+        while (b < iv.size() && iv[b].idx == iv[a].idx) ++b;
+        float sx = 0.f, sy = 0.f, sz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
+        for (size_t k = a; k < b; ++k) {
+            const orc_point &p = pts[iv[k].pt];
+            sx += p.x; sy += p.y; sz += p.z;
+            sr += float((p.rgba >> 16) & 255u); sg += float((p.rgba >> 8) & 255u); sb += float(p.rgba & 255u); sa += float(p.rgba >> 24);
+        }
+        const float fn = float(b - a);
+        orc_point o;
+        o.x = sx / fn; o.y = sy / fn; o.z = sz / fn;
+        o.rgba = (static_cast<uint32_t>(sa / fn) << 24) | (static_cast<uint32_t>(sr / fn) << 16) | (static_cast<uint32_t>(sg / fn) << 8) |
+                 static_cast<uint32_t>(sb / fn);
+        if (out_idx) out_idx[n_out] = int32_t(iv[a].idx);
+        out[n_out++] = o;
+        a = b;
+    }
+    return n_out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// N1: Map::AssociatePlanesByBoundary for the planes of one frame (src/Map.cc:196-283) and
+// Map::PointDistanceFromPlane (src/Map.cc:345-361).  plane_w: world-frame coefficients of the frame's planes
+// (Frame::ComputePlaneWorldCoeff, src/Frame.cc:1146-1150, is the caller's); map planes are visited in the order given
+// (the reference iterates a std::set<MapPlane*>, i.e. in pointer order), first `n_seen` = mspMapPlanes, the rest =
+// mspNotSeenMapPlanes.  Outputs per frame plane: index of the associated / vertical / parallel map plane or -1.
+// ---------------------------------------------------------------------------------------------------------------
+static double point_distance_from_plane(const float pl[4], const orc_point *b, int n) {
+    double res = 100;
+    for (int k = 0; k < n; ++k) {
+        const float e = pl[0] * b[k].x + pl[1] * b[k].y + pl[2] * b[k].z + pl[3];
+        const double dis = std::abs(e);
+        if (dis < res) res = dis;
+    }
+    return res;
+}
+
+void orc_associate_planes(const float *plane_w, int n_planes, const float *map_w, const orc_point *map_bnd, const int64_t *map_off,
+                          int n_seen, int n_map, float dis_th, float ang_th, float ver_th, float par_th,
+                          int32_t *assoc, int32_t *vertical, int32_t *parallel, float *assoc_dist) {
+    for (int i = 0; i < n_planes; ++i) {
+        const float *pM = plane_w + 4 * i;
+        assoc[i] = vertical[i] = parallel[i] = -1;
+        float ldTh = dis_th, lverTh = ver_th, lparTh = par_th;
+        for (int j = 0; j < n_seen; ++j) {
+            const float *pW = map_w + 4 * j;
+            const float angle = pM[0] * pW[0] + pM[1] * pW[1] + pM[2] * pW[2];
+            if (angle > ang_th || angle < -ang_th) {
+                const double dis = point_distance_from_plane(pM, map_bnd + map_off[j], int(map_off[j + 1] - map_off[j]));
+                if (dis < ldTh) { ldTh = float(dis); assoc[i] = j; continue; }
+            }
+            if (angle < lverTh && angle > -lverTh) { lverTh = std::abs(angle); vertical[i] = j; continue; }
+            if (angle > lparTh || angle < -lparTh) { lparTh = std::abs(angle); parallel[i] = j; }
+        }
+        if (ldTh == dis_th) {
+            for (int j = n_seen; j < n_map; ++j) {
+                const float *pW = map_w + 4 * j;
+                const float angle = pM[0] * pW[0] + pM[1] * pW[1] + pM[2] * pW[2];
+                if (angle > ang_th || angle < -ang_th) {
+                    const double dis = point_distance_from_plane(pM, map_bnd + map_off[j], int(map_off[j + 1] - map_off[j]));
+                    if (dis < ldTh) { ldTh = float(dis); assoc[i] = j; }
+                }
+            }
+        }
+        if (assoc_dist) assoc_dist[i] = ldTh;
+    }
+}
+
 }  // extern "C"

@@ -114,6 +114,16 @@ int    orc_sac_line(const orc_point *pts, int n, double threshold, int max_iter,
 /* the index pairs RANSAC would draw for a cloud of n points, ignoring isSampleGood rejections */
 void   orc_ransac_draws(int n, int n_draws, int32_t *pairs /* 2*n_draws */);
 
+/* ---- SURVEY 8(f) rows ---- */
+/* N4: pcl::VoxelGrid<PointXYZRGB> (leaf per axis, defaults otherwise) on one cloud; returns the number of output points;
+ * out_idx (optional): the voxel index of every output point (-1 for the "leaf size too small" copy path) */
+int    orc_voxel_grid(const orc_point *pts, int n, const float leaf[3], orc_point *out, int32_t *out_idx);
+/* N1: Map::AssociatePlanesByBoundary for one frame's planes (world coefficients) against map planes given in visiting
+ * order (first n_seen seen, then not-seen), boundary clouds concatenated with offsets map_off[n_map + 1] */
+void   orc_associate_planes(const float *plane_w, int n_planes, const float *map_w, const orc_point *map_bnd, const int64_t *map_off,
+                            int n_seen, int n_map, float dis_th, float ang_th, float ver_th, float par_th,
+                            int32_t *assoc, int32_t *vertical, int32_t *parallel, float *assoc_dist);
+
 #ifdef __cplusplus
 }
 #endif

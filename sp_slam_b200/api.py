@@ -48,6 +48,7 @@ EXPORTS = (
     "spx_get_models", "spx_get_model_inliers", "spx_get_model_contour", "spx_get_lines",
     "spx_set_upload_mode", "spx_host_register", "spx_host_unregister", "spx_get_transfer_bytes",
     "spx_get_group_timeline",
+    "spx_voxel_grid", "spx_voxel_downsample_results", "spx_map_create", "spx_map_destroy", "spx_map_upload", "spx_map_associate",
 )
 
 
@@ -130,6 +131,13 @@ def lib():
         L.spx_get_model_contour.argtypes = [vp, i32, i32, vp]
         L.spx_get_lines.argtypes = [vp, i32, vp, C.POINTER(i32)]
         L.spx_get_group_timeline.argtypes = [vp, vp, i32, C.POINTER(i32)]
+        L.spx_voxel_grid.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+        L.spx_voxel_downsample_results.argtypes = [vp, C.c_float, i32]
+        L.spx_map_create.argtypes = [vp, C.POINTER(vp)]
+        L.spx_map_destroy.argtypes = [vp]
+        L.spx_map_destroy.restype = None
+        L.spx_map_upload.argtypes = [vp, vp, vp, vp, i32, i32]
+        L.spx_map_associate.argtypes = [vp, vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
         L.spx_set_upload_mode.argtypes = [vp, i32]
         L.spx_host_register.argtypes = [vp, sz]
         L.spx_host_unregister.argtypes = [vp]
@@ -338,6 +346,24 @@ class PlaneExtractor:
         self._ck(lib().spx_get_group_timeline(self._h, t.ctypes.data, 64, C.byref(n)))
         return t[:n.value].copy()
 
+    # ---- SURVEY 8(f) rows ----
+    def voxel_grid(self, clouds, leaf):
+        """pcl::VoxelGrid<PointXYZRGB> with leaf size `leaf` (scalar or 3 values) on a list of POINT_DTYPE arrays (host);
+        returns the list of downsampled clouds (PCL's order: ascending voxel index)."""
+        leaf3 = np.broadcast_to(np.asarray(leaf, np.float32), (3,)).copy()
+        off = np.zeros(len(clouds) + 1, np.int64)
+        off[1:] = np.cumsum([len(c) for c in clouds])
+        pts = np.ascontiguousarray(np.concatenate([np.asarray(c, POINT_DTYPE) for c in clouds]) if len(clouds) else np.empty(0, POINT_DTYPE))
+        out = np.empty(max(len(pts), 1), POINT_DTYPE)
+        out_off = np.zeros(len(clouds) + 1, np.int64)
+        self._ck(lib().spx_voxel_grid(self._h, pts.ctypes.data, off.ctypes.data, len(clouds), leaf3.ctypes.data, out.ctypes.data,
+                                      out_off.ctypes.data))
+        return [out[out_off[s]:out_off[s + 1]].copy() for s in range(len(clouds))]
+
+    def voxel_downsample_results(self, leaf: float, which: int):
+        """Downsample, on the device, every plane's cloud (which=0) or contour (which=1) of the last extract_device call."""
+        self._ck(lib().spx_voxel_downsample_results(self._h, C.c_float(leaf), which))
+
     def set_profile(self, on: bool):
         self._ck(lib().spx_set_profile(self._h, 1 if on else 0))
 
@@ -413,3 +439,45 @@ class PlaneExtractor:
         k = C.c_int()
         self._ck(lib().spx_get_lines(self._h, frame, l.ctypes.data, C.byref(k)))
         return l[:k.value].copy()
+
+
+class PlaneMap:
+    """Device-resident mirror of the map planes for Map::AssociatePlanesByBoundary (src/Map.cc:196-283)."""
+
+    def __init__(self, ext: PlaneExtractor):
+        self._ext = ext
+        self._m = C.c_void_p()
+        ext._ck(lib().spx_map_create(ext._h, C.byref(self._m)))
+
+    def close(self):
+        if getattr(self, "_m", None):
+            lib().spx_map_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, map_w: np.ndarray, boundaries: list, n_seen: int | None = None):
+        """map_w: (n_map, 4) world coefficients in the reference's visiting order; boundaries: per map plane a POINT_DTYPE
+        cloud (world frame); the first n_seen planes are mspMapPlanes, the rest mspNotSeenMapPlanes."""
+        map_w = np.ascontiguousarray(map_w, np.float32).reshape(-1, 4)
+        n_map = len(map_w)
+        off = np.zeros(n_map + 1, np.int64)
+        off[1:] = np.cumsum([len(b) for b in boundaries])
+        pts = np.ascontiguousarray(np.concatenate([np.asarray(b, POINT_DTYPE) for b in boundaries]) if n_map else np.empty(0, POINT_DTYPE))
+        self._ext._ck(lib().spx_map_upload(self._m, map_w.ctypes.data, pts.ctypes.data, off.ctypes.data,
+                                           n_map if n_seen is None else n_seen, n_map))
+
+    def associate(self, plane_w: np.ndarray, dis_th=0.2, ang_th=0.8, ver_th=0.08716, par_th=0.9962):
+        """Returns (assoc, vertical, parallel, dist): per frame plane the index of the matched map plane or -1
+        (defaults: Examples/RGB-D/TUM1.yaml:83-88)."""
+        plane_w = np.ascontiguousarray(plane_w, np.float32).reshape(-1, 4)
+        n = len(plane_w)
+        a, v, p = (np.full(max(n, 1), -1, np.int32) for _ in range(3))
+        d = np.zeros(max(n, 1), np.float32)
+        self._ext._ck(lib().spx_map_associate(self._m, plane_w.ctypes.data, n, C.c_float(dis_th), C.c_float(ang_th), C.c_float(ver_th),
+                                              C.c_float(par_th), a.ctypes.data, v.ctypes.data, p.ctypes.data, d.ctypes.data))
+        return a[:n], v[:n], p[:n], d[:n]

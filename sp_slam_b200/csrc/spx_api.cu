@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#include "spx_internal.h"
 #include "spx_lines.cuh"
 #include "spx_normals.cuh"
 #include "spx_refine.cuh"
@@ -59,12 +60,15 @@ struct spx_ctx {
     int n_streams = 1, min_group = 32, last_groups = 1;
     int refine_fast_max = 700;  // batches of at most this many frames use k_refine2
     bool refine_per_group = true;
-    int group_prio = 0;      // 1: group g's stream gets a priority that falls with g (earlier groups finish first)
+    double edge_weight = 0.5;   // host path: size of the first and the last frame group relative to the others
+    int group_prio = 1;      // 1: group g's stream gets a priority that falls with g (earlier groups finish first)
     int border_grid_cap = 0;
     int upload_mode = 0;     // host input: 0 auto (sparse upload for pinned images of batches >= sparse_min_frames), 1 whole image, 2 sparse whenever possible
     int sparse_min_frames = 1;
     bool use_prio = false;   // back stream with higher priority: measured slower (co-running kernels slow each other), kept as a knob
     std::vector<cudaStream_t> g_streams;      // front: upload, chamfer, normals (low priority)
+    std::vector<cudaStream_t> g_hstreams;     // host path: group g's stream, priority falling with g (the groups start one upload
+                                              // apart; the earlier one should finish first so that its download can start)
     std::vector<cudaStream_t> g_back;         // back: everything after the normals (high priority: it is what frees a group)
     std::vector<cudaEvent_t> g_link;          // fork of the group's side stream
     std::vector<cudaEvent_t> g_side;          // side stream done (real clouds packed)
@@ -266,7 +270,7 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
         if (src.u16) {
             if (st != compute_st) { SPX_CK(c, cudaEventRecord(c->g_xev[2 * g + 0], st)); SPX_CK(c, cudaStreamWaitEvent(compute_st, c->g_xev[2 * g + 0], 0)); st = compute_st; }
             const size_t per = size_t(P.rows) * P.cols;   // cols % 4 == 0 on this path
-            LAUNCH(k_convert_u16_rows, dim3(cdiv(P.cols / 4, 128), P.h * ng), 128, 0, c->d_depth16 + per * size_t(f0), c->d_depth + per * size_t(f0),
+            LAUNCH(k_convert_u16_rows, dim3(P.h * ng, cdiv(P.cols / 4, 128)), 128, 0, c->d_depth16 + per * size_t(f0), c->d_depth + per * size_t(f0),
                    P.cols, P.rows, P.h, P.dis, src.alpha);
         }
     } else if (src.depth) {   // host depth of this group -> staging buffer (tight pitch)
@@ -415,10 +419,23 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, boo
     c->t_call = std::chrono::steady_clock::now();
     c->g_host_ms.assign(size_t(2 * G), 0.f);
     if (group_pack && G > 1) SPX_CK(c, cudaStreamWaitEvent(c->up_stream, c->ev[0], 0));
+    // Host path: the first group is what the device waits for and the last is what the host waits for, so both are
+    // smaller than the ones in between (weights edge_w : 1 ... 1 : edge_w).
+    std::vector<int> bounds(size_t(G) + 1, 0);
+    {
+        const double ew = (group_pack && G >= 4) ? c->edge_weight : 1.0;
+        const double tw = double(G - 2) + 2.0 * ew;
+        double acc = 0.0;
+        for (int g = 0; g < G; ++g) {
+            acc += (g == 0 || g == G - 1) ? ew : 1.0;
+            bounds[size_t(g) + 1] = G == 1 ? F : std::min(F, std::max(bounds[size_t(g)] + 1, int(F * acc / tw + 0.5)));
+        }
+        bounds[size_t(G)] = F;
+    }
     for (int g = 0; g < G; ++g) {
-        const int f0 = int((long long)F * g / G), f1 = int((long long)F * (g + 1) / G);
-        cudaStream_t st = (G == 1) ? main_st : c->g_streams[g];
-        cudaStream_t st_back = (G == 1) ? main_st : (c->use_prio ? c->g_back[g] : c->g_streams[g]);
+        const int f0 = bounds[size_t(g)], f1 = bounds[size_t(g) + 1];
+        cudaStream_t st = (G == 1) ? main_st : (group_pack ? c->g_hstreams[g] : c->g_streams[g]);
+        cudaStream_t st_back = (G == 1) ? main_st : (c->use_prio ? c->g_back[g] : st);
         if (G > 1) SPX_CK(c, cudaStreamWaitEvent(st, c->ev[0], 0));
         SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 0], st));
         c->g_host_ms[2 * g] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - c->t_call).count();
@@ -607,6 +624,10 @@ int get_ctl(spx_ctx *c, int frame, FrameCtl *out) {
 
 }  // namespace
 
+int spx_internal_fail(spx_ctx *c, int code, const char *what, const char *msg) { return fail(c, code, "%s: %s", what, msg); }
+void *spx_internal_stream(spx_ctx *c) { return c->stream; }
+int spx_internal_device(spx_ctx *c) { return c->device; }
+
 extern "C" {
 
 void spx_default_config(spx_config *cfg) {
@@ -699,6 +720,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (const char *e = std::getenv("SPX_UPLOAD")) c->upload_mode = std::atoi(e);   // test / tuning knob (see spx_ctx::upload_mode)
     if (const char *e = std::getenv("SPX_SPARSE_MIN_FRAMES")) c->sparse_min_frames = std::atoi(e);   // tuning knob
     if (const char *e = std::getenv("SPX_REFINE_PER_GROUP")) c->refine_per_group = std::atoi(e) != 0;   // tuning knob
+    if (const char *e = std::getenv("SPX_EDGE_WEIGHT")) { const double v = std::atof(e); if (v > 0.05 && v <= 1.0) c->edge_weight = v; }   // tuning knob
     if (const char *e = std::getenv("SPX_GROUP_PRIO")) c->group_prio = std::atoi(e);   // tuning knob
     if (const char *e = std::getenv("SPX_BORDER_GRID")) c->border_grid_cap = std::atoi(e);   // tuning knob
     if (const char *e = std::getenv("SPX_PRIO")) c->use_prio = std::atoi(e) != 0;   // tuning knob
@@ -707,13 +729,15 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     SPX_CK_CREATE(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // numerically lower = higher priority
     for (int g = 0; g < c->n_streams; ++g) {
         cudaStream_t gs;
+        SPX_CK_CREATE(cudaStreamCreateWithPriority(&gs, cudaStreamNonBlocking, prio_lo));
+        c->g_streams.push_back(gs);
         int pr = prio_lo;
         if (c->group_prio) {   // prio_hi (numerically lowest) for group 0, falling to prio_lo for the last group
             const int levels = prio_lo - prio_hi + 1;
             pr = prio_hi + std::min(levels - 1, g * levels / c->n_streams);
         }
         SPX_CK_CREATE(cudaStreamCreateWithPriority(&gs, cudaStreamNonBlocking, pr));
-        c->g_streams.push_back(gs);
+        c->g_hstreams.push_back(gs);
         SPX_CK_CREATE(cudaStreamCreateWithPriority(&gs, cudaStreamNonBlocking, prio_hi));
         c->g_back.push_back(gs);
         cudaEvent_t le;
@@ -819,6 +843,7 @@ void spx_destroy(spx_ctx *c) {
     for (cudaEvent_t e : c->g_tot_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->g_xev) cudaEventDestroy(e);
     for (cudaStream_t gs : c->g_streams) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
+    for (cudaStream_t gs : c->g_hstreams) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
     for (cudaStream_t gs : c->g_back) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
     for (cudaEvent_t e : c->g_link) cudaEventDestroy(e);
     for (cudaEvent_t e : c->g_side) cudaEventDestroy(e);

@@ -561,9 +561,9 @@ __global__ void __launch_bounds__(256) k_convert_u16(const uint16_t *__restrict_
 // the same for the sampled rows only (sparse upload): row m of frame f sits at its place in the full image, (f * rows + m * dis) * cols
 __global__ void __launch_bounds__(128) k_convert_u16_rows(const uint16_t *__restrict__ src, float *__restrict__ dst, int cols, int rows, int h,
                                                           int dis, float alpha) {
-    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x4 = blockIdx.y * blockDim.x + threadIdx.x;   // rows on grid.x: frames * h exceeds the 65535 of grid.y
     if (x4 >= cols / 4) return;
-    const int f = blockIdx.y / h, m = blockIdx.y - f * h;
+    const int f = blockIdx.x / h, m = blockIdx.x - f * h;
     const size_t off = (size_t(f) * rows + size_t(m) * dis) * cols;
     const ushort4 v = reinterpret_cast<const ushort4 *>(src + off)[x4];
     float4 o;

@@ -391,3 +391,30 @@ def test_sparse_upload_equals_whole_image_upload(seq):
     finally:
         api.host_unregister(padded)
     e2.close()
+
+
+def test_sparse_upload_large_single_group(seq):
+    """One frame group of more than 65535 / h frames (the row-conversion grid of the 16-bit sparse path) and the float path."""
+    reps = 52
+    d8 = np.ascontiguousarray(seq)
+    u8 = np.round(np.clip(d8, 0, 13.0).astype(np.float64) * 5000.0).astype(np.uint16)
+    big = np.ascontiguousarray(np.tile(u8, (reps, 1, 1)))
+    n = len(big)
+    assert n * 160 > 65535
+    factor = float(np.float32(1.0) / np.float32(5000.0))
+    ext = api.PlaneExtractor(max_frames=n, n_streams=1)
+    small = ext.extract_batch_u16(u8, factor)
+    api.host_register(big)
+    try:
+        ext.set_upload_mode(2)
+        res = ext.extract_batch_u16(big, factor)
+        assert ext.transfer_bytes()[0] == n * 160 * 640 * 2
+    finally:
+        api.host_unregister(big)
+    assert np.array_equal(res.frames["n_planes"], np.tile(small.frames["n_planes"], reps))
+    for k in (0, 5, n - 8 + 3, n - 1):
+        a, b = res.frame(k), small.frame(k % 8)
+        assert np.array_equal(a.mvPlaneCoefficients.view(np.uint32), b.mvPlaneCoefficients.view(np.uint32))
+        for p, q in zip(a.mvPlanePoints + a.mvBoundaryPoints, b.mvPlanePoints + b.mvBoundaryPoints):
+            assert np.array_equal(p, q)
+    ext.close()
