@@ -141,6 +141,66 @@ def oracle_fps(depth: np.ndarray, n_threads: int, res: str):
     return len(depth) / dt, dt, int(na.sum()), tp, ts
 
 
+def measure_next_rows(ext, dev, host, F, rows, cols, stream, with_cpu):
+    """N4: device-side voxel downsampling (leaf 0.01 / 0.05) of every contour of the batch, between the extract and the
+    fetch.  N1: per-frame Map::AssociatePlanesByBoundary against a map made of the planes of the first 40 frames."""
+    import torch
+    from sp_slam_b200 import api
+    out = {}
+    ext.set_profile(False)
+    ext.extract_device(dev.data_ptr(), F, rows, cols)
+    base = ext.fetch()
+    n_bnd = len(base.boundary)
+    for leaf in (0.01, 0.05):
+        ts = []
+        for _ in range(3):
+            ext.extract_device(dev.data_ptr(), F, rows, cols)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ext.voxel_downsample_results(leaf, 1)
+            ts.append(time.perf_counter() - t0)
+        down = ext.fetch()
+        rec = {"leaf_m": leaf, "clouds": int(len(base.planes)), "points_in": n_bnd, "points_out": int(len(down.boundary)),
+               "ms": 1e3 * min(ts), "mpoints_per_s": n_bnd / min(ts) / 1e6}
+        if with_cpu:
+            from oracle import pyoracle
+            t0 = time.perf_counter()
+            k = 0
+            npts = 0
+            while time.perf_counter() - t0 < 1.0 and k < len(base.planes):
+                q = base.planes[k]
+                pyoracle.voxel_grid(base.boundary[q["boundary_off"]:q["boundary_off"] + q["n_boundary"]], leaf)
+                npts += int(q["n_boundary"]); k += 1
+            dt = time.perf_counter() - t0
+            rec["cpu_port_mpoints_per_s_1core"] = npts / dt / 1e6
+        out[f"voxel_grid_contours_leaf{leaf}"] = rec
+    fps = [base.frame(k) for k in range(min(F, 140))]
+    map_fps = fps[:40]
+    map_w = np.concatenate([fp.mvPlaneCoefficients for fp in map_fps])
+    bnds = [b for fp in map_fps for b in fp.mvBoundaryPoints]
+    pm = api.PlaneMap(ext)
+    pm.upload(map_w, bnds)
+    ts, tc, n_assoc = [], [], 0
+    for fp in fps[40:]:
+        t0 = time.perf_counter()
+        a, v, p, d = pm.associate(fp.mvPlaneCoefficients)
+        ts.append(time.perf_counter() - t0)
+        n_assoc += int((a >= 0).sum())
+        if with_cpu:
+            from oracle import pyoracle
+            t0 = time.perf_counter()
+            pyoracle.associate_planes(fp.mvPlaneCoefficients, map_w, bnds)
+            tc.append(time.perf_counter() - t0)
+    pm.close()
+    out["plane_association"] = {"map_planes": int(len(map_w)), "map_boundary_points": int(sum(len(b) for b in bnds)),
+                                "frames": len(ts), "associated_planes": n_assoc,
+                                "ms_per_frame_median": 1e3 * float(np.median(ts)),
+                                "cpu_port_ms_per_frame_median": (1e3 * float(np.median(tc))) if tc else None,
+                                "note": "host planes in, indices out, one call per frame (Map::AssociatePlanesByBoundary); "
+                                        "the CPU figure includes the ctypes call of the oracle"}
+    return out
+
+
 def intrinsics(res):
     from sp_slam_b200 import scenes
     return scenes.REALSENSE if res == "720p" else scenes.TUM1
@@ -223,7 +283,7 @@ def _main(out):
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1000, help="frames per step and per GPU")
     ap.add_argument("--ref-frames", type=int, default=500, help="frames per step of the CPU arm")
-    ap.add_argument("--cpu-sample", type=int, default=256, help="frames of the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=1000, help="frames of the cpu_baseline leg")
     ap.add_argument("--noise", default="none", choices=["none", "sensor"])
     ap.add_argument("--res", default="480p", choices=["480p", "720p"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -380,6 +440,10 @@ def _main(out):
         lat_ms["whole_image_upload"] = lat(1)
         lat_ms["sparse_upload"] = lat(2)
         one.close()
+    # SURVEY 8(f) rows either side of the path (N4 VoxelGrid of the contours, N1 plane association), rank 0 at N = 1
+    next_rows = None
+    if rank == 0 and world == 1:
+        next_rows = measure_next_rows(ext, dev, host, F, rows, cols, stream, not args.no_cpu_baseline)
     planes_per_frame = float(res.frames["n_planes"].mean())
     overflow = int((res.frames["flags"] != 0).sum())
 
@@ -427,11 +491,17 @@ def _main(out):
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             ns = min(F, args.cpu_sample)
-            fps, dt, _, tp, ts = oracle_fps(depth_np[:ns], cores, args.res)
+            oracle_fps(depth_np[: max(cores, 8)], cores, args.res)     # thread start-up, page faults
+            reps, dt, tp, ts = 0, 0.0, 0.0, 0.0
+            while reps < 3 or (dt < 2.0 and reps < 12):                # ~10-30 s of CPU work over all threads
+                _, d1, _, a, b = oracle_fps(depth_np[:ns], cores, args.res)
+                reps += 1; dt += d1; tp += a; ts += b
+            fps = reps * ns / dt
             cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"first {ns} frames of the workload, frame-parallel on {cores} host threads, {dt:.1f} s; "
+                   "sample": f"first {ns} frames of the workload x {reps} passes, frame-parallel on {cores} host threads, "
+                             f"{dt:.1f} s wall / {tp + ts:.1f} s of CPU work; "
                              f"oracle/ C++ port of the reference's PCL 1.8 path; per-frame 1-core time "
-                             f"{1e3 * (tp + ts) / ns:.2f} ms (plane {1e3 * tp / ns:.2f} + supposed {1e3 * ts / ns:.2f})"}
+                             f"{1e3 * (tp + ts) / (ns * reps):.2f} ms (plane {1e3 * tp / (ns * reps):.2f} + supposed {1e3 * ts / (ns * reps):.2f})"}
         line = {
             "metric": METRIC if args.res == "480p" else "1280x720 plane-extraction frames/s",
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -445,8 +515,9 @@ def _main(out):
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps,
                     "h2d_copied": xfer[0], "h2d_read_in_place": xfer[1],
                     "note": "spx_extract_batch on the pinned CV_32F batch: the rows the organized cloud samples (every Cloud.Dis-th) "
-                            "are uploaded with one strided copy per frame group, the border tests read their 21x21 full-resolution "
-                            "windows in place from the pinned image over PCIe; all Frame fields (planes + clouds) come back"},
+                            "are uploaded with one strided copy per frame group, the sectors of the 21x21 full-resolution windows the "
+                            "border tests read are fetched from the pinned image over PCIe by k_border_fetch (h2d_read_in_place); "
+                            "all Frame fields (planes + clouds) come back"},
             "e2e_whole_image": {"value": world * F * args.steps / (e2e_whole_ms * 1e-3), "unit": UNIT,
                                 "h2d_bytes_per_step": F * rows * cols * 4, "ms_per_step": e2e_whole_ms / args.steps,
                                 "note": "the same call with the whole image uploaded (spx_set_upload_mode 1; what a pageable buffer gets)"},
@@ -458,6 +529,7 @@ def _main(out):
             "latency_ms_per_frame_in_batch": ms / args.steps / F,
             "single_frame_latency_ms": lat_ms,
             "roofline": roofline,
+            "next_rows": next_rows,
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
         }

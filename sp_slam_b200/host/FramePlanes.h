@@ -97,6 +97,11 @@ public:
 
     spx_ctx *context() { return ctx_; }
 
+    // Page-lock the buffers the depth images live in (e.g. the cv::Mat data a loader recycles): uploads then run at PCIe
+    // rate and only the rows the organized cloud samples are copied (include/spx.h, "Host input").  Optional.
+    static bool PinHostBuffer(void *ptr, size_t bytes) { return spx_host_register(ptr, bytes) == SPX_OK; }
+    static void UnpinHostBuffer(void *ptr) { spx_host_unregister(ptr); }
+
 private:
     void append(int lo, int hi) {
         for (int k = lo; k < hi; ++k) {
@@ -123,6 +128,93 @@ private:
     spx_ctx *ctx_ = nullptr;
     spx_batch_result res_{};
     bool pending_ = false;
+};
+
+inline std::vector<spx_point> pack_cloud(const PointCloud &c) {
+    std::vector<spx_point> v(c.points.size());
+    for (size_t i = 0; i < v.size(); ++i) { v[i].x = c.points[i].x; v[i].y = c.points[i].y; v[i].z = c.points[i].z; v[i].rgba = c.points[i].rgba; }
+    return v;
+}
+
+// ---- N1: the plane-association part of ORB_SLAM2::Map (src/Map.cc:196-283,345-361) against a device copy of the map ----
+// Map calls Upload() whenever a MapPlane is added or its boundary grows (src/Tracking.cc:434-441,1288-1291) with the
+// planes in the order its loops visit them (mspMapPlanes first, then mspNotSeenMapPlanes), and Associate() where it
+// called AssociatePlanesByBoundary; the returned indices address that order (-1 = pointer stays null).
+class PlaneAssociator {
+public:
+    float mfDisTh = 0.2f, mfAngleTh = 0.8f, mfVerTh = 0.08716f, mfParTh = 0.9962f;   // Plane.Association* / Vertical / Parallel, src/Map.cc:30-37
+    explicit PlaneAssociator(spx_ctx *ctx) {
+        if (spx_map_create(ctx, &map_) != SPX_OK) throw std::runtime_error(std::string("spx_map_create: ") + spx_last_error(ctx));
+        ctx_ = ctx;
+    }
+    ~PlaneAssociator() { spx_map_destroy(map_); }
+    PlaneAssociator(const PlaneAssociator &) = delete;
+    PlaneAssociator &operator=(const PlaneAssociator &) = delete;
+
+    // worldPos[j]: MapPlane::GetWorldPos() (4x1), boundary[j]: MapPlane::mvBoundaryPoints (world frame)
+    void Upload(const std::vector<CoefMat> &worldPos, const std::vector<const PointCloud *> &boundary, int nSeen) {
+        std::vector<float> w(worldPos.size() * 4);
+        std::vector<int64_t> off(worldPos.size() + 1, 0);
+        std::vector<spx_point> pts;
+        for (size_t j = 0; j < worldPos.size(); ++j) {
+            for (int k = 0; k < 4; ++k) w[4 * j + size_t(k)] = worldPos[j].template at<float>(k);
+            const std::vector<spx_point> b = pack_cloud(*boundary[j]);
+            pts.insert(pts.end(), b.begin(), b.end());
+            off[j + 1] = int64_t(pts.size());
+        }
+        if (spx_map_upload(map_, w.data(), pts.data(), off.data(), nSeen, int(worldPos.size())) != SPX_OK)
+            throw std::runtime_error(std::string("spx_map_upload: ") + spx_last_error(ctx_));
+    }
+
+    // planeWorld[i]: Frame::ComputePlaneWorldCoeff(i) (src/Frame.cc:1146-1150).  Fills the indices of mvpMapPlanes[i],
+    // mvpVerticalPlanes[i], mvpParallelPlanes[i]; returns pF.mbNewPlane (some plane found no association).
+    bool AssociatePlanesByBoundary(const std::vector<CoefMat> &planeWorld, std::vector<int> &mapPlanes, std::vector<int> &verticalPlanes,
+                                   std::vector<int> &parallelPlanes) {
+        const int n = int(planeWorld.size());
+        std::vector<float> w(size_t(n) * 4);
+        for (int i = 0; i < n; ++i) for (int k = 0; k < 4; ++k) w[size_t(4 * i + k)] = planeWorld[size_t(i)].template at<float>(k);
+        mapPlanes.assign(size_t(n), -1); verticalPlanes.assign(size_t(n), -1); parallelPlanes.assign(size_t(n), -1);
+        if (n && spx_map_associate(map_, w.data(), n, mfDisTh, mfAngleTh, mfVerTh, mfParTh, mapPlanes.data(), verticalPlanes.data(),
+                                   parallelPlanes.data(), nullptr) != SPX_OK)
+            throw std::runtime_error(std::string("spx_map_associate: ") + spx_last_error(ctx_));
+        bool newPlane = false;
+        for (int v : mapPlanes) if (v < 0) newPlane = true;
+        return newPlane;
+    }
+
+private:
+    spx_ctx *ctx_ = nullptr;
+    spx_map *map_ = nullptr;
+};
+
+// ---- N4: the pcl::VoxelGrid<PointT> calls of the drawers (src/MapDrawer.cc:91-92,115-116; src/PointCloudMapping.cc:117-118) ----
+class VoxelGrid {
+public:
+    explicit VoxelGrid(spx_ctx *ctx) : ctx_(ctx) {}
+    void setLeafSize(float lx, float ly, float lz) { leaf_[0] = lx; leaf_[1] = ly; leaf_[2] = lz; }
+    void setInputCloud(const PointCloud *cloud) { in_ = cloud; }
+    void filter(PointCloud &output) {
+        const std::vector<spx_point> src = pack_cloud(*in_);
+        std::vector<spx_point> dst(src.size() ? src.size() : 1);
+        const int64_t off[2] = {0, int64_t(src.size())};
+        int64_t out_off[2] = {0, 0};
+        if (spx_voxel_grid(ctx_, src.data(), off, 1, leaf_, dst.data(), out_off) != SPX_OK)
+            throw std::runtime_error(std::string("spx_voxel_grid: ") + spx_last_error(ctx_));
+        output.points.resize(size_t(out_off[1]));
+        for (size_t i = 0; i < output.points.size(); ++i) {
+            PointT &q = output.points[i];
+            q.x = dst[i].x; q.y = dst[i].y; q.z = dst[i].z; q.rgba = dst[i].rgba;
+#ifndef SPX_WITH_PCL
+            q.data_w = 1.0f;
+#endif
+        }
+        output.width = uint32_t(output.points.size()); output.height = 1; output.is_dense = true;
+    }
+
+private:
+    spx_ctx *ctx_;
+    const PointCloud *in_ = nullptr;
+    float leaf_[3] = {0.01f, 0.01f, 0.01f};
 };
 
 }  // namespace spx_host

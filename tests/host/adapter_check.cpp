@@ -28,5 +28,23 @@ int main(int argc, char **argv) {
         std::printf("plane %d %.9g %.9g %.9g %.9g %zu %zu %.12g\n", i, c.at<float>(0), c.at<float>(1), c.at<float>(2), c.at<float>(3),
                     fp.mvPlanePoints[size_t(i)].points.size(), fp.mvBoundaryPoints[size_t(i)].points.size(), sx);
     }
+    // N1 / N4 adapters: the frame's own planes as the map (identity pose), then the voxel grid of the first cloud
+    if (fp.mnPlaneNum > 0) {
+        spx_host::PlaneAssociator assoc(fp.context());
+        std::vector<const spx_host::PointCloud *> bnd;
+        for (const auto &b : fp.mvBoundaryPoints) bnd.push_back(&b);
+        assoc.Upload(fp.mvPlaneCoefficients, bnd, fp.mnPlaneNum);
+        std::vector<int> a, v, p;
+        const bool newPlane = assoc.AssociatePlanesByBoundary(fp.mvPlaneCoefficients, a, v, p);
+        std::printf("assoc new %d", newPlane ? 1 : 0);
+        for (int i = 0; i < fp.mnPlaneNum; ++i) std::printf(" %d/%d/%d", a[size_t(i)], v[size_t(i)], p[size_t(i)]);
+        std::printf("\n");
+        spx_host::VoxelGrid voxel(fp.context());
+        voxel.setLeafSize(0.05f, 0.05f, 0.05f);
+        voxel.setInputCloud(&fp.mvPlanePoints[0]);
+        spx_host::PointCloud tmp;
+        voxel.filter(tmp);
+        std::printf("voxel %zu -> %zu\n", fp.mvPlanePoints[0].points.size(), tmp.points.size());
+    }
     return 0;
 }

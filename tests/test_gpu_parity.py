@@ -107,6 +107,13 @@ def test_cpp_host_adapter_fills_frame_fields(ext, seq, tmp_path):
     out = subprocess.check_output([str(exe), str(raw), "480", "640"], text=True).splitlines()
     fp = ext.extract(d)
     assert out[0] == f"real {fp.mnRealPlaneNum}" and out[1] == f"all {fp.mnPlaneNum}"
+    extra = [l for l in out[2:] if not l.startswith("plane ")]
+    out = out[:2] + [l for l in out[2:] if l.startswith("plane ")]
+    # the association / voxel-grid adapters on the same frame: every plane associates with itself (distance 0)
+    from oracle import pyoracle
+    a, v, p, _ = pyoracle.associate_planes(fp.mvPlaneCoefficients, fp.mvPlaneCoefficients, fp.mvBoundaryPoints)
+    assert extra[0] == "assoc new %d " % int((a < 0).any()) + " ".join(f"{x}/{y}/{z}" for x, y, z in zip(a, v, p))
+    assert extra[1] == f"voxel {len(fp.mvPlanePoints[0])} -> {len(pyoracle.voxel_grid(fp.mvPlanePoints[0], 0.05)[0])}"
     for i, line in enumerate(out[2:]):
         t = line.split()
         assert np.array_equal(np.array(t[2:6], np.float32).view(np.uint32), fp.mvPlaneCoefficients[i].view(np.uint32))
