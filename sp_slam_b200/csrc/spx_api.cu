@@ -60,6 +60,7 @@ struct spx_ctx {
     int n_streams = 1, min_group = 32, last_groups = 1;
     int refine_fast_max = 700;  // batches of at most this many frames use k_refine2
     bool refine_per_group = true;
+    std::vector<double> group_weights;   // tuning knob SPX_GROUP_WEIGHTS="w0,w1,...": relative group sizes on the host path
     double edge_weight = 0.5;   // host path: size of the first and the last frame group relative to the others
     int group_prio = 1;      // 1: group g's stream gets a priority that falls with g (earlier groups finish first)
     int border_grid_cap = 0;
@@ -80,6 +81,7 @@ struct spx_ctx {
     // host path: every group compacts its own results (at the device offset of its first frame) and ships them itself
     bool group_pack = false;
     std::vector<cudaEvent_t> g_tot_ev;
+    std::vector<cudaEvent_t> g_real_ev;       // host path: the group's real-plane clouds are packed and their sizes are on the host
     struct GroupOut { int f0 = 0, f1 = 0; long long dev_pl = 0, dev_pt = 0, dev_bd = 0; };
     std::vector<GroupOut> g_out;
     Params P;           // geometry of the last call (capacities fixed at create)
@@ -97,7 +99,7 @@ struct spx_ctx {
     spx_plane *h_planes = nullptr;
     spx_point *h_pts = nullptr, *h_bnd = nullptr;
     size_t h_planes_cap = 0, h_pts_cap = 0, h_bnd_cap = 0;
-    long long *h_totals = nullptr;
+    long long *h_totals = nullptr, *h_totals_dev = nullptr;   // page-locked; _dev = the address the device stores through
     // state of the last extract
     bool have_run = false;
     bool debug = false;
@@ -307,8 +309,8 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     if (src.sparse && P.enable_supposed) {
         const size_t words = size_t(P.rows) * size_t(((P.cols + 7) / 8 + 31) / 32);
         SPX_CK(c, cudaMemsetAsync(B.fetch_bits + words * size_t(f0), 0, words * sizeof(unsigned) * size_t(F), st));
-        SPX_CK(c, cudaMemsetAsync(B.out_totals + 8 * (c->group_pack ? g + 1 : 0) + 3, 0, sizeof(long long), st));
     }
+    if (c->group_pack) SPX_CK(c, cudaMemsetAsync(B.out_totals + 8 * (g + 1) + 3, 0, sizeof(long long), st));
     if (!normals_given) {
         const int nb = cdiv(P.h, kBandRows), nch = cdiv(P.w, 32);
         const int dbg = c->debug ? 1 : 0;
@@ -362,7 +364,8 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
             go.dev_pl = (long long)f0 * SPX_MAX_PLANES; go.dev_pt = (long long)f0 * P.pts_cap; go.dev_bd = (long long)f0 * P.bnd_cap;
             base_pl = go.dev_pl; base_pt = go.dev_pt; base_bd = go.dev_bd;
         }
-        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 0, base_pl, base_pt, base_bd, tot);
+        long long *host_tot = c->group_pack ? c->h_totals_dev + 8 * (g + 1) : nullptr;
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 0, base_pl, base_pt, base_bd, tot, host_tot);
         const bool use_side = c->last_groups == 1;   // with several groups in flight the other groups fill the gaps already
         cudaStream_t side = use_side ? c->g_back[g] : st, keep = st;
         if (use_side) {
@@ -374,6 +377,10 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
         LAUNCH(k_pack_contours, dim3(SPX_MAX_MODELS, F), 128, 0, P, B);
         if (use_side) SPX_CK(c, cudaEventRecord(c->g_side[g], side));
         st = keep;
+        if (c->group_pack && c->last_groups > 1) {
+            // the real planes' clouds (95 % of the result bytes) can leave for the host while the line fits still run
+            SPX_CK(c, cudaEventRecord(c->g_real_ev[g], st));   // (their sizes were stored to the host by the stage-0 scan)
+        }
     }
     if (P.enable_supposed) {
         const int lg = std::min(c->lines_grid, F * SPX_MAX_MODELS), bg = std::min(c->border_grid, F * SPX_MAX_MODELS * SPX_MAX_LINES);
@@ -389,14 +396,11 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
         LAUNCH(k_supposed, cdiv(F, 128), 128, 0, P, B);
     }
     if (own_pack) {
-        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 1, base_pl, base_pt, base_bd, tot);
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 1, base_pl, base_pt, base_bd, tot, c->group_pack ? c->h_totals_dev + 8 * (g + 1) : nullptr);
         LAUNCH(k_emit_records, F, 128, 0, P, B);
         if (c->last_groups == 1) SPX_CK(c, cudaStreamWaitEvent(st, c->g_side[g], 0));   // the fallback boundaries read the packed real clouds
         if (P.enable_supposed) LAUNCH(k_pack_supposed, dim3(SPX_MAX_PLANES, F), 128, 0, P, B);
-        if (c->group_pack) {
-            SPX_CK(c, cudaMemcpyAsync(c->h_totals + 8 * (g + 1), tot, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-            SPX_CK(c, cudaEventRecord(c->g_tot_ev[g], st));
-        }
+        if (c->group_pack) SPX_CK(c, cudaEventRecord(c->g_tot_ev[g], st));   // (the totals are on the host already: stage-1 scan)
     }
     SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 2], st));
     return SPX_OK;
@@ -423,11 +427,15 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, boo
     // smaller than the ones in between (weights edge_w : 1 ... 1 : edge_w).
     std::vector<int> bounds(size_t(G) + 1, 0);
     {
-        const double ew = (group_pack && G >= 4) ? c->edge_weight : 1.0;
-        const double tw = double(G - 2) + 2.0 * ew;
-        double acc = 0.0;
+        std::vector<double> wts(size_t(G), 1.0);
+        if (group_pack && G >= 4) {
+            if (int(c->group_weights.size()) == G) wts = c->group_weights;
+            else { wts[0] = c->edge_weight; wts[size_t(G) - 1] = c->edge_weight; }
+        }
+        double tw = 0.0, acc = 0.0;
+        for (double v : wts) tw += v;
         for (int g = 0; g < G; ++g) {
-            acc += (g == 0 || g == G - 1) ? ew : 1.0;
+            acc += wts[size_t(g)];
             bounds[size_t(g) + 1] = G == 1 ? F : std::min(F, std::max(bounds[size_t(g)] + 1, int(F * acc / tw + 0.5)));
         }
         bounds[size_t(G)] = F;
@@ -453,7 +461,7 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, boo
         cudaStream_t side = c->g_back[0];
         cudaStream_t st = side;
         for (int g = 0; g < G; ++g) SPX_CK(c, cudaStreamWaitEvent(side, c->g_ev[3 * g + 1], 0));
-        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 0, 0ll, 0ll, 0ll, B.out_totals);
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 0, 0ll, 0ll, 0ll, B.out_totals, static_cast<long long *>(nullptr));
         LAUNCH(k_pack_points, gpix, 256, 0, P, B);
         LAUNCH(k_pack_contours, dim3(SPX_MAX_MODELS, F), 128, 0, P, B);
         SPX_CK(c, cudaEventRecord(c->g_side[0], side));
@@ -461,7 +469,7 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, boo
         for (int g = 0; g < G; ++g) SPX_CK(c, cudaStreamWaitEvent(main_st, c->g_ev[3 * g + 2], 0));
         SPX_CK(c, cudaStreamWaitEvent(main_st, c->g_side[0], 0));
         SPX_CK(c, cudaEventRecord(c->ev[1], main_st));
-        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 1, 0ll, 0ll, 0ll, B.out_totals);
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 1, 0ll, 0ll, 0ll, B.out_totals, static_cast<long long *>(nullptr));
         LAUNCH(k_emit_records, F, 128, 0, P, B);
         if (P.enable_supposed) LAUNCH(k_pack_supposed, dim3(SPX_MAX_PLANES, F), 128, 0, P, B);
     } else {
@@ -479,14 +487,19 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, boo
 // Host input: may only the sampled rows be uploaded?  Yes when nothing reads full-resolution depth (supposed planes off),
 // or when the caller's image is page-locked (cudaHostAlloc / cudaHostRegister / spx_host_register): then the border tests
 // read their windows in place through the image's device-visible address.  A pageable image is uploaded whole.
-bool sparse_upload(spx_ctx *c, const void *host, int n_frames, HostSrc *src) {
+bool sparse_upload(spx_ctx *c, const void *host, size_t extent_bytes, int n_frames, HostSrc *src) {
     src->sparse = false; src->mapped = nullptr;
     if (c->upload_mode == 1) return false;
     if (c->upload_mode == 0 && n_frames < c->sparse_min_frames) return false;
     if (!c->P.enable_supposed) { src->sparse = true; return true; }
-    cudaPointerAttributes at;
+    cudaPointerAttributes at, at_end;
     if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return false; }
     if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    // the whole batch must be page-locked, not just its first byte (k_border_fetch reads anywhere inside it)
+    const char *last = static_cast<const char *>(host) + (extent_bytes ? extent_bytes - 1 : 0);
+    if (cudaPointerGetAttributes(&at_end, last) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at_end.type != cudaMemoryTypeHost || !at_end.devicePointer ||
+        static_cast<const char *>(at_end.devicePointer) - static_cast<const char *>(at.devicePointer) != last - static_cast<const char *>(host)) return false;
     src->sparse = true; src->mapped = at.devicePointer;
     return true;
 }
@@ -560,6 +573,15 @@ int fetch_groups(spx_ctx *c, spx_batch_result *out) {
     int rc;
     for (int g = 0; g < G; ++g) {
         cudaStream_t st = (G == 1) ? c->stream : c->down_stream;   // the group's kernels are done once its totals have arrived
+        long long early_pt = 0, early_bd = 0;
+        if (G > 1) {   // first the clouds of the real planes, while the group's line fits / border tests still run
+            SPX_CK(c, cudaEventSynchronize(c->g_real_ev[g]));
+            const long long *t0 = c->h_totals + 8 * (g + 1);
+            early_pt = t0[5];   // (the boundary arena waits: k_pack_supposed may still write a real plane's every-20th-inlier fallback boundary)
+            const spx_ctx::GroupOut &go0 = c->g_out[g];
+            if ((rc = grow_pinned_keep(c, &c->h_pts, &c->h_pts_cap, size_t(run_pt + early_pt), size_t(run_pt))) != SPX_OK) return rc;
+            if (early_pt) SPX_CK(c, cudaMemcpyAsync(c->h_pts + run_pt, c->B.out_pts + go0.dev_pt, sizeof(spx_point) * size_t(early_pt), cudaMemcpyDeviceToHost, st));
+        }
         SPX_CK(c, cudaEventSynchronize(c->g_tot_ev[g]));
         c->g_host_ms[2 * g + 1] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - c->t_call).count();
         const long long *t = c->h_totals + 8 * (g + 1);
@@ -568,12 +590,12 @@ int fetch_groups(spx_ctx *c, spx_batch_result *out) {
         c->xfer_d2h += sizeof(spx_frame_header) * size_t(c->g_out[g].f1 - c->g_out[g].f0) + sizeof(spx_plane) * size_t(n_pl) + sizeof(spx_point) * size_t(n_pt + n_bd) + 4 * sizeof(long long);
         const spx_ctx::GroupOut &go = c->g_out[g];
         if ((rc = grow_pinned_keep(c, &c->h_planes, &c->h_planes_cap, size_t(run_pl + n_pl), size_t(run_pl))) != SPX_OK) return rc;
-        if ((rc = grow_pinned_keep(c, &c->h_pts, &c->h_pts_cap, size_t(run_pt + n_pt), size_t(run_pt))) != SPX_OK) return rc;
-        if ((rc = grow_pinned_keep(c, &c->h_bnd, &c->h_bnd_cap, size_t(run_bd + n_bd), size_t(run_bd))) != SPX_OK) return rc;
+        if ((rc = grow_pinned_keep(c, &c->h_pts, &c->h_pts_cap, size_t(run_pt + n_pt), size_t(run_pt + early_pt))) != SPX_OK) return rc;
+        if ((rc = grow_pinned_keep(c, &c->h_bnd, &c->h_bnd_cap, size_t(run_bd + n_bd), size_t(run_bd + early_bd))) != SPX_OK) return rc;
         SPX_CK(c, cudaMemcpyAsync(c->h_frames + go.f0, c->B.out_frames + go.f0, sizeof(spx_frame_header) * size_t(go.f1 - go.f0), cudaMemcpyDeviceToHost, st));
         if (n_pl) SPX_CK(c, cudaMemcpyAsync(c->h_planes + run_pl, c->B.out_planes + go.dev_pl, sizeof(spx_plane) * size_t(n_pl), cudaMemcpyDeviceToHost, st));
-        if (n_pt) SPX_CK(c, cudaMemcpyAsync(c->h_pts + run_pt, c->B.out_pts + go.dev_pt, sizeof(spx_point) * size_t(n_pt), cudaMemcpyDeviceToHost, st));
-        if (n_bd) SPX_CK(c, cudaMemcpyAsync(c->h_bnd + run_bd, c->B.out_bnd + go.dev_bd, sizeof(spx_point) * size_t(n_bd), cudaMemcpyDeviceToHost, st));
+        if (n_pt > early_pt) SPX_CK(c, cudaMemcpyAsync(c->h_pts + run_pt + early_pt, c->B.out_pts + go.dev_pt + early_pt, sizeof(spx_point) * size_t(n_pt - early_pt), cudaMemcpyDeviceToHost, st));
+        if (n_bd > early_bd) SPX_CK(c, cudaMemcpyAsync(c->h_bnd + run_bd + early_bd, c->B.out_bnd + go.dev_bd + early_bd, sizeof(spx_point) * size_t(n_bd - early_bd), cudaMemcpyDeviceToHost, st));
         SPX_CK(c, cudaEventRecord(c->g_xev[2 * g + 1], st));
         host_pl[g] = run_pl; host_pt[g] = run_pt; host_bd[g] = run_bd; n_pls[g] = n_pl;
         run_pl += n_pl; run_pt += n_pt; run_bd += n_bd;
@@ -721,6 +743,10 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (const char *e = std::getenv("SPX_SPARSE_MIN_FRAMES")) c->sparse_min_frames = std::atoi(e);   // tuning knob
     if (const char *e = std::getenv("SPX_REFINE_PER_GROUP")) c->refine_per_group = std::atoi(e) != 0;   // tuning knob
     if (const char *e = std::getenv("SPX_EDGE_WEIGHT")) { const double v = std::atof(e); if (v > 0.05 && v <= 1.0) c->edge_weight = v; }   // tuning knob
+    if (const char *e = std::getenv("SPX_GROUP_WEIGHTS")) {   // tuning knob
+        const char *q = e;
+        while (*q) { char *end = nullptr; const double v = std::strtod(q, &end); if (end == q) break; if (v > 0) c->group_weights.push_back(v); q = (*end == ',') ? end + 1 : end; }
+    }
     if (const char *e = std::getenv("SPX_GROUP_PRIO")) c->group_prio = std::atoi(e);   // tuning knob
     if (const char *e = std::getenv("SPX_BORDER_GRID")) c->border_grid_cap = std::atoi(e);   // tuning knob
     if (const char *e = std::getenv("SPX_PRIO")) c->use_prio = std::atoi(e) != 0;   // tuning knob
@@ -758,6 +784,8 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
         cudaEvent_t te;
         SPX_CK_CREATE(cudaEventCreateWithFlags(&te, cudaEventDisableTiming));
         c->g_tot_ev.push_back(te);
+        SPX_CK_CREATE(cudaEventCreateWithFlags(&te, cudaEventDisableTiming));
+        c->g_real_ev.push_back(te);
         c->g_out.push_back(spx_ctx::GroupOut());
     }
 
@@ -820,7 +848,8 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_link, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kNormalsSmem)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_edge_chamfer<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_edge_chamfer<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_totals), 8 * size_t(c->n_streams + 1) * sizeof(long long), cudaHostAllocDefault));
+    SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_totals), 8 * size_t(c->n_streams + 1) * sizeof(long long), cudaHostAllocMapped));
+    SPX_CK_CREATE(cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->h_totals_dev), c->h_totals, 0));
     SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_frames), F * sizeof(spx_frame_header), cudaHostAllocDefault));
 #undef SPX_CK_CREATE
     *out = c;
@@ -841,6 +870,7 @@ void spx_destroy(spx_ctx *c) {
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->g_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->g_tot_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->g_real_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->g_xev) cudaEventDestroy(e);
     for (cudaStream_t gs : c->g_streams) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
     for (cudaStream_t gs : c->g_hstreams) { cudaStreamSynchronize(gs); cudaStreamDestroy(gs); }
@@ -914,7 +944,7 @@ int spx_extract_batch(spx_ctx *c, const float *depth, int n_frames, int rows, in
     const void *full = c->d_depth;
     c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);   // layout of the device image the kernels read
     c->P.samp_rstep = tight * size_t(c->P.dis); c->P.samp_fstride = c->P.frame_stride;
-    if (sparse_upload(c, depth, n_frames, &src)) {
+    if (sparse_upload(c, depth, frame_stride_bytes * size_t(n_frames - 1) + pitch_bytes * size_t(rows - 1) + tight, n_frames, &src)) {
         // only the sampled rows are uploaded (to their place in the device image); k_border_fetch adds the window sectors
         c->P.host_pitch = pitch_bytes; c->P.host_fstride = frame_stride_bytes; c->P.fetch_skip_sampled = 1;
         c->P.fetch_vec = (reinterpret_cast<uintptr_t>(src.mapped) % 16 == 0 && pitch_bytes % 16 == 0 && frame_stride_bytes % 16 == 0 && cols % 8 == 0) ? 1 : 0;
@@ -938,7 +968,8 @@ int spx_extract_batch_u16(spx_ctx *c, const uint16_t *depth, int n_frames, int r
     HostSrc src;
     src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = frame_stride_bytes; src.u16 = true; src.alpha = depth_map_factor;
     const void *full = c->d_depth;
-    if (cols % 4 == 0 && sparse_upload(c, depth, n_frames, &src)) {
+    if (cols % 4 == 0 && sparse_upload(c, depth, frame_stride_bytes * size_t(n_frames - 1) + pitch_bytes * size_t(rows - 1) + size_t(cols) * sizeof(uint16_t),
+                                       n_frames, &src)) {
         c->P.host_pitch = pitch_bytes; c->P.host_fstride = frame_stride_bytes; c->P.fetch_skip_sampled = 1; c->P.full_alpha = depth_map_factor;
         c->P.fetch_vec = (reinterpret_cast<uintptr_t>(src.mapped) % 16 == 0 && pitch_bytes % 16 == 0 && frame_stride_bytes % 16 == 0 && cols % 8 == 0) ? 1 : 0;
     } else {

@@ -801,8 +801,11 @@ __global__ void __launch_bounds__(128) k_pack_supposed(Params P, Buffers B) {
 // real planes' points / boundary points (their packing then overlaps the line fits); stage 1, after k_supposed: the
 // plane records and the supposed planes' clouds, which follow the real part of the range.
 // tot: 8 values, [0..2] final totals (planes, points, boundary points), [5], [6] the real part of [1], [2].
+// host_tot (optional): the same slot in page-locked host memory; the totals are stored there directly (over PCIe) so that
+// no device-to-host copy -- which would queue behind the other groups' result downloads in the copy engine -- sits on
+// the group's compute stream.
 __global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B, int stage, long long base_pl, long long base_pt, long long base_bd,
-                                                        long long *tot) {
+                                                        long long *tot, long long *host_tot) {
     __shared__ long long s_run[3];
     __shared__ long long s_w[3][32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -849,8 +852,13 @@ __global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B, int s
         __syncthreads();
     }
     if (tid == 0) {
-        if (stage == 0) { tot[5] = s_run[1]; tot[6] = s_run[2]; }
-        else { tot[0] = s_run[0]; tot[1] = real_pt + s_run[1]; tot[2] = real_bd + s_run[2]; }
+        if (stage == 0) {
+            tot[5] = s_run[1]; tot[6] = s_run[2];
+            if (host_tot) { host_tot[5] = s_run[1]; host_tot[6] = s_run[2]; __threadfence_system(); }
+        } else {
+            tot[0] = s_run[0]; tot[1] = real_pt + s_run[1]; tot[2] = real_bd + s_run[2];
+            if (host_tot) { host_tot[0] = tot[0]; host_tot[1] = tot[1]; host_tot[2] = tot[2]; host_tot[3] = tot[3]; __threadfence_system(); }
+        }
     }
 }
 

@@ -367,6 +367,14 @@ def test_sparse_upload_equals_whole_image_upload(seq):
         assert one.mnPlaneNum == ref.mnPlaneNum and np.array_equal(one.mvPlaneCoefficients.view(np.uint32), ref.mvPlaneCoefficients.view(np.uint32))
     finally:
         api.host_unregister(d)
+    # only the first half of the batch is page-locked: the whole image is uploaded (no out-of-range reads by the fetch kernel)
+    half = d[: n // 2]
+    api.host_register(half)
+    try:
+        part = ext.extract_batch(d)
+        assert ext.transfer_bytes()[0] == d.nbytes and _same_batch(part, whole)
+    finally:
+        api.host_unregister(half)
     # 16-bit input
     u16 = np.ascontiguousarray(np.round(np.clip(d, 0, 13.0).astype(np.float64) * 5000.0).astype(np.uint16))
     factor = float(np.float32(1.0) / np.float32(5000.0))
