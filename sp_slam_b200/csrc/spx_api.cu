@@ -428,10 +428,8 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, boo
     std::vector<int> bounds(size_t(G) + 1, 0);
     {
         std::vector<double> wts(size_t(G), 1.0);
-        if (group_pack && G >= 4) {
-            if (int(c->group_weights.size()) == G) wts = c->group_weights;
-            else { wts[0] = c->edge_weight; wts[size_t(G) - 1] = c->edge_weight; }
-        }
+        if (int(c->group_weights.size()) == G) wts = c->group_weights;
+        else if (group_pack && G >= 4) { wts[0] = c->edge_weight; wts[size_t(G) - 1] = c->edge_weight; }
         double tw = 0.0, acc = 0.0;
         for (double v : wts) tw += v;
         for (int g = 0; g < G; ++g) {
