@@ -321,6 +321,31 @@ def test_random_clutter_scenes(oracle_lib, seed):
     orc = oracle_lib.Oracle().run(d)
     rep = compare_frame(e, orc, d, fp)
     assert rep["normals_bit_exact"] and rep["labels_bit_exact"] and rep.get("models_bit_exact", True), rep
+    # the same frame from a page-locked buffer with the sparse upload (windows near the image border, many lines),
+    # as float and as the 16-bit image
+    d = np.ascontiguousarray(d)
+    api.host_register(d)
+    try:
+        e.set_upload_mode(2)
+        sp = e.extract(d)
+        assert e.transfer_bytes()[0] == 160 * 640 * 4
+    finally:
+        api.host_unregister(d)
+    assert sp.mnPlaneNum == fp.mnPlaneNum and np.array_equal(sp.mvPlaneCoefficients.view(np.uint32), fp.mvPlaneCoefficients.view(np.uint32))
+    for p, q in zip(sp.mvPlanePoints + sp.mvBoundaryPoints, fp.mvPlanePoints + fp.mvBoundaryPoints):
+        assert np.array_equal(p, q)
+    u16 = np.ascontiguousarray(np.round(np.clip(d, 0, 13.0).astype(np.float64) * 5000.0).astype(np.uint16))[None]
+    factor = float(np.float32(1.0) / np.float32(5000.0))
+    e.set_upload_mode(1)
+    w16 = e.extract_batch_u16(u16, factor)
+    api.host_register(u16)
+    try:
+        e.set_upload_mode(2)
+        s16 = e.extract_batch_u16(u16, factor)
+        assert e.transfer_bytes()[0] == 160 * 640 * 2
+    finally:
+        api.host_unregister(u16)
+    assert _same_batch(s16, w16)
     e.close()
 
 
@@ -433,3 +458,23 @@ def test_sparse_upload_large_single_group(seq):
         for p, q in zip(a.mvPlanePoints + a.mvBoundaryPoints, b.mvPlanePoints + b.mvBoundaryPoints):
             assert np.array_equal(p, q)
     ext.close()
+
+
+def test_sparse_upload_1280x720(realsense_frames):
+    """the sparse upload on the 1280x720 clutter frames (many lines: thousands of border windows, 427 x 240 cloud)"""
+    it = scenes.REALSENSE
+    d = np.ascontiguousarray(np.stack([scenes.add_noise(f, 100 + k, "realsense") if k else f for k, f in enumerate(realsense_frames)]))
+    e = api.PlaneExtractor(max_frames=len(d), max_rows=720, max_cols=1280, fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy,
+                           max_x=float(it.width), max_y=float(it.height))
+    e.set_upload_mode(1)
+    whole = e.extract_batch(d)
+    api.host_register(d)
+    try:
+        e.set_upload_mode(2)
+        sparse = e.extract_batch(d)
+        up = e.transfer_bytes()
+        assert up[0] == len(d) * 240 * 1280 * 4 and 0 < up[1] < d.nbytes // 3
+    finally:
+        api.host_unregister(d)
+    assert _same_batch(sparse, whole) and int((whole.planes["is_supposed"] == 1).sum()) > 0
+    e.close()
