@@ -191,7 +191,21 @@ def measure_next_rows(ext, dev, host, F, rows, cols, stream, with_cpu):
             t0 = time.perf_counter()
             pyoracle.associate_planes(fp.mvPlaneCoefficients, map_w, bnds)
             tc.append(time.perf_counter() - t0)
+    # MapPlane::UpdateBoundary from the device results of the last extract (frame 60's planes onto map planes 0..)
+    ext.extract_device(dev.data_ptr(), F, rows, cols)
+    torch.cuda.synchronize()
+    tu = []
+    fp60 = fps[min(60, len(fps) - 1)]
+    T = np.eye(4); T[:3, 3] = (0.1, -0.2, 0.05)
+    for rep_ in range(20):
+        for pl in range(fp60.mnPlaneNum):
+            t0 = time.perf_counter()
+            pm.update_boundary_from_result(pl % len(map_w), T, min(60, len(fps) - 1), pl, len(fp60.mvBoundaryPoints[pl]))
+            tu.append(time.perf_counter() - t0)
     pm.close()
+    out["map_boundary_update"] = {"calls": len(tu), "ms_per_call_median": 1e3 * float(np.median(tu)) if tu else None,
+                                  "note": "MapPlane::UpdateBoundary: transform of a frame plane's contour into the map, source read in "
+                                          "place in the device result arena (spx_map_update_boundary_from_result)"}
     out["plane_association"] = {"map_planes": int(len(map_w)), "map_boundary_points": int(sum(len(b) for b in bnds)),
                                 "frames": len(ts), "associated_planes": n_assoc,
                                 "ms_per_frame_median": 1e3 * float(np.median(ts)),

@@ -247,6 +247,19 @@ void spx_map_destroy(spx_map *map);
 int  spx_map_upload(spx_map *map, const float *map_w, const spx_point *boundary, const int64_t *boundary_off, int n_seen, int n_map);
 int  spx_map_associate(spx_map *map, const float *plane_w, int n_planes, float dis_th, float ang_th, float ver_th, float par_th,
                        int32_t *assoc, int32_t *vertical, int32_t *parallel, float *assoc_dist);
+/* replaces: MapPlane::UpdateBoundary(pF, id) and the MapPlane constructor's boundary cloud (src/MapPlane.cc:25-31,144-147):
+ * pcl::transformPointCloud(cloud, *mvBoundaryPoints, T.inverse().matrix()) -- map plane `j`'s boundary cloud BECOMES the
+ * transformed cloud (the reference overwrites, it does not append).  transform: the caller's T.inverse().matrix(),
+ * row-major 4x4 double; x' = float(m00 x + m01 y + m02 z + m03) evaluated in double as PCL 1.8.0 does.  `cloud`: HOST points. */
+int  spx_map_update_boundary(spx_map *map, int j, const double transform[16], const spx_point *cloud, int n);
+/* the same with the cloud read on the device: the boundary of plane `plane` of frame `frame` of the last extract call on the
+ * map's context (either path); n_boundary = mvBoundaryPoints[plane].size(), checked against the device record.  This is the
+ * per-frame call of Tracking (src/Tracking.cc:434-441): no cloud crosses PCIe. */
+int  spx_map_update_boundary_from_result(spx_map *map, int j, const double transform[16], int frame, int plane, int n_boundary);
+/* MapPlane::SetWorldPos: new world coefficients of map plane j */
+int  spx_map_set_world_pos(spx_map *map, int j, const float coef_w[4]);
+/* map plane j's boundary cloud as stored on the device (parity tap / MapPlane::mvBoundaryPoints for the drawers) */
+int  spx_map_get_boundary(spx_map *map, int j, spx_point *out, int cap, int *n);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,8 @@ def lib():
         L.orc_voxel_grid.restype = i32
         L.orc_associate_planes.argtypes = [vp, i32, vp, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
         L.orc_associate_planes.restype = None
+        L.orc_transform_cloud.argtypes = [vp, i32, vp, vp]
+        L.orc_transform_cloud.restype = None
         _lib = L
     return _lib
 
@@ -302,3 +304,13 @@ def associate_planes(plane_w, map_w, boundaries, n_seen=None, dis_th=0.2, ang_th
                                n_map if n_seen is None else n_seen, n_map, dis_th, ang_th, ver_th, par_th,
                                a.ctypes.data, v.ctypes.data, p.ctypes.data, d.ctypes.data)
     return a[:n], v[:n], p[:n], d[:n]
+
+
+def transform_cloud(points: np.ndarray, m: np.ndarray) -> np.ndarray:
+    """pcl::transformPointCloud(cloud, out, Matrix4d m) (MapPlane::UpdateBoundary, src/MapPlane.cc:144-147)"""
+    pts = np.ascontiguousarray(points, dtype=POINT_DTYPE)
+    m = np.ascontiguousarray(m, np.float64).reshape(4, 4)
+    out = np.empty(len(pts), POINT_DTYPE)
+    if len(pts):
+        lib().orc_transform_cloud(pts.ctypes.data, len(pts), m.ctypes.data, out.ctypes.data)
+    return out

@@ -1154,4 +1154,19 @@ void orc_associate_planes(const float *plane_w, int n_planes, const float *map_w
     }
 }
 
+// MapPlane::MapPlane / MapPlane::UpdateBoundary (src/MapPlane.cc:25-31,144-147): pcl::transformPointCloud(cloud, out,
+// T.inverse().matrix()) with a Matrix4d -- PCL 1.8.0 common/impl/transforms.hpp, dense branch, Scalar = double:
+//   out.x = static_cast<float>(t(0,0) * x + t(0,1) * y + t(0,2) * z + t(0,3)), rows 1 and 2 alike; every other field copied.
+// m: row-major 4x4.
+void orc_transform_cloud(const orc_point *pts, int n, const double m[16], orc_point *out) {
+    for (int i = 0; i < n; ++i) {
+        const double x = pts[i].x, y = pts[i].y, z = pts[i].z;
+        orc_point o = pts[i];
+        o.x = static_cast<float>(m[0] * x + m[1] * y + m[2] * z + m[3]);
+        o.y = static_cast<float>(m[4] * x + m[5] * y + m[6] * z + m[7]);
+        o.z = static_cast<float>(m[8] * x + m[9] * y + m[10] * z + m[11]);
+        out[i] = o;
+    }
+}
+
 }  // extern "C"

@@ -124,6 +124,9 @@ void   orc_associate_planes(const float *plane_w, int n_planes, const float *map
                             int n_seen, int n_map, float dis_th, float ang_th, float ver_th, float par_th,
                             int32_t *assoc, int32_t *vertical, int32_t *parallel, float *assoc_dist);
 
+/* N1: pcl::transformPointCloud(cloud, out, Matrix4d) as MapPlane's constructor and MapPlane::UpdateBoundary call it (m row-major) */
+void   orc_transform_cloud(const orc_point *pts, int n, const double m[16], orc_point *out);
+
 #ifdef __cplusplus
 }
 #endif

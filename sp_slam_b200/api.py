@@ -49,6 +49,7 @@ EXPORTS = (
     "spx_set_upload_mode", "spx_host_register", "spx_host_unregister", "spx_get_transfer_bytes",
     "spx_get_group_timeline",
     "spx_voxel_grid", "spx_voxel_downsample_results", "spx_map_create", "spx_map_destroy", "spx_map_upload", "spx_map_associate",
+    "spx_map_update_boundary", "spx_map_update_boundary_from_result", "spx_map_set_world_pos", "spx_map_get_boundary",
 )
 
 
@@ -138,6 +139,10 @@ def lib():
         L.spx_map_destroy.restype = None
         L.spx_map_upload.argtypes = [vp, vp, vp, vp, i32, i32]
         L.spx_map_associate.argtypes = [vp, vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
+        L.spx_map_update_boundary.argtypes = [vp, i32, vp, vp, i32]
+        L.spx_map_update_boundary_from_result.argtypes = [vp, i32, vp, i32, i32, i32]
+        L.spx_map_set_world_pos.argtypes = [vp, i32, vp]
+        L.spx_map_get_boundary.argtypes = [vp, i32, vp, i32, C.POINTER(i32)]
         L.spx_set_upload_mode.argtypes = [vp, i32]
         L.spx_host_register.argtypes = [vp, sz]
         L.spx_host_unregister.argtypes = [vp]
@@ -481,3 +486,25 @@ class PlaneMap:
         self._ext._ck(lib().spx_map_associate(self._m, plane_w.ctypes.data, n, C.c_float(dis_th), C.c_float(ang_th), C.c_float(ver_th),
                                               C.c_float(par_th), a.ctypes.data, v.ctypes.data, p.ctypes.data, d.ctypes.data))
         return a[:n], v[:n], p[:n], d[:n]
+
+    def update_boundary(self, j: int, transform: np.ndarray, cloud: np.ndarray):
+        """MapPlane::UpdateBoundary: map plane j's boundary becomes transform (4x4 double) applied to `cloud` (host)."""
+        t = np.ascontiguousarray(transform, np.float64).reshape(4, 4)
+        pts = np.ascontiguousarray(cloud, POINT_DTYPE)
+        self._ext._ck(lib().spx_map_update_boundary(self._m, j, t.ctypes.data, pts.ctypes.data, len(pts)))
+
+    def update_boundary_from_result(self, j: int, transform: np.ndarray, frame: int, plane: int, n_boundary: int):
+        """The same with the boundary of plane `plane` of frame `frame` of the last extract, read on the device."""
+        t = np.ascontiguousarray(transform, np.float64).reshape(4, 4)
+        self._ext._ck(lib().spx_map_update_boundary_from_result(self._m, j, t.ctypes.data, frame, plane, n_boundary))
+
+    def set_world_pos(self, j: int, coef_w):
+        w = np.ascontiguousarray(coef_w, np.float32).reshape(4)
+        self._ext._ck(lib().spx_map_set_world_pos(self._m, j, w.ctypes.data))
+
+    def boundary(self, j: int) -> np.ndarray:
+        n = C.c_int()
+        self._ext._ck(lib().spx_map_get_boundary(self._m, j, None, 0, C.byref(n)))
+        out = np.empty(max(n.value, 1), POINT_DTYPE)
+        self._ext._ck(lib().spx_map_get_boundary(self._m, j, out.ctypes.data, n.value, C.byref(n)))
+        return out[:n.value].copy()

@@ -647,6 +647,11 @@ int get_ctl(spx_ctx *c, int frame, FrameCtl *out) {
 int spx_internal_fail(spx_ctx *c, int code, const char *what, const char *msg) { return fail(c, code, "%s: %s", what, msg); }
 void *spx_internal_stream(spx_ctx *c) { return c->stream; }
 int spx_internal_device(spx_ctx *c) { return c->device; }
+int spx_internal_last_results(spx_ctx *c, const spx_frame_header **frames, const spx_plane **planes, const spx_point **boundary) {
+    if (!c->have_run) return 0;
+    *frames = c->B.out_frames; *planes = c->B.out_planes; *boundary = c->B.out_bnd;
+    return c->last_frames;
+}
 
 extern "C" {
 

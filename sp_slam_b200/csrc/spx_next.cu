@@ -256,15 +256,15 @@ __global__ void __launch_bounds__(256) k_vox_patch_records(spx_plane *planes, in
 // N1: Map::AssociatePlanesByBoundary (src/Map.cc:196-283) for the planes of one frame.
 // =================================================================================================================
 __global__ void __launch_bounds__(256) k_assoc_dist(const float *__restrict__ plane_w, int n_planes, const float *__restrict__ map_w,
-                                                    const spx_point *__restrict__ bnd, const long long *__restrict__ off, int n_map, float ang_th,
-                                                    float *angle_out, float *dist_out) {
+                                                    const spx_point *__restrict__ bnd, const long long *__restrict__ start,
+                                                    const int *__restrict__ count, int n_map, float ang_th, float *angle_out, float *dist_out) {
     // one CTA per map plane: its boundary cloud against every frame plane that passes the angle test
     // (PointDistanceFromPlane, src/Map.cc:345-361: min over the cloud of |a x + b y + c z + d|, fp32, starting from 100)
     __shared__ float s_min[8];
     const int j = blockIdx.x;
     const float w0 = map_w[4 * j], w1 = map_w[4 * j + 1], w2 = map_w[4 * j + 2];
-    const spx_point *b = bnd + off[j];
-    const int n = int(off[j + 1] - off[j]);
+    const spx_point *b = bnd + start[j];
+    const int n = count[j];
     for (int i = 0; i < n_planes; ++i) {
         const float a0 = plane_w[4 * i], a1 = plane_w[4 * i + 1], a2 = plane_w[4 * i + 2], a3 = plane_w[4 * i + 3];
         const float angle = a0 * w0 + a1 * w1 + a2 * w2;
@@ -287,6 +287,30 @@ __global__ void __launch_bounds__(256) k_assoc_dist(const float *__restrict__ pl
         }
         __syncthreads();
     }
+}
+
+// MapPlane::MapPlane / MapPlane::UpdateBoundary (src/MapPlane.cc:25-31,144-147): pcl::transformPointCloud(cloud, *mvBoundaryPoints,
+// T.inverse().matrix()), PCL 1.8.0 common/impl/transforms.hpp, dense branch with Scalar = double:
+// x' = float(m00 x + m01 y + m02 z + m03) evaluated in double, left to right (no FMA: -fmad=false); other fields copied.
+// The source is either a cloud the caller uploaded or, `from_result`, the boundary cloud of a plane of the last extract
+// read where it lies in the device result arena (no host round trip).
+struct MapXform { double m[12]; };
+__global__ void __launch_bounds__(256) k_map_transform(const spx_point *__restrict__ src, const spx_frame_header *frames, const spx_plane *planes,
+                                                       int frame, int plane, int n, MapXform X, spx_point *__restrict__ dst, int *err) {
+    if (frames) {
+        const spx_plane &R = planes[frames[frame].first_plane + plane];
+        if (plane >= frames[frame].n_planes || R.n_boundary != n) { if (threadIdx.x == 0 && blockIdx.x == 0) *err = 1; return; }
+        src += R.boundary_off;
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const spx_point p = src[i];
+    const double x = p.x, y = p.y, z = p.z;
+    spx_point o = p;
+    o.x = float(X.m[0] * x + X.m[1] * y + X.m[2] * z + X.m[3]);
+    o.y = float(X.m[4] * x + X.m[5] * y + X.m[6] * z + X.m[7]);
+    o.z = float(X.m[8] * x + X.m[9] * y + X.m[10] * z + X.m[11]);
+    dst[i] = o;
 }
 
 // the reference's visiting loop over the map planes (order-dependent thresholds ldTh / lverTh / lparTh), one thread per frame plane
@@ -322,9 +346,14 @@ __global__ void __launch_bounds__(128) k_assoc_select(const float *__restrict__ 
 
 struct spx_map {
     spx_ctx *ctx = nullptr;
-    float *d_w = nullptr; spx_point *d_bnd = nullptr; long long *d_off = nullptr;
-    size_t cap_w = 0, cap_bnd = 0;
+    // map plane j: world coefficients d_w[4j..], boundary cloud d_bnd[start[j] .. start[j] + count[j]) with room for cap[j]
+    // points (a cloud that outgrows its slot moves to the end of the arena; the arena is rebuilt when it runs out)
+    float *d_w = nullptr; spx_point *d_bnd = nullptr; long long *d_start = nullptr; int *d_count = nullptr;
+    std::vector<long long> start; std::vector<int> count, cap;
+    size_t cap_w = 0, cap_bnd = 0, used_bnd = 0;
     int n_map = 0, n_seen = 0;
+    spx_point *d_stage = nullptr; size_t cap_stage = 0;      // upload staging of spx_map_update_boundary
+    int *d_err = nullptr;
     // per-call scratch (frame planes <= SPX_MAX_PLANES)
     float *d_plane_w = nullptr, *d_angle = nullptr, *d_dist = nullptr, *d_res_f = nullptr;
     int *d_res_i = nullptr;
@@ -417,10 +446,12 @@ int spx_map_create(spx_ctx *c, spx_map **out) {
     cudaError_t e = cudaSetDevice(spx_internal_device(c));
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->h_plane_w), SPX_MAX_PLANES * 4 * sizeof(float), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->h_res_f), SPX_MAX_PLANES * sizeof(float), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->h_res_i), SPX_MAX_PLANES * 3 * sizeof(int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->h_res_i), (SPX_MAX_PLANES * 3 + 1) * sizeof(int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&m->d_plane_w), SPX_MAX_PLANES * 4 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&m->d_res_f), SPX_MAX_PLANES * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&m->d_res_i), SPX_MAX_PLANES * 3 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&m->d_err), sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(m->d_err, 0, sizeof(int));
     if (e != cudaSuccess) { spx_map_destroy(m); return spx_internal_fail(c, SPX_ERR_CUDA, "spx_map_create", cudaGetErrorString(e)); }
     *out = m;
     return SPX_OK;
@@ -429,11 +460,82 @@ int spx_map_create(spx_ctx *c, spx_map **out) {
 void spx_map_destroy(spx_map *m) {
     if (!m) return;
     cudaSetDevice(spx_internal_device(m->ctx));
-    cudaFree(m->d_w); cudaFree(m->d_bnd); cudaFree(m->d_off); cudaFree(m->d_plane_w); cudaFree(m->d_angle); cudaFree(m->d_dist);
-    cudaFree(m->d_res_f); cudaFree(m->d_res_i);
+    cudaFree(m->d_w); cudaFree(m->d_bnd); cudaFree(m->d_start); cudaFree(m->d_count); cudaFree(m->d_plane_w); cudaFree(m->d_angle);
+    cudaFree(m->d_dist); cudaFree(m->d_res_f); cudaFree(m->d_res_i); cudaFree(m->d_stage); cudaFree(m->d_err);
     cudaFreeHost(m->h_plane_w); cudaFreeHost(m->h_res_f); cudaFreeHost(m->h_res_i);
     delete m;
 }
+
+}  // extern "C"
+
+namespace {
+
+// room for `need` more boundary points at the end of the arena: grow it (keeping the live clouds) when it is full
+int map_reserve(spx_map *m, cudaStream_t st, size_t need) {
+    spx_ctx *c = m->ctx;
+    if (m->used_bnd + need <= m->cap_bnd) return SPX_OK;
+    size_t live = 0;
+    for (int j = 0; j < m->n_map; ++j) live += size_t(m->cap[size_t(j)]);
+    const size_t ncap = (live + need) * 2 + 4096;
+    spx_point *nb = nullptr;
+    NX_CK(c, cudaMalloc(reinterpret_cast<void **>(&nb), ncap * sizeof(spx_point)));
+    size_t at = 0;
+    for (int j = 0; j < m->n_map; ++j) {          // compaction: every plane keeps its slot size
+        if (m->count[size_t(j)])
+            NX_CK(c, cudaMemcpyAsync(nb + at, m->d_bnd + m->start[size_t(j)], size_t(m->count[size_t(j)]) * sizeof(spx_point), cudaMemcpyDeviceToDevice, st));
+        m->start[size_t(j)] = (long long)at;
+        at += size_t(m->cap[size_t(j)]);
+    }
+    NX_CK(c, cudaStreamSynchronize(st));
+    cudaFree(m->d_bnd);
+    m->d_bnd = nb; m->cap_bnd = ncap; m->used_bnd = at;
+    if (m->n_map) NX_CK(c, cudaMemcpyAsync(m->d_start, m->start.data(), size_t(m->n_map) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    NX_CK(c, cudaStreamSynchronize(st));
+    return SPX_OK;
+}
+
+// map plane j <- transform applied to a cloud (src on the device, or frames/planes/arena of the last extract)
+int map_update(spx_map *m, int j, const double transform[16], const spx_point *d_src, const spx_frame_header *frames, const spx_plane *planes,
+               int frame, int plane, int n) {
+    spx_ctx *c = m->ctx;
+    cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
+    const int old_count = m->count[size_t(j)];
+    if (n > m->cap[size_t(j)]) {                  // the cloud outgrew its slot: a new one (1.5x) at the end of the arena
+        const size_t slot = size_t(n) + size_t(n) / 2 + 64;
+        int rc = map_reserve(m, st, slot);
+        if (rc != SPX_OK) return rc;
+        if (frames && old_count) {                // a refused update must leave the old cloud in place: it moves along
+            NX_CK(c, cudaMemcpyAsync(m->d_bnd + m->used_bnd, m->d_bnd + m->start[size_t(j)], size_t(old_count) * sizeof(spx_point), cudaMemcpyDeviceToDevice, st));
+        }
+        m->start[size_t(j)] = (long long)m->used_bnd; m->cap[size_t(j)] = int(slot); m->used_bnd += slot;
+    }
+    m->count[size_t(j)] = n;
+    MapXform X;
+    for (int k = 0; k < 12; ++k) X.m[k] = transform[k];
+    if (n) k_map_transform<<<cdiv(n, 256), 256, 0, st>>>(d_src, frames, planes, frame, plane, n, X, m->d_bnd + m->start[size_t(j)], m->d_err);
+    NX_CK(c, cudaMemcpyAsync(m->d_start + j, &m->start[size_t(j)], sizeof(long long), cudaMemcpyHostToDevice, st));
+    NX_CK(c, cudaMemcpyAsync(m->d_count + j, &m->count[size_t(j)], sizeof(int), cudaMemcpyHostToDevice, st));
+    NX_CK(c, cudaGetLastError());
+    if (frames) {                                 // the device checked the caller's n against the record
+        int err = 0;
+        NX_CK(c, cudaMemcpyAsync(&err, m->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+        NX_CK(c, cudaStreamSynchronize(st));
+        if (err) {
+            cudaMemsetAsync(m->d_err, 0, sizeof(int), st);
+            m->count[size_t(j)] = old_count;      // nothing was written: the plane keeps its cloud
+            cudaMemcpyAsync(m->d_count + j, &m->count[size_t(j)], sizeof(int), cudaMemcpyHostToDevice, st);
+            cudaStreamSynchronize(st);
+            return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_update_boundary_from_result", "plane index / boundary size do not match the last extract");
+        }
+    } else {
+        NX_CK(c, cudaStreamSynchronize(st));      // (the host arrays handed to the async copies above must stay put)
+    }
+    return SPX_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 int spx_map_upload(spx_map *m, const float *map_w, const spx_point *boundary, const int64_t *boundary_off, int n_seen, int n_map) {
     if (!m) return SPX_ERR_ARG;
@@ -444,19 +546,17 @@ int spx_map_upload(spx_map *m, const float *map_w, const spx_point *boundary, co
     cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
     const long long n_pts = n_map ? boundary_off[n_map] - boundary_off[0] : 0;
     if (n_pts > 0 && !boundary) return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_upload", "null boundary cloud");
+    for (int j = 0; j < n_map; ++j)
+        if (boundary_off[j + 1] < boundary_off[j] || boundary_off[j + 1] - boundary_off[j] > INT_MAX)
+            return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_upload", "offsets must not decrease");
     NX_CK(c, cudaStreamSynchronize(st));
     if (size_t(n_map) > m->cap_w) {
-        cudaFree(m->d_w); cudaFree(m->d_off); m->d_w = nullptr; m->d_off = nullptr; m->cap_w = 0;
+        cudaFree(m->d_w); cudaFree(m->d_start); cudaFree(m->d_count); m->d_w = nullptr; m->d_start = nullptr; m->d_count = nullptr; m->cap_w = 0;
         const size_t cap = size_t(n_map) * 2 + 16;
         NX_CK(c, cudaMalloc(reinterpret_cast<void **>(&m->d_w), cap * 4 * sizeof(float)));
-        NX_CK(c, cudaMalloc(reinterpret_cast<void **>(&m->d_off), (cap + 1) * sizeof(long long)));
+        NX_CK(c, cudaMalloc(reinterpret_cast<void **>(&m->d_start), cap * sizeof(long long)));
+        NX_CK(c, cudaMalloc(reinterpret_cast<void **>(&m->d_count), cap * sizeof(int)));
         m->cap_w = cap;
-    }
-    if (size_t(n_pts) > m->cap_bnd) {
-        cudaFree(m->d_bnd); m->d_bnd = nullptr; m->cap_bnd = 0;
-        const size_t cap = size_t(n_pts) * 2 + 1024;
-        NX_CK(c, cudaMalloc(reinterpret_cast<void **>(&m->d_bnd), cap * sizeof(spx_point)));
-        m->cap_bnd = cap;
     }
     if (size_t(n_map) * SPX_MAX_PLANES > m->cap_mat) {
         cudaFree(m->d_angle); cudaFree(m->d_dist); m->d_angle = m->d_dist = nullptr; m->cap_mat = 0;
@@ -465,18 +565,85 @@ int spx_map_upload(spx_map *m, const float *map_w, const spx_point *boundary, co
         NX_CK(c, cudaMalloc(reinterpret_cast<void **>(&m->d_dist), cap * sizeof(float)));
         m->cap_mat = cap;
     }
+    // every plane gets a slot of 1.5x its cloud (+64), so that a boundary that grows a little is updated in place
+    m->start.assign(size_t(n_map), 0); m->count.assign(size_t(n_map), 0); m->cap.assign(size_t(n_map), 0);
+    size_t at = 0;
+    for (int j = 0; j < n_map; ++j) {
+        const int n = int(boundary_off[j + 1] - boundary_off[j]);
+        m->start[size_t(j)] = (long long)at; m->count[size_t(j)] = n; m->cap[size_t(j)] = n + n / 2 + 64;
+        at += size_t(m->cap[size_t(j)]);
+    }
+    if (at > m->cap_bnd) {
+        cudaFree(m->d_bnd); m->d_bnd = nullptr; m->cap_bnd = 0;
+        const size_t cap = at * 2 + 4096;
+        NX_CK(c, cudaMalloc(reinterpret_cast<void **>(&m->d_bnd), cap * sizeof(spx_point)));
+        m->cap_bnd = cap;
+    }
+    m->used_bnd = at;
+    m->n_map = n_map; m->n_seen = n_seen;
     if (n_map) {
-        std::vector<long long> off(size_t(n_map) + 1);
-        for (int j = 0; j <= n_map; ++j) {
-            off[size_t(j)] = boundary_off[j] - boundary_off[0];
-            if (j && off[size_t(j)] < off[size_t(j) - 1]) return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_upload", "offsets must not decrease");
-        }
         NX_CK(c, cudaMemcpyAsync(m->d_w, map_w, size_t(n_map) * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
-        NX_CK(c, cudaMemcpyAsync(m->d_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
-        if (n_pts) NX_CK(c, cudaMemcpyAsync(m->d_bnd, boundary + boundary_off[0], size_t(n_pts) * sizeof(spx_point), cudaMemcpyHostToDevice, st));
+        NX_CK(c, cudaMemcpyAsync(m->d_start, m->start.data(), size_t(n_map) * sizeof(long long), cudaMemcpyHostToDevice, st));
+        NX_CK(c, cudaMemcpyAsync(m->d_count, m->count.data(), size_t(n_map) * sizeof(int), cudaMemcpyHostToDevice, st));
+        for (int j = 0; j < n_map; ++j)
+            if (m->count[size_t(j)])
+                NX_CK(c, cudaMemcpyAsync(m->d_bnd + m->start[size_t(j)], boundary + boundary_off[j], size_t(m->count[size_t(j)]) * sizeof(spx_point),
+                                         cudaMemcpyHostToDevice, st));
         NX_CK(c, cudaStreamSynchronize(st));
     }
-    m->n_map = n_map; m->n_seen = n_seen;
+    return SPX_OK;
+}
+
+int spx_map_set_world_pos(spx_map *m, int j, const float coef_w[4]) {
+    if (!m) return SPX_ERR_ARG;
+    spx_ctx *c = m->ctx;
+    if (j < 0 || j >= m->n_map || !coef_w) return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_set_world_pos", "bad argument");
+    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
+    NX_CK(c, cudaMemcpyAsync(m->d_w + 4 * j, coef_w, 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+    NX_CK(c, cudaStreamSynchronize(st));
+    return SPX_OK;
+}
+
+int spx_map_update_boundary(spx_map *m, int j, const double transform[16], const spx_point *cloud, int n) {
+    if (!m) return SPX_ERR_ARG;
+    spx_ctx *c = m->ctx;
+    if (j < 0 || j >= m->n_map || !transform || n < 0 || (n > 0 && !cloud)) return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_update_boundary", "bad argument");
+    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
+    if (size_t(n) > m->cap_stage) {
+        NX_CK(c, cudaStreamSynchronize(st));
+        cudaFree(m->d_stage); m->d_stage = nullptr; m->cap_stage = 0;
+        const size_t cap = size_t(n) * 2 + 1024;
+        NX_CK(c, cudaMalloc(reinterpret_cast<void **>(&m->d_stage), cap * sizeof(spx_point)));
+        m->cap_stage = cap;
+    }
+    if (n) NX_CK(c, cudaMemcpyAsync(m->d_stage, cloud, size_t(n) * sizeof(spx_point), cudaMemcpyHostToDevice, st));
+    return map_update(m, j, transform, m->d_stage, nullptr, nullptr, 0, 0, n);
+}
+
+int spx_map_update_boundary_from_result(spx_map *m, int j, const double transform[16], int frame, int plane, int n_boundary) {
+    if (!m) return SPX_ERR_ARG;
+    spx_ctx *c = m->ctx;
+    const spx_frame_header *frames = nullptr; const spx_plane *planes = nullptr; const spx_point *bnd = nullptr;
+    const int n_frames = spx_internal_last_results(c, &frames, &planes, &bnd);
+    if (j < 0 || j >= m->n_map || !transform || n_boundary < 0 || plane < 0 || frame < 0 || frame >= n_frames)
+        return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_update_boundary_from_result", "bad argument (or no extract yet)");
+    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    return map_update(m, j, transform, bnd, frames, planes, frame, plane, n_boundary);
+}
+
+int spx_map_get_boundary(spx_map *m, int j, spx_point *out, int cap, int *n) {
+    if (!m) return SPX_ERR_ARG;
+    spx_ctx *c = m->ctx;
+    if (j < 0 || j >= m->n_map || !n) return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_get_boundary", "bad argument");
+    *n = m->count[size_t(j)];
+    if (!out) return SPX_OK;
+    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
+    const int k = *n < cap ? *n : cap;
+    if (k > 0) NX_CK(c, cudaMemcpyAsync(out, m->d_bnd + m->start[size_t(j)], size_t(k) * sizeof(spx_point), cudaMemcpyDeviceToHost, st));
+    NX_CK(c, cudaStreamSynchronize(st));
     return SPX_OK;
 }
 
@@ -495,7 +662,7 @@ int spx_map_associate(spx_map *m, const float *plane_w, int n_planes, float dis_
     cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
     std::memcpy(m->h_plane_w, plane_w, size_t(n_planes) * 4 * sizeof(float));
     NX_CK(c, cudaMemcpyAsync(m->d_plane_w, m->h_plane_w, size_t(n_planes) * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
-    k_assoc_dist<<<m->n_map, 256, 0, st>>>(m->d_plane_w, n_planes, m->d_w, m->d_bnd, m->d_off, m->n_map, ang_th, m->d_angle, m->d_dist);
+    k_assoc_dist<<<m->n_map, 256, 0, st>>>(m->d_plane_w, n_planes, m->d_w, m->d_bnd, m->d_start, m->d_count, m->n_map, ang_th, m->d_angle, m->d_dist);
     k_assoc_select<<<cdiv(n_planes, 128), 128, 0, st>>>(m->d_angle, m->d_dist, n_planes, m->n_seen, m->n_map, dis_th, ang_th, ver_th, par_th,
                                                        m->d_res_i, m->d_res_i + SPX_MAX_PLANES, m->d_res_i + 2 * SPX_MAX_PLANES, m->d_res_f);
     NX_CK(c, cudaMemcpyAsync(m->h_res_i, m->d_res_i, 3 * SPX_MAX_PLANES * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -182,6 +182,25 @@ public:
         return newPlane;
     }
 
+    // MapPlane::UpdateBoundary(pF, id) (src/MapPlane.cc:144-147) for map plane j (index in the uploaded order): its boundary
+    // cloud becomes TwcMatrix (= T.inverse().matrix(), row-major 4x4 double) applied to mvBoundaryPoints[id] of the frame the
+    // context processed last -- read where it lies on the device, nothing crosses PCIe.
+    void UpdateBoundary(int j, const double TwcMatrix[16], int id, size_t boundarySize, int frameInBatch = 0) {
+        if (spx_map_update_boundary_from_result(map_, j, TwcMatrix, frameInBatch, id, int(boundarySize)) != SPX_OK)
+            throw std::runtime_error(std::string("spx_map_update_boundary_from_result: ") + spx_last_error(ctx_));
+    }
+    // the same from a host cloud (the MapPlane constructor with a KeyFrame's cloud, src/MapPlane.cc:25-31)
+    void UpdateBoundary(int j, const double TwcMatrix[16], const PointCloud &cloud) {
+        const std::vector<spx_point> pts = pack_cloud(cloud);
+        if (spx_map_update_boundary(map_, j, TwcMatrix, pts.data(), int(pts.size())) != SPX_OK)
+            throw std::runtime_error(std::string("spx_map_update_boundary: ") + spx_last_error(ctx_));
+    }
+    void SetWorldPos(int j, const CoefMat &Pos) {
+        float w[4];
+        for (int k = 0; k < 4; ++k) w[k] = Pos.template at<float>(k);
+        if (spx_map_set_world_pos(map_, j, w) != SPX_OK) throw std::runtime_error(std::string("spx_map_set_world_pos: ") + spx_last_error(ctx_));
+    }
+
 private:
     spx_ctx *ctx_ = nullptr;
     spx_map *map_ = nullptr;

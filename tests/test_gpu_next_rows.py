@@ -123,3 +123,63 @@ def test_plane_association_against_the_oracle(frames, oracle_lib):
     a, v, p, dd = pm.associate(fps[0].mvPlaneCoefficients)
     assert np.all(a == -1) and np.all(dd == np.float32(0.2))
     pm.close()
+
+
+def test_map_boundary_updates_against_the_oracle(frames, oracle_lib):
+    """MapPlane::UpdateBoundary on the device: the transformed cloud replaces map plane j's boundary -- from a host cloud
+    and from the device results of the last extract (host-input path and device-resident path) -- bit-identical to
+    pcl::transformPointCloud as restated by the oracle; associations afterwards match the oracle on the updated map."""
+    import torch
+    ext, d, fps = frames
+    rng = np.random.default_rng(9)
+    pm = api.PlaneMap(ext)
+    map_w = np.concatenate([fp.mvPlaneCoefficients for fp in fps[:2]])
+    bnds = [b.copy() for fp in fps[:2] for b in fp.mvBoundaryPoints]
+    pm.upload(map_w, bnds)
+
+    def pose():
+        a = rng.normal(size=3) * 0.05
+        R = np.array([[1, -a[2], a[1]], [a[2], 1, -a[0]], [-a[1], a[0], 1]])
+        u, _, vt = np.linalg.svd(R)
+        T = np.eye(4); T[:3, :3] = u @ vt; T[:3, 3] = rng.normal(size=3) * 0.1
+        return T
+
+    # (1) host clouds, including one much larger than the plane's slot (moves to the end of the arena) and an empty one
+    big = np.concatenate([b for fp in fps for b in fp.mvBoundaryPoints])
+    for j, cloud in ((0, fps[4].mvBoundaryPoints[0]), (1, big), (2 % len(bnds), np.empty(0, api.POINT_DTYPE)), (0, fps[5].mvBoundaryPoints[0])):
+        T = pose()
+        pm.update_boundary(j, T, cloud)
+        bnds[j] = oracle_lib.transform_cloud(cloud, T)
+        assert np.array_equal(pm.boundary(j), bnds[j])
+    for k in range(len(bnds)):
+        assert np.array_equal(pm.boundary(k), bnds[k])                   # the arena rebuild kept every other plane
+    # (2) from the device results: host-input extract, then device-resident extract
+    res = ext.extract_batch(d)
+    dev = torch.from_numpy(d).cuda()
+    for source in ("host", "device"):
+        if source == "device":
+            ext.extract_device(dev.data_ptr(), len(d), 480, 640)
+        for frame in (1, 4):
+            fp = res.frame(frame)
+            for plane in range(fp.mnPlaneNum):
+                j = int(rng.integers(len(bnds)))
+                T = pose()
+                pm.update_boundary_from_result(j, T, frame, plane, len(fp.mvBoundaryPoints[plane]))
+                bnds[j] = oracle_lib.transform_cloud(fp.mvBoundaryPoints[plane], T)
+                assert np.array_equal(pm.boundary(j), bnds[j])
+    with pytest.raises(api.SpxError):
+        pm.update_boundary_from_result(0, np.eye(4), 1, 0, len(res.frame(1).mvBoundaryPoints[0]) + 1)   # size mismatch is refused
+    with pytest.raises(api.SpxError):
+        pm.update_boundary_from_result(1, np.eye(4), 1, 0, 100000)        # ... also when the claimed cloud outgrows the slot
+    for k in range(len(bnds)):
+        assert np.array_equal(pm.boundary(k), bnds[k])                   # ... and leaves the map as it was
+    # (3) world coefficients + association on the updated map
+    map_w = map_w.copy()
+    map_w[0] = fps[3].mvPlaneCoefficients[0]
+    pm.set_world_pos(0, map_w[0])
+    for fp in fps[2:]:
+        got = pm.associate(fp.mvPlaneCoefficients)
+        ref = oracle_lib.associate_planes(fp.mvPlaneCoefficients, map_w, bnds)
+        for g, r in zip(got, ref):
+            assert np.array_equal(g, r)
+    pm.close()

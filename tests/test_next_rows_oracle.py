@@ -94,3 +94,26 @@ def test_association_against_numpy_restatement():
         ref = np_associate(plane_w, map_w, bnds, n_seen)
         for g, r in zip(got, ref):
             assert np.array_equal(g, r)
+
+
+def test_transform_cloud_known_answers():
+    """pcl::transformPointCloud with a Matrix4d (MapPlane::UpdateBoundary): double arithmetic, one rounding to float"""
+    pts = make_points([(1.0, 2.0, 3.0), (0.1, 0.2, 0.3), (-4.5, 0.0, 7.25)], [(255, 1, 2, 3)] * 3)
+    eye = np.eye(4)
+    assert np.array_equal(pyoracle.transform_cloud(pts, eye), pts)
+    rz = np.array([[0, -1, 0, 0.5], [1, 0, 0, -1.0], [0, 0, 1, 2.0], [0, 0, 0, 1.0]])     # 90 degrees about z + translation
+    out = pyoracle.transform_cloud(pts, rz)
+    assert np.array_equal(out["x"], (-pts["y"].astype(np.float64) + 0.5).astype(np.float32))
+    assert np.array_equal(out["y"], (pts["x"].astype(np.float64) - 1.0).astype(np.float32))
+    assert np.array_equal(out["z"], (pts["z"].astype(np.float64) + 2.0).astype(np.float32))
+    assert np.array_equal(out["rgba"], pts["rgba"])
+    # the sum is formed in double, left to right: ((m00 x + m01 y) + m02 z) + m03
+    rng = np.random.default_rng(2)
+    m = np.eye(4); m[:3, :] = rng.normal(size=(3, 4))
+    p = make_points(rng.normal(size=(500, 3)) * 3)
+    out = pyoracle.transform_cloud(p, m)
+    x, y, z = (p[a].astype(np.float64) for a in "xyz")
+    for r, ax in enumerate("xyz"):
+        ref = (((m[r, 0] * x + m[r, 1] * y) + m[r, 2] * z) + m[r, 3]).astype(np.float32)
+        assert np.array_equal(out[ax], ref)
+    assert len(pyoracle.transform_cloud(np.empty(0, POINT), eye)) == 0
