@@ -478,3 +478,45 @@ def test_sparse_upload_1280x720(realsense_frames):
         api.host_unregister(d)
     assert _same_batch(sparse, whole) and int((whole.planes["is_supposed"] == 1).sum()) > 0
     e.close()
+
+
+def test_full_size_batch_is_consistent():
+    """BASELINE configs[1] at full size: the 1000-frame batch gives the same Frame fields through the host-input path
+    (page-locked image, sparse upload, 8 frame groups with unequal sizes, early downloads), through the device-resident
+    path (8 equal groups) and as ten independent 100-frame batches; plane counts per frame are a checksum of the labels,
+    the clouds are compared bit for bit."""
+    import torch
+    n = 1000
+    d = scenes.boxroom_sequence(n)
+    host = torch.from_numpy(d).pin_memory()
+    ext = api.PlaneExtractor(max_frames=n)
+    a = ext.extract_batch_ptr(host.data_ptr(), n, 480, 640, copy=True)
+    assert ext.transfer_bytes()[0] == n * 160 * 640 * 4                 # the sparse path was taken
+    dev = host.cuda()
+    ext.extract_device(dev.data_ptr(), n, 480, 640)
+    b = ext.fetch()
+    small = api.PlaneExtractor(max_frames=100)
+    assert len(a) == len(b) == n and np.array_equal(a.frames["n_planes"], b.frames["n_planes"])
+    assert np.array_equal(a.frames["n_real"], b.frames["n_real"]) and not a.frames["flags"].any()
+    for name in ("coef", "n_points", "n_boundary", "src", "is_supposed"):
+        assert np.array_equal(a.planes[name], b.planes[name]), name
+
+    def clouds(r):
+        # the arenas order real and supposed clouds per group: compare plane by plane through the offsets
+        pts = np.concatenate([r.points[q["points_off"]:q["points_off"] + q["n_points"]] for q in r.planes])
+        bnd = np.concatenate([r.boundary[q["boundary_off"]:q["boundary_off"] + q["n_boundary"]] for q in r.planes])
+        return pts, bnd
+    pa, ba = clouds(a)
+    pb, bb = clouds(b)
+    assert np.array_equal(pa, pb) and np.array_equal(ba, bb)
+    at = 0
+    for c0 in range(0, n, 100):
+        small.extract_device(dev[c0:c0 + 100].data_ptr(), 100, 480, 640)
+        r = small.fetch()
+        k = len(r.planes)
+        assert np.array_equal(r.frames["n_planes"], a.frames["n_planes"][c0:c0 + 100])
+        assert np.array_equal(r.planes["coef"].view(np.uint32), a.planes["coef"][at:at + k].view(np.uint32))
+        assert np.array_equal(r.planes["n_points"], a.planes["n_points"][at:at + k])
+        at += k
+    assert at == len(a.planes) and int(a.frames["n_planes"].sum()) > 2000
+    ext.close(); small.close()
