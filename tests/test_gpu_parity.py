@@ -326,6 +326,7 @@ def test_random_clutter_scenes(oracle_lib, seed):
     d = np.ascontiguousarray(d)
     api.host_register(d)
     try:
+        _poison(e, (1, 480, 640))
         e.set_upload_mode(2)
         sp = e.extract(d)
         assert e.transfer_bytes()[0] == 160 * 640 * 4
@@ -340,6 +341,7 @@ def test_random_clutter_scenes(oracle_lib, seed):
     w16 = e.extract_batch_u16(u16, factor)
     api.host_register(u16)
     try:
+        _poison(e, (1, 480, 640))
         e.set_upload_mode(2)
         s16 = e.extract_batch_u16(u16, factor)
         assert e.transfer_bytes()[0] == 160 * 640 * 2
@@ -358,6 +360,13 @@ def test_line_fits_on_the_global_memory_path(seq, oracle_lib, k):
     rep = compare_frame(e, orc, seq[k], fp)
     assert rep.get("models_bit_exact", True) and len(orc.line_recs()) > 0
     e.close()
+
+
+def _poison(ext, shape):
+    """Overwrite the context's device image with a wrong depth (whole-image upload of a constant) so that a sparse
+    upload that failed to fetch a window sector could not get away with the previous call's data."""
+    ext.set_upload_mode(1)
+    ext.extract_batch(np.full(shape, 7.0, np.float32))
 
 
 def _same_batch(a, b):
@@ -383,10 +392,14 @@ def test_sparse_upload_equals_whole_image_upload(seq):
     assert _same_batch(pageable, whole) and ext.transfer_bytes()[0] == d.nbytes
     api.host_register(d)
     try:
+        _poison(ext, d.shape)
+        ext.set_upload_mode(2)
         sparse = ext.extract_batch(d)
         up = ext.transfer_bytes()
         assert up[0] == n * 160 * 640 * 4 and 0 < up[1] < d.nbytes // 2 and up[2] == up_whole[2]
         assert _same_batch(sparse, whole)
+        _poison(ext, d.shape)
+        ext.set_upload_mode(2)
         one = ext.extract(d[7])                                          # a single frame of a registered buffer
         ref = whole.frame(7)
         assert one.mnPlaneNum == ref.mnPlaneNum and np.array_equal(one.mvPlaneCoefficients.view(np.uint32), ref.mvPlaneCoefficients.view(np.uint32))
@@ -407,6 +420,7 @@ def test_sparse_upload_equals_whole_image_upload(seq):
     whole16 = ext.extract_batch_u16(u16, factor)
     api.host_register(u16)
     try:
+        _poison(ext, d.shape)
         ext.set_upload_mode(2)
         sparse16 = ext.extract_batch_u16(u16, factor)
         assert ext.transfer_bytes()[0] == n * 160 * 640 * 2
@@ -424,6 +438,7 @@ def test_sparse_upload_equals_whole_image_upload(seq):
     a = e2.extract_batch(view)
     api.host_register(padded)
     try:
+        _poison(e2, (m, 401, 500))
         e2.set_upload_mode(2)
         b = e2.extract_batch(view)
         assert e2.transfer_bytes()[0] == m * 134 * 500 * 4
@@ -470,6 +485,7 @@ def test_sparse_upload_1280x720(realsense_frames):
     whole = e.extract_batch(d)
     api.host_register(d)
     try:
+        _poison(e, d.shape)
         e.set_upload_mode(2)
         sparse = e.extract_batch(d)
         up = e.transfer_bytes()

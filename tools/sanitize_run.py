@@ -24,3 +24,28 @@ e3 = api.PlaneExtractor(max_frames=8)
 e3.extract_batch(d[:8])
 e3.close()
 print("planes", len(r.planes), len(r2.planes), len(r3.planes), f.mnPlaneNum)
+# sparse upload (page-locked input: k_border_fetch, strided copies, early downloads), float and 16-bit, several groups
+os.environ.pop("SPX_REFINE_FAST_MAX", None)
+dd = np.ascontiguousarray(np.nan_to_num(d))
+hp = torch.from_numpy(dd).pin_memory()
+hp16 = torch.from_numpy(u16).pin_memory()
+e4 = api.PlaneExtractor(max_frames=66, n_streams=3)
+s1 = e4.extract_batch_ptr(hp.data_ptr(), 66, 480, 640, copy=True)
+s2 = e4.extract_batch_u16_ptr(hp16.data_ptr(), 66, 480, 640, float(np.float32(1.0) / np.float32(5000.0)), copy=True)
+print("sparse", len(s1.planes), len(s2.planes), e4.transfer_bytes())
+# voxel grid (host clouds and device results), map upload / associate / boundary updates
+fr = s1.frame(10)
+outs = e4.voxel_grid(fr.mvPlanePoints + fr.mvBoundaryPoints + [np.empty(0, api.POINT_DTYPE)], 0.03)
+e4.extract_device(dev.data_ptr(), 66, 480, 640)
+e4.voxel_downsample_results(0.05, 1)
+r5 = e4.fetch()
+pm = api.PlaneMap(e4)
+pm.upload(fr.mvPlaneCoefficients, fr.mvBoundaryPoints)
+a = pm.associate(s1.frame(11).mvPlaneCoefficients)
+pm.update_boundary(0, np.eye(4), np.concatenate(fr.mvBoundaryPoints))
+e4.extract_device(dev.data_ptr(), 66, 480, 640)
+f12 = r3.frame(12)
+pm.update_boundary_from_result(1 % fr.mnPlaneNum, np.eye(4), 12, 0, len(f12.mvBoundaryPoints[0]))
+a2 = pm.associate(s1.frame(12).mvPlaneCoefficients)
+pm.close(); e4.close()
+print("next rows", [len(o) for o in outs][:4], len(r5.boundary), a[0], a2[0])
