@@ -12,6 +12,7 @@
 #include <climits>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -29,7 +30,8 @@ namespace {
 
 inline int cdiv(long long a, int b) { return int((a + b - 1) / b); }
 
-// ---- growable device scratch owned by this file (one per context would be tidier; the calls are synchronous) ----
+// ---- growable device scratch of the voxel-grid calls: one set per device, guarded by a mutex (the calls are synchronous) ----
+constexpr int kMaxDevices = 64;
 struct Scratch {
     void *p = nullptr;
     size_t cap = 0;
@@ -193,7 +195,8 @@ struct VoxPlan {           // device buffers of one run, carved from the scratch
     spx_point *out; void *cub_tmp; size_t cub_bytes;
 };
 
-Scratch g_vox_scratch;
+Scratch g_vox_scratch[kMaxDevices], g_vox_in[kMaxDevices];
+std::mutex g_vox_mutex[kMaxDevices];
 
 // core: `d_pts` device points, segments described on the host; leaves out / seg_count / seg_off(exclusive) on the device
 int voxel_core(spx_ctx *c, cudaStream_t st, const spx_point *d_pts, std::vector<VoxSeg> &segs, int total, const float leaf[3], VoxPlan *plan,
@@ -210,8 +213,9 @@ int voxel_core(spx_ctx *c, cudaStream_t st, const spx_point *d_pts, std::vector<
     const size_t T = size_t(total > 0 ? total : 1), S = size_t(n_seg) + 1;
     size_t need = Carver::bytes<VoxSeg>(S) + 2 * Carver::bytes<unsigned long long>(T) + 5 * Carver::bytes<int>(T) + 2 * Carver::bytes<int>(S) +
                   Carver::bytes<spx_point>(T) + cub_bytes + 4096;
-    NX_CK(c, g_vox_scratch.need(need));
-    Carver A(g_vox_scratch.p);
+    Scratch &scratch = g_vox_scratch[spx_internal_device(c) % kMaxDevices];
+    NX_CK(c, scratch.need(need));
+    Carver A(scratch.p);
     VoxPlan &P = *plan;
     P.segs = A.take<VoxSeg>(S); P.keys = A.take<unsigned long long>(T); P.keys2 = A.take<unsigned long long>(T);
     P.vals = A.take<int>(T); P.vals2 = A.take<int>(T); P.head = A.take<int>(T); P.slot = A.take<int>(T); P.out_idx = A.take<int>(T);
@@ -373,6 +377,7 @@ int spx_voxel_grid(spx_ctx *c, const spx_point *points, const int64_t *cloud_off
     if (total > INT_MAX || n_clouds >= (1 << 24)) return spx_internal_fail(c, SPX_ERR_ARG, "spx_voxel_grid", "more than 2^31 points or 2^24 clouds in one call");
     if (total > 0 && !out) return spx_internal_fail(c, SPX_ERR_ARG, "spx_voxel_grid", "null output");
     NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    std::lock_guard<std::mutex> lock(g_vox_mutex[spx_internal_device(c) % kMaxDevices]);
     cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
     std::vector<VoxSeg> segs(static_cast<size_t>(n_clouds));
     for (int s = 0; s < n_clouds; ++s) {
@@ -380,7 +385,7 @@ int spx_voxel_grid(spx_ctx *c, const spx_point *points, const int64_t *cloud_off
         std::memset(&segs[s], 0, sizeof(VoxSeg));
         segs[s].start = cloud_off[s] - cloud_off[0]; segs[s].len = int(cloud_off[s + 1] - cloud_off[s]); segs[s].gpos = int(segs[s].start);
     }
-    static Scratch in_scratch;
+    Scratch &in_scratch = g_vox_in[spx_internal_device(c) % kMaxDevices];
     NX_CK(c, in_scratch.need(size_t(total > 0 ? total : 1) * sizeof(spx_point)));
     spx_point *d_in = static_cast<spx_point *>(in_scratch.p);
     if (total) NX_CK(c, cudaMemcpyAsync(d_in, points + cloud_off[0], size_t(total) * sizeof(spx_point), cudaMemcpyHostToDevice, st));
@@ -403,6 +408,7 @@ int spx_voxel_downsample_results(spx_ctx *c, float leaf, int which) {
     int rc = spx_get_device_results(c, &R);     // fails unless the last call was spx_extract_batch_device
     if (rc != SPX_OK) return rc;
     NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    std::lock_guard<std::mutex> lock(g_vox_mutex[spx_internal_device(c) % kMaxDevices]);
     cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
     long long tot[3];
     NX_CK(c, cudaMemcpyAsync(tot, R.totals, sizeof(tot), cudaMemcpyDeviceToHost, st));
