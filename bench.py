@@ -49,6 +49,7 @@ def algorithmic_bytes_per_frame(rows=ROWS, cols=COLS, dis=3):
         "k_edge_chamfer": n * 4 + n * 1,                 # one depth sample per organized pixel in, window size out
         "k_normals_link": n * 4 + n * 1 + n * 12 + n * 9, # depth sample + window size in; x y z, link bits, forest, counts out
         "k_ccl_merge": n * 1 + n * 4,                    # link bits in, forest touched
+        "k_ccl_merge4": n * 1 + n * 4,                   # (the four-pixels-per-thread variant of the same pass)
         "k_ccl_flatten": n * 4 + n * 4 + n * 4,          # forest in/out, counts
         "k_ccl_rank": n * 8 + n * 2 + n * 8,             # forest + sizes in, index lists + positions out (upper bound)
         "k_ccl_label": n * 8,

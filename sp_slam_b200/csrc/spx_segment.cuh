@@ -125,6 +125,51 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(Params P, Buffers B) {
     if (valid && (__ffs(peers) - 1) == int(threadIdx.x & 31)) atomicAdd(B.cnt + fo + root, __popc(peers));
 }
 
+// K4b with four consecutive pixels per thread (organized clouds with N % 4 == 0): the link bytes of the four pixels and
+// of the four pixels above them arrive as one 32-bit word each (the upper row is not word aligned: two aligned words
+// and a funnel shift), and a thread whose four pixels have no links leaves at once.  Same unions, same skip rules, same
+// result as k_ccl_merge with tile_h = 1 (0.18 vs 0.32 ms per 1000 frames).  The same treatment of the flatten pass was
+// slower (0.41 vs 0.33 ms: four warp matches per thread instead of one, fewer threads to hide the pointer chases).
+__global__ void __launch_bounds__(256) k_ccl_merge4(Params P, Buffers B) {
+    const int f = P.frame0 + blockIdx.y;
+    const int q0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (q0 >= P.N) return;
+    const int w = P.w;
+    const size_t fo = size_t(f) * P.N;
+    const uint8_t *conn = B.conn + fo;
+    int *parent = B.parent + fo;
+    const unsigned cb4 = *reinterpret_cast<const unsigned *>(conn + q0);
+    if (!(cb4 & 0x03030303u)) return;                       // no links at all in these four pixels
+    unsigned up4 = 0;
+    if (q0 >= w) {                                          // link bytes of q0 - w .. q0 - w + 3 (inside the frame)
+        const int a = q0 - w, al = a & ~3;
+        const unsigned lo = *reinterpret_cast<const unsigned *>(conn + al);
+        const unsigned hi = (a & 3) ? *reinterpret_cast<const unsigned *>(conn + al + 4) : 0u;
+        up4 = __funnelshift_r(lo, hi, 8 * (a & 3));
+    } else if (q0 + 3 >= w) {                               // the four pixels straddle rows 0 and 1
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (q0 + k >= w) up4 |= unsigned(conn[q0 + k - w]) << (8 * k);
+    }
+    unsigned left = q0 > 0 ? conn[q0 - 1] : 0u;
+    int r = q0 / w, c = q0 - r * w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int q = q0 + k;
+        const unsigned cb = (cb4 >> (8 * k)) & 0xffu, up = (up4 >> (8 * k)) & 0xffu;
+        if ((cb & 1u) && (c & 31) == 0) {
+            const bool skip = r > 0 && (cb & 2u) && (left & 2u) && (up & 1u);
+            if (!skip) uf_unite(parent, q, q - 1);
+        }
+        if (cb & 2u) {
+            const bool skip = (c & 31) != 0 && (cb & 1u) && (up & 1u) && (left & 2u);
+            if (!skip) uf_unite(parent, q, q - w);
+        }
+        left = cb;
+        if (++c == w) { c = 0; ++r; }
+    }
+}
+
 // K4d: one CTA per frame, one pass over the frame in 2048-pixel chunks (raster order).
 //  (1) exclusive prefix count of roots = PCL's dense label of each component; components with size > Plane.MinSize
 //      become plane candidates, in label order, and get the offset of their index list;

@@ -536,3 +536,14 @@ def test_full_size_batch_is_consistent():
         at += k
     assert at == len(a.planes) and int(a.frames["n_planes"].sum()) > 2000
     ext.close(); small.close()
+
+
+def test_one_pixel_per_thread_ccl_merge(seq, oracle_lib):
+    """the fallback union kernel (organized clouds whose size is not a multiple of 4 use it) on the standard frames"""
+    e = extractor_with_env({"SPX_CCL_FOUR": "0"}, debug=True)
+    for k in (2, 5):
+        fp = e.extract(seq[k])
+        orc = oracle_lib.Oracle().run(seq[k])
+        rep = compare_frame(e, orc, seq[k], fp)
+        assert rep["labels_bit_exact"], rep
+    e.close()
