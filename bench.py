@@ -56,6 +56,7 @@ def algorithmic_bytes_per_frame(rows=ROWS, cols=COLS, dis=3):
         "k_moments_fit": n * 4 + n * 12,                 # index list + xyz of the members in
         "k_models": 8192,
         "k_pid_init": n * 4 + n * 1,
+        "k_pid_init4": n * 4 + n * 1,
         "k_refine": 2 * 2 * n + n * 12 + n * 4,          # plane ids in/out twice, xyz of free pixels, positions
         "k_refine2": 2 * 2 * n + n * 12 + n * 4,
         "k_contour": n * 1 + 16384,                      # plane-id map in, contour indices out

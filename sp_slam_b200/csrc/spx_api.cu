@@ -337,7 +337,8 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     if (c->debug) LAUNCH(k_ccl_label, gpix, 256, 0, P, B);
     LAUNCH(k_moments_fit, dim3(kMomCands, F), 96, 0, P, B);
     LAUNCH(k_models, cdiv(F, 128), 128, 0, P, B);
-    LAUNCH(k_pid_init, gpix, 256, 0, P, B);
+    if (c->ccl_four && N % 4 == 0) LAUNCH(k_pid_init4, dim3(cdiv(N / 4, 256), F), 256, 0, P, B);
+    else LAUNCH(k_pid_init, gpix, 256, 0, P, B);
     {
         if (P.refine_fast) {
             if (P.w <= 224) LAUNCH(k_refine2<7>, F, 7 * 32, size_t(2) * P.h * 7 * 4 + kRefTableCap * 4, P, B);

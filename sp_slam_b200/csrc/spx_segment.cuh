@@ -543,4 +543,16 @@ __global__ void __launch_bounds__(256) k_pid_init(Params P, Buffers B) {
     B.pid[fo + q] = int8_t(B.root_model[fo + B.parent[fo + q]]);   // k_ccl_rank left -2 at the roots of unlabelled points
 }
 
+// the same, four pixels per thread (N % 4 == 0): one 16-byte load of the forest, four gathers, one 4-byte store
+__global__ void __launch_bounds__(256) k_pid_init4(Params P, Buffers B) {
+    const int f = P.frame0 + blockIdx.y;
+    const int q0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (q0 >= P.N) return;
+    const size_t fo = size_t(f) * P.N;
+    const int4 p4 = *reinterpret_cast<const int4 *>(B.parent + fo + q0);
+    const int16_t *rm = B.root_model + fo;
+    const unsigned a = uint8_t(int8_t(rm[p4.x])), b = uint8_t(int8_t(rm[p4.y])), c = uint8_t(int8_t(rm[p4.z])), d = uint8_t(int8_t(rm[p4.w]));
+    *reinterpret_cast<unsigned *>(B.pid + fo + q0) = a | (b << 8) | (c << 16) | (d << 24);
+}
+
 }  // namespace spx
