@@ -60,6 +60,7 @@ struct spx_ctx {
     int n_streams = 1, min_group = 32, last_groups = 1;
     int refine_fast_max = 700;  // batches of at most this many frames use k_refine2
     bool ccl_four = true;      // k_ccl_merge4 (N % 4 == 0) instead of the one-pixel-per-thread k_ccl_merge
+    bool flatten_runs = true;  // k_ccl_flatten_runs (one pointer chase per row run) instead of k_ccl_flatten (one per pixel)
     bool refine_per_group = true;
     std::vector<double> group_weights;   // tuning knob SPX_GROUP_WEIGHTS="w0,w1,...": relative group sizes on the host path
     double edge_weight = 0.5;   // host path: size of the first and the last frame group relative to the others
@@ -332,7 +333,8 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     }
     if (c->ccl_four && N % 4 == 0) LAUNCH(k_ccl_merge4, dim3(cdiv(N / 4, 256), F), 256, 0, P, B);   // four pixels per thread
     else LAUNCH(k_ccl_merge, gpix, 256, 0, P, B, 1);
-    LAUNCH(k_ccl_flatten, gpix, 256, 0, P, B);
+    if (c->flatten_runs) LAUNCH(k_ccl_flatten_runs, dim3(cdiv(P.w, 32), cdiv(P.h, 8 * kFlatRows), F), dim3(32, 8), 0, P, B);
+    else LAUNCH(k_ccl_flatten, gpix, 256, 0, P, B);
     LAUNCH(k_ccl_rank, F, kRankThreads, 0, P, B);
     if (c->debug) LAUNCH(k_ccl_label, gpix, 256, 0, P, B);
     LAUNCH(k_moments_fit, dim3(kMomCands, F), 96, 0, P, B);
@@ -748,6 +750,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (const char *e = std::getenv("SPX_UPLOAD")) c->upload_mode = std::atoi(e);   // test / tuning knob (see spx_ctx::upload_mode)
     if (const char *e = std::getenv("SPX_SPARSE_MIN_FRAMES")) c->sparse_min_frames = std::atoi(e);   // tuning knob
     if (const char *e = std::getenv("SPX_CCL_FOUR")) c->ccl_four = std::atoi(e) != 0;   // test knob: the one-pixel-per-thread kernel
+    if (const char *e = std::getenv("SPX_FLATTEN_RUNS")) c->flatten_runs = std::atoi(e) != 0;   // test knob
     if (const char *e = std::getenv("SPX_REFINE_PER_GROUP")) c->refine_per_group = std::atoi(e) != 0;   // tuning knob
     if (const char *e = std::getenv("SPX_EDGE_WEIGHT")) { const double v = std::atof(e); if (v > 0.05 && v <= 1.0) c->edge_weight = v; }   // tuning knob
     if (const char *e = std::getenv("SPX_GROUP_WEIGHTS")) {   // tuning knob

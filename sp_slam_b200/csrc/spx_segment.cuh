@@ -170,6 +170,60 @@ __global__ void __launch_bounds__(256) k_ccl_merge4(Params P, Buffers B) {
     }
 }
 
+// K4c by row runs.  The forest was initialised with one tree per row run (maximal chain of left links inside a 32-column
+// segment: k_normals_link / k_ccl_link) and unions only ever merge trees, so all pixels of a run share their root: a warp
+// takes one 32-column segment of a row, rebuilds the runs from the link bits with a ballot, only the first pixel of a run
+// chases the pointers and adds the run's length to the root's counter, and the root reaches the run's lanes by shuffle.
+constexpr int kFlatRows = 4;        // row segments per warp: their pointer chases are in flight together
+__global__ void __launch_bounds__(256) k_ccl_flatten_runs(Params P, Buffers B) {
+    const int f = P.frame0 + blockIdx.z, lane = threadIdx.x;
+    const int r0 = (blockIdx.y * 8 + threadIdx.y) * kFlatRows;
+    const int c = blockIdx.x * 32 + lane;
+    const int w = P.w;
+    if (r0 >= P.h) return;                                  // warp uniform
+    const size_t fo = size_t(f) * P.N;
+    int *parent = B.parent + fo;
+    const int n_valid = min(32, w - blockIdx.x * 32);
+    const bool cvalid = c < w;
+    unsigned cb[kFlatRows];
+#pragma unroll
+    for (int k = 0; k < kFlatRows; ++k) cb[k] = (cvalid && r0 + k < P.h) ? B.conn[fo + (r0 + k) * w + c] : 0u;
+    int s0[kFlatRows], len[kFlatRows], x[kFlatRows];
+    bool start[kFlatRows], done[kFlatRows];
+#pragma unroll
+    for (int k = 0; k < kFlatRows; ++k) {
+        const bool valid = cvalid && r0 + k < P.h;
+        const unsigned linked = __ballot_sync(SPX_FULL, valid && (cb[k] & 1u));
+        const unsigned starts = ~linked | 1u;               // lane 0 always starts a run inside the segment
+        s0[k] = 31 - __clz(starts & (SPX_FULL >> (31 - lane)));
+        const unsigned above = lane == 31 ? 0u : (starts & (SPX_FULL << (lane + 1)));
+        const int next = above ? __ffs(above) - 1 : 32;
+        start[k] = valid && s0[k] == lane;
+        len[k] = min(next, n_valid) - lane;
+        x[k] = (r0 + k) * w + c;
+        done[k] = !start[k];
+    }
+    // the run starts chase their pointers, all rows of the warp together
+    while (true) {
+        bool all = true;
+        int nx[kFlatRows];
+#pragma unroll
+        for (int k = 0; k < kFlatRows; ++k) nx[k] = done[k] ? x[k] : __ldcg(parent + x[k]);
+#pragma unroll
+        for (int k = 0; k < kFlatRows; ++k) {
+            if (!done[k]) { done[k] = nx[k] == x[k]; x[k] = nx[k]; }
+            all = all && done[k];
+        }
+        if (__all_sync(SPX_FULL, all)) break;
+    }
+#pragma unroll
+    for (int k = 0; k < kFlatRows; ++k) {
+        const int root = __shfl_sync(SPX_FULL, x[k], s0[k]);
+        if (cvalid && r0 + k < P.h) parent[(r0 + k) * w + c] = root;
+        if (start[k]) atomicAdd(B.cnt + fo + root, len[k]);
+    }
+}
+
 // K4d: one CTA per frame, one pass over the frame in 2048-pixel chunks (raster order).
 //  (1) exclusive prefix count of roots = PCL's dense label of each component; components with size > Plane.MinSize
 //      become plane candidates, in label order, and get the offset of their index list;

@@ -547,3 +547,13 @@ def test_one_pixel_per_thread_ccl_merge(seq, oracle_lib):
         rep = compare_frame(e, orc, seq[k], fp)
         assert rep["labels_bit_exact"], rep
     e.close()
+
+
+def test_per_pixel_flatten_kernel(seq, oracle_lib):
+    """the one-pointer-chase-per-pixel flatten kernel (test knob) against the oracle"""
+    e = extractor_with_env({"SPX_FLATTEN_RUNS": "0"}, debug=True)
+    fp = e.extract(seq[3])
+    orc = oracle_lib.Oracle().run(seq[3])
+    rep = compare_frame(e, orc, seq[3], fp)
+    assert rep["labels_bit_exact"], rep
+    e.close()
