@@ -353,12 +353,16 @@ def _main(out):
         ext1.set_stream(stream.cuda_stream)
         ext1.set_profile(True)
 
+    gathered = [None]
+
     def gather_planes():
         """the one collective of the path: plane lists (frame headers + plane records) to every rank over NCCL"""
         if world == 1:
             return
         from sp_slam_b200 import sharding
-        sharding.gather_plane_lists(ext, F)
+        # an upper bound of 16 planes per frame lets the three collectives be enqueued without reading the counts back
+        # (no host wait inside the step); the counts of the last step are validated after the timed region
+        gathered[0] = sharding.gather_plane_lists(ext, F, max_planes_hint=16 * F)
 
     def step_device():
         ext.extract_device(dev.data_ptr(), F, rows, cols)
@@ -385,6 +389,10 @@ def _main(out):
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
+        if world > 1:
+            from sp_slam_b200 import sharding
+            if not sharding.check_gather(gathered[0][2], 16 * F):
+                raise SystemExit("a rank produced more than 16 planes per frame: the gather hint was too small")
         ms_one = None
         if ext1 is not None:
             for _ in range(2):

@@ -33,14 +33,19 @@ def _as_tensor(ptr: int, nbytes: int, device):
     return torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
 
 
-def gather_records(hdr, planes_buf, totals, to_host: bool = False):
+def gather_records(hdr, planes_buf, totals, to_host: bool = False, max_planes_hint: int | None = None):
     """All-gather of per-rank frame headers and plane records; works on any backend (NCCL on device buffers, gloo on
     host tensors in the CPU tests).
 
     hdr: uint8 tensor, n_frames * 16 bytes (same n_frames on every rank);  planes_buf: uint8 tensor holding at least
     this rank's plane records (48 bytes each), and at least max-over-ranks records of capacity;  totals: int64[3]
     (planes, points, boundary points).  Plane counts differ per rank, so counts are gathered first and the records
-    padded to the maximum."""
+    padded to the maximum.
+
+    max_planes_hint: an upper bound on any rank's plane count known to the caller (e.g. 16 planes per frame).  With it
+    the three collectives are enqueued without reading the counts back, so the host never waits for the device inside
+    the step; the counts come back as a device tensor and `check_gather` validates them at the caller's next
+    synchronisation point (a rank that exceeded the hint => the gather must be repeated without it)."""
     import torch
     import torch.distributed as dist
 
@@ -50,9 +55,14 @@ def gather_records(hdr, planes_buf, totals, to_host: bool = False):
     dist.all_gather_into_tensor(counts, totals)
     hdrs = torch.empty(world * hdr.numel(), dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(hdrs, hdr)
+    rec = api.PLANE_DTYPE.itemsize
+    if max_planes_hint is not None and not to_host:
+        n = max(min(int(max_planes_hint), planes_buf.numel() // rec), 1)
+        planes = torch.empty(world * n * rec, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(planes, planes_buf[: n * rec])
+        return hdrs.view(world, -1), planes.view(world, -1), counts.view(world, 3)
     counts_h = counts.view(world, 3).cpu()
     max_planes = int(counts_h[:, 0].max())
-    rec = api.PLANE_DTYPE.itemsize
     planes = torch.empty(world * max(max_planes, 1) * rec, dtype=torch.uint8, device=dev)
     if max_planes > 0:
         if planes_buf.numel() < max_planes * rec:
@@ -70,7 +80,12 @@ def gather_records(hdr, planes_buf, totals, to_host: bool = False):
     return out
 
 
-def gather_plane_lists(ext: "api.PlaneExtractor", n_frames: int, to_host: bool = False):
+def check_gather(counts, max_planes_hint: int) -> bool:
+    """True when no rank's plane list was longer than the hint the gather was issued with (reads the counts: synchronises)."""
+    return int(counts[:, 0].max()) <= int(max_planes_hint)
+
+
+def gather_plane_lists(ext: "api.PlaneExtractor", n_frames: int, to_host: bool = False, max_planes_hint: int | None = None):
     """NCCL all-gather of every rank's frame headers and plane records straight from the device buffers of the last
     extract (no host round trip for the payload)."""
     import torch
@@ -80,4 +95,4 @@ def gather_plane_lists(ext: "api.PlaneExtractor", n_frames: int, to_host: bool =
     hdr = _as_tensor(r.frames, n_frames * api.HEADER_DTYPE.itemsize, dev)
     totals = _as_tensor(r.totals, 24, dev).view(torch.int64)
     planes_buf = _as_tensor(r.planes, int(r.planes_capacity) * api.PLANE_DTYPE.itemsize, dev)
-    return gather_records(hdr, planes_buf, totals, to_host)
+    return gather_records(hdr, planes_buf, totals, to_host, max_planes_hint)

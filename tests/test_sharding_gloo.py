@@ -48,6 +48,16 @@ def _worker(rank, world, port, n_frames, q):
     for k in range(world):
         eh, ep = _fake_results(k, n_frames)
         ok &= np.array_equal(out[k][0], eh) and np.array_equal(out[k][1], ep)
+    # the same with an upper bound on the plane count: no read-back of the counts inside the call, validation afterwards
+    hint = 10 * n_frames
+    hdrs, planes, counts = sharding.gather_records(torch.from_numpy(hdr.view(np.uint8).copy()),
+                                                   torch.from_numpy(buf.view(np.uint8).copy()),
+                                                   torch.tensor([len(pl), 0, 0], dtype=torch.int64), max_planes_hint=hint)
+    ok &= sharding.check_gather(counts, hint) and not sharding.check_gather(counts, 3)
+    for k in range(world):
+        eh, ep = _fake_results(k, n_frames)
+        got = np.frombuffer(planes[k].numpy().tobytes(), dtype=api.PLANE_DTYPE)[: int(counts[k, 0])]
+        ok &= np.array_equal(np.frombuffer(hdrs[k].numpy().tobytes(), dtype=api.HEADER_DTYPE), eh) and np.array_equal(got, ep)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
