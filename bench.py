@@ -465,19 +465,28 @@ def _main(out):
         lat_ms["budget_ms"] = 33.3
         lat_ms["whole_image_upload"] = lat(1)
         lat_ms["sparse_upload"] = lat(2)
-        # the loop of BASELINE configs[4] as far as it is built: extraction of one frame, association of its planes against a
-        # device-resident map (Map::AssociatePlanesByBoundary), boundary update of the associated map planes
-        # (MapPlane::UpdateBoundary); the pose optimisation between the two (g2o, CPU) is not part of this repository
+        # the loop of BASELINE configs[4] for the plane landmarks: extraction of one frame, association of its planes against
+        # a device-resident map (Map::AssociatePlanesByBoundary), pose-only optimisation with the plane edges
+        # (Optimizer::PoseOptimization's plane part, host code as in the reference), boundary update of the associated map
+        # planes (MapPlane::UpdateBoundary).  The ORB point pipeline of the same loop is outside this repository.
         one.set_upload_mode(0)
         first = one.extract_batch_ptr(host[0].data_ptr(), 1, rows, cols, copy=True).frame(0)
         pm = api.PlaneMap(one)
         pm.upload(first.mvPlaneCoefficients, first.mvBoundaryPoints)
         eye = np.eye(4)
-        tl, n_up = [], 0
+        tl, n_up, n_edges = [], 0, 0
         for k in range(1, min(F, 61)):
             t1 = time.perf_counter()
             fr = one.extract_batch_ptr(host[k].data_ptr(), 1, rows, cols).frame(0)
             a, v, p, dd = pm.associate(fr.mvPlaneCoefficients)
+            kinds, pw, ms = [], [], []
+            for kind, idx in ((0, a), (1, p), (2, v)):
+                for i, j in enumerate(idx):
+                    if j >= 0:
+                        kinds.append(kind); pw.append(first.mvPlaneCoefficients[j]); ms.append(fr.mvPlaneCoefficients[i])
+            if kinds:
+                api.pose_optimize_planes(eye, api.plane_edges(kinds, pw, ms))
+                n_edges += len(kinds)
             for i, j in enumerate(a):
                 if j >= 0:
                     pm.update_boundary_from_result(int(j), eye, 0, i, len(fr.mvBoundaryPoints[i]))
@@ -486,9 +495,9 @@ def _main(out):
         pm.close()
         tl = np.array(tl[10:])
         lat_ms["tracking_loop"] = {"median": float(np.median(tl)), "p95": float(np.percentile(tl, 95)), "frames": len(tl),
-                                   "boundary_updates": n_up,
-                                   "note": "extract + associate + update boundaries per frame through the Python binding; "
-                                           "pose optimisation (g2o, CPU) not included"}
+                                   "boundary_updates": n_up, "plane_edges": n_edges,
+                                   "note": "extract + associate + pose optimisation with the plane edges (host) + boundary updates "
+                                           "per frame, through the Python binding"}
         one.close()
     # SURVEY 8(f) rows either side of the path (N4 VoxelGrid of the contours, N1 plane association), rank 0 at N = 1
     next_rows = None

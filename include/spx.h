@@ -261,6 +261,31 @@ int  spx_map_set_world_pos(spx_map *map, int j, const float coef_w[4]);
 /* map plane j's boundary cloud as stored on the device (parity tap / MapPlane::mvBoundaryPoints for the drawers) */
 int  spx_map_get_boundary(spx_map *map, int j, spx_point *out, int cap, int *n);
 
+/* N3.  replaces: the plane part of Optimizer::PoseOptimization (src/Optimizer.cc:519-1160): pose-only Levenberg-Marquardt
+ * with the unary plane edges of g2oAddition (EdgePlane, EdgeParallelPlane, EdgeVerticalPlane; Plane3D's azimuth /
+ * elevation / distance parametrisation), Huber kernels and the four outlier rounds.  HOST code (a 6x6 system a few
+ * times per frame), double precision; no CUDA context involved.  Tcw: row-major 4x4, in = Frame::mTcw, out = the
+ * optimised pose.  One record per edge, as PoseOptimization builds them (src/Optimizer.cc:695-907):
+ *   kind 0 EdgePlane          info = (angleInfo, angleInfo, disInfo) [x2 for a not-seen map plane], delta = sqrt(Plane.Chi),   chi2_max = Plane.Chi
+ *   kind 1 EdgeParallelPlane  info = (parInfo, parInfo),                                           delta = sqrt(Plane.VPChi), chi2_max = Plane.VPChi
+ *   kind 2 EdgeVerticalPlane  info = (verInfo, verInfo),                                           delta = sqrt(Plane.VPChi), chi2_max = Plane.VPChi
+ * with angleInfo = 3282.8 / Plane.AngleInfo^2, disInfo = Plane.DistanceInfo^2, parInfo / verInfo = 3282.8 / Plane.ParallelInfo^2 / VerticalInfo^2.
+ * outlier[i] (optional) = mvbPlaneOutlier / mvbParPlaneOutlier / mvbVerPlaneOutlier of edge i; chi2[i] (optional) = its last chi2;
+ * *n_bad = nBad of the last round. */
+typedef struct spx_plane_edge {
+    int32_t kind;
+    int32_t reserved;
+    float   plane_w[4];        /* MapPlane::GetWorldPos() of the associated / parallel / vertical map plane */
+    float   measurement[4];    /* mvPlaneCoefficients[i] */
+    double  info[3];
+    double  huber_delta;
+    double  chi2_max;
+} spx_plane_edge;
+int spx_pose_optimize_planes(double Tcw[16], const spx_plane_edge *edges, int n_edges, int rounds, int iterations,
+                             uint8_t *outlier, double *chi2, int *n_bad);
+/* parity tap: the residuals of the edges at the pose Tcw (computeError of each edge; 3 doubles per edge, the third is 0 for the 2-d edges) */
+int spx_plane_edge_errors(const double Tcw[16], const spx_plane_edge *edges, int n_edges, double *errors);
+
 #ifdef __cplusplus
 }
 #endif

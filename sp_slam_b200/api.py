@@ -34,6 +34,8 @@ PLANE_DTYPE = np.dtype([("coef", "<f4", 4), ("n_points", "<i4"), ("n_boundary", 
 HEADER_DTYPE = np.dtype([("n_real", "<i4"), ("n_planes", "<i4"), ("first_plane", "<i4"), ("flags", "<u4")])
 MODEL_DTYPE = np.dtype([("coef", "<f4", 4), ("centroid", "<f4", 3), ("cov", "<f4", 9), ("curvature", "<f4"),
                         ("label", "<u4"), ("n_segment", "<i4"), ("n_inliers", "<i4"), ("n_contour", "<i4")])
+EDGE_DTYPE = np.dtype([("kind", "<i4"), ("reserved", "<i4"), ("plane_w", "<f4", 4), ("measurement", "<f4", 4),
+                       ("info", "<f8", 3), ("huber_delta", "<f8"), ("chi2_max", "<f8")])
 LINE_DTYPE = np.dtype([("plane", "<i4"), ("round", "<i4"), ("n_points", "<i4"), ("iterations", "<i4"),
                        ("n_inliers", "<i4"), ("in_range", "<i4"), ("is_border", "<i4"), ("emitted", "<i4"),
                        ("coef", "<f4", 6)])
@@ -50,6 +52,7 @@ EXPORTS = (
     "spx_get_group_timeline",
     "spx_voxel_grid", "spx_voxel_downsample_results", "spx_map_create", "spx_map_destroy", "spx_map_upload", "spx_map_associate",
     "spx_map_update_boundary", "spx_map_update_boundary_from_result", "spx_map_set_world_pos", "spx_map_get_boundary",
+    "spx_pose_optimize_planes", "spx_plane_edge_errors",
 )
 
 
@@ -143,6 +146,8 @@ def lib():
         L.spx_map_update_boundary_from_result.argtypes = [vp, i32, vp, i32, i32, i32]
         L.spx_map_set_world_pos.argtypes = [vp, i32, vp]
         L.spx_map_get_boundary.argtypes = [vp, i32, vp, i32, C.POINTER(i32)]
+        L.spx_pose_optimize_planes.argtypes = [vp, vp, i32, i32, i32, vp, vp, C.POINTER(i32)]
+        L.spx_plane_edge_errors.argtypes = [vp, vp, i32, vp]
         L.spx_set_upload_mode.argtypes = [vp, i32]
         L.spx_host_register.argtypes = [vp, sz]
         L.spx_host_unregister.argtypes = [vp]
@@ -508,3 +513,51 @@ class PlaneMap:
         out = np.empty(max(n.value, 1), POINT_DTYPE)
         self._ext._ck(lib().spx_map_get_boundary(self._m, j, out.ctypes.data, n.value, C.byref(n)))
         return out[:n.value].copy()
+
+
+def plane_edges(kinds, planes_w, measurements, angle_info=1.0, distance_info=100.0, parallel_info=0.5, vertical_info=0.5,
+                chi=300.0, vp_chi=300.0, not_seen=None) -> np.ndarray:
+    """The edge records Optimizer::PoseOptimization builds (src/Optimizer.cc:695-907) from the YAML keys Plane.AngleInfo,
+    DistanceInfo, ParallelInfo, VerticalInfo, Chi, VPChi (defaults: Examples/RGB-D/TUM1.yaml:89-94)."""
+    kinds = np.asarray(kinds, np.int32)
+    e = np.zeros(len(kinds), EDGE_DTYPE)
+    e["kind"] = kinds
+    e["plane_w"] = np.asarray(planes_w, np.float32).reshape(-1, 4)
+    e["measurement"] = np.asarray(measurements, np.float32).reshape(-1, 4)
+    a, d = 3282.8 / (angle_info * angle_info), distance_info * distance_info
+    par, ver = 3282.8 / (parallel_info * parallel_info), 3282.8 / (vertical_info * vertical_info)
+    for i, k in enumerate(kinds):
+        if k == 0:
+            f = 2.0 if (not_seen is not None and not_seen[i]) else 1.0
+            e["info"][i] = (f * a, f * a, f * d)
+            e["huber_delta"][i], e["chi2_max"][i] = np.float32(np.sqrt(chi)), chi
+        else:
+            w = par if k == 1 else ver
+            e["info"][i] = (w, w, 0.0)
+            e["huber_delta"][i], e["chi2_max"][i] = np.float32(np.sqrt(vp_chi)), vp_chi
+    return e
+
+
+def pose_optimize_planes(Tcw: np.ndarray, edges: np.ndarray, rounds: int = 4, iterations: int = 10):
+    """The plane part of Optimizer::PoseOptimization (host code, no GPU): returns (Tcw optimised, outlier flags, chi2, nBad)."""
+    T = np.ascontiguousarray(Tcw, np.float64).reshape(4, 4).copy()
+    edges = np.ascontiguousarray(edges, EDGE_DTYPE)
+    out = np.zeros(max(len(edges), 1), np.uint8)
+    chi2 = np.zeros(max(len(edges), 1), np.float64)
+    bad = C.c_int()
+    rc = lib().spx_pose_optimize_planes(T.ctypes.data, edges.ctypes.data, len(edges), rounds, iterations, out.ctypes.data,
+                                        chi2.ctypes.data, C.byref(bad))
+    if rc != SPX_OK:
+        raise SpxError(rc, "spx_pose_optimize_planes: bad argument")
+    return T, out[:len(edges)].astype(bool), chi2[:len(edges)], bad.value
+
+
+def plane_edge_errors(Tcw: np.ndarray, edges: np.ndarray) -> np.ndarray:
+    """computeError of every edge at the pose Tcw: (n, 3) doubles (third column 0 for the 2-d edges)."""
+    T = np.ascontiguousarray(Tcw, np.float64).reshape(4, 4)
+    edges = np.ascontiguousarray(edges, EDGE_DTYPE)
+    err = np.zeros((max(len(edges), 1), 3), np.float64)
+    rc = lib().spx_plane_edge_errors(T.ctypes.data, edges.ctypes.data, len(edges), err.ctypes.data)
+    if rc != SPX_OK:
+        raise SpxError(rc, "spx_plane_edge_errors: bad argument")
+    return err[:len(edges)]

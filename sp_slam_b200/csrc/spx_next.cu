@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/spx.h"
+#include "../host/PlanePoseOptimizer.h"
 #include "spx_internal.h"
 
 namespace {
@@ -678,6 +679,46 @@ int spx_map_associate(spx_map *m, const float *plane_w, int n_planes, float dis_
     for (int i = 0; i < n_planes; ++i) {
         assoc[i] = m->h_res_i[i]; vertical[i] = m->h_res_i[SPX_MAX_PLANES + i]; parallel[i] = m->h_res_i[2 * SPX_MAX_PLANES + i];
         if (assoc_dist) assoc_dist[i] = m->h_res_f[i];
+    }
+    return SPX_OK;
+}
+
+// ---- N3: host-side pose-only optimisation with plane edges (sp_slam_b200/host/PlanePoseOptimizer.h) ----
+int spx_pose_optimize_planes(double Tcw[16], const spx_plane_edge *edges, int n_edges, int rounds, int iterations, uint8_t *outlier,
+                             double *chi2, int *n_bad) {
+    if (!Tcw || n_edges < 0 || (n_edges > 0 && !edges) || rounds < 1 || iterations < 1) return SPX_ERR_ARG;
+    spx_host::PlanePoseOptimizer opt;
+    opt.edges.resize(size_t(n_edges));
+    for (int i = 0; i < n_edges; ++i) {
+        if (edges[i].kind < 0 || edges[i].kind > 2) return SPX_ERR_ARG;
+        spx_host::PlaneEdge &e = opt.edges[size_t(i)];
+        e.kind = edges[i].kind;
+        e.world = spx_host::Plane3D::from_coefficients(edges[i].plane_w);
+        e.measurement = spx_host::Plane3D::from_coefficients(edges[i].measurement);
+        for (int k = 0; k < 3; ++k) e.info[k] = edges[i].info[k];
+        e.huber_delta = edges[i].huber_delta;
+        e.chi2_max = edges[i].chi2_max;
+    }
+    const int bad = opt.PoseOptimization(Tcw, rounds, iterations);
+    for (int i = 0; i < n_edges; ++i) {
+        if (outlier) outlier[i] = opt.edges[size_t(i)].outlier ? 1 : 0;
+        if (chi2) chi2[i] = opt.edges[size_t(i)].chi2();
+    }
+    if (n_bad) *n_bad = bad;
+    return SPX_OK;
+}
+
+int spx_plane_edge_errors(const double Tcw[16], const spx_plane_edge *edges, int n_edges, double *errors) {
+    if (!Tcw || n_edges < 0 || (n_edges > 0 && (!edges || !errors))) return SPX_ERR_ARG;
+    const spx_host::Pose pose = spx_host::Pose::from_matrix(Tcw);
+    for (int i = 0; i < n_edges; ++i) {
+        if (edges[i].kind < 0 || edges[i].kind > 2) return SPX_ERR_ARG;
+        spx_host::PlaneEdge e;
+        e.kind = edges[i].kind;
+        e.world = spx_host::Plane3D::from_coefficients(edges[i].plane_w);
+        e.measurement = spx_host::Plane3D::from_coefficients(edges[i].measurement);
+        e.compute_error(pose);
+        for (int k = 0; k < 3; ++k) errors[3 * i + k] = k < e.dim() ? e.error[k] : 0.0;
     }
     return SPX_OK;
 }
