@@ -479,13 +479,13 @@ def _main(out):
             t1 = time.perf_counter()
             fr = one.extract_batch_ptr(host[k].data_ptr(), 1, rows, cols).frame(0)
             a, v, p, dd = pm.associate(fr.mvPlaneCoefficients)
-            kinds, pw, ms = [], [], []
+            kinds, map_pl, frame_pl = [], [], []
             for kind, idx in ((0, a), (1, p), (2, v)):
                 for i, j in enumerate(idx):
                     if j >= 0:
-                        kinds.append(kind); pw.append(first.mvPlaneCoefficients[j]); ms.append(fr.mvPlaneCoefficients[i])
+                        kinds.append(kind); map_pl.append(first.mvPlaneCoefficients[j]); frame_pl.append(fr.mvPlaneCoefficients[i])
             if kinds:
-                api.pose_optimize_planes(eye, api.plane_edges(kinds, pw, ms))
+                api.pose_optimize_planes(eye, api.plane_edges(kinds, map_pl, frame_pl))
                 n_edges += len(kinds)
             for i, j in enumerate(a):
                 if j >= 0:
