@@ -120,13 +120,15 @@ int spx_extract_batch(spx_ctx *ctx, const float *depth, int n_frames, int rows, 
  * (src/Frame.cc:857-872); full-resolution depth is read only by IsBorderPoint's 21x21 windows around line points
  * (src/Frame.cc:1038-1052).  When the caller's image is page-locked (cudaHostAlloc, cudaHostRegister or
  * spx_host_register below) the library uploads only the sampled rows (1/Cloud.Dis of the bytes, one strided copy) and the
- * border tests read their windows in place over PCIe; a pageable image is uploaded whole.  Results are identical.
+ * window sectors the border tests will read are fetched from the image over PCIe by a kernel, each once; a pageable
+ * image is uploaded whole.  Results are identical.
  * mode 0 = automatic (default), 1 = always upload the whole image, 2 = sparse whenever the image is page-locked. */
 int spx_set_upload_mode(spx_ctx *ctx, int mode);
 /* page-lock / release a caller-owned host buffer (e.g. the cv::Mat data of the depth images a loader recycles) */
 int spx_host_register(void *ptr, size_t bytes);
 int spx_host_unregister(void *ptr);
-/* bytes moved by the last host-input extract: uploaded by copies, read in place by the border tests, results copied back */
+/* bytes moved by the last host-input extract: uploaded by copies, fetched from the page-locked image by k_border_fetch
+ * (the border tests' window sectors), results copied back */
 int spx_get_transfer_bytes(const spx_ctx *ctx, unsigned long long *h2d_copied, unsigned long long *h2d_in_place,
                            unsigned long long *d2h);
 

@@ -338,11 +338,11 @@ class PlaneExtractor:
         return lib().spx_last_launch_count(self._h)
 
     def set_upload_mode(self, mode: int):
-        """0 automatic, 1 whole image, 2 sparse (sampled rows uploaded, border windows read in place) when page-locked."""
+        """0 automatic, 1 whole image, 2 sparse (sampled rows uploaded, border-test window sectors fetched on demand) when page-locked."""
         self._ck(lib().spx_set_upload_mode(self._h, mode))
 
     def transfer_bytes(self):
-        """(bytes uploaded by copies, bytes read in place from the caller's pinned image, bytes copied back) of the last
+        """(bytes uploaded by copies, bytes fetched from the caller's pinned image by the device, bytes copied back) of the last
         host-input extract."""
         a, b, d = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
         self._ck(lib().spx_get_transfer_bytes(self._h, C.byref(a), C.byref(b), C.byref(d)))
