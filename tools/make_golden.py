@@ -45,6 +45,42 @@ def summarize(o):
     )
 
 
+def next_rows_fixture():
+    """inputs and oracle outputs of the SURVEY 8(f) rows: VoxelGrid (N4), plane association + boundary transform (N1)"""
+    rng = np.random.default_rng(2024)
+    POINT = pyoracle.POINT_DTYPE
+    def cloud(n, spread):
+        p = np.zeros(n, POINT)
+        xyz = (rng.normal(size=(n, 3)) * spread + [0.2, -0.1, 2.0]).astype(np.float32)
+        p["x"], p["y"], p["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+        c = rng.integers(0, 256, size=(n, 4)).astype(np.uint32)
+        p["rgba"] = (c[:, 0] << 24) | (c[:, 1] << 16) | (c[:, 2] << 8) | c[:, 3]
+        return p
+    vox_in = cloud(3000, [0.25, 0.15, 0.03])
+    vox = {}
+    for leaf in (0.01, 0.05):
+        out, idx = pyoracle.voxel_grid(vox_in, leaf)
+        vox[f"vox_out_{leaf}"] = out
+        vox[f"vox_idx_{leaf}"] = idx
+    n_map, n_pl = 9, 6
+    nrm = np.eye(3)[rng.integers(0, 3, n_map)] * rng.choice([-1, 1], (n_map, 1)) + 0.03 * rng.normal(size=(n_map, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    map_w = np.concatenate([nrm, rng.uniform(-3, 3, (n_map, 1))], 1).astype(np.float32)
+    sizes = rng.integers(0, 400, n_map)
+    bnd = cloud(int(sizes.sum()), [3.0, 3.0, 3.0])
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    pn = np.eye(3)[rng.integers(0, 3, n_pl)] + 0.03 * rng.normal(size=(n_pl, 3))
+    pn /= np.linalg.norm(pn, axis=1, keepdims=True)
+    plane_w = np.concatenate([pn, rng.uniform(-3, 3, (n_pl, 1))], 1).astype(np.float32)
+    bnds = [bnd[off[j]:off[j + 1]] for j in range(n_map)]
+    a, v, p, d = pyoracle.associate_planes(plane_w, map_w, bnds, n_seen=6)
+    m = np.eye(4)
+    m[:3, :] = rng.normal(size=(3, 4))
+    return dict(vox_in=vox_in, **vox, map_w=map_w, map_bnd=bnd, map_off=off, plane_w=plane_w, n_seen=6, assoc=a, vertical=v,
+                parallel=p, assoc_dist=d, xform=m, xform_out=pyoracle.transform_cloud(bnds[int(np.argmax(sizes))], m),
+                xform_src=int(np.argmax(sizes)))
+
+
 def main():
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
@@ -59,6 +95,7 @@ def main():
         np.savez_compressed(os.path.join(out, name + ".npz"), frame=f, noisy=noisy, depth_sha=sha(d), **extra,
                             **summarize(o))
         print(name, "planes", o.n_real, o.n_planes, "depth", sha(d)[:12])
+    np.savez_compressed(os.path.join(out, "next_rows.npz"), **next_rows_fixture())
 
 
 if __name__ == "__main__":
