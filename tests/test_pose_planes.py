@@ -143,3 +143,30 @@ def test_few_edges_stop_after_the_first_round_and_bad_arguments():
         api.pose_optimize_planes(np.eye(4), bad_e)
     T_same, outl, _, nb = api.pose_optimize_planes(T_gt, np.zeros(0, api.EDGE_DTYPE))
     assert np.allclose(T_same, T_gt, atol=1e-15) and nb == 0
+
+
+def test_cpp_header_stand_alone_with_extra_terms(tmp_path):
+    """sp_slam_b200/host/PlanePoseOptimizer.h used directly from C++ (no CUDA, no libspx): plane edges alone, and two
+    planes plus a caller-supplied quadratic term through the `extra` hook (how the ORB point edges would enter)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "pose_check"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-o", str(exe),
+                           os.path.join(root, "tests", "host", "pose_check.cpp")])
+    out = subprocess.check_output([str(exe)], text=True).splitlines()
+    a, b = out[0].split(), out[1].split()
+    assert a[0] == "planes_only" and int(a[2]) == 0 and float(a[4]) < 1e-6
+    assert b[0] == "with_prior" and int(b[2]) == 0 and float(b[4]) < 1e-6
+
+
+def test_singular_start_is_left_alone():
+    """With the camera axes exactly on the plane normals the azimuth of Plane3D is atan2(0, 0): the numeric Jacobian of
+    the reference (restated) carries no information, every trial step is rejected and the pose comes back unchanged --
+    documented behaviour of the parametrisation, not something to 'fix' on this side of the interface."""
+    T_gt = pose([0.04, -0.08, 0.03], [0.2, -0.1, 0.3])
+    e = api.plane_edges([0] * 6, ROOM[:6], measurements(T_gt, ROOM[:6]))
+    T, outlier, chi2, bad = api.pose_optimize_planes(np.eye(4), e)
+    assert np.array_equal(T, np.eye(4)) and bad > 0
+    T2, _, _, bad2 = api.pose_optimize_planes(pose([1e-3, 2e-3, -1e-3], [0.01, 0, 0]), e)
+    assert bad2 == 0 and np.abs(T2 - T_gt).max() < 1e-6
