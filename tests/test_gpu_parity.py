@@ -557,3 +557,23 @@ def test_per_pixel_flatten_kernel(seq, oracle_lib):
     rep = compare_frame(e, orc, seq[3], fp)
     assert rep["labels_bit_exact"], rep
     e.close()
+
+
+def test_sparse_upload_without_supposed_planes(seq):
+    """enable_supposed = 0: nothing reads full-resolution depth, so the sampled rows are all that is uploaded -- also from a
+    pageable image -- and the real planes equal those of the full path"""
+    d = np.ascontiguousarray(seq)
+    full = api.PlaneExtractor(max_frames=len(d))
+    ref = full.extract_batch(d)
+    e = api.PlaneExtractor(max_frames=len(d), enable_supposed=0)
+    _poison(e, d.shape)
+    e.set_upload_mode(0)
+    got = e.extract_batch(d)                                            # pageable
+    assert e.transfer_bytes()[:2] == (len(d) * 160 * 640 * 4, 0)
+    assert np.array_equal(got.frames["n_real"], ref.frames["n_real"]) and np.array_equal(got.frames["n_planes"], ref.frames["n_real"])
+    for k in range(len(d)):
+        a, b = got.frame(k), ref.frame(k)
+        assert np.array_equal(a.mvPlaneCoefficients.view(np.uint32), b.mvPlaneCoefficients[:b.mnRealPlaneNum].view(np.uint32))
+        for p, q in zip(a.mvPlanePoints, b.mvPlanePoints):
+            assert np.array_equal(p, q)
+    full.close(); e.close()
