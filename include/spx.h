@@ -243,6 +243,8 @@ int spx_voxel_downsample_results(spx_ctx *ctx, float leaf, int which);
  * ParallelThreshold; src/Map.cc:30-37) and returns, per frame plane, the index of the associated / vertical / parallel
  * map plane in that order (or -1: mvpMapPlanes[i] / mvpVerticalPlanes[i] / mvpParallelPlanes[i] stay null) and the
  * final ldTh. */
+/* A map belongs to the context it was created on (same device, same stream, same single-thread rule) and must be
+ * destroyed before that context. */
 typedef struct spx_map spx_map;
 int  spx_map_create(spx_ctx *ctx, spx_map **out);
 void spx_map_destroy(spx_map *map);

@@ -9,6 +9,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cfloat>
+#include <cmath>
 #include <climits>
 #include <cstdint>
 #include <cstring>
@@ -687,10 +688,15 @@ int spx_map_associate(spx_map *m, const float *plane_w, int n_planes, float dis_
 int spx_pose_optimize_planes(double Tcw[16], const spx_plane_edge *edges, int n_edges, int rounds, int iterations, uint8_t *outlier,
                              double *chi2, int *n_bad) {
     if (!Tcw || n_edges < 0 || (n_edges > 0 && !edges) || rounds < 1 || iterations < 1) return SPX_ERR_ARG;
+    for (int k = 0; k < 16; ++k) if (!std::isfinite(Tcw[k])) return SPX_ERR_ARG;
     spx_host::PlanePoseOptimizer opt;
     opt.edges.resize(size_t(n_edges));
     for (int i = 0; i < n_edges; ++i) {
         if (edges[i].kind < 0 || edges[i].kind > 2) return SPX_ERR_ARG;
+        for (const float *v : {edges[i].plane_w, edges[i].measurement}) {     // a plane needs a finite, non-zero normal
+            const float n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+            if (!std::isfinite(n2) || !std::isfinite(v[3]) || n2 == 0.0f) return SPX_ERR_ARG;
+        }
         spx_host::PlaneEdge &e = opt.edges[size_t(i)];
         e.kind = edges[i].kind;
         e.world = spx_host::Plane3D::from_coefficients(edges[i].plane_w);

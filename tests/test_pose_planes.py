@@ -170,3 +170,14 @@ def test_singular_start_is_left_alone():
     assert np.array_equal(T, np.eye(4)) and bad > 0
     T2, _, _, bad2 = api.pose_optimize_planes(pose([1e-3, 2e-3, -1e-3], [0.01, 0, 0]), e)
     assert bad2 == 0 and np.abs(T2 - T_gt).max() < 1e-6
+
+
+def test_degenerate_planes_are_refused():
+    for bad_plane in ([0, 0, 0, 1.0], [np.nan, 0, 1, 1.0], [0, 0, 1, np.inf]):
+        with pytest.raises(api.SpxError):
+            api.pose_optimize_planes(np.eye(4), api.plane_edges([0], [bad_plane], [[0, 0, 1, 1.0]]))
+        with pytest.raises(api.SpxError):
+            api.pose_optimize_planes(np.eye(4), api.plane_edges([1], [[0, 0, 1, 1.0]], [bad_plane]))
+    T = np.eye(4); T[0, 3] = np.nan
+    with pytest.raises(api.SpxError):
+        api.pose_optimize_planes(T, api.plane_edges([0], [[0, 0, 1, 1.0]], [[0, 0, 1, 1.0]]))
