@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define SPX_VERSION 100
+#define SPX_VERSION 200
 
 /* per-frame capacities (a frame exceeding one sets SPX_FRAME_OVERFLOW in spx_frame_header.flags) */
 #define SPX_MAX_CAND    96   /* connected components larger than Plane.MinSize                    */
@@ -145,6 +145,47 @@ int spx_extract_batch_device(spx_ctx *ctx, const float *depth_dev, int n_frames,
 int spx_fetch_results(spx_ctx *ctx, spx_batch_result *out);
 /* only the frame headers and plane records (coefficients and counts), not the clouds */
 int spx_fetch_planes(spx_ctx *ctx, spx_batch_result *out);
+
+/* ---- compact results: ordered inlier index lists instead of the real planes' point clouds ----
+ * mvPlanePoints[i] of a REAL plane is ExtractIndices(inputCloud, inliers[i]) (src/Frame.cc:907-928): point k is the
+ * back-projection (src/Frame.cc:861-868) of organized pixel inliers[i].indices[k], colour (0, 0, 250) -- a pure function of
+ * (index, depth image, intrinsics).  95 % of the result bytes of a frame are these clouds, so the compact calls return
+ * inlier_indices itself (2 bytes per point when the organized cloud has at most 65536 points, else 4) and the host adapter
+ * (sp_slam_b200/host/FramePlanes.h) rebuilds pcl::PointXYZRGB from the caller's depth image with the reference's fp32
+ * expression; bit-identical to the 16-byte path (tests/test_gpu_compact.py).  Boundary clouds (contours) and the supposed
+ * planes' clouds (50x50 grid + line inliers) come back as 16-byte points, as in spx_batch_result.
+ *   real plane:     points_off indexes point_index (n_points entries, inlier_indices order)
+ *   supposed plane: points_off indexes points
+ *   any plane:      boundary_off indexes boundary
+ * organized pixel q = r * cloud_width + c samples depth(r * cloud_dis, c * cloud_dis). */
+typedef struct spx_compact_result {
+    int32_t  n_frames;
+    int32_t  n_planes_total;
+    int32_t  index_width;            /* bytes per entry of point_index: 2 or 4 */
+    int32_t  cloud_width, cloud_height, cloud_dis;
+    int64_t  n_index_total;          /* entries of point_index (real planes' inliers) */
+    int64_t  n_points_total;         /* entries of points (supposed planes only)      */
+    int64_t  n_boundary_total;
+    const spx_frame_header *frames;
+    const spx_plane        *planes;
+    const void             *point_index;
+    const spx_point        *points;
+    const spx_point        *boundary;
+} spx_compact_result;
+/* same contract as spx_extract_batch / spx_extract_batch_u16 (host depth in, results in host memory owned by the context) */
+int spx_extract_batch_compact(spx_ctx *ctx, const float *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
+                              size_t frame_stride_bytes, spx_compact_result *out);
+int spx_extract_batch_u16_compact(spx_ctx *ctx, const uint16_t *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
+                                  size_t frame_stride_bytes, float depth_map_factor, spx_compact_result *out);
+/* what spx_extract_batch_device packs: 0 = point clouds (default; spx_fetch_results), 1 = compact (spx_fetch_compact) */
+int spx_set_result_mode(spx_ctx *ctx, int mode);
+int spx_fetch_compact(spx_ctx *ctx, spx_compact_result *out);
+/* Streaming delivery for the compact host-input calls: a batch runs as frame groups; `fn` is called on the calling thread,
+ * inside spx_extract_batch*_compact, as soon as the results of frames [frame0, frame1) are final in host memory (offsets
+ * already in host layout), while later groups are still on the device -- the adapter starts filling Frame fields then.
+ * `view` and the arrays it points to stay valid until the next extract call on the context.  fn = NULL turns it off. */
+typedef void (*spx_group_fn)(void *user, int frame0, int frame1, const spx_compact_result *view);
+int spx_set_group_callback(spx_ctx *ctx, spx_group_fn fn, void *user);
 
 /* Device-side view of the last extract's results (valid until the next extract on the context; read them on the
  * context's stream or after synchronising it).  This is what a multi-GPU caller hands to NCCL for the end-of-sequence

@@ -50,6 +50,8 @@ EXPORTS = (
     "spx_get_models", "spx_get_model_inliers", "spx_get_model_contour", "spx_get_lines",
     "spx_set_upload_mode", "spx_host_register", "spx_host_unregister", "spx_get_transfer_bytes",
     "spx_get_group_timeline",
+    "spx_extract_batch_compact", "spx_extract_batch_u16_compact", "spx_set_result_mode", "spx_fetch_compact",
+    "spx_set_group_callback",
     "spx_voxel_grid", "spx_voxel_downsample_results", "spx_map_create", "spx_map_destroy", "spx_map_upload", "spx_map_associate",
     "spx_map_update_boundary", "spx_map_update_boundary_from_result", "spx_map_set_world_pos", "spx_map_get_boundary",
     "spx_pose_optimize_planes", "spx_plane_edge_errors",
@@ -75,6 +77,19 @@ class SpxBatchResult(C.Structure):
         ("n_boundary_total", C.c_int64),
         ("frames", C.c_void_p), ("planes", C.c_void_p), ("points", C.c_void_p), ("boundary", C.c_void_p),
     ]
+
+
+class SpxCompactResult(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int32), ("n_planes_total", C.c_int32), ("index_width", C.c_int32),
+        ("cloud_width", C.c_int32), ("cloud_height", C.c_int32), ("cloud_dis", C.c_int32),
+        ("n_index_total", C.c_int64), ("n_points_total", C.c_int64), ("n_boundary_total", C.c_int64),
+        ("frames", C.c_void_p), ("planes", C.c_void_p), ("point_index", C.c_void_p), ("points", C.c_void_p),
+        ("boundary", C.c_void_p),
+    ]
+
+
+GROUP_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.POINTER(SpxCompactResult))
 
 
 class SpxDeviceResult(C.Structure):
@@ -153,6 +168,11 @@ def lib():
         L.spx_host_unregister.argtypes = [vp]
         u64p = C.POINTER(C.c_ulonglong)
         L.spx_get_transfer_bytes.argtypes = [vp, u64p, u64p, u64p]
+        L.spx_extract_batch_compact.argtypes = [vp, vp, i32, i32, i32, sz, sz, C.POINTER(SpxCompactResult)]
+        L.spx_extract_batch_u16_compact.argtypes = [vp, vp, i32, i32, i32, sz, sz, C.c_float, C.POINTER(SpxCompactResult)]
+        L.spx_set_result_mode.argtypes = [vp, i32]
+        L.spx_fetch_compact.argtypes = [vp, C.POINTER(SpxCompactResult)]
+        L.spx_set_group_callback.argtypes = [vp, GROUP_FN, vp]
         for name in EXPORTS:
             getattr(L, name)   # AttributeError here = the library is stale
         _lib = L
@@ -227,6 +247,61 @@ class BatchResult:
                            pl["is_supposed"].copy(), int(h["flags"]))
 
 
+RGBA_CLOUD = 0xFF0000FA      # a = 255, (r, g, b) = (0, 0, 250): the colour of every organized-cloud point (src/Frame.cc:866-868)
+
+
+def backproject(idx: np.ndarray, depth: np.ndarray, cfg, w: int, dis: int) -> np.ndarray:
+    """inputCloud.points[idx] (src/Frame.cc:857-870) in fp32, one rounding per operation: what the host adapter rebuilds from
+    a compact result.  depth: one CV_32F frame."""
+    idx = idx.astype(np.int64)
+    r, c = idx // w, idx % w
+    z = depth[r * dis, c * dis].astype(np.float32)
+    out = np.empty(len(idx), POINT_DTYPE)
+    out["x"] = ((c * dis).astype(np.float32) - np.float32(cfg.cx)) * z / np.float32(cfg.fx)
+    out["y"] = ((r * dis).astype(np.float32) - np.float32(cfg.cy)) * z / np.float32(cfg.fy)
+    out["z"] = z
+    out["rgba"] = RGBA_CLOUD
+    return out
+
+
+class CompactResult:
+    """spx_compact_result: the real planes' clouds as ordered inlier index lists (2 or 4 bytes per point)."""
+
+    def __init__(self, r: SpxCompactResult, copy: bool = True):
+        self.index_width = int(r.index_width)
+        self.cloud_width, self.cloud_height, self.cloud_dis = int(r.cloud_width), int(r.cloud_height), int(r.cloud_dis)
+        f = _view(r.frames, r.n_frames, HEADER_DTYPE)
+        p = _view(r.planes, r.n_planes_total, PLANE_DTYPE)
+        ix = _view(r.point_index, r.n_index_total, np.dtype("<u2" if r.index_width == 2 else "<u4"))
+        pts = _view(r.points, r.n_points_total, POINT_DTYPE)
+        bnd = _view(r.boundary, r.n_boundary_total, POINT_DTYPE)
+        if copy:
+            f, p, ix, pts, bnd = f.copy(), p.copy(), ix.copy(), pts.copy(), bnd.copy()
+        self.frames, self.planes, self.point_index, self.points, self.boundary = f, p, ix, pts, bnd
+
+    def __len__(self):
+        return len(self.frames)
+
+    @property
+    def nbytes(self):
+        return self.frames.nbytes + self.planes.nbytes + self.point_index.nbytes + self.points.nbytes + self.boundary.nbytes
+
+    def frame(self, i: int, depth: np.ndarray, cfg) -> FramePlanes:
+        """The Frame fields of frame i, the real planes' clouds rebuilt from `depth` (that frame's CV_32F image)."""
+        h = self.frames[i]
+        pl = self.planes[h["first_plane"]: h["first_plane"] + h["n_planes"]]
+        pts = []
+        for q in pl:
+            if q["is_supposed"]:
+                pts.append(self.points[q["points_off"]: q["points_off"] + q["n_points"]])
+            else:
+                pts.append(backproject(self.point_index[q["points_off"]: q["points_off"] + q["n_points"]], depth, cfg,
+                                       self.cloud_width, self.cloud_dis))
+        bnd = [self.boundary[q["boundary_off"]: q["boundary_off"] + q["n_boundary"]] for q in pl]
+        return FramePlanes(int(h["n_real"]), int(h["n_planes"]), pl["coef"].copy(), pts, bnd, pl["src"].copy(),
+                           pl["is_supposed"].copy(), int(h["flags"]))
+
+
 class PlaneExtractor:
     """One context = one CUDA device + fixed capacity (frames per batch, image size)."""
 
@@ -293,6 +368,54 @@ class PlaneExtractor:
         self._ck(lib().spx_extract_batch_u16(self._h, host_ptr, n, rows, cols, cols * 2, rows * cols * 2,
                                              C.c_float(depth_map_factor), C.byref(r)))
         return BatchResult(r, copy=copy)
+
+    # ---- compact results ----
+    def extract_batch_compact(self, depth: np.ndarray, copy: bool = True) -> CompactResult:
+        if depth.dtype != np.float32 or depth.ndim != 3 or depth.strides[2] != 4:
+            depth = np.ascontiguousarray(depth, dtype=np.float32)
+        n, rows, cols = depth.shape
+        r = SpxCompactResult()
+        self._ck(lib().spx_extract_batch_compact(self._h, depth.ctypes.data, n, rows, cols, depth.strides[1], depth.strides[0], C.byref(r)))
+        return CompactResult(r, copy=copy)
+
+    def extract_batch_compact_ptr(self, host_ptr: int, n: int, rows: int, cols: int, copy: bool = False) -> CompactResult:
+        r = SpxCompactResult()
+        self._ck(lib().spx_extract_batch_compact(self._h, host_ptr, n, rows, cols, cols * 4, rows * cols * 4, C.byref(r)))
+        return CompactResult(r, copy=copy)
+
+    def extract_batch_u16_compact(self, depth_u16: np.ndarray, depth_map_factor: float = float(np.float32(1.0) / np.float32(5000.0)),
+                                  copy: bool = True) -> CompactResult:
+        if depth_u16.dtype != np.uint16 or depth_u16.ndim != 3 or depth_u16.strides[2] != 2:
+            depth_u16 = np.ascontiguousarray(depth_u16, dtype=np.uint16)
+        n, rows, cols = depth_u16.shape
+        r = SpxCompactResult()
+        self._ck(lib().spx_extract_batch_u16_compact(self._h, depth_u16.ctypes.data, n, rows, cols, depth_u16.strides[1],
+                                                     depth_u16.strides[0], C.c_float(depth_map_factor), C.byref(r)))
+        return CompactResult(r, copy=copy)
+
+    def extract_batch_u16_compact_ptr(self, host_ptr: int, n: int, rows: int, cols: int, depth_map_factor: float, copy: bool = False):
+        r = SpxCompactResult()
+        self._ck(lib().spx_extract_batch_u16_compact(self._h, host_ptr, n, rows, cols, cols * 2, rows * cols * 2,
+                                                     C.c_float(depth_map_factor), C.byref(r)))
+        return CompactResult(r, copy=copy)
+
+    def set_result_mode(self, compact: bool):
+        """What extract_device packs: point clouds (fetch) or compact results (fetch_compact)."""
+        self._ck(lib().spx_set_result_mode(self._h, 1 if compact else 0))
+
+    def fetch_compact(self, copy: bool = True) -> CompactResult:
+        r = SpxCompactResult()
+        self._ck(lib().spx_fetch_compact(self._h, C.byref(r)))
+        return CompactResult(r, copy=copy)
+
+    def set_group_callback(self, fn):
+        """fn(frame0, frame1, CompactResult view) as soon as a frame group of a compact host-input call is on the host; None = off."""
+        if fn is None:
+            self._cb = None
+            self._ck(lib().spx_set_group_callback(self._h, None, None))
+            return
+        self._cb = GROUP_FN(lambda user, f0, f1, view: fn(f0, f1, CompactResult(view.contents, copy=True)))
+        self._ck(lib().spx_set_group_callback(self._h, self._cb, None))
 
     def extract_device(self, dev_ptr: int, n: int, rows: int, cols: int, pitch: int | None = None,
                        frame_stride: int | None = None):
@@ -449,6 +572,107 @@ class PlaneExtractor:
         k = C.c_int()
         self._ck(lib().spx_get_lines(self._h, frame, l.ctypes.data, C.byref(k)))
         return l[:k.value].copy()
+
+
+HOST_LIB_PATH = os.path.join(_HERE, "libspx_host.so")
+POINT32_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("data_w", "<f4"), ("rgba", "<u4"), ("pad", "<u4", 3)])   # pcl::PointXYZRGB
+_host_lib = None
+
+
+def host_lib():
+    """libspx_host.so: the C++ host adapter (sp_slam_b200/host/SequencePlanes.h) behind a plain-C handle."""
+    global _host_lib
+    if _host_lib is None:
+        lib()
+        if not os.path.exists(HOST_LIB_PATH):
+            raise RuntimeError(f"{HOST_LIB_PATH} is missing: build it with `make -C sp_slam_b200/csrc`")
+        H = C.CDLL(HOST_LIB_PATH)
+        vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+        H.spx_seq_create.argtypes = [C.POINTER(SpxConfig), i32]
+        H.spx_seq_create.restype = vp
+        H.spx_seq_destroy.argtypes = [vp]
+        H.spx_seq_destroy.restype = None
+        H.spx_seq_threads.argtypes = [vp]
+        H.spx_seq_context.argtypes = [vp]
+        H.spx_seq_context.restype = vp
+        H.spx_seq_last_error.restype = C.c_char_p
+        H.spx_seq_process.argtypes = [vp, vp, i32, i32, i32, sz, sz]
+        H.spx_seq_process.restype = C.c_double
+        H.spx_seq_process_u16.argtypes = [vp, vp, i32, i32, i32, sz, sz, C.c_float]
+        H.spx_seq_process_u16.restype = C.c_double
+        H.spx_seq_summary.argtypes = [vp, vp]
+        H.spx_seq_summary.restype = None
+        H.spx_seq_frame.argtypes = [vp, i32, vp]
+        H.spx_seq_plane.argtypes = [vp, i32, i32, vp, vp, C.POINTER(vp), C.POINTER(vp)]
+        H.spx_seq_hash.argtypes = [vp]
+        H.spx_seq_hash.restype = C.c_ulonglong
+        _host_lib = H
+    return _host_lib
+
+
+class SequenceAdapter:
+    """spx_host::SequencePlanes: a whole depth sequence through the C++ host adapter, every Frame field of every frame filled
+    (32-byte pcl::PointXYZRGB-layout clouds) by a pool of host threads while later frame groups are still on the device."""
+
+    def __init__(self, cfg: SpxConfig, n_threads: int = 0):
+        self.cfg = cfg
+        self._s = host_lib().spx_seq_create(C.byref(cfg), n_threads)
+        if not self._s:
+            raise SpxError(SPX_ERR_CUDA, (host_lib().spx_seq_last_error() or b"").decode())
+        self.threads = host_lib().spx_seq_threads(self._s)
+
+    def close(self):
+        if getattr(self, "_s", None):
+            host_lib().spx_seq_destroy(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process_ptr(self, host_ptr: int, n: int, rows: int, cols: int) -> float:
+        """One batch of tight CV_32F frames; returns the wall time of the call in ms."""
+        ms = host_lib().spx_seq_process(self._s, host_ptr, n, rows, cols, cols * 4, rows * cols * 4)
+        if ms < 0:
+            raise SpxError(SPX_ERR_CUDA, (host_lib().spx_seq_last_error() or b"").decode())
+        return ms
+
+    def process_u16_ptr(self, host_ptr: int, n: int, rows: int, cols: int, factor: float) -> float:
+        ms = host_lib().spx_seq_process_u16(self._s, host_ptr, n, rows, cols, cols * 2, rows * cols * 2, C.c_float(factor))
+        if ms < 0:
+            raise SpxError(SPX_ERR_CUDA, (host_lib().spx_seq_last_error() or b"").decode())
+        return ms
+
+    def summary(self):
+        """(planes, points of mvPlanePoints, points of mvBoundaryPoints, bytes of the filled fields) of the last batch."""
+        out = (C.c_longlong * 4)()
+        host_lib().spx_seq_summary(self._s, out)
+        return tuple(int(v) for v in out)
+
+    def hash(self) -> int:
+        return int(host_lib().spx_seq_hash(self._s))
+
+    def frame(self, f: int) -> FramePlanes:
+        """Copies of the fields of frame f (clouds as POINT32_DTYPE arrays) plus (width, height) of every cloud in `dims`."""
+        hd = (C.c_int * 3)()
+        if host_lib().spx_seq_frame(self._s, f, hd):
+            raise IndexError(f)
+        coefs, pts, bnd, dims = [], [], [], []
+        for i in range(hd[1]):
+            coef = (C.c_float * 4)()
+            sizes = (C.c_int * 6)()
+            p, b = C.c_void_p(), C.c_void_p()
+            host_lib().spx_seq_plane(self._s, f, i, coef, sizes, C.byref(p), C.byref(b))
+            coefs.append(np.array(coef[:], np.float32))
+            pts.append(_view(p.value, sizes[0], POINT32_DTYPE).copy())
+            bnd.append(_view(b.value, sizes[3], POINT32_DTYPE).copy())
+            dims.append(((sizes[1], sizes[2]), (sizes[4], sizes[5])))
+        fp = FramePlanes(hd[0], hd[1], np.array(coefs, np.float32).reshape(-1, 4), pts, bnd, np.zeros(hd[1], np.int32),
+                         np.zeros(hd[1], np.int32), hd[2])
+        fp.dims = dims
+        return fp
 
 
 class PlaneMap:

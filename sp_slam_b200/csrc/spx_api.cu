@@ -84,7 +84,7 @@ struct spx_ctx {
     bool group_pack = false;
     std::vector<cudaEvent_t> g_tot_ev;
     std::vector<cudaEvent_t> g_real_ev;       // host path: the group's real-plane clouds are packed and their sizes are on the host
-    struct GroupOut { int f0 = 0, f1 = 0; long long dev_pl = 0, dev_pt = 0, dev_bd = 0; };
+    struct GroupOut { int f0 = 0, f1 = 0; long long dev_pl = 0, dev_pt = 0, dev_bd = 0, dev_ix = 0; };
     std::vector<GroupOut> g_out;
     Params P;           // geometry of the last call (capacities fixed at create)
     Buffers B;
@@ -102,6 +102,16 @@ struct spx_ctx {
     spx_point *h_pts = nullptr, *h_bnd = nullptr;
     size_t h_planes_cap = 0, h_pts_cap = 0, h_bnd_cap = 0;
     long long *h_totals = nullptr, *h_totals_dev = nullptr;   // page-locked; _dev = the address the device stores through
+    // compact results (include/spx.h): the real planes' clouds travel as inlier index lists
+    int result_mode = 0;               // what spx_extract_batch_device packs (spx_set_result_mode)
+    bool compact = false;              // mode of the last run
+    unsigned char *h_pidx = nullptr;   // page-locked, index_width bytes per entry
+    size_t h_pidx_cap = 0;             // bytes
+    spx_group_fn group_fn = nullptr;   // streaming delivery of the host-input compact calls
+    void *group_user = nullptr;
+    spx_compact_result view;           // what the callback sees
+    std::vector<void *> graveyard;     // page-locked buffers outgrown during a call: a callback's view may still point into
+                                       // them, so they are released at the start of the next call
     // state of the last extract
     bool have_run = false;
     bool debug = false;
@@ -361,16 +371,18 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     // GPU is mostly idle) continue here; the supposed planes' clouds follow once k_supposed has run.
     const bool own_pack = c->group_pack || c->last_groups == 1;
     long long *tot = B.out_totals + 8 * (c->group_pack ? g + 1 : 0);
-    long long base_pl = 0, base_pt = 0, base_bd = 0;
+    long long base_pl = 0, base_pt = 0, base_bd = 0, base_ix = 0;
     if (own_pack) {
         if (c->group_pack) {
             spx_ctx::GroupOut &go = c->g_out[g];
             go.f0 = f0; go.f1 = f0 + ng;
             go.dev_pl = (long long)f0 * SPX_MAX_PLANES; go.dev_pt = (long long)f0 * P.pts_cap; go.dev_bd = (long long)f0 * P.bnd_cap;
-            base_pl = go.dev_pl; base_pt = go.dev_pt; base_bd = go.dev_bd;
+            go.dev_ix = (long long)f0 * P.N;
+            base_pl = go.dev_pl; base_pt = go.dev_pt; base_bd = go.dev_bd; base_ix = go.dev_ix;
         }
         long long *host_tot = c->group_pack ? c->h_totals_dev + 8 * (g + 1) : nullptr;
-        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 0, base_pl, base_pt, base_bd, tot, host_tot);
+        // (compact results: the real planes' points are entries of the index arena, N per frame)
+        LAUNCH(k_scan_frames, 1, 1024, 0, P, B, 0, base_pl, P.compact ? base_ix : base_pt, base_bd, tot, host_tot);
         const bool use_side = c->last_groups == 1;   // with several groups in flight the other groups fill the gaps already
         cudaStream_t side = use_side ? c->g_back[g] : st, keep = st;
         if (use_side) {
@@ -413,9 +425,15 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
 
 // depth_dev: what the sampling kernels read (layout P.samp_*); depth_full: the full-resolution image of the border tests
 // (layout P.pitch / P.frame_stride; device memory, or the caller's mapped host image on the sparse-upload path)
-int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, bool normals_given, const HostSrc &src, bool group_pack) {
+int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, bool normals_given, const HostSrc &src, bool group_pack,
+                 bool compact = false) {
     cudaStream_t main_st = c->stream;
     c->group_pack = group_pack;
+    c->compact = compact;
+    c->P.compact = compact ? 1 : 0;
+    c->P.idx16 = c->P.N <= 65536 ? 1 : 0;
+    for (void *p : c->graveyard) cudaFreeHost(p);
+    c->graveyard.clear();
     const int F = c->P.n_frames;
     c->P.frame0 = 0;
     c->launches = 0;
@@ -519,26 +537,44 @@ int grow_pinned(spx_ctx *c, T **p, size_t *cap, size_t need) {
     return SPX_OK;
 }
 
-int fetch(spx_ctx *c, spx_batch_result *out, bool with_clouds) {
+void fill_view(const spx_ctx *c, spx_compact_result *v, int n_frames, long long n_pl, long long n_ix, long long n_pt, long long n_bd) {
+    v->n_frames = n_frames;
+    v->n_planes_total = int(n_pl);
+    v->index_width = c->P.idx16 ? 2 : 4;
+    v->cloud_width = c->P.w; v->cloud_height = c->P.h; v->cloud_dis = c->P.dis;
+    v->n_index_total = n_ix; v->n_points_total = n_pt; v->n_boundary_total = n_bd;
+    v->frames = c->h_frames; v->planes = c->h_planes;
+    v->point_index = c->h_pidx; v->points = c->h_pts; v->boundary = c->h_bnd;
+}
+
+// results of spx_extract_batch_device -> host.  cout: the compact layout (the run must have packed it), else `out`.
+int fetch(spx_ctx *c, spx_batch_result *out, bool with_clouds, spx_compact_result *cout = nullptr) {
     if (!c->have_run) return fail(c, SPX_ERR_STATE, "no extract call has been made on this context");
     if (c->group_pack) return fail(c, SPX_ERR_STATE, "the last extract already delivered its results to the host; fetch follows spx_extract_batch_device");
+    if (c->compact != (cout != nullptr))
+        return fail(c, SPX_ERR_STATE, c->compact ? "the last extract packed compact results: use spx_fetch_compact" : "the last extract packed point clouds: use spx_fetch_results (spx_set_result_mode selects what is packed)");
     cudaStream_t st = c->stream;
     const int F = c->last_frames;
-    SPX_CK(c, cudaMemcpyAsync(c->h_totals, c->B.out_totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    SPX_CK(c, cudaMemcpyAsync(c->h_totals, c->B.out_totals, 8 * sizeof(long long), cudaMemcpyDeviceToHost, st));
     SPX_CK(c, cudaMemcpyAsync(c->h_frames, c->B.out_frames, sizeof(spx_frame_header) * size_t(F), cudaMemcpyDeviceToHost, st));
     SPX_CK(c, cudaStreamSynchronize(st));
-    const long long n_pl = c->h_totals[0], n_pt = c->h_totals[1], n_bd = c->h_totals[2];
+    const long long n_pl = c->h_totals[0], n_pt = c->h_totals[1], n_bd = c->h_totals[2], n_ix = cout ? c->h_totals[5] : 0;
+    const size_t iw = c->P.idx16 ? 2 : 4;
     int rc;
     if ((rc = grow_pinned(c, &c->h_planes, &c->h_planes_cap, size_t(n_pl))) != SPX_OK) return rc;
     if (n_pl) SPX_CK(c, cudaMemcpyAsync(c->h_planes, c->B.out_planes, sizeof(spx_plane) * size_t(n_pl), cudaMemcpyDeviceToHost, st));
     if (with_clouds) {
         if ((rc = grow_pinned(c, &c->h_pts, &c->h_pts_cap, size_t(n_pt))) != SPX_OK) return rc;
         if ((rc = grow_pinned(c, &c->h_bnd, &c->h_bnd_cap, size_t(n_bd))) != SPX_OK) return rc;
+        if ((rc = grow_pinned(c, &c->h_pidx, &c->h_pidx_cap, size_t(n_ix) * iw)) != SPX_OK) return rc;
         if (n_pt) SPX_CK(c, cudaMemcpyAsync(c->h_pts, c->B.out_pts, sizeof(spx_point) * size_t(n_pt), cudaMemcpyDeviceToHost, st));
         if (n_bd) SPX_CK(c, cudaMemcpyAsync(c->h_bnd, c->B.out_bnd, sizeof(spx_point) * size_t(n_bd), cudaMemcpyDeviceToHost, st));
+        if (n_ix) SPX_CK(c, cudaMemcpyAsync(c->h_pidx, c->B.out_pidx, size_t(n_ix) * iw, cudaMemcpyDeviceToHost, st));
     }
     SPX_CK(c, cudaStreamSynchronize(st));
-    if (out) {
+    if (cout) {
+        fill_view(c, cout, F, n_pl, n_ix, n_pt, n_bd);
+    } else if (out) {
         out->n_frames = F;
         out->n_planes_total = int(n_pl);
         out->n_points_total = with_clouds ? n_pt : 0;
@@ -551,7 +587,8 @@ int fetch(spx_ctx *c, spx_batch_result *out, bool with_clouds) {
     return SPX_OK;
 }
 
-// pinned buffer growth that keeps the first `used` elements (other groups' copies may already have landed there)
+// pinned buffer growth that keeps the first `used` elements (other groups' copies may already have landed there).  The old
+// buffer is not released before the next extract call: a group callback's view may still point into it.
 template <typename T>
 int grow_pinned_keep(spx_ctx *c, T **p, size_t *cap, size_t need, size_t used) {
     if (need <= *cap) return SPX_OK;
@@ -561,67 +598,94 @@ int grow_pinned_keep(spx_ctx *c, T **p, size_t *cap, size_t need, size_t used) {
     T *np = nullptr;
     SPX_CK(c, cudaHostAlloc(reinterpret_cast<void **>(&np), ncap * sizeof(T), cudaHostAllocDefault));
     if (*p && used) std::memcpy(np, *p, used * sizeof(T));
-    if (*p) SPX_CK(c, cudaFreeHost(*p));
+    if (*p) c->graveyard.push_back(*p);
     *p = np; *cap = ncap;
     return SPX_OK;
 }
 
 // host path: as soon as a group's totals are known its frame headers, plane records and clouds are copied to where
-// they belong in the contiguous host arrays (on the group's own stream, overlapping the other groups' work); the
-// offsets inside the records are rebased from the device layout to the host layout at the end.
-int fetch_groups(spx_ctx *c, spx_batch_result *out) {
+// they belong in the contiguous host arrays (on the download stream, overlapping the other groups' work).  When a
+// group's copies have landed, the offsets inside its records are rebased from the device layout to the host layout and
+// (compact calls) the group is handed to the caller's callback while the later groups are still on the device.
+int fetch_groups(spx_ctx *c, spx_batch_result *out, spx_compact_result *cout) {
     const int F = c->last_frames, G = c->last_groups;
-    long long run_pl = 0, run_pt = 0, run_bd = 0;
-    std::vector<long long> host_pl(G), host_pt(G), host_bd(G), n_pls(G);
+    const bool cp = c->compact;
+    const size_t iw = c->P.idx16 ? 2 : 4;
+    long long run_pl = 0, run_pt = 0, run_bd = 0, run_ix = 0;
+    std::vector<long long> host_pl(G), host_pt(G), host_bd(G), host_ix(G), n_pls(G), end_ix(G), end_pt(G), end_bd(G);
     int rc;
+    auto finalize = [&](int g) -> int {
+        if (G > 1) SPX_CK(c, cudaEventSynchronize(c->g_xev[2 * g + 1])); else SPX_CK(c, cudaStreamSynchronize(c->stream));
+        const spx_ctx::GroupOut &go = c->g_out[g];
+        const long long d_pl = host_pl[g] - go.dev_pl, d_pt = host_pt[g] - go.dev_pt, d_bd = host_bd[g] - go.dev_bd, d_ix = host_ix[g] - go.dev_ix;
+        for (int f = go.f0; f < go.f1; ++f) c->h_frames[f].first_plane += int(d_pl);
+        for (long long k = 0; k < n_pls[g]; ++k) {
+            spx_plane &pl = c->h_planes[host_pl[g] + k];
+            pl.points_off += (cp && !pl.is_supposed) ? d_ix : d_pt;
+            pl.boundary_off += d_bd;
+        }
+        if (cp && c->group_fn) {
+            fill_view(c, &c->view, go.f1, host_pl[g] + n_pls[g], end_ix[g], end_pt[g], end_bd[g]);
+            c->group_fn(c->group_user, go.f0, go.f1, &c->view);
+        }
+        return SPX_OK;
+    };
     for (int g = 0; g < G; ++g) {
         cudaStream_t st = (G == 1) ? c->stream : c->down_stream;   // the group's kernels are done once its totals have arrived
-        long long early_pt = 0, early_bd = 0;
+        const spx_ctx::GroupOut &go = c->g_out[g];
+        long long early = 0;   // entries of the real planes' clouds (points, or indices) already on their way
         if (G > 1) {   // first the clouds of the real planes, while the group's line fits / border tests still run
             SPX_CK(c, cudaEventSynchronize(c->g_real_ev[g]));
             const long long *t0 = c->h_totals + 8 * (g + 1);
-            early_pt = t0[5];   // (the boundary arena waits: k_pack_supposed may still write a real plane's every-20th-inlier fallback boundary)
-            const spx_ctx::GroupOut &go0 = c->g_out[g];
-            if ((rc = grow_pinned_keep(c, &c->h_pts, &c->h_pts_cap, size_t(run_pt + early_pt), size_t(run_pt))) != SPX_OK) return rc;
-            if (early_pt) SPX_CK(c, cudaMemcpyAsync(c->h_pts + run_pt, c->B.out_pts + go0.dev_pt, sizeof(spx_point) * size_t(early_pt), cudaMemcpyDeviceToHost, st));
+            early = t0[5];   // (the boundary arena waits: k_pack_supposed may still write a real plane's every-20th-inlier fallback boundary)
+            if (cp) {
+                if ((rc = grow_pinned_keep(c, &c->h_pidx, &c->h_pidx_cap, size_t(run_ix + early) * iw, size_t(run_ix) * iw)) != SPX_OK) return rc;
+                if (early) SPX_CK(c, cudaMemcpyAsync(c->h_pidx + size_t(run_ix) * iw, static_cast<const unsigned char *>(c->B.out_pidx) + size_t(go.dev_ix) * iw,
+                                                     size_t(early) * iw, cudaMemcpyDeviceToHost, st));
+            } else {
+                if ((rc = grow_pinned_keep(c, &c->h_pts, &c->h_pts_cap, size_t(run_pt + early), size_t(run_pt))) != SPX_OK) return rc;
+                if (early) SPX_CK(c, cudaMemcpyAsync(c->h_pts + run_pt, c->B.out_pts + go.dev_pt, sizeof(spx_point) * size_t(early), cudaMemcpyDeviceToHost, st));
+            }
         }
         SPX_CK(c, cudaEventSynchronize(c->g_tot_ev[g]));
         c->g_host_ms[2 * g + 1] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - c->t_call).count();
         const long long *t = c->h_totals + 8 * (g + 1);
-        const long long n_pl = t[0], n_pt = t[1], n_bd = t[2];
+        const long long n_pl = t[0], n_pt = t[1], n_bd = t[2], n_ix = cp ? t[5] : 0;
         c->xfer_inplace += (unsigned long long)t[3] * 8ull * c->inplace_esz;   // sectors of 8 pixels
-        c->xfer_d2h += sizeof(spx_frame_header) * size_t(c->g_out[g].f1 - c->g_out[g].f0) + sizeof(spx_plane) * size_t(n_pl) + sizeof(spx_point) * size_t(n_pt + n_bd) + 4 * sizeof(long long);
-        const spx_ctx::GroupOut &go = c->g_out[g];
+        c->xfer_d2h += sizeof(spx_frame_header) * size_t(go.f1 - go.f0) + sizeof(spx_plane) * size_t(n_pl) + sizeof(spx_point) * size_t(n_pt + n_bd) +
+                       iw * size_t(n_ix) + 4 * sizeof(long long);
+        const long long early_pt = cp ? 0 : early, early_ix = cp ? early : 0;
         if ((rc = grow_pinned_keep(c, &c->h_planes, &c->h_planes_cap, size_t(run_pl + n_pl), size_t(run_pl))) != SPX_OK) return rc;
         if ((rc = grow_pinned_keep(c, &c->h_pts, &c->h_pts_cap, size_t(run_pt + n_pt), size_t(run_pt + early_pt))) != SPX_OK) return rc;
-        if ((rc = grow_pinned_keep(c, &c->h_bnd, &c->h_bnd_cap, size_t(run_bd + n_bd), size_t(run_bd + early_bd))) != SPX_OK) return rc;
+        if ((rc = grow_pinned_keep(c, &c->h_bnd, &c->h_bnd_cap, size_t(run_bd + n_bd), size_t(run_bd))) != SPX_OK) return rc;
+        if ((rc = grow_pinned_keep(c, &c->h_pidx, &c->h_pidx_cap, size_t(run_ix + n_ix) * iw, size_t(run_ix + early_ix) * iw)) != SPX_OK) return rc;
         SPX_CK(c, cudaMemcpyAsync(c->h_frames + go.f0, c->B.out_frames + go.f0, sizeof(spx_frame_header) * size_t(go.f1 - go.f0), cudaMemcpyDeviceToHost, st));
         if (n_pl) SPX_CK(c, cudaMemcpyAsync(c->h_planes + run_pl, c->B.out_planes + go.dev_pl, sizeof(spx_plane) * size_t(n_pl), cudaMemcpyDeviceToHost, st));
+        if (n_ix > early_ix) SPX_CK(c, cudaMemcpyAsync(c->h_pidx + size_t(run_ix + early_ix) * iw, static_cast<const unsigned char *>(c->B.out_pidx) + size_t(go.dev_ix + early_ix) * iw,
+                                                       size_t(n_ix - early_ix) * iw, cudaMemcpyDeviceToHost, st));
         if (n_pt > early_pt) SPX_CK(c, cudaMemcpyAsync(c->h_pts + run_pt + early_pt, c->B.out_pts + go.dev_pt + early_pt, sizeof(spx_point) * size_t(n_pt - early_pt), cudaMemcpyDeviceToHost, st));
-        if (n_bd > early_bd) SPX_CK(c, cudaMemcpyAsync(c->h_bnd + run_bd + early_bd, c->B.out_bnd + go.dev_bd + early_bd, sizeof(spx_point) * size_t(n_bd - early_bd), cudaMemcpyDeviceToHost, st));
+        if (n_bd) SPX_CK(c, cudaMemcpyAsync(c->h_bnd + run_bd, c->B.out_bnd + go.dev_bd, sizeof(spx_point) * size_t(n_bd), cudaMemcpyDeviceToHost, st));
         SPX_CK(c, cudaEventRecord(c->g_xev[2 * g + 1], st));
-        host_pl[g] = run_pl; host_pt[g] = run_pt; host_bd[g] = run_bd; n_pls[g] = n_pl;
-        run_pl += n_pl; run_pt += n_pt; run_bd += n_bd;
+        host_pl[g] = run_pl; host_pt[g] = run_pt; host_bd[g] = run_bd; host_ix[g] = run_ix; n_pls[g] = n_pl;
+        run_pl += n_pl; run_pt += n_pt; run_bd += n_bd; run_ix += n_ix;
+        end_ix[g] = run_ix; end_pt[g] = run_pt; end_bd[g] = run_bd;
+        if (g > 0 && (rc = finalize(g - 1)) != SPX_OK) return rc;   // (its copies were enqueued one group ago: landed by now)
     }
+    if ((rc = finalize(G - 1)) != SPX_OK) return rc;
     if (G > 1) SPX_CK(c, cudaStreamSynchronize(c->down_stream));
     SPX_CK(c, cudaStreamSynchronize(c->stream));
-    for (int g = 0; g < G; ++g) {
-        const spx_ctx::GroupOut &go = c->g_out[g];
-        const long long d_pl = host_pl[g] - go.dev_pl, d_pt = host_pt[g] - go.dev_pt, d_bd = host_bd[g] - go.dev_bd;
-        for (int f = go.f0; f < go.f1; ++f) c->h_frames[f].first_plane += int(d_pl);
-        for (long long k = 0; k < n_pls[g]; ++k) {
-            spx_plane &pl = c->h_planes[host_pl[g] + k];
-            pl.points_off += d_pt; pl.boundary_off += d_bd;
-        }
+    if (cout) {
+        fill_view(c, cout, F, run_pl, run_ix, run_pt, run_bd);
+    } else {
+        out->n_frames = F;
+        out->n_planes_total = int(run_pl);
+        out->n_points_total = run_pt;
+        out->n_boundary_total = run_bd;
+        out->frames = c->h_frames;
+        out->planes = c->h_planes;
+        out->points = c->h_pts;
+        out->boundary = c->h_bnd;
     }
-    out->n_frames = F;
-    out->n_planes_total = int(run_pl);
-    out->n_points_total = run_pt;
-    out->n_boundary_total = run_bd;
-    out->frames = c->h_frames;
-    out->planes = c->h_planes;
-    out->points = c->h_pts;
-    out->boundary = c->h_bnd;
     return SPX_OK;
 }
 
@@ -813,6 +877,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     total += padded<spx_frame_header>(F) + padded<spx_plane>(F * SPX_MAX_PLANES);
     total += padded<spx_point>(F * size_t(P.pts_cap)) + padded<spx_point>(F * size_t(P.bnd_cap));
     total += padded<long long>(8 * size_t(c->n_streams + 1)) + padded<long long>(5 * F);
+    total += padded<uint32_t>(FN);                         // out_pidx
     total += padded<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4) + padded<uint16_t>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     SPX_CK_CREATE(cudaMalloc(reinterpret_cast<void **>(&c->arena.base), total));
     c->arena.size = total;
@@ -831,6 +896,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     B.out_frames = A.take<spx_frame_header>(F); B.out_planes = A.take<spx_plane>(F * SPX_MAX_PLANES);
     B.out_pts = A.take<spx_point>(F * size_t(P.pts_cap)); B.out_bnd = A.take<spx_point>(F * size_t(P.bnd_cap));
     B.out_totals = A.take<long long>(8 * size_t(c->n_streams + 1)); B.frame_offs = A.take<long long>(5 * F);
+    B.out_pidx = A.take<uint32_t>(FN);
     c->d_depth = A.take<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     c->d_depth16 = A.take<uint16_t>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     if (A.used > A.size) { fail(nullptr, SPX_ERR_ARG, "internal: arena accounting"); spx_destroy(c); return SPX_ERR_ARG; }
@@ -876,6 +942,8 @@ void spx_destroy(spx_ctx *c) {
     if (c->h_planes) cudaFreeHost(c->h_planes);
     if (c->h_pts) cudaFreeHost(c->h_pts);
     if (c->h_bnd) cudaFreeHost(c->h_bnd);
+    if (c->h_pidx) cudaFreeHost(c->h_pidx);
+    for (void *p : c->graveyard) cudaFreeHost(p);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->g_ev) cudaEventDestroy(e);
@@ -916,7 +984,7 @@ int spx_extract_batch_device(spx_ctx *c, const float *depth_dev, int n_frames, i
     SPX_CK(c, cudaSetDevice(c->device));
     int rc = set_geometry(c, n_frames, rows, cols, pitch_bytes, frame_stride_bytes);
     if (rc != SPX_OK) return rc;
-    return run_pipeline(c, depth_dev, depth_dev, false, HostSrc(), false);
+    return run_pipeline(c, depth_dev, depth_dev, false, HostSrc(), false, c->result_mode == 1);
 }
 
 int spx_fetch_results(spx_ctx *c, spx_batch_result *out) {
@@ -934,6 +1002,7 @@ int spx_fetch_planes(spx_ctx *c, spx_batch_result *out) {
 int spx_get_device_results(spx_ctx *c, spx_device_result *out) {
     if (!c || !out) return SPX_ERR_ARG;
     if (!c->have_run || c->group_pack) return fail(c, SPX_ERR_STATE, "device results follow spx_extract_batch_device");
+    if (c->compact) return fail(c, SPX_ERR_STATE, "the last extract packed compact results (spx_set_result_mode): the device view describes point clouds");
     out->n_frames = c->last_frames;
     out->frames = c->B.out_frames; out->planes = c->B.out_planes; out->points = c->B.out_pts; out->boundary = c->B.out_bnd;
     out->totals = c->B.out_totals;
@@ -941,52 +1010,83 @@ int spx_get_device_results(spx_ctx *c, spx_device_result *out) {
     return SPX_OK;
 }
 
-int spx_extract_batch(spx_ctx *c, const float *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
-                      size_t frame_stride_bytes, spx_batch_result *out) {
+// host input, float or 16-bit, results as point clouds (`out`) or compact (`cout`)
+static int extract_host(spx_ctx *c, const void *depth, bool u16, float depth_map_factor, int n_frames, int rows, int cols, size_t pitch_bytes,
+                        size_t frame_stride_bytes, spx_batch_result *out, spx_compact_result *cout) {
     if (!c) return SPX_ERR_ARG;
-    if (!depth || !out) return fail(c, SPX_ERR_ARG, "null argument");
+    if (!depth || (!out && !cout)) return fail(c, SPX_ERR_ARG, "null argument");
     SPX_CK(c, cudaSetDevice(c->device));
     const size_t tight = size_t(cols) * sizeof(float);
-    int rc = set_geometry(c, n_frames, rows, cols, pitch_bytes, frame_stride_bytes);
+    const size_t esz = u16 ? sizeof(uint16_t) : sizeof(float);
+    int rc;
+    if (u16) {
+        // geometry checks are stated for the float image; the 16-bit pitch / stride are validated here
+        if (pitch_bytes < size_t(cols) * sizeof(uint16_t) || pitch_bytes % sizeof(uint16_t)) return fail(c, SPX_ERR_ARG, "bad pitch");
+        if (n_frames > 1 && frame_stride_bytes < pitch_bytes * size_t(rows > 0 ? rows : 0)) return fail(c, SPX_ERR_ARG, "bad frame stride");
+        if ((size_t(rows) * size_t(cols)) % 4 != 0 && n_frames > 1) return fail(c, SPX_ERR_ARG, "16-bit batches need rows * cols to be a multiple of 4");
+        rc = set_geometry(c, n_frames, rows, cols, tight, tight * size_t(rows));
+    } else {
+        rc = set_geometry(c, n_frames, rows, cols, pitch_bytes, frame_stride_bytes);
+    }
     if (rc != SPX_OK) return rc;
     HostSrc src;
-    src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = frame_stride_bytes;
+    src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = frame_stride_bytes; src.u16 = u16; src.alpha = u16 ? depth_map_factor : 1.0f;
     const void *full = c->d_depth;
     c->P.pitch = tight; c->P.frame_stride = tight * size_t(rows);   // layout of the device image the kernels read
     c->P.samp_rstep = tight * size_t(c->P.dis); c->P.samp_fstride = c->P.frame_stride;
-    if (sparse_upload(c, depth, frame_stride_bytes * size_t(n_frames - 1) + pitch_bytes * size_t(rows - 1) + tight, n_frames, &src)) {
+    if ((!u16 || cols % 4 == 0) &&
+        sparse_upload(c, depth, frame_stride_bytes * size_t(n_frames - 1) + pitch_bytes * size_t(rows - 1) + size_t(cols) * esz, n_frames, &src)) {
         // only the sampled rows are uploaded (to their place in the device image); k_border_fetch adds the window sectors
         c->P.host_pitch = pitch_bytes; c->P.host_fstride = frame_stride_bytes; c->P.fetch_skip_sampled = 1;
-        c->P.fetch_vec = (reinterpret_cast<uintptr_t>(src.mapped) % 16 == 0 && pitch_bytes % 16 == 0 && frame_stride_bytes % 16 == 0 && cols % 8 == 0) ? 1 : 0;
-    }
-    if ((rc = run_pipeline(c, c->d_depth, full, false, src, true)) != SPX_OK) return rc;
-    return fetch_groups(c, out);
-}
-
-int spx_extract_batch_u16(spx_ctx *c, const uint16_t *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
-                          size_t frame_stride_bytes, float depth_map_factor, spx_batch_result *out) {
-    if (!c) return SPX_ERR_ARG;
-    if (!depth || !out) return fail(c, SPX_ERR_ARG, "null argument");
-    SPX_CK(c, cudaSetDevice(c->device));
-    const size_t tight = size_t(cols) * sizeof(float);
-    // geometry checks are stated for the float image; the 16-bit pitch / stride are validated here
-    if (pitch_bytes < size_t(cols) * sizeof(uint16_t) || pitch_bytes % sizeof(uint16_t)) return fail(c, SPX_ERR_ARG, "bad pitch");
-    if (n_frames > 1 && frame_stride_bytes < pitch_bytes * size_t(rows > 0 ? rows : 0)) return fail(c, SPX_ERR_ARG, "bad frame stride");
-    if ((size_t(rows) * size_t(cols)) % 4 != 0 && n_frames > 1) return fail(c, SPX_ERR_ARG, "16-bit batches need rows * cols to be a multiple of 4");
-    int rc = set_geometry(c, n_frames, rows, cols, tight, tight * size_t(rows));
-    if (rc != SPX_OK) return rc;
-    HostSrc src;
-    src.depth = depth; src.pitch = pitch_bytes; src.frame_stride = frame_stride_bytes; src.u16 = true; src.alpha = depth_map_factor;
-    const void *full = c->d_depth;
-    if (cols % 4 == 0 && sparse_upload(c, depth, frame_stride_bytes * size_t(n_frames - 1) + pitch_bytes * size_t(rows - 1) + size_t(cols) * sizeof(uint16_t),
-                                       n_frames, &src)) {
-        c->P.host_pitch = pitch_bytes; c->P.host_fstride = frame_stride_bytes; c->P.fetch_skip_sampled = 1; c->P.full_alpha = depth_map_factor;
+        if (u16) c->P.full_alpha = depth_map_factor;
         c->P.fetch_vec = (reinterpret_cast<uintptr_t>(src.mapped) % 16 == 0 && pitch_bytes % 16 == 0 && frame_stride_bytes % 16 == 0 && cols % 8 == 0) ? 1 : 0;
     } else {
         src.sparse = false;
     }
-    if ((rc = run_pipeline(c, c->d_depth, full, false, src, true)) != SPX_OK) return rc;
-    return fetch_groups(c, out);
+    if ((rc = run_pipeline(c, c->d_depth, full, false, src, true, cout != nullptr)) != SPX_OK) return rc;
+    return fetch_groups(c, out, cout);
+}
+
+int spx_extract_batch(spx_ctx *c, const float *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
+                      size_t frame_stride_bytes, spx_batch_result *out) {
+    if (c && !out) return fail(c, SPX_ERR_ARG, "null argument");
+    return extract_host(c, depth, false, 1.0f, n_frames, rows, cols, pitch_bytes, frame_stride_bytes, out, nullptr);
+}
+
+int spx_extract_batch_u16(spx_ctx *c, const uint16_t *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
+                          size_t frame_stride_bytes, float depth_map_factor, spx_batch_result *out) {
+    if (c && !out) return fail(c, SPX_ERR_ARG, "null argument");
+    return extract_host(c, depth, true, depth_map_factor, n_frames, rows, cols, pitch_bytes, frame_stride_bytes, out, nullptr);
+}
+
+int spx_extract_batch_compact(spx_ctx *c, const float *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
+                              size_t frame_stride_bytes, spx_compact_result *out) {
+    if (c && !out) return fail(c, SPX_ERR_ARG, "null argument");
+    return extract_host(c, depth, false, 1.0f, n_frames, rows, cols, pitch_bytes, frame_stride_bytes, nullptr, out);
+}
+
+int spx_extract_batch_u16_compact(spx_ctx *c, const uint16_t *depth, int n_frames, int rows, int cols, size_t pitch_bytes,
+                                  size_t frame_stride_bytes, float depth_map_factor, spx_compact_result *out) {
+    if (c && !out) return fail(c, SPX_ERR_ARG, "null argument");
+    return extract_host(c, depth, true, depth_map_factor, n_frames, rows, cols, pitch_bytes, frame_stride_bytes, nullptr, out);
+}
+
+int spx_set_result_mode(spx_ctx *c, int mode) {
+    if (!c || mode < 0 || mode > 1) return SPX_ERR_ARG;
+    c->result_mode = mode;
+    return SPX_OK;
+}
+
+int spx_fetch_compact(spx_ctx *c, spx_compact_result *out) {
+    if (!c || !out) return SPX_ERR_ARG;
+    SPX_CK(c, cudaSetDevice(c->device));
+    return fetch(c, nullptr, true, out);
+}
+
+int spx_set_group_callback(spx_ctx *c, spx_group_fn fn, void *user) {
+    if (!c) return SPX_ERR_ARG;
+    c->group_fn = fn; c->group_user = user;
+    return SPX_OK;
 }
 
 int spx_extract(spx_ctx *c, const float *depth, int rows, int cols, size_t pitch_bytes, spx_batch_result *out) {

@@ -767,8 +767,16 @@ __global__ void __launch_bounds__(128) k_pack_supposed(Params P, Buffers B) {
     spx_point *bnd = B.out_bnd + B.frame_offs[size_t(f) * 5 + (R.is_supposed ? 4 : 2)] + R.boundary_off;
     if (!R.is_supposed) {
         if (ctl.models[R.src].n_contour == 0 && P.enable_supposed) {
+            const size_t fo = size_t(f) * P.N;
+            const long long io = B.frame_offs[size_t(f) * 5 + 1] + R.points_off;   // compact results: the plane's index list
             for (int j = threadIdx.x; j < R.n_boundary; j += blockDim.x) {
-                spx_point q = pts[j * 20];
+                spx_point q;
+                if (P.compact) {
+                    const int ix = P.idx16 ? int(static_cast<const uint16_t *>(B.out_pidx)[io + j * 20]) : int(static_cast<const uint32_t *>(B.out_pidx)[io + j * 20]);
+                    q.x = B.px[fo + ix]; q.y = B.py[fo + ix]; q.z = B.pz[fo + ix];
+                } else {
+                    q = pts[j * 20];
+                }
                 q.rgba = pack_rgba(0, 0, 0);
                 bnd[j] = q;
             }
@@ -809,7 +817,8 @@ __global__ void __launch_bounds__(1024) k_scan_frames(Params P, Buffers B, int s
     __shared__ long long s_run[3];
     __shared__ long long s_w[3][32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long real_pt = stage ? tot[5] : 0, real_bd = stage ? tot[6] : 0;
+    // (compact results: the real planes' clouds live in the index arena, the point arena holds the supposed planes only)
+    const long long real_pt = (stage && !P.compact) ? tot[5] : 0, real_bd = stage ? tot[6] : 0;
     if (tid < 3) s_run[tid] = 0;
     __syncthreads();
     for (int base = 0; base < P.n_frames; base += 1024) {

@@ -659,9 +659,15 @@ __global__ void __launch_bounds__(256) k_pack_points(Params P, Buffers B) {
     const FrameCtl &ctl = B.ctl[f];
     const int k = ctl.models[m].plane;
     if (k < 0) return;
+    const long long o = B.frame_offs[size_t(f) * 5 + 1] + ctl.planes[k].points_off + B.pos[fo + q];
+    if (P.compact) {
+        // compact results: the cloud is a pure function of (index, depth), so only inlier_indices[k] leaves the device
+        if (P.idx16) static_cast<uint16_t *>(B.out_pidx)[o] = uint16_t(q); else static_cast<uint32_t *>(B.out_pidx)[o] = uint32_t(q);
+        return;
+    }
     spx_point pt;
     pt.x = B.px[fo + q]; pt.y = B.py[fo + q]; pt.z = B.pz[fo + q]; pt.rgba = pack_rgba(0, 0, 250);
-    B.out_pts[B.frame_offs[size_t(f) * 5 + 1] + ctl.planes[k].points_off + B.pos[fo + q]] = pt;
+    B.out_pts[o] = pt;
 }
 
 // regions[i].getContour() of the kept planes (src/Frame.cc:930-932); one CTA per (model, frame)

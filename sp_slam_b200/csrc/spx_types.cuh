@@ -23,6 +23,8 @@ struct Params {
     int n_frames;          // frames of this launch group
     int lines_in_global;   // test knob: run every k_lines item on the global-memory path (contours beyond the smem buffer use it)
     int refine_fast;       // 1: k_refine2 (a CTA per frame) where its table fits; 0: k_refine (a warp per frame) for all
+    int compact;           // 1: the real planes' clouds leave as ordered inlier INDEX lists (out_pidx) instead of 16-byte points
+    int idx16;             // compact: 16-bit indices (organized cloud of at most 65536 points), else 32-bit
     int frame0;            // first frame of the group (frames are independent: groups run on separate streams)
     // organized cloud (src/Frame.cc:856-874)
     int dis, w, h, N;
@@ -138,6 +140,7 @@ struct Buffers {
     spx_plane *out_planes;
     spx_point *out_pts;
     spx_point *out_bnd;
+    void *out_pidx;               // compact results: inlier_indices of the real planes (uint16_t or uint32_t, N per frame)
     long long *out_totals;        // slots of 8: [0] planes, [1] points, [2] boundary points; [5], [6] the real-plane part of [1], [2]
     long long *frame_offs;        // 5 per frame
 };
