@@ -3,10 +3,15 @@
 
 A step = one pass of the whole hot path (back-projection .. supposed planes .. packed Frame fields) over one batch of
 synthetic depth frames (the box-room orbit of SURVEY.md section 8d, configs[1]); every rank owns its own batch (weak
-scaling, frames are independent) and the plane lists are gathered over NCCL at the end of every step.
+scaling, frames are independent) and the plane lists are gathered over NCCL once, after the last step (inside the
+timed region).  `strong_scaling` (N > 1) is the SAME batch split across the ranks (BASELINE configs[2] as worded).
 
   value        frames/s, depth batch already resident in HBM, CUDA-event timed, max over ranks
-  e2e          frames/s through the C ABI with HOST buffers: pinned host depth -> device, kernels, Frame fields -> host
+  e2e          frames/s through the C ABI with HOST buffers (spx_extract_batch_compact): pinned host depth -> device,
+               kernels, results -> host (the real planes' clouds as ordered inlier index lists)
+  e2e_adapter  the same through the C++ host adapter (spx_host::SequencePlanes) until every Frame field of every frame
+               is filled (mvPlanePoints / mvBoundaryPoints as 32-byte pcl::PointXYZRGB-layout clouds)
+  e2e_full_clouds  the 16-byte-cloud call (spx_extract_batch), round 1's e2e
   roofline     the kernel with the largest share of the step, its algorithmic bytes (table below) over its
                CUDA-event duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline the CPU oracle (a port of the reference's PCL path; oracle/) on the host cores, bounded sample
@@ -137,6 +142,7 @@ def make_frames(n_frames: int, rank: int, noise: str, res: str):
 
 def oracle_fps(depth: np.ndarray, n_threads: int, res: str):
     from oracle import pyoracle
+    pyoracle.use_native()     # the CPU arm is built for the host it runs on (reference CMakeLists.txt:10-11: -O3 -march=native)
     cfg = oracle_config(res)
     t0 = time.perf_counter()
     nr, na, tp, ts = pyoracle.run_batch(depth, n_threads, cfg)
@@ -253,13 +259,18 @@ def run_reference(args, rank, world, out):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "frames_per_step_per_gpu": args.frames, "noise": args.noise,
                    "cloud_dis": 3, "sample_frames_per_step": n},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "build": oracle_build_flags(),
                          "sample": f"{n} frames of the workload per step, frame-parallel on {cores} host threads; "
                                    "oracle/ C++ port of the reference's PCL 1.8 path (PCL itself cannot be built here)"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "planes_per_frame": planes / (args.steps * n),
     }
     out.emit(json.dumps(line))
+
+
+def oracle_build_flags():
+    from oracle import pyoracle
+    return pyoracle.BUILD_FLAGS
 
 
 def workload_name(args):
@@ -300,7 +311,10 @@ def _main(out):
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1000, help="frames per step and per GPU")
-    ap.add_argument("--ref-frames", type=int, default=500, help="frames per step of the CPU arm")
+    ap.add_argument("--ref-frames", type=int, default=1000, help="frames per step of the CPU arm (default: the whole workload)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank owns --frames frames; strong: --frames frames in total, split across the ranks")
+    ap.add_argument("--no-720p", action="store_true", help="skip the short 1280x720 summary (BASELINE configs[3]) of the default line")
     ap.add_argument("--cpu-sample", type=int, default=1000, help="frames of the cpu_baseline leg")
     ap.add_argument("--noise", default="none", choices=["none", "sensor"])
     ap.add_argument("--res", default="480p", choices=["480p", "720p"])
@@ -315,7 +329,8 @@ def _main(out):
     if args.impl == "reference":
         run_reference(args, rank, world, out)
         return
-    args.warmup = max(args.warmup, 3)
+    warmup_requested = args.warmup
+    args.warmup = max(args.warmup, 3)     # timing rule: at least 3 untimed steps; the JSON line states both numbers
 
     import torch
     import torch.distributed as dist
@@ -330,18 +345,27 @@ def _main(out):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     rows, cols = (720, 1280) if args.res == "720p" else (ROWS, COLS)
-    F = args.frames
     it = intrinsics(args.res)
-    depth_np = make_frames(F, rank, args.noise, args.res)
-    host = torch.from_numpy(depth_np).pin_memory()
+    strong = args.scaling == "strong" and world > 1
+    if strong:      # the same --frames frames for any N: rank r owns the contiguous range shard_range gives it
+        from sp_slam_b200 import sharding
+        lo, hi = sharding.shard_range(args.frames, rank, world)
+        depth_np = make_frames(args.frames, 0, args.noise, args.res)[lo:hi]
+        frames_cap = -(-args.frames // world)
+    else:
+        depth_np = make_frames(args.frames, rank, args.noise, args.res)
+        frames_cap = args.frames
+    F = len(depth_np)
+    total_frames = args.frames if strong else world * F
+    host = torch.from_numpy(np.ascontiguousarray(depth_np)).pin_memory()
     dev = host.cuda(non_blocking=False)
-    ext = api.PlaneExtractor(max_frames=F, max_rows=rows, max_cols=cols, device=local_rank, fx=it.fx, fy=it.fy, cx=it.cx,
-                             cy=it.cy, max_x=float(it.width), max_y=float(it.height), n_streams=args.streams)
+    kw = dict(max_rows=rows, max_cols=cols, device=local_rank, fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy,
+              max_x=float(it.width), max_y=float(it.height))
+    ext = api.PlaneExtractor(max_frames=max(F, frames_cap), n_streams=args.streams, **kw)
     if not args.profile_groups and (args.streams == 0 or args.streams > 1):
         # the per-kernel table comes from one extra profiled step in which the batch runs as ONE group (kernels back to
         # back on one stream, so their CUDA-event times add up to the step and can be compared with an ncu launch list)
-        ext1 = api.PlaneExtractor(max_frames=F, max_rows=rows, max_cols=cols, device=local_rank, fx=it.fx, fy=it.fy,
-                                  cx=it.cx, cy=it.cy, max_x=float(it.width), max_y=float(it.height), n_streams=1)
+        ext1 = api.PlaneExtractor(max_frames=F, n_streams=1, **kw)
     else:
         ext1 = None
     # a real (non-default) stream shared by torch and the library, so torch.cuda.Event brackets the kernels
@@ -354,45 +378,48 @@ def _main(out):
         ext1.set_profile(True)
 
     gathered = [None]
+    PLANES_HINT = 16   # planes per frame the gather buffers are sized for (validated after the timed region)
 
-    def gather_planes():
+    def gather_planes(n_frames):
         """the one collective of the path: plane lists (frame headers + plane records) to every rank over NCCL"""
         if world == 1:
             return
         from sp_slam_b200 import sharding
         # an upper bound of 16 planes per frame lets the three collectives be enqueued without reading the counts back
-        # (no host wait inside the step); the counts of the last step are validated after the timed region
-        gathered[0] = sharding.gather_plane_lists(ext, F, max_planes_hint=16 * F)
-
-    def step_device():
-        ext.extract_device(dev.data_ptr(), F, rows, cols)
-        gather_planes()
+        # (the host never waits for the device); the counts are validated after the timed region
+        gathered[0] = sharding.gather_plane_lists(ext, n_frames, max_planes_hint=PLANES_HINT * frames_cap, frames_cap=frames_cap)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    ktimes: dict[str, float] = {}
-    kcount: dict[str, int] = {}
-    launches = 0
-    with ClockSampler(local_rank) as clk:
+    def timed_resident(dev_ptr, n_frames, steps):
+        """K passes over the resident batch + ONE final gather of the plane lists, CUDA-event timed on the shared stream."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
-        for _ in range(args.steps):
-            step_device()
-            launches += ext.launches
+        n_launch = 0
+        for _ in range(steps):
+            ext.extract_device(dev_ptr, n_frames, rows, cols)
+            n_launch += ext.launches
+        gather_planes(n_frames)
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
         if world > 1:
             from sp_slam_b200 import sharding
-            if not sharding.check_gather(gathered[0][2], 16 * F):
+            if not sharding.check_gather(gathered[0][2], PLANES_HINT * frames_cap, frames_cap):
                 raise SystemExit("a rank produced more than 16 planes per frame: the gather hint was too small")
+        return e0.elapsed_time(e1), n_launch
+
+    for _ in range(args.warmup):
+        ext.extract_device(dev.data_ptr(), F, rows, cols)
+    gather_planes(F)
+    barrier()
+    ktimes: dict[str, float] = {}
+    kcount: dict[str, int] = {}
+    with ClockSampler(local_rank) as clk:
+        ms, launches = timed_resident(dev.data_ptr(), F, args.steps)
         ms_one = None
         if ext1 is not None:
             for _ in range(2):
@@ -408,50 +435,70 @@ def _main(out):
             name = name.split("<")[0]
             ktimes[name] = ktimes.get(name, 0.0) + t
             kcount[name] = kcount.get(name, 0) + 1
-        # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
-        res = None
-        for _ in range(2):
-            res = ext.extract_batch_ptr(host.data_ptr(), F, rows, cols)
-        barrier()
-        t0 = time.perf_counter()
-        d2h = 0
-        for _ in range(args.steps):
-            res = ext.extract_batch_ptr(host.data_ptr(), F, rows, cols)
-            d2h += res.frames.nbytes + res.planes.nbytes + res.points.nbytes + res.boundary.nbytes + 24
-            launches_e2e = ext.launches
-        barrier()
-        e2e_s = time.perf_counter() - t0
+        if ext1 is not None:
+            ext1.close()
+            ext1 = None
+
+        def timed_host(call, steps):
+            """wall clock around `steps` host-buffer calls (copies inside), after 2 untimed ones"""
+            r = None
+            for _ in range(2):
+                r = call()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                r = call()
+            barrier()
+            return time.perf_counter() - t0, r
+
+        # ---- e2e: host buffers through the C ABI, copies inside the timed region; compact results ----
+        e2e_s, res = timed_host(lambda: ext.extract_batch_compact_ptr(host.data_ptr(), F, rows, cols), args.steps)
+        launches_e2e = ext.launches
         xfer = ext.transfer_bytes()   # (uploaded by copies, read in place from the pinned image, copied back) of the last step
-        # the same with the whole image uploaded (what a pageable caller buffer gets)
+        planes_per_frame = float(res.frames["n_planes"].mean())
+        overflow = int((res.frames["flags"] & api.SPX_FRAME_OVERFLOW != 0).sum())
+        d2h_compact = res.nbytes
+        # ---- the same with 16-byte point clouds back (round 1's e2e) ----
+        e2e_full_s, resf = timed_host(lambda: ext.extract_batch_ptr(host.data_ptr(), F, rows, cols), args.steps)
+        xfer_full = ext.transfer_bytes()
+        # ---- the same with the whole image uploaded (what a pageable caller buffer gets) ----
         ext.set_upload_mode(1)
-        for _ in range(2):
-            ext.extract_batch_ptr(host.data_ptr(), F, rows, cols)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            ext.extract_batch_ptr(host.data_ptr(), F, rows, cols)
-        barrier()
-        e2e_whole_s = time.perf_counter() - t0
+        e2e_whole_s, _ = timed_host(lambda: ext.extract_batch_compact_ptr(host.data_ptr(), F, rows, cols), args.steps)
         ext.set_upload_mode(0)
+        # ---- through the C++ host adapter until every Frame field of every frame is filled ----
+        adapter = None
+        try:
+            ncpu = os.cpu_count() or 1
+            ad = api.SequenceAdapter(api.default_config(max_frames=F, **kw), n_threads=max(1, ncpu // world - 1))
+            ad_s, _ = timed_host(lambda: ad.process_ptr(host.data_ptr(), F, rows, cols), args.steps)
+            n_pl, n_pt, n_bd, nbytes = ad.summary()
+            adapter = {"seconds": ad_s, "threads": ad.threads, "planes": n_pl, "points": n_pt, "boundary_points": n_bd,
+                       "bytes_filled_per_step": nbytes}
+            ad.close()
+        except Exception as e:   # noqa: BLE001  (reported, never hidden)
+            adapter = {"error": repr(e)}
     # the same end to end from the raw 16-bit depth image (SURVEY 8f N2: the convertTo of Tracking::GrabImageRGBD fused in)
     e2e16_s = None
     if (rows * cols) % 4 == 0:
         factor = float(np.float32(1.0) / np.float32(5000.0))
         host16 = torch.from_numpy(np.round(np.clip(depth_np, 0, 13.0).astype(np.float64) * 5000.0).astype(np.uint16)).pin_memory()
-        for _ in range(2):
-            ext.extract_batch_u16_ptr(host16.data_ptr(), F, rows, cols, factor)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            ext.extract_batch_u16_ptr(host16.data_ptr(), F, rows, cols, factor)
-        barrier()
-        e2e16_s = time.perf_counter() - t0
+        e2e16_s, _ = timed_host(lambda: ext.extract_batch_u16_compact_ptr(host16.data_ptr(), F, rows, cols, factor), args.steps)
         xfer16 = ext.transfer_bytes()
+    # BASELINE configs[2] as worded: the SAME batch split across the ranks (strong scaling), resident, + the final gather
+    strong_ms = None
+    if world > 1 and not strong:
+        from sp_slam_b200 import sharding
+        lo, hi = sharding.shard_range(F, rank, world)
+        frames_cap_weak, frames_cap = frames_cap, -(-F // world)
+        fb = rows * cols * 4
+        for _ in range(2):
+            ext.extract_device(dev.data_ptr() + lo * fb, hi - lo, rows, cols)
+        strong_ms, _ = timed_resident(dev.data_ptr() + lo * fb, hi - lo, args.steps)
+        frames_cap = frames_cap_weak
     # BASELINE configs[4] (tracking loop): one frame at a time through the host-buffer call, as Frame's constructor would
     lat_ms = None
     if rank == 0:
-        one = api.PlaneExtractor(max_frames=1, max_rows=rows, max_cols=cols, device=local_rank, fx=it.fx, fy=it.fy, cx=it.cx,
-                                 cy=it.cy, max_x=float(it.width), max_y=float(it.height))
+        one = api.PlaneExtractor(max_frames=1, **kw)
         def lat(mode):
             one.set_upload_mode(mode)
             ts = []
@@ -503,32 +550,37 @@ def _main(out):
     next_rows = None
     if rank == 0 and world == 1:
         next_rows = measure_next_rows(ext, dev, host, F, rows, cols, stream, not args.no_cpu_baseline)
-    planes_per_frame = float(res.frames["n_planes"].mean())
-    overflow = int((res.frames["flags"] != 0).sum())
+    ext.close()
+    del dev
 
-    t = torch.tensor([ms, e2e_s * 1e3, (e2e16_s or 0.0) * 1e3, e2e_whole_s * 1e3], dtype=torch.float64, device="cuda")
+    # BASELINE configs[3]: a short 1280x720 RealSense-shaped run folded into the default line (rank 0, N = 1)
+    cfg720 = None
+    if rank == 0 and world == 1 and args.res == "480p" and not args.no_720p:
+        cfg720 = measure_720p(stream, not args.no_cpu_baseline)
+
+    t = torch.tensor([ms, e2e_s * 1e3, (e2e16_s or 0.0) * 1e3, e2e_whole_s * 1e3, e2e_full_s * 1e3,
+                      (adapter or {}).get("seconds", 0.0) * 1e3, strong_ms or 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, e2e16_ms, e2e_whole_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
-    value = world * F * args.steps / (ms * 1e-3)
-    e2e_val = world * F * args.steps / (e2e_ms * 1e-3)
+    ms, e2e_ms, e2e16_ms, e2e_whole_ms, e2e_full_ms, ad_ms, strong_ms = (float(x) for x in t)
+    K = args.steps
+    value = total_frames * K / (ms * 1e-3)
+    per_s = lambda t_ms: total_frames * K / (t_ms * 1e-3) if t_ms else None   # noqa: E731
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        peak, peak_src = hbm_peak()
         path_bytes, kbytes, n = algorithmic_bytes_per_frame(rows, cols)
         top = max(ktimes, key=ktimes.get)
         step_kernel_ms = sum(ktimes.values())
         achieved = kbytes.get(top, 0) * F / (ktimes[top] * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, scaled to this launch
-            tj = json.load(open(tpath)).get(top)
-            if tj and rows == ROWS and cols == COLS:
-                traffic = tj["dram_bytes_per_frame"] * F / max(kcount[top], 1)
+        traffic, path_traffic = None, None
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic_all.json")
+        if os.path.exists(tpath) and rows == ROWS and cols == COLS:
+            # dram__bytes_read.sum + dram__bytes_write.sum per kernel from one ncu pass over a 1000-frame single-group step
+            tj = json.load(open(tpath))
+            if top in tj.get("kernels", {}):
+                traffic = tj["kernels"][top]["dram_bytes_per_frame"] * F / max(kcount[top], 1)
+            path_traffic = tj.get("path_dram_bytes_per_frame")
         roofline = {
             "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": peak_src,
@@ -539,7 +591,9 @@ def _main(out):
                     "back to back on one stream); `value` is timed with the batch cut into frame groups on internal streams",
             "algorithmic_bytes_per_frame": kbytes.get(top, 0),
             "path": {"algorithmic_bytes_per_frame": path_bytes,
-                     "achieved": (value / world) * path_bytes / 1e9, "frac": (value / world) * path_bytes / 1e9 / peak},
+                     "achieved": (value / world) * path_bytes / 1e9, "frac": (value / world) * path_bytes / 1e9 / peak,
+                     "measured_dram_bytes_per_frame": path_traffic,
+                     "measured_over_algorithmic": (path_traffic / path_bytes) if path_traffic else None},
             "kernels_ms": {k: round(v, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1])},
             "kernels": [{"kernel": k, "ms": round(v, 4), "algorithmic_bytes_per_frame": kbytes.get(k, 0),
                          "achieved_gbs": round(kbytes.get(k, 0) * F / (v * 1e-3) / 1e9, 1) if v > 0 else None,
@@ -548,56 +602,135 @@ def _main(out):
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            ns = min(F, args.cpu_sample)
-            oracle_fps(depth_np[: max(cores, 8)], cores, args.res)     # thread start-up, page faults
-            reps, dt, tp, ts = 0, 0.0, 0.0, 0.0
-            while reps < 3 or (dt < 2.0 and reps < 12):                # ~10-30 s of CPU work over all threads
-                _, d1, _, a, b = oracle_fps(depth_np[:ns], cores, args.res)
-                reps += 1; dt += d1; tp += a; ts += b
-            fps = reps * ns / dt
-            cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"first {ns} frames of the workload x {reps} passes, frame-parallel on {cores} host threads, "
-                             f"{dt:.1f} s wall / {tp + ts:.1f} s of CPU work; "
-                             f"oracle/ C++ port of the reference's PCL 1.8 path; per-frame 1-core time "
-                             f"{1e3 * (tp + ts) / (ns * reps):.2f} ms (plane {1e3 * tp / (ns * reps):.2f} + supposed {1e3 * ts / (ns * reps):.2f})"}
+            cpu = cpu_baseline_leg(depth_np, min(F, args.cpu_sample), args.res)
         line = {
             "metric": METRIC if args.res == "480p" else "1280x720 plane-extraction frames/s",
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup_requested": warmup_requested,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "frames_per_step_per_gpu": F, "noise": args.noise,
+            "config": {"workload": workload_name(args), "frames_per_step_per_gpu": F, "frames_per_step_total": total_frames,
+                       "noise": args.noise,
                        "cloud_dis": 3, "organized_cloud": n, "l2": "inputs larger than L2 (depth batch "
                        f"{F * rows * cols * 4 / 1e6:.0f} MB per GPU)", "parallelism": f"frame-sharded x{world}",
-                       "planes_per_frame": planes_per_frame, "overflow_frames": overflow},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": xfer[0] + xfer[1],
-                    "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_copied": xfer[0], "h2d_read_in_place": xfer[1],
-                    "note": "spx_extract_batch on the pinned CV_32F batch: the rows the organized cloud samples (every Cloud.Dis-th) "
+                       "planes_per_frame": planes_per_frame, "overflow_frames": overflow,
+                       "collective": "none" if world == 1 else "one NCCL all-gather of the plane lists after the last step, inside the timed region"},
+            "e2e": {"value": per_s(e2e_ms), "unit": UNIT, "h2d_bytes_per_step": xfer[0] + xfer[1],
+                    "d2h_bytes_per_step": xfer[2], "ms_per_step": e2e_ms / K,
+                    "h2d_copied": xfer[0], "h2d_read_in_place": xfer[1], "result_bytes": d2h_compact, "gpu_launches_per_step": launches_e2e,
+                    "note": "spx_extract_batch_compact on the pinned CV_32F batch: the rows the organized cloud samples (every Cloud.Dis-th) "
                             "are uploaded with one strided copy per frame group, the sectors of the 21x21 full-resolution windows the "
-                            "border tests read are fetched from the pinned image over PCIe by k_border_fetch (h2d_read_in_place); "
-                            "all Frame fields (planes + clouds) come back"},
-            "e2e_whole_image": {"value": world * F * args.steps / (e2e_whole_ms * 1e-3), "unit": UNIT,
-                                "h2d_bytes_per_step": F * rows * cols * 4, "ms_per_step": e2e_whole_ms / args.steps,
-                                "note": "the same call with the whole image uploaded (spx_set_upload_mode 1; what a pageable buffer gets)"},
+                            "border tests read are fetched from the pinned image over PCIe by k_border_fetch (h2d_read_in_place); back come "
+                            "frame headers, plane records, boundary clouds, the supposed planes' clouds and -- instead of the real planes' "
+                            "clouds -- their ordered inlier index lists, from which the host adapter rebuilds pcl::PointXYZRGB bit-exactly"},
+            "e2e_adapter": None if not adapter else (adapter if "error" in adapter else {
+                "value": per_s(ad_ms), "unit": UNIT, "ms_per_step": ad_ms / K, "host_threads": adapter["threads"],
+                "bytes_filled_per_step": adapter["bytes_filled_per_step"], "points_per_step": adapter["points"] + adapter["boundary_points"],
+                "note": "spx_host::SequencePlanes (C++): the same call, then every Frame field of every frame filled -- mvPlanePoints / "
+                        "mvBoundaryPoints as 32-byte pcl::PointXYZRGB-layout clouds in pooled storage, mvPlaneCoefficients -- by host threads "
+                        "that start on a frame group as soon as it is on the host (spx_set_group_callback)"}),
+            "e2e_full_clouds": {"value": per_s(e2e_full_ms), "unit": UNIT, "h2d_bytes_per_step": xfer_full[0] + xfer_full[1],
+                                "d2h_bytes_per_step": xfer_full[2], "ms_per_step": e2e_full_ms / K,
+                                "note": "spx_extract_batch: all clouds back as 16-byte points (round 1's e2e)"},
+            "e2e_whole_image": {"value": per_s(e2e_whole_ms), "unit": UNIT,
+                                "h2d_bytes_per_step": F * rows * cols * 4, "ms_per_step": e2e_whole_ms / K,
+                                "note": "the compact call with the whole image uploaded (spx_set_upload_mode 1; what a pageable buffer gets)"},
             "e2e_u16": None if not e2e16_ms else {
-                "value": world * F * args.steps / (e2e16_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": xfer16[0] + xfer16[1],
-                "ms_per_step": e2e16_ms / args.steps,
-                "note": "host input = the raw CV_16U depth image, DepthMapFactor conversion on the device (spx_extract_batch_u16)"},
+                "value": per_s(e2e16_ms), "unit": UNIT, "h2d_bytes_per_step": xfer16[0] + xfer16[1], "d2h_bytes_per_step": xfer16[2],
+                "ms_per_step": e2e16_ms / K,
+                "note": "host input = the raw CV_16U depth image, DepthMapFactor conversion on the device (spx_extract_batch_u16_compact)"},
+            "strong_scaling": None if not strong_ms else {
+                "value": F * K / (strong_ms * 1e-3), "unit": UNIT, "frames_total": F, "ms_per_step": strong_ms / K,
+                "note": f"the same {F}-frame batch split across the {world} ranks (shard_range), resident, K steps + one final "
+                        "gather of the plane lists; BASELINE configs[2] as worded"},
             "gpu_launches": launches,
             "latency_ms_per_frame_in_batch": ms / args.steps / F,
             "single_frame_latency_ms": lat_ms,
             "roofline": roofline,
+            "config4_720p": cfg720,
             "next_rows": next_rows,
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
         }
         out.emit(json.dumps(line))
-    ext.close()
-    if ext1 is not None:
-        ext1.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline_leg(depth_np, ns, res):
+    """The oracle port on all host threads, bounded sample: ~10-30 s of CPU work over all threads."""
+    cores = os.cpu_count() or 1
+    oracle_fps(depth_np[: max(cores, 8)], cores, res)     # thread start-up, page faults
+    reps, dt, tp, ts = 0, 0.0, 0.0, 0.0
+    while reps < 3 or (dt < 2.0 and reps < 12):
+        _, d1, _, a, b = oracle_fps(depth_np[:ns], cores, res)
+        reps += 1; dt += d1; tp += a; ts += b
+    fps = reps * ns / dt
+    return {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "build": oracle_build_flags(),
+            "sample": f"first {ns} frames of the workload x {reps} passes, frame-parallel on {cores} host threads, "
+                      f"{dt:.1f} s wall / {tp + ts:.1f} s of CPU work; "
+                      f"oracle/ C++ port of the reference's PCL 1.8 path; per-frame 1-core time "
+                      f"{1e3 * (tp + ts) / (ns * reps):.2f} ms (plane {1e3 * tp / (ns * reps):.2f} + supposed {1e3 * ts / (ns * reps):.2f})"}
+
+
+def measure_720p(stream, with_cpu, n_frames=120, steps=3):
+    """BASELINE configs[3]: 1280x720 noisy RealSense-shaped clutter frames (many small planes, edge-generated supposed planes):
+    resident frames/s, end to end (compact), HBM-roofline fraction of the path, overflow frames, CPU port beside it."""
+    import torch
+    from sp_slam_b200 import api, scenes
+    rows, cols = 720, 1280
+    it = scenes.REALSENSE
+    d = scenes.realsense_sequence(n_frames)
+    d = np.stack([scenes.add_noise(d[k], k, "realsense") for k in range(n_frames)])
+    host = torch.from_numpy(d).pin_memory()
+    dev = host.cuda()
+    ext = api.PlaneExtractor(max_frames=n_frames, max_rows=rows, max_cols=cols, fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy,
+                             max_x=float(it.width), max_y=float(it.height), device=torch.cuda.current_device())
+    ext.set_stream(stream.cuda_stream)
+    for _ in range(3):
+        ext.extract_device(dev.data_ptr(), n_frames, rows, cols)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        ext.extract_device(dev.data_ptr(), n_frames, rows, cols)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    for _ in range(2):
+        res = ext.extract_batch_compact_ptr(host.data_ptr(), n_frames, rows, cols)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = ext.extract_batch_compact_ptr(host.data_ptr(), n_frames, rows, cols)
+    e2e_s = (time.perf_counter() - t0) / steps
+    xfer = ext.transfer_bytes()
+    peak, _ = hbm_peak()
+    path_bytes, _, n = algorithmic_bytes_per_frame(rows, cols)
+    value = n_frames / (ms * 1e-3)
+    out = {"workload": f"{n_frames}-frame synthetic 1280x720 RealSense-shaped clutter sequence with sensor noise, Plane.MinSize 500",
+           "value": value, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+           "e2e": {"value": n_frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": xfer[0] + xfer[1], "d2h_bytes_per_step": xfer[2]},
+           "organized_cloud": n, "planes_per_frame": float(res.frames["n_planes"].mean()),
+           "real_planes_per_frame": float(res.frames["n_real"].mean()),
+           "overflow_frames": int((res.frames["flags"] & api.SPX_FRAME_OVERFLOW != 0).sum()),
+           "roofline_path": {"algorithmic_bytes_per_frame": path_bytes, "achieved": value * path_bytes / 1e9,
+                             "frac": value * path_bytes / 1e9 / peak}}
+    ext.close()
+    if with_cpu:
+        cores = os.cpu_count() or 1
+        oracle_fps(d[:cores], cores, "720p")
+        fps, dt, _, tp, ts = oracle_fps(d, cores, "720p")
+        out["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "build": oracle_build_flags(),
+                               "sample": f"the same {n_frames} frames, one pass, frame-parallel on {cores} host threads, {dt:.1f} s wall"}
+    return out
 
 
 if __name__ == "__main__":

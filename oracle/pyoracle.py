@@ -23,7 +23,11 @@ class OrcConfig(C.Structure):
         ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
         ("max_depth_change_factor", C.c_float), ("normal_smoothing_size", C.c_float),
         ("ransac_max_iter", C.c_int32), ("enable_supposed", C.c_int32),
+        ("alt", C.c_uint32),      # alternative readings of PCL 1.8.0 (ORC_ALT_*), 0 = the default restatement
     ]
+
+
+ALT_VP_RESET, ALT_CHAMFER_NO_WRAP, ALT_REFINE_NO_WRAP, ALT_SAMPLE_GOOD_OR, ALT_RNG_MASK = 1, 2, 4, 8, 16
 
 
 class OrcLineRec(C.Structure):
@@ -46,14 +50,37 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_lib_path = _LIB_PATH
+BUILD_FLAGS = "-O3 -ffp-contract=off (portable build)"
+
+
+def use_native() -> str:
+    """Rebuild the oracle for THIS host (-O3 -march=native -ffp-contract=off, the reference's CMakeLists.txt:10-11 flags plus
+    the no-contraction rule) into oracle/_native/ and use it from now on; bench.py's CPU legs call this on the box they run
+    on.  Falls back to the portable build (and says so) when the compiler is missing.  Returns the flags in use."""
+    global _lib, _lib_path, BUILD_FLAGS
+    if _lib is not None:
+        return BUILD_FLAGS
+    out_dir = os.path.join(_HERE, "_native")
+    out = os.path.join(out_dir, "libspx_oracle_native.so")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-shared",
+                               "-pthread", "-o", out, os.path.join(_HERE, "spx_oracle.cpp")], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL, timeout=300)
+        _lib_path = out
+        BUILD_FLAGS = "-O3 -march=native -ffp-contract=off (built on this host)"
+    except Exception as e:   # noqa: BLE001
+        BUILD_FLAGS = f"-O3 -ffp-contract=off (portable build; the native rebuild failed: {type(e).__name__})"
+    return BUILD_FLAGS
 
 
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
+        if _lib_path == _LIB_PATH and not os.path.exists(_LIB_PATH):
             build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(_lib_path)
         vp, i32, f32p = C.c_void_p, C.c_int, C.c_void_p
         L.orc_default_config.argtypes = [C.POINTER(OrcConfig)]
         L.orc_create.argtypes = [C.POINTER(OrcConfig)]
@@ -88,6 +115,12 @@ def lib():
         L.orc_eigen33_largest.argtypes = [vp, vp, vp]
         L.orc_sac_line.argtypes = [vp, i32, C.c_double, i32, vp, vp, C.POINTER(i32)]
         L.orc_sac_line.restype = i32
+        L.orc_sac_line_alt.argtypes = [vp, i32, C.c_double, i32, vp, vp, C.POINTER(i32), C.c_uint32]
+        L.orc_sac_line_alt.restype = i32
+        L.orc_chamfer_alt.argtypes = [vp, i32, i32, vp, C.c_uint32]
+        L.orc_is_border_point.argtypes = [C.POINTER(OrcConfig), vp, i32, i32, C.c_float, C.c_float, C.c_float]
+        L.orc_is_border_point.restype = i32
+        L.orc_sat_exact_batch.argtypes = [C.POINTER(OrcConfig), vp, i32, i32, i32, i32, vp]
         L.orc_ransac_draws.argtypes = [i32, i32, vp]
         L.orc_voxel_grid.argtypes = [vp, i32, vp, vp, vp]
         L.orc_voxel_grid.restype = i32
@@ -240,12 +273,30 @@ def run_batch(depth: np.ndarray, n_threads: int, cfg: OrcConfig | None = None):
     return nr, na, a.value, b.value
 
 
-def chamfer(mask: np.ndarray) -> np.ndarray:
+def sat_exact_batch(depth: np.ndarray, n_threads: int, cfg: OrcConfig | None = None) -> np.ndarray:
+    """Per frame: were all fp64 integral-image partial sums and window sums exact (error-free-transformation check)?"""
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    n, rows, cols = depth.shape
+    cfg = cfg if cfg is not None else default_config()
+    out = np.zeros(n, np.uint8)
+    lib().orc_sat_exact_batch(C.byref(cfg), depth.ctypes.data, n, rows, cols, int(n_threads), out.ctypes.data)
+    return out.astype(bool)
+
+
+def chamfer(mask: np.ndarray, alt: int = 0) -> np.ndarray:
     mask = np.ascontiguousarray(mask, dtype=np.uint8)
     h, w = mask.shape
     out = np.empty((h, w), np.float32)
-    lib().orc_chamfer(mask.ctypes.data, w, h, out.ctypes.data)
+    lib().orc_chamfer_alt(mask.ctypes.data, w, h, out.ctypes.data, alt)
     return out
+
+
+def is_border_point(depth: np.ndarray, x: float, y: float, z: float, cfg: OrcConfig | None = None) -> bool:
+    """Frame::IsBorderPoint (src/Frame.cc:1026-1056) of a camera-frame point against a CV_32F depth image."""
+    cfg = cfg if cfg is not None else default_config()
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    return bool(lib().orc_is_border_point(C.byref(cfg), depth.ctypes.data, depth.shape[0], depth.shape[1],
+                                          C.c_float(x), C.c_float(y), C.c_float(z)))
 
 
 def eigen33_smallest(cov: np.ndarray):
@@ -264,13 +315,13 @@ def eigen33_largest(cov: np.ndarray):
     return evals, vec
 
 
-def sac_line(points: np.ndarray, threshold: float = float(np.float32(0.01)), max_iter: int = 1000):
+def sac_line(points: np.ndarray, threshold: float = float(np.float32(0.01)), max_iter: int = 1000, alt: int = 0):
     pts = np.ascontiguousarray(points, dtype=POINT_DTYPE)
     coef = np.empty(6, np.float32)
     inl = np.empty(max(len(pts), 1), np.int32)
     it = C.c_int()
-    n = lib().orc_sac_line(pts.ctypes.data, len(pts), float(threshold), int(max_iter), coef.ctypes.data,
-                           inl.ctypes.data, C.byref(it))
+    n = lib().orc_sac_line_alt(pts.ctypes.data, len(pts), float(threshold), int(max_iter), coef.ctypes.data,
+                               inl.ctypes.data, C.byref(it), alt)
     return coef, inl[:n].copy(), it.value
 
 

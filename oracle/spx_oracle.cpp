@@ -167,7 +167,8 @@ static void corresponding_eigvec(const float mat[9], float eigenvalue, float vec
 // ------------------------------------------------------------------------------------------------
 // chamfer distance map of IntegralImageNormalEstimation::computeFeature (integral_image_normal.hpp)
 // ------------------------------------------------------------------------------------------------
-static void chamfer(const uint8_t *mask, int w, int h, float *dist) {
+static void chamfer(const uint8_t *mask, int w, int h, float *dist, bool wrap = true) {
+    const float far_ = 3.0e38f;   // (no-wrap alternative: the aliased neighbour does not exist)
     const int N = w * h;
     for (int i = 0; i < N; ++i) dist[i] = mask[i] == 0 ? 0.0f : float(w + h);
     // first pass; at ci = w-1, previous_row[ci+1] aliases current_row[0] (in-bounds row wrap)
@@ -177,7 +178,7 @@ static void chamfer(const uint8_t *mask, int w, int h, float *dist) {
         for (int ci = 1; ci < w; ++ci) {
             const float upLeft = prev[ci - 1] + 1.4f;
             const float up = prev[ci] + 1.0f;
-            const float upRight = prev[ci + 1] + 1.4f;
+            const float upRight = (wrap || ci + 1 < w) ? prev[ci + 1] + 1.4f : far_;
             const float left = cur[ci - 1] + 1.0f;
             const float center = cur[ci];
             const float minValue = std::min(std::min(upLeft, up), std::min(left, upRight));
@@ -189,7 +190,7 @@ static void chamfer(const uint8_t *mask, int w, int h, float *dist) {
         float *cur = dist + size_t(ri) * w;
         float *next = cur + w;
         for (int ci = w - 2; ci >= 0; --ci) {
-            const float lowerLeft = next[ci - 1] + 1.4f;
+            const float lowerLeft = (wrap || ci >= 1) ? next[ci - 1] + 1.4f : far_;
             const float lower = next[ci] + 1.0f;
             const float lowerRight = next[ci + 1] + 1.4f;
             const float right = cur[ci + 1] + 1.0f;
@@ -265,17 +266,19 @@ struct SacLine {
     const Pt *pts; int n;
     std::vector<int> shuffled;
     std::mt19937 rng;          // boost::mt19937 is the same generator
-    explicit SacLine(const Pt *p, int n_) : pts(p), n(n_), rng(12345u) {
+    unsigned alt = 0;
+    explicit SacLine(const Pt *p, int n_, unsigned alt_ = 0) : pts(p), n(n_), rng(12345u), alt(alt_) {
         shuffled.resize(n);
         for (int i = 0; i < n; ++i) shuffled[i] = i;
     }
-    int rnd() { return int(rng() >> 1); }   // E4
+    int rnd() { return (alt & ORC_ALT_RNG_MASK) ? int(rng() & 0x7fffffffu) : int(rng() >> 1); }   // E4
     void draw(int s[2]) {
         for (unsigned i = 0; i < 2; ++i)
             std::swap(shuffled[i], shuffled[i + (size_t(rnd()) % size_t(n - i))]);
         s[0] = shuffled[0]; s[1] = shuffled[1];
     }
     bool sample_good(const int s[2]) const {   // E6
+        if (alt & ORC_ALT_SAMPLE_GOOD_OR) return pts[s[0]].x != pts[s[1]].x || pts[s[0]].y != pts[s[1]].y || pts[s[0]].z != pts[s[1]].z;
         return pts[s[0]].x != pts[s[1]].x && pts[s[0]].y != pts[s[1]].y && pts[s[0]].z != pts[s[1]].z;
     }
     // getSamples: false = "no samples could be selected"
@@ -494,7 +497,7 @@ void orc_ctx::estimate_normals() {
                 mask[index] = 0; mask[index + w] = 0;
             }
         }
-    chamfer(mask.data(), w, h, dist.data());
+    chamfer(mask.data(), w, h, dist.data(), !(cfg.alt & ORC_ALT_CHAMFER_NO_WRAP));
 
     // computeFeatureFull, BORDER_POLICY_IGNORE
     const int border = int(cfg.normal_smoothing_size);
@@ -620,6 +623,7 @@ void orc_ctx::segment_and_refine() {
         eigen33_smallest(cov, eigen_value, ev);
         float pp[4] = {ev[0], ev[1], ev[2], 0.0f};
         pp[3] = -1 * dot4f(pp, m.centroid);
+        if (cfg.alt & ORC_ALT_VP_RESET) vp[0] = vp[1] = vp[2] = vp[3] = 0.0f;
         for (int k = 0; k < 4; ++k) vp[k] -= m.centroid[k];   // vp is never reset between clusters
         float cos_theta = dot4f(vp, pp);
         if (cos_theta < 0) {
@@ -681,7 +685,7 @@ void orc_ctx::segment_and_refine() {
                 int current_label = int(labels[cur + c]);
                 int left_label = int(labels[cur + c - 1]);   // c == 0: last pixel of the previous row
                 if (current_label < 0 || left_label < 0) continue;
-                if (rcompare(cur + c, cur + c - 1)) claim(current_label, cur + c - 1);
+                if ((c > 0 || !(cfg.alt & ORC_ALT_REFINE_NO_WRAP)) && rcompare(cur + c, cur + c - 1)) claim(current_label, cur + c - 1);
                 int upper_label = int(labels[prev + c]);
                 if (upper_label < 0) continue;
                 if (rcompare(cur + c, prev + c)) claim(current_label, prev + c);
@@ -769,7 +773,12 @@ bool orc_ctx::is_border_point(float PcX, float PcY, float PcZ) const {
     const float invz = 1.0f / PcZ;
     const float u = cfg.fx * PcX * invz + cfg.cx;
     const float v = cfg.fy * PcY * invz + cfg.cy;
-    if (!std::isfinite(u) || !std::isfinite(v)) return false;   // E7
+    // not finite (a point at depth 0: u = fx * (+-0) * inf + cx = NaN): with v NaN or -inf the loop over j below never runs, with
+    // u NaN or -inf the loop over i never does; res / num = NaN, the final test is false and the reference returns true.  Only
+    // +inf, where the reference walks out of the image buffer, is answered false (E7)
+    const float pinf = std::numeric_limits<float>::infinity();
+    if (!std::isfinite(v)) return v != pinf;
+    if (!std::isfinite(u)) return u != pinf;
     int num = 0, nan = 0;
     float res = 0;
     int b = 10;
@@ -855,7 +864,7 @@ void orc_ctx::generate_supposed() {
             int iters = 0;
             inl.clear();
             if (!bound.empty()) {   // PCLBase::initCompute fails on an empty cloud -> outputs cleared
-                SacLine sac(bound.data(), int(bound.size()));
+                SacLine sac(bound.data(), int(bound.size()), cfg.alt);
                 ok = sac.segment(thr, cfg.ransac_max_iter, coef, inl, iters);
             }
             if (!ok) inl.clear();
@@ -908,6 +917,7 @@ void orc_default_config(orc_config *c) {
     c->min_x = 0.0f; c->max_x = 640.0f; c->min_y = 0.0f; c->max_y = 480.0f;
     c->max_depth_change_factor = 0.05f; c->normal_smoothing_size = 10.0f;
     c->ransac_max_iter = 1000; c->enable_supposed = 1;
+    c->alt = 0;
 }
 
 orc_ctx *orc_create(const orc_config *cfg) { orc_ctx *c = new orc_ctx(); c->cfg = *cfg; return c; }
@@ -1015,16 +1025,45 @@ int orc_run_batch(const orc_config *cfg, const float *depth, int n_frames, int r
     return 0;
 }
 
+// exactness of the integral-image arithmetic for a batch of frames (cloud + normal estimation only), frame-parallel
+int orc_sat_exact_batch(const orc_config *cfg, const float *depth, int n_frames, int rows, int cols, int n_threads, uint8_t *exact) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_frames) n_threads = n_frames > 0 ? n_frames : 1;
+    std::vector<std::thread> pool;
+    for (int tid = 0; tid < n_threads; ++tid)
+        pool.emplace_back([&, tid]() {
+            orc_ctx *c = orc_create(cfg);
+            for (int f = tid; f < n_frames; f += n_threads) {
+                c->depth = depth + size_t(f) * rows * cols; c->rows = rows; c->cols = cols;
+                c->back_project();
+                c->estimate_normals();
+                exact[f] = c->sat_exact ? 1 : 0;
+            }
+            orc_destroy(c);
+        });
+    for (auto &t : pool) t.join();
+    return 0;
+}
+
 void orc_chamfer(const uint8_t *mask, int w, int h, float *dist) { chamfer(mask, w, h, dist); }
+void orc_chamfer_alt(const uint8_t *mask, int w, int h, float *dist, uint32_t alt) { chamfer(mask, w, h, dist, !(alt & ORC_ALT_CHAMFER_NO_WRAP)); }
+int orc_is_border_point(const orc_config *cfg, const float *depth, int rows, int cols, float x, float y, float z) {
+    orc_ctx c;
+    c.cfg = *cfg; c.depth = depth; c.rows = rows; c.cols = cols;
+    return c.is_border_point(x, y, z) ? 1 : 0;
+}
 void orc_eigen33_smallest(const float cov[9], float *ev, float vec[3]) { eigen33_smallest(cov, *ev, vec); }
 void orc_eigen33_largest(const float cov[9], float evals[3], float vec[3]) {
     eigen33_values(cov, evals); corresponding_eigvec(cov, evals[2], vec);
 }
 int orc_sac_line(const orc_point *pts, int n, double thr, int max_iter, float coef[6], int32_t *inliers, int *iterations) {
+    return orc_sac_line_alt(pts, n, thr, max_iter, coef, inliers, iterations, 0u);
+}
+int orc_sac_line_alt(const orc_point *pts, int n, double thr, int max_iter, float coef[6], int32_t *inliers, int *iterations, uint32_t alt) {
     std::vector<int> inl; int it = 0;
     for (int k = 0; k < 6; ++k) coef[k] = 0;
     bool ok = false;
-    if (n > 0) { SacLine sac(pts, n); ok = sac.segment(thr, max_iter, coef, inl, it); }
+    if (n > 0) { SacLine sac(pts, n, alt); ok = sac.segment(thr, max_iter, coef, inl, it); }
     if (!ok) inl.clear();
     if (iterations) *iterations = it;
     if (inliers) std::memcpy(inliers, inl.data(), inl.size() * 4);

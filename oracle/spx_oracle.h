@@ -35,7 +35,16 @@ typedef struct orc_config {
     float   normal_smoothing_size;     /* 10.0f */
     int32_t ransac_max_iter;           /* 1000  */
     int32_t enable_supposed;           /* run GeneratePlanesFromBoundries (src/Frame.cc:194) */
+    /* Alternative readings of PCL 1.8.0 where the restatement rests on recollection (SURVEY.md Appendix A, items marked
+     * with a warning sign).  0 = the reading this oracle and the CUDA path implement.  A future run of tools/pcl_pin against
+     * real PCL that disagrees with the oracle can be bisected by flipping these one at a time. */
+    uint32_t alt;
 } orc_config;
+#define ORC_ALT_VP_RESET         1u   /* A.4: segment()'s viewpoint vector is reset for every cluster (default: it accumulates -centroid) */
+#define ORC_ALT_CHAMFER_NO_WRAP  2u   /* A.2: no row wrap-around in the distance-map passes (default: previous_row[w] aliases current_row[0]) */
+#define ORC_ALT_REFINE_NO_WRAP   4u   /* A.5: refine()'s second pass makes no left claim at column 0 (default: it claims the previous row's last pixel) */
+#define ORC_ALT_SAMPLE_GOOD_OR   8u   /* A.8: isSampleGood accepts a pair when ANY coordinate differs (default: x, y and z must all differ) */
+#define ORC_ALT_RNG_MASK        16u   /* A.8: rnd() = mt() & INT_MAX (default: boost::uniform_int(0, INT_MAX) = mt() >> 1) */
 
 /* 16-byte packed point: xyz + packed rgba (a<<24|r<<16|g<<8|b), the payload of pcl::PointXYZRGB */
 typedef struct orc_point { float x, y, z; uint32_t rgba; } orc_point;
@@ -101,9 +110,16 @@ void   orc_get_times(const orc_ctx *, double *t_plane, double *t_splane);
 int    orc_run_batch(const orc_config *cfg, const float *depth, int n_frames, int rows, int cols, int n_threads,
                      int32_t *n_real, int32_t *n_planes, double *t_plane_sum, double *t_splane_sum);
 
+/* exact[f] = 1 when every fp64 partial sum of frame f's integral images (and every window sum) was exact: the device's
+ * tile-local integral images then give bit-identical window sums to PCL's whole-image ones.  Runs cloud + normals only. */
+int    orc_sat_exact_batch(const orc_config *cfg, const float *depth, int n_frames, int rows, int cols, int n_threads, uint8_t *exact);
+
 /* ---- stage-level entry points used by known-answer tests ---- */
 /* two-pass chamfer of PCL's computeFeature on a caller-supplied mask (0 = edge) */
 void   orc_chamfer(const uint8_t *mask, int width, int height, float *dist);
+void   orc_chamfer_alt(const uint8_t *mask, int width, int height, float *dist, uint32_t alt);
+/* Frame::IsBorderPoint (src/Frame.cc:1026-1056) of the camera-frame point (x, y, z) against a depth image */
+int    orc_is_border_point(const orc_config *cfg, const float *depth, int rows, int cols, float x, float y, float z);
 /* pcl::eigen33(mat, eigenvalue, eigenvector): smallest eigenpair of a symmetric 3x3 (row-major) */
 void   orc_eigen33_smallest(const float cov[9], float *eigenvalue, float eigenvector[3]);
 /* pcl::eigen33(mat, evals) + computeCorrespondingEigenVector(mat, evals[2]) */
@@ -111,6 +127,8 @@ void   orc_eigen33_largest(const float cov[9], float evals[3], float eigenvector
 /* SACSegmentation<LINE>::segment on a point list; returns n_inliers, fills coef[6], inlier idx, iterations */
 int    orc_sac_line(const orc_point *pts, int n, double threshold, int max_iter,
                     float coef[6], int32_t *inliers, int *iterations);
+int    orc_sac_line_alt(const orc_point *pts, int n, double threshold, int max_iter,
+                        float coef[6], int32_t *inliers, int *iterations, uint32_t alt);
 /* the index pairs RANSAC would draw for a cloud of n points, ignoring isSampleGood rejections */
 void   orc_ransac_draws(int n, int n_draws, int32_t *pairs /* 2*n_draws */);
 

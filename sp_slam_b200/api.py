@@ -445,6 +445,12 @@ class PlaneExtractor:
 
     def set_stream(self, cuda_stream: int | None):
         self._ck(lib().spx_set_stream(self._h, cuda_stream))
+        self._stream = cuda_stream or None
+
+    @property
+    def stream(self):
+        """The caller-owned cudaStream_t the context is bound to (None: the context's own non-blocking stream)."""
+        return getattr(self, "_stream", None)
 
     def cloud_dims(self, rows: int, cols: int):
         w, h = C.c_int(), C.c_int()

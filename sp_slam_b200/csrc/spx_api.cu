@@ -29,7 +29,7 @@ using namespace spx;
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;   // spx_last_error(NULL): the calling thread's last failed spx_create / spx_host_register
 
 struct DevArena {
     char *base = nullptr;
@@ -149,6 +149,8 @@ int fail(spx_ctx *c, int code, const char *fmt, ...) {
     } while (0)
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+#define SPX_DEVICE(c) DeviceGuard dev_guard_((c)->device); SPX_CK((c), dev_guard_.err)
 
 // organized-cloud size (src/Frame.cc:873-874): ceil(cols / dis) x ceil(rows / dis), evaluated in float as there
 void cloud_dims(int rows, int cols, int dis, int *w, int *h) {
@@ -694,7 +696,7 @@ int check_frame(spx_ctx *c, int frame) {
     if (!c->have_run) return fail(c, SPX_ERR_STATE, "no extract call has been made on this context");
     if (!c->debug) return fail(c, SPX_ERR_STATE, "debug taps are off: call spx_set_debug(ctx, 1) before the extract");
     if (frame < 0 || frame >= c->last_frames) return fail(c, SPX_ERR_ARG, "frame %d outside the last batch", frame);
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     SPX_CK(c, cudaStreamSynchronize(c->stream));
     return SPX_OK;
 }
@@ -751,16 +753,17 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
 
     // A batch runs as several frame groups on their own streams plus an upload and a download stream.  The driver maps
     // streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue serialise, which
-    // costs the host path ~20 %.  The variable is read when the CUDA context is created: if this library is the first CUDA
-    // user of the process (SP-SLAM itself has no other), ask for the maximum unless the caller has chosen a value.
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    // costs the host path ~20 %.  The variable is read when the process creates its CUDA context, so it is the HOST's to
+    // set (the Python binding and bench.py export 32 before CUDA starts): this library does not touch the
+    // process environment.
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
         return fail(nullptr, SPX_ERR_CUDA, "no CUDA device (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
     if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, SPX_ERR_ARG, "device %d out of range (%d devices)", cfg->device, n_dev);
     cudaDeviceProp prop;
-    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess)
+    DeviceGuard dev_guard_(cfg->device);
+    if ((e = dev_guard_.err) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess)
         return fail(nullptr, SPX_ERR_CUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e));
     if (prop.major != 10)
         return fail(nullptr, SPX_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
@@ -934,7 +937,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
 
 void spx_destroy(spx_ctx *c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard dev_guard_(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     if (c->arena.base) cudaFree(c->arena.base);
     if (c->h_totals) cudaFreeHost(c->h_totals);
@@ -965,7 +968,7 @@ const char *spx_last_error(const spx_ctx *c) { return c ? c->err.c_str() : g_cre
 
 int spx_set_stream(spx_ctx *c, void *cuda_stream) {
     if (!c) return SPX_ERR_ARG;
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     SPX_CK(c, cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
     return SPX_OK;
@@ -981,7 +984,7 @@ int spx_extract_batch_device(spx_ctx *c, const float *depth_dev, int n_frames, i
                              size_t frame_stride_bytes) {
     if (!c) return SPX_ERR_ARG;
     if (!depth_dev) return fail(c, SPX_ERR_ARG, "null depth pointer");
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     int rc = set_geometry(c, n_frames, rows, cols, pitch_bytes, frame_stride_bytes);
     if (rc != SPX_OK) return rc;
     return run_pipeline(c, depth_dev, depth_dev, false, HostSrc(), false, c->result_mode == 1);
@@ -989,13 +992,13 @@ int spx_extract_batch_device(spx_ctx *c, const float *depth_dev, int n_frames, i
 
 int spx_fetch_results(spx_ctx *c, spx_batch_result *out) {
     if (!c || !out) return SPX_ERR_ARG;
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     return fetch(c, out, true);
 }
 
 int spx_fetch_planes(spx_ctx *c, spx_batch_result *out) {
     if (!c || !out) return SPX_ERR_ARG;
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     return fetch(c, out, false);
 }
 
@@ -1015,7 +1018,7 @@ static int extract_host(spx_ctx *c, const void *depth, bool u16, float depth_map
                         size_t frame_stride_bytes, spx_batch_result *out, spx_compact_result *cout) {
     if (!c) return SPX_ERR_ARG;
     if (!depth || (!out && !cout)) return fail(c, SPX_ERR_ARG, "null argument");
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     const size_t tight = size_t(cols) * sizeof(float);
     const size_t esz = u16 ? sizeof(uint16_t) : sizeof(float);
     int rc;
@@ -1079,7 +1082,7 @@ int spx_set_result_mode(spx_ctx *c, int mode) {
 
 int spx_fetch_compact(spx_ctx *c, spx_compact_result *out) {
     if (!c || !out) return SPX_ERR_ARG;
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     return fetch(c, nullptr, true, out);
 }
 
@@ -1097,7 +1100,7 @@ int spx_segment_from_normals(spx_ctx *c, const float *depth, int rows, int cols,
                              spx_batch_result *out) {
     if (!c) return SPX_ERR_ARG;
     if (!depth || !normals || !out) return fail(c, SPX_ERR_ARG, "null argument");
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     const size_t tight = size_t(cols) * sizeof(float);
     int rc = set_geometry(c, 1, rows, cols, pitch_bytes, pitch_bytes * size_t(rows));
     if (rc != SPX_OK) return rc;
@@ -1122,7 +1125,7 @@ int spx_cloud_dims(const spx_ctx *c, int rows, int cols, int *width, int *height
 int spx_get_times(spx_ctx *c, double *t_plane, double *t_splane) {
     if (!c) return SPX_ERR_ARG;
     if (!c->have_run) return fail(c, SPX_ERR_STATE, "no extract call has been made on this context");
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     SPX_CK(c, cudaEventSynchronize(c->ev[2]));
     float total = 0;
     SPX_CK(c, cudaEventElapsedTime(&total, c->ev[0], c->ev[2]));
@@ -1143,7 +1146,7 @@ int spx_get_times(spx_ctx *c, double *t_plane, double *t_splane) {
 int spx_get_group_timeline(spx_ctx *c, float *t_ms, int cap_groups, int *n_groups) {
     if (!c || !n_groups) return SPX_ERR_ARG;
     if (!c->have_run || !c->group_pack) return fail(c, SPX_ERR_STATE, "the group timeline follows a host-input extract");
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     *n_groups = c->last_groups;
     for (int g = 0; g < c->last_groups && g < cap_groups && t_ms; ++g) {
         cudaEvent_t evs[5] = {c->g_ev[3 * g + 0], c->g_xev[2 * g + 0], c->g_ev[3 * g + 1], c->g_ev[3 * g + 2], c->g_xev[2 * g + 1]};
@@ -1192,7 +1195,7 @@ int spx_set_profile(spx_ctx *c, int on) {
 int spx_get_kernel_times(spx_ctx *c, const char **names, float *ms, int cap, int *n) {
     if (!c || !n) return SPX_ERR_ARG;
     if (!c->have_run || !c->profile || c->prof_n == 0) return fail(c, SPX_ERR_STATE, "no profiled extract call (spx_set_profile) on this context");
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     SPX_CK(c, cudaEventSynchronize(c->ev[2]));
     *n = c->prof_n;
     for (int k = 0; k < c->prof_n && k < cap; ++k) {
@@ -1205,7 +1208,7 @@ int spx_get_kernel_times(spx_ctx *c, const char **names, float *ms, int cap, int
 int spx_get_kernel_timeline(spx_ctx *c, const char **names, float *start_ms, float *end_ms, int cap, int *n) {
     if (!c || !n) return SPX_ERR_ARG;
     if (!c->have_run || !c->profile || c->prof_n == 0) return fail(c, SPX_ERR_STATE, "no profiled extract call (spx_set_profile) on this context");
-    SPX_CK(c, cudaSetDevice(c->device));
+    SPX_DEVICE(c);
     SPX_CK(c, cudaEventSynchronize(c->ev[2]));
     *n = c->prof_n;
     for (int k = 0; k < c->prof_n && k < cap; ++k) {

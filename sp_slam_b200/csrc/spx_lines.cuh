@@ -128,20 +128,29 @@ __device__ int block_select(int n, IdxT *out, int *s_warp, Pred pred) {
 constexpr int kBorderWarps = 4;
 
 // window of IsBorderPoint around a line point (src/Frame.cc:1030-1037): columns i0 .. while < u + 10, rows j0 .. while < v + 10
-struct BorderWin { int i0, j0; float ue, ve; bool live; };
+// A projection that is not finite (a line point at depth 0: u = fx * (+-0) * inf + cx = NaN) follows the reference's loops
+// `for(int j = v - b; j < v + b; ++j) for(int i = u - b; i < u + b; ++i)`: with v NaN or -inf the outer loop never runs, with
+// u NaN or -inf the inner one never does, res / num = 0 / 0 = NaN, `PcZ - NaN > 0.1` is false and IsBorderPoint returns TRUE
+// (`empty`).  Only +inf, where the reference walks out of the image buffer, is answered "not a border point" (convention E7).
+struct BorderWin { int i0, j0; float ue, ve; bool live, empty; };
 __device__ __forceinline__ BorderWin border_window(const Params &P, const spx_point &p) {
     BorderWin W;
-    W.i0 = 0; W.j0 = 0; W.ue = 0.f; W.ve = 0.f; W.live = false;
+    W.i0 = 0; W.j0 = 0; W.ue = 0.f; W.ve = 0.f; W.live = false; W.empty = false;
     const int b = 10;
     const float PcZ = p.z;
     if (!(PcZ < 0.0f)) {
         const float invz = 1.0f / PcZ;
         const float u = P.fx * p.x * invz + P.cx;
         const float v = P.fy * p.y * invz + P.cy;
+        const float pinf = __int_as_float(0x7f800000);
         if (isfinite(u) && isfinite(v)) {
             W.live = true;
             W.i0 = int(u - b); W.j0 = int(v - b);
             W.ue = u + b; W.ve = v + b;
+        } else if (!isfinite(v)) {
+            W.empty = v != pinf;
+        } else {
+            W.empty = u != pinf;
         }
     }
     return W;
@@ -282,14 +291,14 @@ __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__res
             const int pi = base + lane;
             // per-point window geometry (lane = point)
             bool live = false;   // still needs its window walked
-            bool result = false;
+            bool result = false, forced = false;
             float PcZ = 0.f, ue = 0.f, ve = 0.f;
             int i0 = 0, j0 = 0;
             if (pi < n_pts) {
                 const spx_point p = pts[pi];
                 PcZ = p.z;
                 const BorderWin W = border_window(P, p);
-                live = W.live; i0 = W.i0; j0 = W.j0; ue = W.ue; ve = W.ve;
+                live = W.live; forced = W.empty; i0 = W.i0; j0 = W.j0; ue = W.ue; ve = W.ve;
             }
             int num = 0, nan = 0;
             float res = 0.f;
@@ -352,6 +361,7 @@ __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__res
                 __syncwarp();
             }
             if (live) result = !(double(PcZ - res / num) > 0.1);
+            if (forced) result = true;   // a window without samples: the reference's test on NaN is false, the point counts as border
             if (pi < n_pts && !result) ++fails;
         }
         fails = __reduce_add_sync(SPX_FULL, fails);

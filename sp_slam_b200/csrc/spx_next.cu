@@ -378,7 +378,7 @@ int spx_voxel_grid(spx_ctx *c, const spx_point *points, const int64_t *cloud_off
     const long long total = n_clouds ? cloud_off[n_clouds] - cloud_off[0] : 0;
     if (total > INT_MAX || n_clouds >= (1 << 24)) return spx_internal_fail(c, SPX_ERR_ARG, "spx_voxel_grid", "more than 2^31 points or 2^24 clouds in one call");
     if (total > 0 && !out) return spx_internal_fail(c, SPX_ERR_ARG, "spx_voxel_grid", "null output");
-    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    DeviceGuard dev_guard_(spx_internal_device(c)); NX_CK(c, dev_guard_.err);
     std::lock_guard<std::mutex> lock(g_vox_mutex[spx_internal_device(c) % kMaxDevices]);
     cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
     std::vector<VoxSeg> segs(static_cast<size_t>(n_clouds));
@@ -409,7 +409,7 @@ int spx_voxel_downsample_results(spx_ctx *c, float leaf, int which) {
     spx_device_result R;
     int rc = spx_get_device_results(c, &R);     // fails unless the last call was spx_extract_batch_device
     if (rc != SPX_OK) return rc;
-    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    DeviceGuard dev_guard_(spx_internal_device(c)); NX_CK(c, dev_guard_.err);
     std::lock_guard<std::mutex> lock(g_vox_mutex[spx_internal_device(c) % kMaxDevices]);
     cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
     long long tot[3];
@@ -451,7 +451,8 @@ int spx_map_create(spx_ctx *c, spx_map **out) {
     spx_map *m = new (std::nothrow) spx_map();
     if (!m) return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_create", "out of host memory");
     m->ctx = c;
-    cudaError_t e = cudaSetDevice(spx_internal_device(c));
+    DeviceGuard dev_guard_(spx_internal_device(c));
+    cudaError_t e = dev_guard_.err;
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->h_plane_w), SPX_MAX_PLANES * 4 * sizeof(float), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->h_res_f), SPX_MAX_PLANES * sizeof(float), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->h_res_i), (SPX_MAX_PLANES * 3 + 1) * sizeof(int), cudaHostAllocDefault);
@@ -467,7 +468,7 @@ int spx_map_create(spx_ctx *c, spx_map **out) {
 
 void spx_map_destroy(spx_map *m) {
     if (!m) return;
-    cudaSetDevice(spx_internal_device(m->ctx));
+    DeviceGuard dev_guard_(spx_internal_device(m->ctx));
     cudaFree(m->d_w); cudaFree(m->d_bnd); cudaFree(m->d_start); cudaFree(m->d_count); cudaFree(m->d_plane_w); cudaFree(m->d_angle);
     cudaFree(m->d_dist); cudaFree(m->d_res_f); cudaFree(m->d_res_i); cudaFree(m->d_stage); cudaFree(m->d_err);
     cudaFreeHost(m->h_plane_w); cudaFreeHost(m->h_res_f); cudaFreeHost(m->h_res_i);
@@ -550,7 +551,7 @@ int spx_map_upload(spx_map *m, const float *map_w, const spx_point *boundary, co
     spx_ctx *c = m->ctx;
     if (n_map < 0 || n_seen < 0 || n_seen > n_map || (n_map > 0 && (!map_w || !boundary_off)))
         return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_upload", "bad argument");
-    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    DeviceGuard dev_guard_(spx_internal_device(c)); NX_CK(c, dev_guard_.err);
     cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
     const long long n_pts = n_map ? boundary_off[n_map] - boundary_off[0] : 0;
     if (n_pts > 0 && !boundary) return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_upload", "null boundary cloud");
@@ -606,7 +607,7 @@ int spx_map_set_world_pos(spx_map *m, int j, const float coef_w[4]) {
     if (!m) return SPX_ERR_ARG;
     spx_ctx *c = m->ctx;
     if (j < 0 || j >= m->n_map || !coef_w) return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_set_world_pos", "bad argument");
-    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    DeviceGuard dev_guard_(spx_internal_device(c)); NX_CK(c, dev_guard_.err);
     cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
     NX_CK(c, cudaMemcpyAsync(m->d_w + 4 * j, coef_w, 4 * sizeof(float), cudaMemcpyHostToDevice, st));
     NX_CK(c, cudaStreamSynchronize(st));
@@ -617,7 +618,7 @@ int spx_map_update_boundary(spx_map *m, int j, const double transform[16], const
     if (!m) return SPX_ERR_ARG;
     spx_ctx *c = m->ctx;
     if (j < 0 || j >= m->n_map || !transform || n < 0 || (n > 0 && !cloud)) return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_update_boundary", "bad argument");
-    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    DeviceGuard dev_guard_(spx_internal_device(c)); NX_CK(c, dev_guard_.err);
     cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
     if (size_t(n) > m->cap_stage) {
         NX_CK(c, cudaStreamSynchronize(st));
@@ -637,7 +638,7 @@ int spx_map_update_boundary_from_result(spx_map *m, int j, const double transfor
     const int n_frames = spx_internal_last_results(c, &frames, &planes, &bnd);
     if (j < 0 || j >= m->n_map || !transform || n_boundary < 0 || plane < 0 || frame < 0 || frame >= n_frames)
         return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_update_boundary_from_result", "bad argument (or no extract yet)");
-    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    DeviceGuard dev_guard_(spx_internal_device(c)); NX_CK(c, dev_guard_.err);
     return map_update(m, j, transform, bnd, frames, planes, frame, plane, n_boundary);
 }
 
@@ -647,7 +648,7 @@ int spx_map_get_boundary(spx_map *m, int j, spx_point *out, int cap, int *n) {
     if (j < 0 || j >= m->n_map || !n) return spx_internal_fail(c, SPX_ERR_ARG, "spx_map_get_boundary", "bad argument");
     *n = m->count[size_t(j)];
     if (!out) return SPX_OK;
-    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    DeviceGuard dev_guard_(spx_internal_device(c)); NX_CK(c, dev_guard_.err);
     cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
     const int k = *n < cap ? *n : cap;
     if (k > 0) NX_CK(c, cudaMemcpyAsync(out, m->d_bnd + m->start[size_t(j)], size_t(k) * sizeof(spx_point), cudaMemcpyDeviceToHost, st));
@@ -666,7 +667,7 @@ int spx_map_associate(spx_map *m, const float *plane_w, int n_planes, float dis_
         for (int i = 0; i < n_planes; ++i) { assoc[i] = vertical[i] = parallel[i] = -1; if (assoc_dist) assoc_dist[i] = dis_th; }
         return SPX_OK;
     }
-    NX_CK(c, cudaSetDevice(spx_internal_device(c)));
+    DeviceGuard dev_guard_(spx_internal_device(c)); NX_CK(c, dev_guard_.err);
     cudaStream_t st = static_cast<cudaStream_t>(spx_internal_stream(c));
     std::memcpy(m->h_plane_w, plane_w, size_t(n_planes) * 4 * sizeof(float));
     NX_CK(c, cudaMemcpyAsync(m->d_plane_w, m->h_plane_w, size_t(n_planes) * 4 * sizeof(float), cudaMemcpyHostToDevice, st));

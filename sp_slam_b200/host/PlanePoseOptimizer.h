@@ -228,6 +228,7 @@ public:
     std::vector<PlaneEdge> edges;
     ExtraTerms extra = nullptr;
     void *extra_user = nullptr;
+    int extra_edges = 0;      // how many graph edges the extra-terms hook stands for (the caller's ORB point edges)
     int iterations_run = 0;
     double final_chi2 = 0;
 
@@ -245,11 +246,12 @@ public:
             nBad = 0;
             for (PlaneEdge &e : edges) {
                 if (e.outlier) e.compute_error(pose);
-                if (e.chi2() > e.chi2_max) { e.outlier = true; e.level = 1; ++nBad; }
+                const float chi2 = float(e.chi2());          // `const float chi2 = e->chi2();` (src/Optimizer.cc:1003): truncated before the test
+                if (double(chi2) > e.chi2_max) { e.outlier = true; e.level = 1; ++nBad; }
                 else { e.outlier = false; e.level = 0; }
                 if (it == 2) e.robust = false;
             }
-            if (edges.size() < 10 && !extra) break;          // `if(optimizer.edges().size()<10) break;`
+            if (edges.size() + size_t(extra_edges) < 10) break;   // `if(optimizer.edges().size()<10) break;` counts ALL edges of the graph
         }
         pose.to_matrix(Tcw);
         return nBad;

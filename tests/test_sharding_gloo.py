@@ -58,6 +58,26 @@ def _worker(rank, world, port, n_frames, q):
         eh, ep = _fake_results(k, n_frames)
         got = np.frombuffer(planes[k].numpy().tobytes(), dtype=api.PLANE_DTYPE)[: int(counts[k, 0])]
         ok &= np.array_equal(np.frombuffer(hdrs[k].numpy().tobytes(), dtype=api.HEADER_DTYPE), eh) and np.array_equal(got, ep)
+    # ragged shards (shard_range on a sequence the world size does not divide): per-rank frame counts travel with the
+    # plane counts, headers are padded to frames_cap for the collective
+    total = 2 * n_frames - 1
+    lo, hi = sharding.shard_range(total, rank, world)
+    cap_fr = -(-total // world)
+    rh, rp = _fake_results(rank, hi - lo)
+    rbuf = np.zeros(cap, api.PLANE_DTYPE)
+    rbuf[: len(rp)] = rp
+    out = sharding.gather_records(torch.from_numpy(rh.view(np.uint8).copy()), torch.from_numpy(rbuf.view(np.uint8).copy()),
+                                  torch.tensor([len(rp), 0, 0], dtype=torch.int64), to_host=True, n_frames=hi - lo, frames_cap=cap_fr)
+    for k in range(world):
+        a, b = sharding.shard_range(total, k, world)
+        eh, ep = _fake_results(k, b - a)
+        ok &= len(out[k][0]) == b - a and np.array_equal(out[k][0], eh) and np.array_equal(out[k][1], ep)
+    try:     # a rank that owns more frames than the stated bound is an error, not a hang
+        sharding.gather_records(torch.from_numpy(rh.view(np.uint8).copy()), torch.from_numpy(rbuf.view(np.uint8).copy()),
+                                torch.tensor([len(rp), 0, 0], dtype=torch.int64), to_host=True, n_frames=hi - lo, frames_cap=hi - lo - 1)
+        ok = False
+    except ValueError:
+        pass
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
