@@ -53,6 +53,8 @@ def algorithmic_bytes_per_frame(rows=ROWS, cols=COLS, dis=3):
     k = {
         "k_edge_chamfer": n * 4 + n * 1,                 # one depth sample per organized pixel in, window size out
         "k_normals_link": n * 4 + n * 1 + n * 12 + n * 9, # depth sample + window size in; x y z, link bits, forest, counts out
+        "k_normals_strip": n * 4 + n * 1 + n * 12 + n * 9,  # the same stage as a strip kernel (TMA-staged depth chunks)
+        "k_normals_link_list": 0,                        # frames with NaN / Inf depth only: empty on sensor data
         "k_ccl_merge": n * 1 + n * 4,                    # link bits in, forest touched
         "k_ccl_merge4": n * 1 + n * 4,                   # (the four-pixels-per-thread variant of the same pass)
         "k_ccl_flatten": n * 4 + n * 4 + n * 4,          # forest in/out, counts
@@ -336,6 +338,9 @@ def _main(out):
     import torch.distributed as dist
 
     from sp_slam_b200 import api
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle
+        pyoracle.use_native()      # before anything loads the portable build: the CPU legs run the oracle built for this host
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")

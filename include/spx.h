@@ -34,7 +34,11 @@ enum {
 
 enum {
     SPX_FRAME_OVERFLOW = 1u,    /* a per-frame capacity above was exceeded; the frame's plane list is truncated */
-    SPX_FRAME_NONFINITE = 2u    /* the depth image held NaN / Inf samples (such points stay unlabelled, as in PCL) */
+    SPX_FRAME_NONFINITE = 2u,   /* the depth image held NaN / Inf samples (such points stay unlabelled, as in PCL) */
+    SPX_FRAME_SAT_UNPROVEN = 4u /* PCL's double-precision integral images could not be PROVEN free of rounding for this frame
+                                   (depth values spanning more than ~2^28 in magnitude): the normals may then differ from PCL's
+                                   in the last bit, because PCL's own result depends on its summation order.  Never set on the
+                                   3 200 frames of the bench workloads (profiles/r2_sat_exact_sweep.json). */
 };
 
 /* Thresholds the reference reads from YAML through Config::Get (Examples/RGB-D/TUM1.yaml:73-78,99-100), the Frame

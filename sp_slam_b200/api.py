@@ -26,6 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libspx.so")
 SPX_OK, SPX_ERR_ARG, SPX_ERR_CUDA, SPX_ERR_STATE = 0, 1, 2, 3
 SPX_FRAME_OVERFLOW = 1
 SPX_FRAME_NONFINITE = 2
+SPX_FRAME_SAT_UNPROVEN = 4
 SPX_MAX_CAND, SPX_MAX_MODELS, SPX_MAX_PLANES, SPX_MAX_LINES = 96, 64, 128, 4
 
 POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgba", "<u4")])
@@ -412,7 +413,7 @@ class PlaneExtractor:
         """fn(frame0, frame1, CompactResult view) as soon as a frame group of a compact host-input call is on the host; None = off."""
         if fn is None:
             self._cb = None
-            self._ck(lib().spx_set_group_callback(self._h, None, None))
+            self._ck(lib().spx_set_group_callback(self._h, GROUP_FN(), None))   # a NULL function pointer
             return
         self._cb = GROUP_FN(lambda user, f0, f1, view: fn(f0, f1, CompactResult(view.contents, copy=True)))
         self._ck(lib().spx_set_group_callback(self._h, self._cb, None))

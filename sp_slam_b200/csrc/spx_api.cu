@@ -22,6 +22,7 @@
 #include "spx_internal.h"
 #include "spx_lines.cuh"
 #include "spx_normals.cuh"
+#include "spx_normals_strip.cuh"
 #include "spx_refine.cuh"
 #include "spx_segment.cuh"
 
@@ -59,6 +60,16 @@ struct spx_ctx {
     // frame groups: internal streams + per group events (start, end of the plane section, end of the supposed-plane section)
     int n_streams = 1, min_group = 32, last_groups = 1;
     int refine_fast_max = 700;  // batches of at most this many frames use k_refine2
+    // K3: 2 = strip kernel with TMA-staged depth chunks (production), 1 = strip kernel with plain loads (also what a depth
+    // pointer / pitch that TMA cannot describe gets), 0 = the 32x16 tile kernel of round 1 (test knob SPX_NORMALS)
+    int normals_mode = 2;
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeTiledFn encode_tiled = nullptr;      // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (libcuda is not linked)
+    CUtensorMap tmap;                          // the depth batch of the current call as a (columns, sampled rows, frames) tensor
+    bool tmap_ok = false;
+    int list_grid = 148 * 2;
     bool ccl_four = true;      // k_ccl_merge4 (N % 4 == 0) instead of the one-pixel-per-thread k_ccl_merge
     bool flatten_runs = true;  // k_ccl_flatten_runs (one pointer chase per row run) instead of k_ccl_flatten (one per pixel)
     bool refine_per_group = true;
@@ -255,6 +266,7 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     Buffers B = c->B;
     B.work = c->B.work + size_t(g) * c->work_stride;
     B.work2 = c->B.work2 + size_t(g) * c->work2_stride;
+    B.nf_list = c->B.nf_list + size_t(g) * size_t(1 + c->cfg.max_frames);
     const int F = ng, N = P.N;
     const dim3 gpix(cdiv(N, 256), F);
     int &L = c->launches;
@@ -320,6 +332,7 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     SPX_CK(c, cudaMemsetAsync(B.ctl + f0, 0, sizeof(FrameCtl) * size_t(F), st));
     SPX_CK(c, cudaMemsetAsync(B.work, 0, 2 * sizeof(int), st));
     SPX_CK(c, cudaMemsetAsync(B.work2, 0, 2 * sizeof(int), st));
+    SPX_CK(c, cudaMemsetAsync(B.nf_list, 0, sizeof(int), st));
     if (src.sparse && P.enable_supposed) {
         const size_t words = size_t(P.rows) * size_t(((P.cols + 7) / 8 + 31) / 32);
         SPX_CK(c, cudaMemsetAsync(B.fetch_bits + words * size_t(f0), 0, words * sizeof(unsigned) * size_t(F), st));
@@ -332,7 +345,15 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
         if (nch <= 7) LAUNCH(k_edge_chamfer<7>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
         else if (nch <= 14) LAUNCH(k_edge_chamfer<14>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
         else LAUNCH(k_edge_chamfer<16>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
-        LAUNCH(k_normals_link, dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), kNormThreads, kNormalsSmem, depth_dev, P, B, dbg);
+        if (c->normals_mode == 0) {
+            LAUNCH(k_normals_link, dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), kNormThreads, kNormalsSmem, depth_dev, P, B, dbg);
+        } else {
+            const dim3 sgrid(cdiv(P.w, kStW), F);
+            if (c->tmap_ok) LAUNCH(k_normals_strip<true>, sgrid, kSThreads, strip_smem_bytes(P.dis, true), c->tmap, depth_dev, P, B, dbg);
+            else LAUNCH(k_normals_strip<false>, sgrid, kSThreads, strip_smem_bytes(P.dis, false), c->tmap, depth_dev, P, B, dbg);
+            // frames with NaN / Inf depth (queued by k_edge_chamfer; none on sensor data: the CTAs leave at once)
+            LAUNCH(k_normals_link_list, std::min(c->list_grid, F * cdiv(P.w, kTW) * cdiv(P.h, kTH)), kNormThreads, kNormalsSmem, depth_dev, P, B, dbg);
+        }
     } else {
         LAUNCH(k_backproject, gpix, 256, 0, depth_dev, P, B);
         LAUNCH(k_plane_d, gpix, 256, 0, P, B);
@@ -436,6 +457,21 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, boo
     c->P.idx16 = c->P.N <= 65536 ? 1 : 0;
     for (void *p : c->graveyard) cudaFreeHost(p);
     c->graveyard.clear();
+    // the depth batch as a 3-d tensor for the strip kernel's TMA loads: (image columns, SAMPLED rows, frames) -- the row stride
+    // is Cloud.Dis image rows, so only the rows the organized cloud samples are ever touched
+    c->tmap_ok = false;
+    if (!normals_given && c->normals_mode == 2 && c->encode_tiled && strip_tma_ok(c->P.dis) && reinterpret_cast<uintptr_t>(depth_dev) % 16 == 0 &&
+        c->P.samp_rstep % 16 == 0 && (c->P.n_frames == 1 || c->P.samp_fstride % 16 == 0)) {
+        const Params &Q = c->P;
+        const cuuint64_t gdim[3] = {cuuint64_t(Q.cols), cuuint64_t(Q.h), cuuint64_t(Q.n_frames)};
+        const cuuint64_t gstr[2] = {cuuint64_t(Q.samp_rstep), cuuint64_t(Q.n_frames == 1 ? Q.samp_rstep * size_t(Q.h) : Q.samp_fstride)};
+        const cuuint32_t box[3] = {cuuint32_t(kSCW * Q.dis), cuuint32_t(kSB), 1u};
+        const cuuint32_t es[3] = {1u, 1u, 1u};
+        const CUresult r = c->encode_tiled(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(depth_dev), gdim, gstr, box, es,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        c->tmap_ok = r == CUDA_SUCCESS;
+    }
     const int F = c->P.n_frames;
     c->P.frame0 = 0;
     c->launches = 0;
@@ -816,6 +852,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (const char *e = std::getenv("SPX_LINES_GLOBAL")) c->P.lines_in_global = std::atoi(e) != 0 ? 1 : 0;   // test knob
     if (const char *e = std::getenv("SPX_UPLOAD")) c->upload_mode = std::atoi(e);   // test / tuning knob (see spx_ctx::upload_mode)
     if (const char *e = std::getenv("SPX_SPARSE_MIN_FRAMES")) c->sparse_min_frames = std::atoi(e);   // tuning knob
+    if (const char *e = std::getenv("SPX_NORMALS")) { const int v = std::atoi(e); if (v >= 0 && v <= 2) c->normals_mode = v; }   // test knob
     if (const char *e = std::getenv("SPX_CCL_FOUR")) c->ccl_four = std::atoi(e) != 0;   // test knob: the one-pixel-per-thread kernel
     if (const char *e = std::getenv("SPX_FLATTEN_RUNS")) c->flatten_runs = std::atoi(e) != 0;   // test knob
     if (const char *e = std::getenv("SPX_REFINE_PER_GROUP")) c->refine_per_group = std::atoi(e) != 0;   // tuning knob
@@ -875,6 +912,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     total += padded<int16_t>(FN) + 2 * padded<int8_t>(FN + 16 * F);     // root_model pid pid_bak
     total += 3 * padded<int>(FC) + padded<float4>(FC) + padded<spx_point>(FC) + padded<int>(c->n_streams * (2 + F * SPX_MAX_MODELS)) + padded<int>(c->n_streams * (2 + F * SPX_MAX_MODELS * SPX_MAX_LINES));
     total += padded<FrameCtl>(F);
+    total += padded<int>(size_t(c->n_streams) * (1 + F));   // nf_list
     const size_t fetch_words = F * size_t(cfg->max_rows) * size_t(((cfg->max_cols + 7) / 8 + 31) / 32);
     total += padded<unsigned>(fetch_words);
     total += padded<spx_frame_header>(F) + padded<spx_plane>(F * SPX_MAX_PLANES);
@@ -895,6 +933,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     B.line_a = A.take<float4>(FC); B.line_pts = A.take<spx_point>(FC); c->work_stride = 2 + F * SPX_MAX_MODELS; c->work2_stride = 2 + F * SPX_MAX_MODELS * SPX_MAX_LINES;
     B.work = A.take<int>(c->n_streams * c->work_stride); B.work2 = A.take<int>(c->n_streams * c->work2_stride);
     B.ctl = A.take<FrameCtl>(F);
+    B.nf_list = A.take<int>(size_t(c->n_streams) * (1 + F));
     B.fetch_bits = A.take<unsigned>(fetch_words);
     B.out_frames = A.take<spx_frame_header>(F); B.out_planes = A.take<spx_plane>(F * SPX_MAX_PLANES);
     B.out_pts = A.take<spx_point>(F * size_t(P.pts_cap)); B.out_bnd = A.take<spx_point>(F * size_t(P.bnd_cap));
@@ -925,6 +964,33 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     }
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_grid, grid, sizeof(grid)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_link, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kNormalsSmem)));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_link_list, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kNormalsSmem)));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_strip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(strip_smem_bytes(P.dis, strip_tma_ok(P.dis)))));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_strip<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(strip_smem_bytes(P.dis, false))));
+    c->list_grid = prop.multiProcessorCount * 2;
+    {
+        // cuTensorMapEncodeTiled without linking libcuda
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            c->encode_tiled = reinterpret_cast<spx_ctx::EncodeTiledFn>(fn);
+        else
+            cudaGetLastError();
+        // the strip kernel divides by the constants fx, fy with a reciprocal and one fused correction: verified here against
+        // the IEEE quotient for every significand, per constant; a constant that fails keeps the true division
+        P.rfx = 1.0f / P.fx; P.rfy = 1.0f / P.fy; P.fast_div = 0;
+        int *d_mis = nullptr, h_mis[2] = {1, 1};
+        SPX_CK_CREATE(cudaMalloc(reinterpret_cast<void **>(&d_mis), 2 * sizeof(int)));
+        cudaMemset(d_mis, 0, 2 * sizeof(int));
+        if (std::isfinite(P.rfx) && P.fx != 0.0f) k_check_div<<<(1u << 23) / 256, 256>>>(P.fx, P.rfx, d_mis); else h_mis[0] = -1;
+        if (std::isfinite(P.rfy) && P.fy != 0.0f) k_check_div<<<(1u << 23) / 256, 256>>>(P.fy, P.rfy, d_mis + 1); else h_mis[1] = -1;
+        int got[2] = {1, 1};
+        const cudaError_t ce = cudaMemcpy(got, d_mis, sizeof(got), cudaMemcpyDeviceToHost);
+        cudaFree(d_mis);
+        if (ce != cudaSuccess) { fail(nullptr, SPX_ERR_CUDA, "division check: %s", cudaGetErrorString(ce)); spx_destroy(c); return SPX_ERR_CUDA; }
+        if (h_mis[0] >= 0 && got[0] == 0) P.fast_div |= 1;
+        if (h_mis[1] >= 0 && got[1] == 0) P.fast_div |= 2;
+    }
     SPX_CK_CREATE(cudaFuncSetAttribute(k_edge_chamfer<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_edge_chamfer<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     SPX_CK_CREATE(cudaHostAlloc(reinterpret_cast<void **>(&c->h_totals), 8 * size_t(c->n_streams + 1) * sizeof(long long), cudaHostAllocMapped));

@@ -118,6 +118,34 @@ SPX_HD void eigen33_largest_vec(const float mat[9], float vec[3]) {
     eigvec_from_shifted(S, evals[2] / scale, vec);
 }
 
+#ifdef __CUDACC__
+// (n0, n1, n2) / sqrt(len) rounded to float -- the bits of `float(n_i / sqrt(len))` evaluated in IEEE double (Eigen's
+// `normal_vector /= sqrt(length)` followed by the cast in computePointNormal) -- without the three double divisions.
+// q_i = RN(n_i * rsqrt(len)) with rsqrt good to 1 ulp; the reference t_i = RN(n_i / RN(sqrt(len))) then differs from q_i by
+// at most 2^-52 + 3 * 2^-53 relative, i.e. less than 5 units in the last place of a double.  A float keeps 23 of the 52
+// fraction bits: q_i and t_i round to the same float unless the 29 dropped bits of q_i lie within 8 units of the tie pattern
+// 0x10000000 (probability 2^-24 per component), in which case -- like for results a float would hold as a subnormal, and for
+// a len outside the comfortable range -- the exact sequence is evaluated.
+__device__ __forceinline__ void normalize_to_float(double n0, double n1, double n2, double len, float &x, float &y, float &z) {
+    bool exact_path = !(len > 1.0e-280 && len < 1.0e280);
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+    if (!exact_path) {
+        const double r = rsqrt(len);
+        q0 = n0 * r; q1 = n1 * r; q2 = n2 * r;
+        auto risky = [](double q) -> bool {
+            const unsigned lo = unsigned(__double2loint(q)) & 0x1fffffffu;
+            return (lo - 0x0ffffff8u) <= 16u || (fabs(q) < 1.0e-30 && q != 0.0);
+        };
+        exact_path = risky(q0) || risky(q1) || risky(q2);
+    }
+    if (exact_path) {
+        const double sl = sqrt(len);
+        q0 = n0 / sl; q1 = n1 / sl; q2 = n2 / sl;
+    }
+    x = float(q0); y = float(q1); z = float(q2);
+}
+#endif
+
 SPX_HD uint32_t pack_rgba(uint32_t r, uint32_t g, uint32_t b, uint32_t a = 255u) {
     return (a << 24) | (r << 16) | (g << 8) | b;
 }

@@ -133,12 +133,14 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_edge_chamfer(const float
         };
         auto thr = [&](float z) -> float { return (P.mdcf * (fabsf(z) + 1.0f)) * 2.0f; };
         load_row(ra - 1, zU); load_row(ra, zC); load_row(ra + 1, zD);
+        bool nonfinite = false;
         for (int r = ra; r < rb; ++r) {
             load_row(r + 2, zN);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int c = ch * 32 + lane;
                 const float z = zC[ch];
+                if (c < w && !isfinite(z)) nonfinite = true;
                 float zR = __shfl_down_sync(SPX_FULL, z, 1), zL = __shfl_up_sync(SPX_FULL, z, 1);
                 if (ch + 1 < NCH) { const float t = __shfl_sync(SPX_FULL, zC[ch + 1 < NCH ? ch + 1 : ch], 0); if (lane == 31) zR = t; }
                 if (ch >= 1) { const float t = __shfl_sync(SPX_FULL, zC[ch >= 1 ? ch - 1 : ch], 31); if (lane == 0) zL = t; }
@@ -161,6 +163,12 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_edge_chamfer(const float
             }
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) { zU[ch] = zC[ch]; zC[ch] = zD[ch]; zD[ch] = zN[ch]; }
+        }
+        // a frame with NaN / Inf depth is flagged and queued for k_normals_link_list (finite-count integral images); the strip
+        // kernel skips it
+        if (__any_sync(SPX_FULL, nonfinite) && lane == 0) {
+            const unsigned old = atomicOr(&B.ctl[f].flags, unsigned(SPX_FRAME_NONFINITE));
+            if (!(old & unsigned(SPX_FRAME_NONFINITE))) B.nf_list[1 + atomicAdd(&B.nf_list[0], 1)] = f;
         }
     }
     __syncwarp();
@@ -271,7 +279,7 @@ constexpr int kNormThreads = 288;                // 9 warps: the 33 x 17 = 561 n
 constexpr size_t kNormalsSmem = size_t(3) * kSH * kSATStride * sizeof(double) + size_t(3) * kCHt * kCStride * sizeof(float) +
                                 size_t(kSH) * kSATStride * sizeof(int);
 
-__global__ void __launch_bounds__(kNormThreads) k_normals_link(const float *__restrict__ depth, Params P, Buffers B, int write_normals) {
+__device__ __forceinline__ void normals_tile(const float *__restrict__ depth, const Params &P, const Buffers &B, int write_normals, int f, int tc, int tr) {
     extern __shared__ double sm_d[];
     double *S = sm_d;                                                    // [3][kSH][kSATStride]: DX, then DY
     float *C = reinterpret_cast<float *>(S + 3 * kSH * kSATStride);      // [3][kCHt][kCStride]
@@ -279,8 +287,6 @@ __global__ void __launch_bounds__(kNormThreads) k_normals_link(const float *__re
     float *Nrm = reinterpret_cast<float *>(S);                           // [4][kNH][kNStride], aliases S after step 3
     constexpr int cs = kSH * kSATStride;          // channel stride of S
     constexpr int ccs = kCHt * kCStride;          // channel stride of C
-    const int f = P.frame0 + blockIdx.z;
-    const int tc = blockIdx.x * kTW, tr = blockIdx.y * kTH;
     const int w = P.w, h = P.h;
     const size_t fo = size_t(f) * P.N;
     const int tid = threadIdx.x;
@@ -544,6 +550,24 @@ __global__ void __launch_bounds__(kNormThreads) k_normals_link(const float *__re
         const unsigned starts = ~linked | 1u;                       // lane 0 always starts a run inside the segment
         const int s0 = 31 - __clz(starts & (SPX_FULL >> (31 - lane)));
         if (valid) B.parent[fo + q] = r * w + tc + s0;
+    }
+}
+
+// one CTA per tile of every frame of the group (test knob SPX_NORMALS=0; the strip kernel is the production path)
+__global__ void __launch_bounds__(kNormThreads) k_normals_link(const float *__restrict__ depth, Params P, Buffers B, int write_normals) {
+    normals_tile(depth, P, B, write_normals, P.frame0 + blockIdx.z, blockIdx.x * kTW, blockIdx.y * kTH);
+}
+
+// the frames k_edge_chamfer queued because their depth holds NaN / Inf: a few persistent CTAs walk (frame, tile) items; with
+// an empty queue -- every frame of a real sensor -- they leave at once
+__global__ void __launch_bounds__(kNormThreads) k_normals_link_list(const float *__restrict__ depth, Params P, Buffers B, int write_normals) {
+    const int n = B.nf_list[0];
+    if (n == 0) return;
+    const int tx = (P.w + kTW - 1) / kTW, ty = (P.h + kTH - 1) / kTH;
+    for (int item = blockIdx.x; item < n * tx * ty; item += gridDim.x) {
+        const int fi = item / (tx * ty), t = item - fi * (tx * ty);
+        normals_tile(depth, P, B, write_normals, B.nf_list[1 + fi], (t % tx) * kTW, (t / tx) * kTH);
+        __syncthreads();
     }
 }
 

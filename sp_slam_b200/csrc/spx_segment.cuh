@@ -585,6 +585,17 @@ __global__ void __launch_bounds__(128) k_models(Params P, Buffers B) {
         }
     }
     ctl.n_models = nm;
+    // were PCL's double-precision integral images provably free of rounding on this frame?  Every partial sum of channel ch is
+    // an integer multiple of 2^-negexp[axis] and smaller than sat_sum[ch] < 2^e, i.e. an integer below 2^(e + negexp) in units of
+    // 2^-negexp: a double holds it exactly when e + negexp <= 53
+    for (int ch = 0; ch < 6; ++ch) {
+        const float s = ctl.sat_sum[ch];
+        if (s > 0.0f) {
+            int e = 0;
+            frexpf(s * 1.001f, &e);
+            if (e + ctl.sat_negexp[ch % 3] > 53) ctl.flags |= unsigned(SPX_FRAME_SAT_UNPROVEN);
+        }
+    }
 }
 
 // K5c: plane id per pixel = model of its component (or -1)

@@ -29,6 +29,8 @@ struct Params {
     // organized cloud (src/Frame.cc:856-874)
     int dis, w, h, N;
     float fx, fy, cx, cy;
+    float rfx, rfy;        // RN(1 / fx), RN(1 / fy) for the strip kernel's division by a constant
+    int   fast_div;        // bit 0 / 1: that division was verified against the IEEE quotient for fx / fy (k_check_div)
     float min_x, max_x, min_y, max_y;
     float mdcf;            // max depth change factor
     int   min_size;
@@ -101,7 +103,11 @@ struct FrameCtl {
     int pts_used, bnd_used;   // points / boundary points of the REAL planes (set by k_postfilter)
     int pts_sup, bnd_sup;     // ... of the supposed planes (set by k_supposed)
     int n_lines;
-    int pad[1];
+    // exactness bound of the integral images (k_normals_strip; evaluated by k_models): per axis x y z the max over the cloud's
+    // non-zero coordinates of -(exponent of their unit in the last place), per gradient channel the sum of |central differences|
+    int sat_negexp[3];
+    float sat_sum[6];
+    int pad[2];
     Cand     cand[SPX_MAX_CAND];
     Model    models[SPX_MAX_MODELS];
     PlaneRec planes[SPX_MAX_PLANES];
@@ -132,6 +138,7 @@ struct Buffers {
     int   *line_inl;              // inlier index scratch (contour_cap per frame)
     spx_point *line_pts;          // accepted line inlier points (contour_cap per frame)
     FrameCtl *ctl;
+    int *nf_list;                 // frames of a group whose depth holds NaN / Inf ([0] = count, then frame indices): they take k_normals_link_list
     unsigned *fetch_bits;         // sparse upload: claimed 8-pixel sectors, rows x ceil(ceil(cols/8)/32) words per frame
     // compacted outputs.  The point / boundary arenas hold the clouds of all REAL planes first and those of all supposed
     // planes behind them, so the real part can be packed while the line fits still run.  frame_offs[5f + k]: k = 0 plane

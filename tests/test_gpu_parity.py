@@ -577,3 +577,76 @@ def test_sparse_upload_without_supposed_planes(seq):
         for p, q in zip(a.mvPlanePoints, b.mvPlanePoints):
             assert np.array_equal(p, q)
     full.close(); e.close()
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_normals_kernel_variants(seq, oracle_lib, mode):
+    """K3 three ways -- the 32x16 tile kernel of round 1 (0), the strip kernel with plain loads (1, also what a depth pointer TMA
+    cannot describe gets) and with TMA-staged depth chunks (2, production) -- each bit-exact against the oracle, clean and noisy,
+    480p and 720p (14 strips, 30 batches), one frame and a batch."""
+    e = extractor_with_env({"SPX_NORMALS": mode}, debug=True, max_frames=8)
+    for k in (0, 2, 5, 7):
+        d = seq[k] if k != 5 else scenes.add_noise(seq[k], FRAMES[k])
+        fp = e.extract(d)
+        orc = oracle_lib.Oracle().run(d)
+        rep = compare_frame(e, orc, d, fp)
+        assert rep["normals_bit_exact"] and rep["labels_bit_exact"], rep
+    res = e.extract_batch(seq)                      # several frames in one launch (grid.y = frame)
+    for k in (1, 6):
+        orc = oracle_lib.Oracle().run(seq[k])
+        compare_frame(e, orc, seq[k], res.frame(k), frame=k)
+    e.close()
+    it = scenes.REALSENSE
+    big = scenes.add_noise(scenes.realsense_sequence(1, start=40)[0], 40, "realsense")
+    e = extractor_with_env({"SPX_NORMALS": mode}, debug=True, max_rows=720, max_cols=1280, fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy,
+                           max_x=float(it.width), max_y=float(it.height))
+    fp = e.extract(big)
+    orc = oracle_lib.Oracle(fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy, max_x=float(it.width), max_y=float(it.height)).run(big)
+    rep = compare_frame(e, orc, big, fp)
+    assert rep["normals_bit_exact"] and rep["labels_bit_exact"], rep
+    e.close()
+
+
+def test_strip_kernel_odd_sizes_and_unaligned_views(oracle_lib):
+    """image sizes whose organized cloud is not a multiple of the strip width / batch height, a device view TMA cannot describe
+    (row pitch not a multiple of 16 bytes: plain-load variant), negative fy (ICL.yaml)"""
+    import torch
+    big = scenes.render(scenes.boxroom_rects(), scenes.poses(1000)[[200]], scenes.TUM1)[0]
+    for rows, cols in ((401, 500), (250, 333), (97, 130)):
+        small = np.ascontiguousarray(big[:rows, :cols])
+        e = api.PlaneExtractor(debug=True, max_rows=rows, max_cols=cols, max_x=float(cols), max_y=float(rows), min_size=200)
+        fp = e.extract(small)
+        orc = oracle_lib.Oracle(max_x=float(cols), max_y=float(rows), min_size=200).run(small)
+        rep = compare_frame(e, orc, small, fp)
+        assert rep["normals_bit_exact"] and rep["labels_bit_exact"], (rows, cols, rep)
+        e.close()
+    # device-resident view with a pitch of 641 floats
+    padded = torch.zeros((2, 480, 641), dtype=torch.float32, device="cuda")
+    padded[:, :, :640] = torch.from_numpy(np.stack([big, big[::-1].copy()]))
+    e = api.PlaneExtractor(debug=True, max_frames=2)
+    e.extract_device(padded.data_ptr(), 2, 480, 640, pitch=641 * 4, frame_stride=480 * 641 * 4)
+    res = e.fetch()
+    orc = oracle_lib.Oracle().run(big)
+    compare_frame(e, orc, big, res.frame(0), frame=0)
+    e.close()
+    # negative fy: the y axis flips, every division by fy changes sign
+    e = api.PlaneExtractor(debug=True, fy=-516.469215)
+    fp = e.extract(big)
+    orc = oracle_lib.Oracle(fy=-516.469215).run(big)
+    rep = compare_frame(e, orc, big, fp)
+    assert rep["normals_bit_exact"], rep
+    e.close()
+
+
+def test_sat_unproven_flag(oracle_lib, seq):
+    """A frame whose depth spans ~2^30 in magnitude cannot be proven free of rounding in PCL's double integral images: the
+    library says so (SPX_FRAME_SAT_UNPROVEN) instead of promising bit-identical normals; ordinary frames never carry the flag."""
+    e = api.PlaneExtractor(max_frames=2)
+    d = seq[2].copy()
+    assert not (e.extract(d).flags & api.SPX_FRAME_SAT_UNPROVEN)
+    d[200:203, 300:340] = 1.0e-7          # a few absurdly small (but positive, finite) depths next to metres
+    d[30, 30] = 3.0e4
+    fp = e.extract(d)
+    assert fp.flags & api.SPX_FRAME_SAT_UNPROVEN
+    assert fp.mnRealPlaneNum >= 1          # the frame is still processed
+    e.close()
