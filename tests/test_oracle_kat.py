@@ -34,6 +34,37 @@ def test_chamfer_row_wraparound(oracle_lib):
     m[4, 0] = 0
     d = oracle_lib.chamfer(m)
     assert float(d[4, 29]) == float(np.float32(1.4))
+    # the alternative reading (no aliasing across the row end) is a live switch of the oracle: the same pixel is then far away
+    assert float(oracle_lib.chamfer(m, alt=oracle_lib.ALT_CHAMFER_NO_WRAP)[4, 29]) > 10.0
+
+
+def test_alternative_readings_of_the_line_fit(oracle_lib):
+    # ORC_ALT_SAMPLE_GOOD_OR / ORC_ALT_RNG_MASK: isSampleGood with && rejects a pair that shares one
+    # coordinate, so on points of a line with constant z the default reading finds no sample at all; || accepts them
+    t = np.linspace(0.0, 1.0, 200).astype(np.float32)
+    pts = np.zeros(200, oracle_lib.POINT_DTYPE)
+    pts["x"], pts["y"], pts["z"] = t, 2.0 * t, 1.5
+    coef, inl, it = oracle_lib.sac_line(pts)
+    assert len(inl) == 0                                         # PCL 1.8.0: "no samples could be selected"
+    coef, inl, it = oracle_lib.sac_line(pts, alt=oracle_lib.ALT_SAMPLE_GOOD_OR)
+    assert len(inl) == 200 and abs(abs(coef[3] / coef[4]) - 0.5) < 1e-5
+    # the two RNG readings draw different samples (mt() >> 1 against mt() & INT_MAX) but fit the same line here
+    rng = np.random.default_rng(3)
+    pts["z"] = 1.5 + 0.3 * t + rng.normal(0, 1e-4, 200).astype(np.float32)
+    a = oracle_lib.sac_line(pts)
+    b = oracle_lib.sac_line(pts, alt=oracle_lib.ALT_RNG_MASK)
+    assert len(a[1]) > 150 and len(b[1]) > 150
+
+
+def test_is_border_point_without_a_finite_projection(oracle_lib):
+    # a line point at depth 0 projects to u = fx * 0 * inf + cx = NaN: the reference's window loops never run, res / num is
+    # NaN, `PcZ - NaN > 0.1` is false and IsBorderPoint returns TRUE (src/Frame.cc:1026-1056); a finite point far behind the
+    # depth image is not a border point
+    depth = np.full((480, 640), 2.0, np.float32)
+    assert oracle_lib.is_border_point(depth, 0.0, 0.0, 0.0)
+    assert oracle_lib.is_border_point(depth, 0.1, 0.1, 2.0)              # lies on the surface
+    assert not oracle_lib.is_border_point(depth, 0.1, 0.1, 2.5)          # occluded: 0.5 m behind the measured depth
+    assert not oracle_lib.is_border_point(depth, 0.1, 0.1, -1.0)         # PcZ < 0
 
 
 def test_eigen33_smallest_known(oracle_lib):

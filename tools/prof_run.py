@@ -7,7 +7,8 @@ from sp_slam_b200 import api, scenes
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 d = scenes.boxroom_sequence(n, start=150)
 dev = torch.from_numpy(d).cuda()
-ext = api.PlaneExtractor(max_frames=n)
+st = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # frame groups (internal streams); 1 = every kernel once per pass
+ext = api.PlaneExtractor(max_frames=n, n_streams=st)
 for _ in range(3):
     ext.extract_device(dev.data_ptr(), n, 480, 640)
 r = ext.fetch(clouds=False)
