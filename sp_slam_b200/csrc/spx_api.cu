@@ -73,6 +73,7 @@ struct spx_ctx {
     bool ccl_four = true;      // k_ccl_merge4 (N % 4 == 0) instead of the one-pixel-per-thread k_ccl_merge
     bool flatten_runs = true;  // k_ccl_flatten_runs (one pointer chase per row run) instead of k_ccl_flatten (one per pixel)
     bool refine_per_group = true;
+    bool refine_dev_group = false;   // tuning knob SPX_REFINE_DEV_GROUP: the k_refine / k_refine2 choice per frame group on the resident path too
     std::vector<double> group_weights;   // tuning knob SPX_GROUP_WEIGHTS="w0,w1,...": relative group sizes on the host path
     double edge_weight = 0.5;   // host path: size of the first and the last frame group relative to the others
     int group_prio = 1;      // 1: group g's stream gets a priority that falls with g (earlier groups finish first)
@@ -210,6 +211,10 @@ int set_geometry(spx_ctx *c, int n_frames, int rows, int cols, size_t pitch, siz
     P.samp_rstep = size_t(P.dis) * pitch; P.samp_fstride = frame_stride; P.full_alpha = 1.0f;
     cloud_dims(rows, cols, P.dis, &P.w, &P.h);
     P.N = P.w * P.h;
+    // smallest non-zero |n - cx|, |m - cy| over the sampled columns / rows (the exactness bound of k_models)
+    P.min_axf = P.min_ayf = 3.0e38f;
+    for (int x = 0; x < P.w; ++x) { const float v = std::fabs(float(x * P.dis) - P.cx); if (v > 0.f && v < P.min_axf) P.min_axf = v; }
+    for (int y = 0; y < P.h; ++y) { const float v = std::fabs(float(y * P.dis) - P.cy); if (v > 0.f && v < P.min_ayf) P.min_ayf = v; }
     if (P.N > c->capN) return fail(c, SPX_ERR_ARG, "organized cloud exceeds the context capacity");
     return SPX_OK;
 }
@@ -261,7 +266,7 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     // k_refine2 (a CTA per frame) has the shorter critical path but executes ~1.8x the instructions of k_refine (a warp per
     // frame): it wins while the whole batch fits the machine in about one wave (measured cross-over ~700 frames)
     // On the host path the groups start one upload apart instead of together, so the decision is made per group there.
-    const int refine_load = (c->group_pack && c->refine_per_group) ? ng : c->P.n_frames;
+    const int refine_load = ((c->group_pack && c->refine_per_group) || c->refine_dev_group) ? ng : c->P.n_frames;
     P.refine_fast = (refine_load <= c->refine_fast_max && P.h <= kRefMaxH) ? 1 : 0;   // small launches are latency bound: parallelism inside the frame
     Buffers B = c->B;
     B.work = c->B.work + size_t(g) * c->work_stride;
@@ -465,7 +470,7 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, boo
         const Params &Q = c->P;
         const cuuint64_t gdim[3] = {cuuint64_t(Q.cols), cuuint64_t(Q.h), cuuint64_t(Q.n_frames)};
         const cuuint64_t gstr[2] = {cuuint64_t(Q.samp_rstep), cuuint64_t(Q.n_frames == 1 ? Q.samp_rstep * size_t(Q.h) : Q.samp_fstride)};
-        const cuuint32_t box[3] = {cuuint32_t(kSCW * Q.dis), cuuint32_t(kSB), 1u};
+        const cuuint32_t box[3] = {cuuint32_t(strip_box_w(Q.dis)), cuuint32_t(kSB), 1u};
         const cuuint32_t es[3] = {1u, 1u, 1u};
         const CUresult r = c->encode_tiled(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(depth_dev), gdim, gstr, box, es,
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -856,6 +861,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (const char *e = std::getenv("SPX_CCL_FOUR")) c->ccl_four = std::atoi(e) != 0;   // test knob: the one-pixel-per-thread kernel
     if (const char *e = std::getenv("SPX_FLATTEN_RUNS")) c->flatten_runs = std::atoi(e) != 0;   // test knob
     if (const char *e = std::getenv("SPX_REFINE_PER_GROUP")) c->refine_per_group = std::atoi(e) != 0;   // tuning knob
+    if (const char *e = std::getenv("SPX_REFINE_DEV_GROUP")) c->refine_dev_group = std::atoi(e) != 0;   // tuning knob
     if (const char *e = std::getenv("SPX_EDGE_WEIGHT")) { const double v = std::atof(e); if (v > 0.05 && v <= 1.0) c->edge_weight = v; }   // tuning knob
     if (const char *e = std::getenv("SPX_GROUP_WEIGHTS")) {   // tuning knob
         const char *q = e;

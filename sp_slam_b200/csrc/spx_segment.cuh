@@ -586,14 +586,20 @@ __global__ void __launch_bounds__(128) k_models(Params P, Buffers B) {
     }
     ctl.n_models = nm;
     // were PCL's double-precision integral images provably free of rounding on this frame?  Every partial sum of channel ch is
-    // an integer multiple of 2^-negexp[axis] and smaller than sat_sum[ch] < 2^e, i.e. an integer below 2^(e + negexp) in units of
-    // 2^-negexp: a double holds it exactly when e + negexp <= 53
-    for (int ch = 0; ch < 6; ++ch) {
-        const float s = ctl.sat_sum[ch];
-        if (s > 0.0f) {
-            int e = 0;
-            frexpf(s * 1.001f, &e);
-            if (e + ctl.sat_negexp[ch % 3] > 53) ctl.flags |= unsigned(SPX_FRAME_SAT_UNPROVEN);
+    // an integer multiple of the finest unit in the last place u of that axis' coordinates and smaller than sat_sum[ch] < 2^e,
+    // i.e. an integer below 2^e / u: a double holds it exactly when that is <= 2^53.  |x| >= min|n - cx| zmin / |fx| and
+    // |y| >= min|m - cy| zmin / |fy| for every non-zero coordinate (two roundings: the factor 0.999).
+    if (ctl.sat_zinv != 0u) {
+        const float zmin = __uint_as_float(0x7f800000u - ctl.sat_zinv);
+        const float lb[3] = {P.min_axf * zmin / fabsf(P.fx) * 0.999f, P.min_ayf * zmin / fabsf(P.fy) * 0.999f, zmin};
+        for (int ch = 0; ch < 6; ++ch) {
+            const float s = ctl.sat_sum[ch];
+            if (s > 0.0f) {
+                int e = 0, eu = 0;
+                frexpf(s * 1.001f, &e);                       // s < 2^e
+                frexpf(fmaxf(lb[ch % 3], 1.0e-45f), &eu);     // lb >= 2^(eu - 1): its unit in the last place is >= 2^(eu - 24)
+                if (!(lb[ch % 3] > 0.0f) || e - (eu - 24) > 53) ctl.flags |= unsigned(SPX_FRAME_SAT_UNPROVEN);
+            }
         }
     }
 }

@@ -30,6 +30,7 @@ struct Params {
     int dis, w, h, N;
     float fx, fy, cx, cy;
     float rfx, rfy;        // RN(1 / fx), RN(1 / fy) for the strip kernel's division by a constant
+    float min_axf, min_ayf; // smallest non-zero |n - cx| / |m - cy| over the sampled columns / rows of the current image
     int   fast_div;        // bit 0 / 1: that division was verified against the IEEE quotient for fx / fy (k_check_div)
     float min_x, max_x, min_y, max_y;
     float mdcf;            // max depth change factor
@@ -103,11 +104,12 @@ struct FrameCtl {
     int pts_used, bnd_used;   // points / boundary points of the REAL planes (set by k_postfilter)
     int pts_sup, bnd_sup;     // ... of the supposed planes (set by k_supposed)
     int n_lines;
-    // exactness bound of the integral images (k_normals_strip; evaluated by k_models): per axis x y z the max over the cloud's
-    // non-zero coordinates of -(exponent of their unit in the last place), per gradient channel the sum of |central differences|
-    int sat_negexp[3];
+    // exactness bound of the integral images (k_normals_strip; evaluated by k_models): the smallest non-zero depth of the frame
+    // (with the smallest |n - cx|, |m - cy| of the image it bounds the finest unit in the last place of the cloud's coordinates)
+    // and per gradient channel the sum of |central differences|
+    unsigned sat_zinv;     // 0x7f800000 - bits of the smallest non-zero |z| of the cloud (0: none)
     float sat_sum[6];
-    int pad[2];
+    int pad[4];
     Cand     cand[SPX_MAX_CAND];
     Model    models[SPX_MAX_MODELS];
     PlaneRec planes[SPX_MAX_PLANES];

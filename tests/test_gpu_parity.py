@@ -650,3 +650,41 @@ def test_sat_unproven_flag(oracle_lib, seq):
     assert fp.flags & api.SPX_FRAME_SAT_UNPROVEN
     assert fp.mnRealPlaneNum >= 1          # the frame is still processed
     e.close()
+
+
+def test_frame_overflow_returns_a_prefix_of_the_reference_list(oracle_lib):
+    """More plane candidates than the per-frame capacities (SPX_MAX_CAND 96 components, SPX_MAX_MODELS 64 models; the reference's
+    vectors are unbounded): the frame is flagged SPX_FRAME_OVERFLOW and what comes back is the reference's plane list cut off
+    after the models of the first 96 components / the first 64 models -- never a wrong plane, never a crash."""
+    rows, cols, ps = 480, 640, 40
+    rng = np.random.default_rng(11)
+    d = np.zeros((rows, cols), np.float32)
+    yy, xx = np.mgrid[0:ps, 0:ps].astype(np.float32)
+    k = 0
+    for by in range(rows // ps):
+        for bx in range(cols // ps):
+            z0 = 1.0 + 0.35 * ((3 * by + 5 * bx + k) % 9) + 0.01 * k       # neighbours differ by a clear depth step
+            a, b = rng.uniform(-0.002, 0.002, 2)
+            d[by * ps:(by + 1) * ps, bx * ps:(bx + 1) * ps] = z0 + a * xx + b * yy
+            k += 1
+    cfgkw = dict(min_size=60, enable_supposed=0)
+    e = api.PlaneExtractor(debug=True, **cfgkw)
+    fp = e.extract(d)
+    orc = oracle_lib.Oracle(**cfgkw).run(d)
+    cand_labels = [l for l, n in zip(*np.unique(orc.labels_raw()[0], return_counts=True)) if n > 60 and l != 0xFFFFFFFF]
+    models = orc.models()
+    assert len(cand_labels) > api.SPX_MAX_CAND and len(models) > api.SPX_MAX_MODELS          # the scene does exceed both capacities
+    assert fp.flags & api.SPX_FRAME_OVERFLOW
+    kept_labels = set(cand_labels[:api.SPX_MAX_CAND])
+    kept_models = [i for i, m in enumerate(models) if m["label"] in kept_labels][:api.SPX_MAX_MODELS]
+    # the reference's planes whose model survived the cut, in order (PlaneNotSeen only looks at EARLIER planes, and every
+    # earlier plane of a kept model is kept too, so the de-duplication decisions are the same)
+    want = [p for p in orc.planes() if p["src"] in set(kept_models)]
+    assert 0 < fp.mnRealPlaneNum == len(want) <= api.SPX_MAX_MODELS
+    for i, p in enumerate(want):
+        assert np.array_equal(fp.mvPlaneCoefficients[i].view(np.uint32), p["coef"].view(np.uint32)), i
+        assert np.array_equal(fp.mvPlanePoints[i], p["points"]) and np.array_equal(fp.mvBoundaryPoints[i], p["boundary"]), i
+    # an ordinary frame on the same context afterwards is unaffected
+    ok = scenes.render(scenes.boxroom_rects(), scenes.poses(1000)[[200]], scenes.TUM1)[0]
+    assert not (e.extract(ok).flags & api.SPX_FRAME_OVERFLOW)
+    e.close()
