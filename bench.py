@@ -438,6 +438,8 @@ def _main(out):
             ms_one = p0.elapsed_time(p1)
         for name, t in (ext1 or ext).kernel_times():   # CUDA events around every launch of the profiled step
             name = name.split("<")[0]
+            if name.endswith("_fn"):       # launched through a function pointer that selects the template instance
+                name = name[:-3]
             ktimes[name] = ktimes.get(name, 0.0) + t
             kcount[name] = kcount.get(name, 0) + 1
         if ext1 is not None:

@@ -70,6 +70,7 @@ struct spx_ctx {
     CUtensorMap tmap;                          // the depth batch of the current call as a (columns, sampled rows, frames) tensor
     bool tmap_ok = false;
     int list_grid = 148 * 2;
+    int strip_occ = 4;                         // CTAs of k_normals_strip per SM the register budget is set for (tuning knob SPX_STRIP_OCC: 3 or 4)
     bool ccl_four = true;      // k_ccl_merge4 (N % 4 == 0) instead of the one-pixel-per-thread k_ccl_merge
     bool flatten_runs = true;  // k_ccl_flatten_runs (one pointer chase per row run) instead of k_ccl_flatten (one per pixel)
     bool refine_per_group = true;
@@ -354,8 +355,10 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
             LAUNCH(k_normals_link, dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), kNormThreads, kNormalsSmem, depth_dev, P, B, dbg);
         } else {
             const dim3 sgrid(cdiv(P.w, kStW), F);
-            if (c->tmap_ok) LAUNCH(k_normals_strip<true>, sgrid, kSThreads, strip_smem_bytes(P.dis, true), c->tmap, depth_dev, P, B, dbg);
-            else LAUNCH(k_normals_strip<false>, sgrid, kSThreads, strip_smem_bytes(P.dis, false), c->tmap, depth_dev, P, B, dbg);
+            void (*k_normals_strip_fn)(const CUtensorMap, const float *, Params, Buffers, int) =
+                c->tmap_ok ? (c->strip_occ == 3 ? k_normals_strip<true, 3> : k_normals_strip<true, 4>)
+                           : (c->strip_occ == 3 ? k_normals_strip<false, 3> : k_normals_strip<false, 4>);
+            LAUNCH(k_normals_strip_fn, sgrid, kSThreads, strip_smem_bytes(P.dis, c->tmap_ok), c->tmap, depth_dev, P, B, dbg);
             // frames with NaN / Inf depth (queued by k_edge_chamfer; none on sensor data: the CTAs leave at once)
             LAUNCH(k_normals_link_list, std::min(c->list_grid, F * cdiv(P.w, kTW) * cdiv(P.h, kTH)), kNormThreads, kNormalsSmem, depth_dev, P, B, dbg);
         }
@@ -857,6 +860,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (const char *e = std::getenv("SPX_LINES_GLOBAL")) c->P.lines_in_global = std::atoi(e) != 0 ? 1 : 0;   // test knob
     if (const char *e = std::getenv("SPX_UPLOAD")) c->upload_mode = std::atoi(e);   // test / tuning knob (see spx_ctx::upload_mode)
     if (const char *e = std::getenv("SPX_SPARSE_MIN_FRAMES")) c->sparse_min_frames = std::atoi(e);   // tuning knob
+    if (const char *e = std::getenv("SPX_STRIP_OCC")) { const int v = std::atoi(e); if (v == 3 || v == 4) c->strip_occ = v; }   // tuning knob
     if (const char *e = std::getenv("SPX_NORMALS")) { const int v = std::atoi(e); if (v >= 0 && v <= 2) c->normals_mode = v; }   // test knob
     if (const char *e = std::getenv("SPX_CCL_FOUR")) c->ccl_four = std::atoi(e) != 0;   // test knob: the one-pixel-per-thread kernel
     if (const char *e = std::getenv("SPX_FLATTEN_RUNS")) c->flatten_runs = std::atoi(e) != 0;   // test knob
@@ -971,8 +975,10 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_grid, grid, sizeof(grid)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_link, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kNormalsSmem)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_link_list, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kNormalsSmem)));
-    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_strip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(strip_smem_bytes(P.dis, strip_tma_ok(P.dis)))));
-    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_strip<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(strip_smem_bytes(P.dis, false))));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_strip<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(strip_smem_bytes(P.dis, strip_tma_ok(P.dis)))));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_strip<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(strip_smem_bytes(P.dis, false))));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_strip<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(strip_smem_bytes(P.dis, strip_tma_ok(P.dis)))));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_strip<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(strip_smem_bytes(P.dis, false))));
     c->list_grid = prop.multiProcessorCount * 2;
     {
         // cuTensorMapEncodeTiled without linking libcuda

@@ -120,21 +120,25 @@ SPX_HD void eigen33_largest_vec(const float mat[9], float vec[3]) {
 
 #ifdef __CUDACC__
 // (n0, n1, n2) / sqrt(len) rounded to float -- the bits of `float(n_i / sqrt(len))` evaluated in IEEE double (Eigen's
-// `normal_vector /= sqrt(length)` followed by the cast in computePointNormal) -- without the three double divisions.
-// q_i = RN(n_i * rsqrt(len)) with rsqrt good to 1 ulp; the reference t_i = RN(n_i / RN(sqrt(len))) then differs from q_i by
-// at most 2^-52 + 3 * 2^-53 relative, i.e. less than 5 units in the last place of a double.  A float keeps 23 of the 52
-// fraction bits: q_i and t_i round to the same float unless the 29 dropped bits of q_i lie within 8 units of the tie pattern
-// 0x10000000 (probability 2^-24 per component), in which case -- like for results a float would hold as a subnormal, and for
-// a len outside the comfortable range -- the exact sequence is evaluated.
+// `normal_vector /= sqrt(length)` followed by the cast in computePointNormal) -- without the double square root and the
+// three double divisions.  r ~ len^-1/2 comes from the single-precision rsqrt refined by two Newton steps in double
+// (relative error below 2^-50 whatever the seed's last bits are); q_i = RN(n_i * r) and the reference
+// t_i = RN(n_i / RN(sqrt(len))) then differ by less than 2^-49 relative, i.e. fewer than 16 units in the last place of a
+// double.  A float keeps 23 of the 52 fraction bits: q_i and t_i round to the same float unless the 29 dropped bits of q_i
+// lie within 32 units of the tie pattern 0x10000000 (probability 2^-22 per component), in which case -- like for results a
+// float would hold as a subnormal, and for a len outside the range the float seed covers -- the exact sequence is evaluated.
 __device__ __forceinline__ void normalize_to_float(double n0, double n1, double n2, double len, float &x, float &y, float &z) {
-    bool exact_path = !(len > 1.0e-280 && len < 1.0e280);
+    bool exact_path = !(len > 1.0e-30 && len < 1.0e30);
     double q0 = 0.0, q1 = 0.0, q2 = 0.0;
     if (!exact_path) {
-        const double r = rsqrt(len);
+        double r = double(rsqrtf(float(len)));          // ~2^-22
+        const double hl = 0.5 * len;
+        r = r * (1.5 - hl * r * r);                     // ~2^-43
+        r = r * (1.5 - hl * r * r);                     // rounding only
         q0 = n0 * r; q1 = n1 * r; q2 = n2 * r;
         auto risky = [](double q) -> bool {
             const unsigned lo = unsigned(__double2loint(q)) & 0x1fffffffu;
-            return (lo - 0x0ffffff8u) <= 16u || (fabs(q) < 1.0e-30 && q != 0.0);
+            return (lo - 0x0fffffe0u) <= 64u || (fabs(q) < 1.0e-30 && q != 0.0);
         };
         exact_path = risky(q0) || risky(q1) || risky(q2);
     }

@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(256) k_check_div(float b, float rb, int *misma
 template <bool V> struct StripBool { static constexpr bool value = V; };
 template <int V> struct StripInt { static constexpr int value = V; };
 
-template <bool kTMA>
-__global__ void __launch_bounds__(kSThreads, 4)
+template <bool kTMA, int kOcc>
+__global__ void __launch_bounds__(kSThreads, kOcc)
 k_normals_strip(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ depth, Params P, Buffers B, int write_normals) {
     extern __shared__ __align__(128) unsigned char strip_raw[];
     StripSmem &S = *reinterpret_cast<StripSmem *>(strip_raw);
@@ -248,13 +248,14 @@ k_normals_strip(const __grid_constant__ CUtensorMap tmap, const float *__restric
         constexpr bool kEdge = decltype(edge_c)::value;
         constexpr int kPar = decltype(par_c)::value;
         if (!cs_on) return;
-        const int wrap_at = kSRing - nb;                                  // rows i >= wrap_at of this batch wrap around the node ring
-        double *const nd0 = nd_base + cs_nd + nb * kNdRow;
+        const int wrap_at = kSRing - nb;                                  // row i == wrap_at of this batch wraps around the node ring
+        double *nd = nd_base + cs_nd + nb * kNdRow;
         const float *const cl0 = cl_base + cs_cl;
 #pragma unroll
         for (int i = 0; i < kSB; ++i) {
             const int y = r0 + 4 + i;                                     // (row tests are uniform over the CTA)
-            if (kEdge && (y < 0 || y >= h)) continue;
+            if (i == wrap_at) nd -= kSRing * kNdRow;                      // (uniform)
+            if (kEdge && (y < 0 || y >= h)) { nd += kNdRow; continue; }
             const bool inner = !kEdge || (y >= 1 && y <= h - 2);
             float d = 0.0f;
             if (cs_dx) {
@@ -268,7 +269,8 @@ k_normals_strip(const __grid_constant__ CUtensorMap tmap, const float *__restric
             }
             colsum += double(d);
             if (cs_owncol) sabs += fabsf(d);
-            nd0[(i - (i >= wrap_at ? kSRing : 0)) * kNdRow] = colsum;
+            *nd = colsum;
+            nd += kNdRow;
         }
     };
     // ================= phase C: row prefix of node rows [r0 + 5, r0 + 13) =================

@@ -656,19 +656,20 @@ def test_frame_overflow_returns_a_prefix_of_the_reference_list(oracle_lib):
     """More plane candidates than the per-frame capacities (SPX_MAX_CAND 96 components, SPX_MAX_MODELS 64 models; the reference's
     vectors are unbounded): the frame is flagged SPX_FRAME_OVERFLOW and what comes back is the reference's plane list cut off
     after the models of the first 96 components / the first 64 models -- never a wrong plane, never a crash."""
-    rows, cols, ps = 480, 640, 40
+    rows, cols, pw, ph = 720, 1280, 64, 48
     rng = np.random.default_rng(11)
     d = np.zeros((rows, cols), np.float32)
-    yy, xx = np.mgrid[0:ps, 0:ps].astype(np.float32)
+    yy, xx = np.mgrid[0:ph, 0:pw].astype(np.float32)
     k = 0
-    for by in range(rows // ps):
-        for bx in range(cols // ps):
-            z0 = 1.0 + 0.35 * ((3 * by + 5 * bx + k) % 9) + 0.01 * k       # neighbours differ by a clear depth step
+    for by in range(rows // ph):
+        for bx in range(cols // pw):
+            z0 = 1.0 + 0.35 * ((3 * by + 5 * bx + k) % 9) + 0.01 * (k % 7)       # neighbours differ by a clear depth step
             a, b = rng.uniform(-0.002, 0.002, 2)
-            d[by * ps:(by + 1) * ps, bx * ps:(bx + 1) * ps] = z0 + a * xx + b * yy
+            d[by * ph:(by + 1) * ph, bx * pw:(bx + 1) * pw] = z0 + a * xx + b * yy
             k += 1
-    cfgkw = dict(min_size=60, enable_supposed=0)
-    e = api.PlaneExtractor(debug=True, **cfgkw)
+    intr = dict(fx=640.0, fy=640.0, cx=639.5, cy=359.5, max_x=1280.0, max_y=720.0)
+    cfgkw = dict(min_size=60, enable_supposed=0, **intr)
+    e = api.PlaneExtractor(debug=True, max_rows=rows, max_cols=cols, **cfgkw)
     fp = e.extract(d)
     orc = oracle_lib.Oracle(**cfgkw).run(d)
     cand_labels = [l for l, n in zip(*np.unique(orc.labels_raw()[0], return_counts=True)) if n > 60 and l != 0xFFFFFFFF]
@@ -685,6 +686,6 @@ def test_frame_overflow_returns_a_prefix_of_the_reference_list(oracle_lib):
         assert np.array_equal(fp.mvPlaneCoefficients[i].view(np.uint32), p["coef"].view(np.uint32)), i
         assert np.array_equal(fp.mvPlanePoints[i], p["points"]) and np.array_equal(fp.mvBoundaryPoints[i], p["boundary"]), i
     # an ordinary frame on the same context afterwards is unaffected
-    ok = scenes.render(scenes.boxroom_rects(), scenes.poses(1000)[[200]], scenes.TUM1)[0]
+    ok = scenes.realsense_sequence(1, start=40)[0]
     assert not (e.extract(ok).flags & api.SPX_FRAME_OVERFLOW)
     e.close()
