@@ -70,6 +70,8 @@ struct spx_ctx {
     CUtensorMap tmap;                          // the depth batch of the current call as a (columns, sampled rows, frames) tensor
     bool tmap_ok = false;
     int list_grid = 148 * 2;
+    int sm_count = 148;
+    bool strip_always = false;                 // test knob SPX_STRIP_ALWAYS: the strip kernel for small launches too
     int strip_occ = 4;                         // CTAs of k_normals_strip per SM the register budget is set for (tuning knob SPX_STRIP_OCC: 3 or 4)
     bool ccl_four = true;      // k_ccl_merge4 (N % 4 == 0) instead of the one-pixel-per-thread k_ccl_merge
     bool flatten_runs = true;  // k_ccl_flatten_runs (one pointer chase per row run) instead of k_ccl_flatten (one per pixel)
@@ -351,7 +353,11 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
         if (nch <= 7) LAUNCH(k_edge_chamfer<7>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
         else if (nch <= 14) LAUNCH(k_edge_chamfer<14>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
         else LAUNCH(k_edge_chamfer<16>, cdiv(F * nb, kChamferWarps), kChamferWarps * 32, csm, depth_dev, P, B, dbg);
-        if (c->normals_mode == 0) {
+        // a strip walks the frame's rows in sequence (22 batches at 480p): a throughput design.  A launch with fewer strips than SMs
+        // (the tracking loop's single frame) is latency bound instead and takes the 32x16 tile kernel, whose 70 CTAs per frame
+        // run side by side (0.05 ms against 0.12 ms for one frame).
+        const bool few = F * cdiv(P.w, kStW) < c->sm_count;
+        if (c->normals_mode == 0 || (few && !c->strip_always)) {
             LAUNCH(k_normals_link, dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), kNormThreads, kNormalsSmem, depth_dev, P, B, dbg);
         } else {
             const dim3 sgrid(cdiv(P.w, kStW), F);
@@ -980,6 +986,8 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_strip<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(strip_smem_bytes(P.dis, strip_tma_ok(P.dis)))));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_normals_strip<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(strip_smem_bytes(P.dis, false))));
     c->list_grid = prop.multiProcessorCount * 2;
+    c->sm_count = prop.multiProcessorCount;
+    if (const char *e = std::getenv("SPX_STRIP_ALWAYS")) c->strip_always = std::atoi(e) != 0;   // test knob
     {
         // cuTensorMapEncodeTiled without linking libcuda
         void *fn = nullptr;

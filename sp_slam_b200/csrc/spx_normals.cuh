@@ -294,6 +294,7 @@ __device__ __forceinline__ void normals_tile(const float *__restrict__ depth, co
 
     // ---- 1. cloud region: thread = one region column, 5 region rows per sweep (all loads of a thread in flight) ----
     int nonfinite = 0;
+    unsigned zinv = 0u;
     if (tid < 5 * kCW) {
         const int lx = tid % kCW, ly0 = tid / kCW;
         const int c = tc - 7 + lx;
@@ -322,6 +323,8 @@ __device__ __forceinline__ void normals_tile(const float *__restrict__ depth, co
                     if (cown && ly >= 7 && ly < 7 + kTH) {
                         const size_t o = fo + size_t(r * w + c);
                         B.px[o] = x; B.py[o] = y; B.pz[o] = z;
+                        const unsigned uz = __float_as_uint(z) & 0x7fffffffu;      // exactness bound (see k_normals_strip / k_models)
+                        if (uz && uz < 0x7f800000u) zinv = max(zinv, 0x7f800000u - uz);
                     }
                 }
                 const int o = ly * kCStride + lx;
@@ -330,6 +333,8 @@ __device__ __forceinline__ void normals_tile(const float *__restrict__ depth, co
         }
     }
     const int anynf = __syncthreads_or(nonfinite);
+    zinv = __reduce_max_sync(SPX_FULL, zinv);
+    if ((tid & 31) == 0 && zinv) atomicMax(&B.ctl[f].sat_zinv, zinv);
 
     // ---- per-pixel window geometry of the kNW x kNH pixels that get a normal (two per thread) ----
     const float qnan = __int_as_float(0x7fc00000);
@@ -394,6 +399,8 @@ __device__ __forceinline__ void normals_tile(const float *__restrict__ depth, co
                 const bool rowok = r >= 1 && r <= h - 2;
                 const int lo = rowok ? max(0, 7 - tc) : 0, hi = rowok ? min(kRW, w + 5 - tc) : 0;
                 double run = 0.0;
+                float sabs = 0.0f;                                     // sum of |differences| over the tile's own pixels
+                const bool ownrow = ly >= 6 && ly < 6 + kTH;
                 if (pass == 0) {
                     const float *p = Ck + (ly + 1) * kCStride;         // dx = P(r, c+1) - P(r, c-1)
                     float pa = p[0], pb = p[1];
@@ -403,6 +410,7 @@ __device__ __forceinline__ void normals_tile(const float *__restrict__ depth, co
                         const float d = (lx >= lo && lx < hi) ? pc - pa : 0.0f;
                         pa = pb; pb = pc;
                         run += double(d);
+                        if (lx >= 6 && lx < 6 + kTW) sabs += fabsf(d);
                         row[lx + 1] = run;
                     }
                 } else {
@@ -411,9 +419,11 @@ __device__ __forceinline__ void normals_tile(const float *__restrict__ depth, co
                     for (int lx = 0; lx < kRW; ++lx) {
                         const float d = (lx >= lo && lx < hi) ? pd[lx] - pu[lx] : 0.0f;
                         run += double(d);
+                        if (lx >= 6 && lx < 6 + kTW) sabs += fabsf(d);
                         row[lx + 1] = run;
                     }
                 }
+                if (ownrow && sabs > 0.0f) atomicAdd(&B.ctl[f].sat_sum[pass * 3 + ch], sabs);
             }
         } else {
             // generic path: a difference enters its image only if isfinite(d0 + (d1 + d2)); Cn counts the finite ones

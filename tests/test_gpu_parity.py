@@ -584,7 +584,7 @@ def test_normals_kernel_variants(seq, oracle_lib, mode):
     """K3 three ways -- the 32x16 tile kernel of round 1 (0), the strip kernel with plain loads (1, also what a depth pointer TMA
     cannot describe gets) and with TMA-staged depth chunks (2, production) -- each bit-exact against the oracle, clean and noisy,
     480p and 720p (14 strips, 30 batches), one frame and a batch."""
-    e = extractor_with_env({"SPX_NORMALS": mode}, debug=True, max_frames=8)
+    e = extractor_with_env({"SPX_NORMALS": mode, "SPX_STRIP_ALWAYS": "1"}, debug=True, max_frames=8)   # (small launches would take the tile kernel)
     for k in (0, 2, 5, 7):
         d = seq[k] if k != 5 else scenes.add_noise(seq[k], FRAMES[k])
         fp = e.extract(d)
@@ -598,8 +598,8 @@ def test_normals_kernel_variants(seq, oracle_lib, mode):
     e.close()
     it = scenes.REALSENSE
     big = scenes.add_noise(scenes.realsense_sequence(1, start=40)[0], 40, "realsense")
-    e = extractor_with_env({"SPX_NORMALS": mode}, debug=True, max_rows=720, max_cols=1280, fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy,
-                           max_x=float(it.width), max_y=float(it.height))
+    e = extractor_with_env({"SPX_NORMALS": mode, "SPX_STRIP_ALWAYS": "1"}, debug=True, max_rows=720, max_cols=1280, fx=it.fx, fy=it.fy,
+                           cx=it.cx, cy=it.cy, max_x=float(it.width), max_y=float(it.height))
     fp = e.extract(big)
     orc = oracle_lib.Oracle(fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy, max_x=float(it.width), max_y=float(it.height)).run(big)
     rep = compare_frame(e, orc, big, fp)
@@ -614,7 +614,7 @@ def test_strip_kernel_odd_sizes_and_unaligned_views(oracle_lib):
     big = scenes.render(scenes.boxroom_rects(), scenes.poses(1000)[[200]], scenes.TUM1)[0]
     for rows, cols in ((401, 500), (250, 333), (97, 130)):
         small = np.ascontiguousarray(big[:rows, :cols])
-        e = api.PlaneExtractor(debug=True, max_rows=rows, max_cols=cols, max_x=float(cols), max_y=float(rows), min_size=200)
+        e = extractor_with_env({"SPX_STRIP_ALWAYS": "1"}, debug=True, max_rows=rows, max_cols=cols, max_x=float(cols), max_y=float(rows), min_size=200)
         fp = e.extract(small)
         orc = oracle_lib.Oracle(max_x=float(cols), max_y=float(rows), min_size=200).run(small)
         rep = compare_frame(e, orc, small, fp)
@@ -623,14 +623,14 @@ def test_strip_kernel_odd_sizes_and_unaligned_views(oracle_lib):
     # device-resident view with a pitch of 641 floats
     padded = torch.zeros((2, 480, 641), dtype=torch.float32, device="cuda")
     padded[:, :, :640] = torch.from_numpy(np.stack([big, big[::-1].copy()]))
-    e = api.PlaneExtractor(debug=True, max_frames=2)
+    e = extractor_with_env({"SPX_STRIP_ALWAYS": "1"}, debug=True, max_frames=2)
     e.extract_device(padded.data_ptr(), 2, 480, 640, pitch=641 * 4, frame_stride=480 * 641 * 4)
     res = e.fetch()
     orc = oracle_lib.Oracle().run(big)
     compare_frame(e, orc, big, res.frame(0), frame=0)
     e.close()
     # negative fy: the y axis flips, every division by fy changes sign
-    e = api.PlaneExtractor(debug=True, fy=-516.469215)
+    e = extractor_with_env({"SPX_STRIP_ALWAYS": "1"}, debug=True, fy=-516.469215)
     fp = e.extract(big)
     orc = oracle_lib.Oracle(fy=-516.469215).run(big)
     rep = compare_frame(e, orc, big, fp)
@@ -640,16 +640,18 @@ def test_strip_kernel_odd_sizes_and_unaligned_views(oracle_lib):
 
 def test_sat_unproven_flag(oracle_lib, seq):
     """A frame whose depth spans ~2^30 in magnitude cannot be proven free of rounding in PCL's double integral images: the
-    library says so (SPX_FRAME_SAT_UNPROVEN) instead of promising bit-identical normals; ordinary frames never carry the flag."""
-    e = api.PlaneExtractor(max_frames=2)
-    d = seq[2].copy()
-    assert not (e.extract(d).flags & api.SPX_FRAME_SAT_UNPROVEN)
-    d[200:203, 300:340] = 1.0e-7          # a few absurdly small (but positive, finite) depths next to metres
-    d[30, 30] = 3.0e4
-    fp = e.extract(d)
-    assert fp.flags & api.SPX_FRAME_SAT_UNPROVEN
-    assert fp.mnRealPlaneNum >= 1          # the frame is still processed
-    e.close()
+    library says so (SPX_FRAME_SAT_UNPROVEN) instead of promising bit-identical normals; ordinary frames never carry the flag.
+    Both normal kernels evaluate the bound (the strip kernel of large launches, the tile kernel of small ones)."""
+    for env in ({"SPX_STRIP_ALWAYS": "1"}, {"SPX_NORMALS": "0"}):
+        e = extractor_with_env(env, max_frames=2)
+        d = seq[2].copy()
+        assert not (e.extract(d).flags & api.SPX_FRAME_SAT_UNPROVEN)
+        d[200:203, 300:340] = 1.0e-7          # a few absurdly small (but positive, finite) depths next to metres
+        d[30, 30] = 3.0e4
+        fp = e.extract(d)
+        assert fp.flags & api.SPX_FRAME_SAT_UNPROVEN, env
+        assert fp.mnRealPlaneNum >= 1          # the frame is still processed
+        e.close()
 
 
 def test_frame_overflow_returns_a_prefix_of_the_reference_list(oracle_lib):
