@@ -61,6 +61,9 @@ typedef struct spx_config {
     int32_t max_rows, max_cols;        /* depth image size */
     int32_t device;                    /* CUDA device ordinal */
     int32_t n_streams;                 /* internal streams a batch's frame groups run on; 0 = default (8) */
+    int32_t normal_method;             /* ne.setNormalEstimationMethod (src/Frame.cc:880): 0 = AVERAGE_3D_GRADIENT (the reference's choice,
+                                          default), 1 = COVARIANCE_MATRIX (9-channel integral image, per-pixel covariance + eigen33 +
+                                          curvature; slower, for callers that want PCL's other method; spx_get_curvature taps it) */
 } spx_config;
 
 /* payload of pcl::PointXYZRGB: xyz + rgba packed as (a<<24 | r<<16 | g<<8 | b) */
@@ -239,6 +242,7 @@ int spx_set_debug(spx_ctx *ctx, int on);
 int spx_get_cloud(spx_ctx *ctx, int frame, float *x, float *y, float *z);                 /* N each */
 int spx_get_distance_map(spx_ctx *ctx, int frame, float *dist);                           /* N, min(PCL distance map, 10) */
 int spx_get_normals(spx_ctx *ctx, int frame, float *nx, float *ny, float *nz, float *plane_d);
+int spx_get_curvature(spx_ctx *ctx, int frame, float *curvature);    /* N, pcl::Normal::curvature (COVARIANCE_MATRIX method only) */
 int spx_get_labels_raw(spx_ctx *ctx, int frame, uint32_t *labels, int *n_label_lists);    /* CCL labels before refine */
 int spx_get_plane_ids(spx_ctx *ctx, int frame, int8_t *ids);     /* after refine: model index per pixel, -1 = none */
 

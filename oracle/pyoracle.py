@@ -24,10 +24,11 @@ class OrcConfig(C.Structure):
         ("max_depth_change_factor", C.c_float), ("normal_smoothing_size", C.c_float),
         ("ransac_max_iter", C.c_int32), ("enable_supposed", C.c_int32),
         ("alt", C.c_uint32),      # alternative readings of PCL 1.8.0 (ORC_ALT_*), 0 = the default restatement
+        ("normal_method", C.c_int32),   # 0 AVERAGE_3D_GRADIENT (the reference), 1 COVARIANCE_MATRIX
     ]
 
 
-ALT_VP_RESET, ALT_CHAMFER_NO_WRAP, ALT_REFINE_NO_WRAP, ALT_SAMPLE_GOOD_OR, ALT_RNG_MASK = 1, 2, 4, 8, 16
+ALT_VP_RESET, ALT_CHAMFER_NO_WRAP, ALT_REFINE_NO_WRAP, ALT_SAMPLE_GOOD_OR, ALT_RNG_MASK, ALT_SO_DOUBLE, ALT_COV_TRACE = 1, 2, 4, 8, 16, 32, 64
 
 
 class OrcLineRec(C.Structure):
@@ -91,7 +92,7 @@ def lib():
         L.orc_dims.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
         for name in ("orc_get_cloud", "orc_get_normals"):
             getattr(L, name).argtypes = [vp, vp, vp, vp]
-        for name in ("orc_get_distance_map", "orc_get_plane_d", "orc_get_labels_refined"):
+        for name in ("orc_get_distance_map", "orc_get_plane_d", "orc_get_labels_refined", "orc_get_curvature"):
             getattr(L, name).argtypes = [vp, vp]
         L.orc_get_labels_raw.argtypes = [vp, vp]
         L.orc_get_labels_raw.restype = i32
@@ -188,6 +189,11 @@ class Oracle:
         d = np.empty(self.n, np.float32)
         lib().orc_get_distance_map(self._h, d.ctypes.data)
         return d.reshape(self.height, self.width)
+
+    def curvature(self):
+        d = np.empty(self.n, np.float32)
+        lib().orc_get_curvature(self._h, d.ctypes.data)
+        return d
 
     def plane_d(self):
         d = np.empty(self.n, np.float32)

@@ -258,6 +258,51 @@ struct Sat3 {
     }
 };
 
+// IntegralImage2D<float,3> with second-order computation (COVARIANCE_MATRIX method): x y z and their six products
+// xx xy xz yy yz zz in double, one finite-element count; the recurrence and its operand order are PCL's
+// (computeIntegralImages): cur[c+1] = prev[c+1] + cur[c] - prev[c], then += element when the point is finite.  These
+// sums DO round, so the order is part of the result.
+struct Sat9 {
+    int w = 0, h = 0;
+    std::vector<double> F, S;     // (w+1)*(h+1) * 3 / * 6
+    std::vector<unsigned> cnt;
+    void build(const Pt *pts, int w_, int h_, bool products_in_double) {
+        w = w_; h = h_;
+        const int W1 = w + 1;
+        F.assign(size_t(W1) * (h + 1) * 3, 0.0); S.assign(size_t(W1) * (h + 1) * 6, 0.0);
+        cnt.assign(size_t(W1) * (h + 1), 0u);
+        for (int r = 0; r < h; ++r) {
+            const size_t p0 = size_t(r) * W1, c0 = size_t(r + 1) * W1;
+            for (int c = 0; c < w; ++c) {
+                const Pt &q = pts[size_t(r) * w + c];
+                const float e[3] = {q.x, q.y, q.z};
+                for (int k = 0; k < 3; ++k) F[(c0 + c + 1) * 3 + k] = (F[(p0 + c + 1) * 3 + k] + F[(c0 + c) * 3 + k]) - F[(p0 + c) * 3 + k];
+                for (int k = 0; k < 6; ++k) S[(c0 + c + 1) * 6 + k] = (S[(p0 + c + 1) * 6 + k] + S[(c0 + c) * 6 + k]) - S[(p0 + c) * 6 + k];
+                cnt[c0 + c + 1] = cnt[p0 + c + 1] + cnt[c0 + c] - cnt[p0 + c];
+                if (std::isfinite(e[0] + (e[1] + e[2]))) {
+                    for (int k = 0; k < 3; ++k) F[(c0 + c + 1) * 3 + k] += double(e[k]);
+                    int el = 0;
+                    for (int a = 0; a < 3; ++a)
+                        for (int b = a; b < 3; ++b, ++el)
+                            S[(c0 + c + 1) * 6 + el] += products_in_double ? double(e[a]) * double(e[b]) : double(e[a] * e[b]);
+                    ++cnt[c0 + c + 1];
+                }
+            }
+        }
+    }
+    unsigned count(int x0, int y0, int kw, int kh) const {
+        const int W1 = w + 1;
+        const size_t ul = size_t(y0) * W1 + x0, ur = ul + kw, ll = size_t(y0 + kh) * W1 + x0, lr = ll + kw;
+        return cnt[lr] + cnt[ul] - cnt[ur] - cnt[ll];
+    }
+    void sums(int x0, int y0, int kw, int kh, double fo[3], double so[6]) const {
+        const int W1 = w + 1;
+        const size_t ul = size_t(y0) * W1 + x0, ur = ul + kw, ll = size_t(y0 + kh) * W1 + x0, lr = ll + kw;
+        for (int k = 0; k < 3; ++k) fo[k] = ((F[lr * 3 + k] + F[ul * 3 + k]) - F[ur * 3 + k]) - F[ll * 3 + k];
+        for (int k = 0; k < 6; ++k) so[k] = ((S[lr * 6 + k] + S[ul * 6 + k]) - S[ur * 6 + k]) - S[ll * 6 + k];
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // SACSegmentation<PointT> with SACMODEL_LINE / RANSAC (sac_segmentation.hpp, ransac.hpp, sac_model.h,
 // sac_model_line.hpp); indices_ is the identity over the input cloud.
@@ -419,7 +464,7 @@ struct orc_ctx {
     int rows = 0, cols = 0, w = 0, h = 0;
     const float *depth = nullptr;
     std::vector<Pt> cloud;
-    std::vector<float> dist, nx, ny, nz, plane_d;
+    std::vector<float> dist, nx, ny, nz, plane_d, curv;
     std::vector<uint32_t> labels_raw, labels;
     int n_label_lists = 0;
     bool sat_exact = true;
@@ -465,9 +510,10 @@ void orc_ctx::back_project() {
 void orc_ctx::estimate_normals() {
     const int N = w * h;
     const float qnan = std::numeric_limits<float>::quiet_NaN();
-    nx.assign(N, qnan); ny.assign(N, qnan); nz.assign(N, qnan);
+    nx.assign(N, qnan); ny.assign(N, qnan); nz.assign(N, qnan); curv.assign(N, qnan);
     dist.assign(N, 0.0f);
     if (w < 3 || h < 3) return;
+    const bool cov_method = cfg.normal_method == 1;
 
     // initAverage3DGradientMethod
     std::vector<float> dfx(size_t(N) * 4, 0.0f), dfy(size_t(N) * 4, 0.0f);
@@ -479,9 +525,15 @@ void orc_ctx::estimate_normals() {
             dfy[i * 4 + 0] = D.x - U.x; dfy[i * 4 + 1] = D.y - U.y; dfy[i * 4 + 2] = D.z - U.z;
         }
     Sat3 DX, DY;
-    DX.build(dfx.data(), w, h);
-    DY.build(dfy.data(), w, h);
-    sat_exact = DX.exact && DY.exact;
+    Sat9 XYZ;
+    if (!cov_method) {
+        DX.build(dfx.data(), w, h);
+        DY.build(dfy.data(), w, h);
+        sat_exact = DX.exact && DY.exact;
+    } else {
+        XYZ.build(cloud.data(), w, h, (cfg.alt & ORC_ALT_SO_DOUBLE) != 0);
+        sat_exact = false;      // sums of products round: PCL's result depends on its summation order, which Sat9 follows
+    }
 
     // computeFeature: depth change map
     std::vector<uint8_t> mask(N, 255);
@@ -509,8 +561,32 @@ void orc_ctx::estimate_normals() {
             float smoothing = std::min(dist[index], smoothing_constant);
             if (!(smoothing > 2.0f)) continue;
             const int k = int(smoothing), half = k / 2;
-            // computePointNormal, AVERAGE_3D_GRADIENT
             const int x0 = ci - half, y0 = ri - half;
+            if (cov_method) {
+                // computePointNormal, COVARIANCE_MATRIX
+                const unsigned count = XYZ.count(x0, y0, k, k);
+                if (count == 0) continue;
+                double fo[3], so[6];
+                XYZ.sums(x0, y0, k, k, fo, so);
+                const float center[3] = {float(fo[0]), float(fo[1]), float(fo[2])};
+                float C[9];
+                C[0] = float(so[0]); C[1] = C[3] = float(so[1]); C[2] = C[6] = float(so[2]);
+                C[4] = float(so[3]); C[5] = C[7] = float(so[4]); C[8] = float(so[5]);
+                const float cntf = float(count);
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) C[a * 3 + b] -= (center[a] * center[b]) / cntf;   // covariance_matrix -= (center * center^T) / count
+                float eigen_value, ev[3];
+                eigen33_smallest(C, eigen_value, ev);
+                float fx_ = ev[0], fy_ = ev[1], fz_ = ev[2];
+                float vpx = 0.0f - cloud[index].x, vpy = 0.0f - cloud[index].y, vpz = 0.0f - cloud[index].z;
+                float cos_theta = (vpx * fx_ + vpy * fy_ + vpz * fz_);
+                if (cos_theta < 0) { fx_ *= -1; fy_ *= -1; fz_ *= -1; }
+                nx[index] = fx_; ny[index] = fy_; nz[index] = fz_;
+                const float den = (cfg.alt & ORC_ALT_COV_TRACE) ? (C[0] + C[4] + C[8]) : (C[0] + C[2] + C[4]);
+                curv[index] = eigen_value > 0.0f ? fabsf(eigen_value / den) : 0.0f;
+                continue;
+            }
+            // computePointNormal, AVERAGE_3D_GRADIENT
             if (DX.count(x0, y0, k, k) == 0 || DY.count(x0, y0, k, k) == 0) continue;
             double gx[3], gy[3];
             DX.sum(x0, y0, k, k, gx, sat_exact);
@@ -918,6 +994,7 @@ void orc_default_config(orc_config *c) {
     c->max_depth_change_factor = 0.05f; c->normal_smoothing_size = 10.0f;
     c->ransac_max_iter = 1000; c->enable_supposed = 1;
     c->alt = 0;
+    c->normal_method = 0;
 }
 
 orc_ctx *orc_create(const orc_config *cfg) { orc_ctx *c = new orc_ctx(); c->cfg = *cfg; return c; }
@@ -961,6 +1038,7 @@ void orc_get_normals(const orc_ctx *c, float *x, float *y, float *z) {
     std::memcpy(z, c->nz.data(), c->nz.size() * 4);
 }
 void orc_get_plane_d(const orc_ctx *c, float *d) { std::memcpy(d, c->plane_d.data(), c->plane_d.size() * 4); }
+void orc_get_curvature(const orc_ctx *c, float *d) { std::memcpy(d, c->curv.data(), c->curv.size() * 4); }
 int orc_get_labels_raw(const orc_ctx *c, uint32_t *l) {
     std::memcpy(l, c->labels_raw.data(), c->labels_raw.size() * 4); return c->n_label_lists;
 }

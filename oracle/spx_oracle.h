@@ -39,12 +39,18 @@ typedef struct orc_config {
      * with a warning sign).  0 = the reading this oracle and the CUDA path implement.  A future run of tools/pcl_pin against
      * real PCL that disagrees with the oracle can be bisected by flipping these one at a time. */
     uint32_t alt;
+    /* normal estimation method of IntegralImageNormalEstimation: 0 = AVERAGE_3D_GRADIENT (what the reference selects,
+     * src/Frame.cc:880), 1 = COVARIANCE_MATRIX (PCL's 9-channel integral image of x y z and their products, per-pixel covariance,
+     * eigen33, curvature: the method BASELINE.json's north_star words; not used by the reference) */
+    int32_t normal_method;
 } orc_config;
 #define ORC_ALT_VP_RESET         1u   /* A.4: segment()'s viewpoint vector is reset for every cluster (default: it accumulates -centroid) */
 #define ORC_ALT_CHAMFER_NO_WRAP  2u   /* A.2: no row wrap-around in the distance-map passes (default: previous_row[w] aliases current_row[0]) */
 #define ORC_ALT_REFINE_NO_WRAP   4u   /* A.5: refine()'s second pass makes no left claim at column 0 (default: it claims the previous row's last pixel) */
 #define ORC_ALT_SAMPLE_GOOD_OR   8u   /* A.8: isSampleGood accepts a pair when ANY coordinate differs (default: x, y and z must all differ) */
 #define ORC_ALT_RNG_MASK        16u   /* A.8: rnd() = mt() & INT_MAX (default: boost::uniform_int(0, INT_MAX) = mt() >> 1) */
+#define ORC_ALT_SO_DOUBLE       32u   /* A.2(5): the second-order products x*x, x*y, ... are formed in double (default: float product, then widened) */
+#define ORC_ALT_COV_TRACE       64u   /* A.2(5): curvature = lambda / (C00 + C11 + C22) (default: PCL's coeff(0) + coeff(2) + coeff(4)) */
 
 /* 16-byte packed point: xyz + packed rgba (a<<24|r<<16|g<<8|b), the payload of pcl::PointXYZRGB */
 typedef struct orc_point { float x, y, z; uint32_t rgba; } orc_point;
@@ -66,6 +72,7 @@ void   orc_get_cloud(const orc_ctx *, float *x, float *y, float *z);          /*
 void   orc_get_distance_map(const orc_ctx *, float *dist);                    /* N, unclamped */
 void   orc_get_normals(const orc_ctx *, float *nx, float *ny, float *nz);     /* N each, NaN = invalid */
 void   orc_get_plane_d(const orc_ctx *, float *d);                            /* N */
+void   orc_get_curvature(const orc_ctx *, float *curv);                       /* N: Normal::curvature (NaN under AVERAGE_3D_GRADIENT) */
 int    orc_get_labels_raw(const orc_ctx *, uint32_t *labels);                 /* N; returns label_indices.size() */
 void   orc_get_labels_refined(const orc_ctx *, uint32_t *labels);             /* N */
 /* models accepted by OrganizedMultiPlaneSegmentation::segment (before SP-SLAM's post filter) */

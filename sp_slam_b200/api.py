@@ -47,7 +47,7 @@ EXPORTS = (
     "spx_extract_batch", "spx_extract_batch_u16", "spx_extract_batch_device", "spx_fetch_results", "spx_fetch_planes",
     "spx_segment_from_normals", "spx_cloud_dims", "spx_get_times", "spx_last_launch_count", "spx_set_debug",
     "spx_set_profile", "spx_get_kernel_times", "spx_get_kernel_timeline", "spx_get_device_results",
-    "spx_get_cloud", "spx_get_distance_map", "spx_get_normals", "spx_get_labels_raw", "spx_get_plane_ids",
+    "spx_get_cloud", "spx_get_distance_map", "spx_get_normals", "spx_get_curvature", "spx_get_labels_raw", "spx_get_plane_ids",
     "spx_get_models", "spx_get_model_inliers", "spx_get_model_contour", "spx_get_lines",
     "spx_set_upload_mode", "spx_host_register", "spx_host_unregister", "spx_get_transfer_bytes",
     "spx_get_group_timeline",
@@ -68,7 +68,7 @@ class SpxConfig(C.Structure):
         ("max_depth_change_factor", C.c_float), ("normal_smoothing_size", C.c_float),
         ("ransac_max_iter", C.c_int32), ("enable_supposed", C.c_int32),
         ("max_frames", C.c_int32), ("max_rows", C.c_int32), ("max_cols", C.c_int32), ("device", C.c_int32),
-        ("n_streams", C.c_int32),
+        ("n_streams", C.c_int32), ("normal_method", C.c_int32),
     ]
 
 
@@ -144,6 +144,7 @@ def lib():
         L.spx_get_cloud.argtypes = [vp, i32, vp, vp, vp]
         L.spx_get_distance_map.argtypes = [vp, i32, vp]
         L.spx_get_normals.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.spx_get_curvature.argtypes = [vp, i32, vp]
         L.spx_get_labels_raw.argtypes = [vp, i32, vp, C.POINTER(i32)]
         L.spx_get_plane_ids.argtypes = [vp, i32, vp]
         L.spx_get_models.argtypes = [vp, i32, vp, C.POINTER(i32)]
@@ -545,6 +546,11 @@ class PlaneExtractor:
         a = [np.empty(n, np.float32) for _ in range(4)]
         self._ck(lib().spx_get_normals(self._h, frame, *(x.ctypes.data for x in a)))
         return np.stack(a[:3]), a[3]
+
+    def curvature(self, frame, n):
+        d = np.empty(n, np.float32)
+        self._ck(lib().spx_get_curvature(self._h, frame, d.ctypes.data))
+        return d
 
     def labels_raw(self, frame, n):
         l = np.empty(n, np.uint32)

@@ -23,6 +23,7 @@
 #include "spx_lines.cuh"
 #include "spx_normals.cuh"
 #include "spx_normals_strip.cuh"
+#include "spx_normals_cov.cuh"
 #include "spx_refine.cuh"
 #include "spx_segment.cuh"
 
@@ -104,6 +105,9 @@ struct spx_ctx {
     Params P;           // geometry of the last call (capacities fixed at create)
     Buffers B;
     DevArena arena;
+    double *d_cov_sat = nullptr;       // COVARIANCE_MATRIX method only: 9-channel integral images, (w+1)(h+1) nodes per frame
+    unsigned *d_cov_cnt = nullptr;
+    float *d_curv = nullptr;           // ... and the curvature tap
     float *d_depth = nullptr;          // staging for host-side depth (tight pitch)
     uint16_t *d_depth16 = nullptr;     // staging for CV_16U host depth
     int capN = 0, cap_w = 0, cap_h = 0;
@@ -346,6 +350,8 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
         SPX_CK(c, cudaMemsetAsync(B.fetch_bits + words * size_t(f0), 0, words * sizeof(unsigned) * size_t(F), st));
     }
     if (c->group_pack) SPX_CK(c, cudaMemsetAsync(B.out_totals + 8 * (g + 1) + 3, 0, sizeof(long long), st));
+    const bool cov_method = !normals_given && c->cfg.normal_method == 1;
+    if (cov_method) LAUNCH(k_backproject, gpix, 256, 0, depth_dev, P, B);      // (before the chamfer: it clears the distance tap)
     if (!normals_given) {
         const int nb = cdiv(P.h, kBandRows), nch = cdiv(P.w, 32);
         const int dbg = c->debug ? 1 : 0;
@@ -357,7 +363,13 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
         // (the tracking loop's single frame) is latency bound instead and takes the 32x16 tile kernel, whose 70 CTAs per frame
         // run side by side (0.05 ms against 0.12 ms for one frame).
         const bool few = F * cdiv(P.w, kStW) < c->sm_count;
-        if (c->normals_mode == 0 || (few && !c->strip_always)) {
+        if (cov_method) {
+            // COVARIANCE_MATRIX: whole-image 9-channel integral images in PCL's recurrence order, then one thread per pixel
+            LAUNCH(k_cov_sat, F, kCovThreads, 0, P, B, c->d_cov_sat, c->d_cov_cnt);
+            LAUNCH(k_cov_normals, gpix, 256, 0, P, B, c->d_cov_sat, c->d_cov_cnt, c->d_curv, 0);
+            LAUNCH(k_plane_d, gpix, 256, 0, P, B);
+            LAUNCH(k_ccl_link, dim3(cdiv(P.w, 32), cdiv(P.h, 8), F), dim3(32, 8), 0, P, B);
+        } else if (c->normals_mode == 0 || (few && !c->strip_always)) {
             LAUNCH(k_normals_link, dim3(cdiv(P.w, kTW), cdiv(P.h, kTH), F), kNormThreads, kNormalsSmem, depth_dev, P, B, dbg);
         } else {
             const dim3 sgrid(cdiv(P.w, kStW), F);
@@ -795,6 +807,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
         return fail(nullptr, SPX_ERR_ARG, "bad capacity / Cloud.Dis (1 <= max_frames <= 65535)");
     if (cfg->normal_smoothing_size != 10.0f) return fail(nullptr, SPX_ERR_ARG, "only normal_smoothing_size = 10 is supported");
     if (cfg->min_size < 0 || cfg->ransac_max_iter < 1) return fail(nullptr, SPX_ERR_ARG, "bad Plane.MinSize / RANSAC iteration count");
+    if (cfg->normal_method != 0 && cfg->normal_method != 1) return fail(nullptr, SPX_ERR_ARG, "normal_method must be 0 (AVERAGE_3D_GRADIENT) or 1 (COVARIANCE_MATRIX)");
     int w, h;
     cloud_dims(cfg->max_rows, cfg->max_cols, cfg->cloud_dis, &w, &h);
     if (w > kMaxW) return fail(nullptr, SPX_ERR_ARG, "organized cloud wider than %d columns", kMaxW);
@@ -935,6 +948,8 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     total += padded<spx_point>(F * size_t(P.pts_cap)) + padded<spx_point>(F * size_t(P.bnd_cap));
     total += padded<long long>(8 * size_t(c->n_streams + 1)) + padded<long long>(5 * F);
     total += padded<uint32_t>(FN);                         // out_pidx
+    const size_t cov_nodes = cfg->normal_method == 1 ? F * size_t(w + 1) * size_t(h + 1) : 0;
+    total += padded<double>(cov_nodes * kCovCh) + padded<unsigned>(cov_nodes) + padded<float>(cfg->normal_method == 1 ? FN : 0);
     total += padded<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4) + padded<uint16_t>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     SPX_CK_CREATE(cudaMalloc(reinterpret_cast<void **>(&c->arena.base), total));
     c->arena.size = total;
@@ -955,6 +970,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     B.out_pts = A.take<spx_point>(F * size_t(P.pts_cap)); B.out_bnd = A.take<spx_point>(F * size_t(P.bnd_cap));
     B.out_totals = A.take<long long>(8 * size_t(c->n_streams + 1)); B.frame_offs = A.take<long long>(5 * F);
     B.out_pidx = A.take<uint32_t>(FN);
+    if (cfg->normal_method == 1) { c->d_cov_sat = A.take<double>(cov_nodes * kCovCh); c->d_cov_cnt = A.take<unsigned>(cov_nodes); c->d_curv = A.take<float>(FN); }
     c->d_depth = A.take<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     c->d_depth16 = A.take<uint16_t>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     if (A.used > A.size) { fail(nullptr, SPX_ERR_ARG, "internal: arena accounting"); spx_destroy(c); return SPX_ERR_ARG; }
@@ -1329,6 +1345,13 @@ int spx_get_normals(spx_ctx *c, int frame, float *nx, float *ny, float *nz, floa
     if ((rc = d2h(c, ny, c->B.ny + o, N)) != SPX_OK) return rc;
     if ((rc = d2h(c, nz, c->B.nz + o, N)) != SPX_OK) return rc;
     return d2h(c, plane_d, c->B.pd + o, N);
+}
+
+int spx_get_curvature(spx_ctx *c, int frame, float *curvature) {
+    int rc = check_frame(c, frame);
+    if (rc != SPX_OK) return rc;
+    if (!c->d_curv) return fail(c, SPX_ERR_STATE, "curvature exists under normal_method = 1 (COVARIANCE_MATRIX) only");
+    return d2h(c, curvature, c->d_curv + size_t(c->P.N) * size_t(frame), size_t(c->P.N));
 }
 
 int spx_get_labels_raw(spx_ctx *c, int frame, uint32_t *labels, int *n_label_lists) {

@@ -691,3 +691,40 @@ def test_frame_overflow_returns_a_prefix_of_the_reference_list(oracle_lib):
     ok = scenes.realsense_sequence(1, start=40)[0]
     assert not (e.extract(ok).flags & api.SPX_FRAME_OVERFLOW)
     e.close()
+
+
+def test_covariance_matrix_normal_method(seq, oracle_lib):
+    """spx_config::normal_method = 1: PCL's COVARIANCE_MATRIX method (9-channel integral image of x y z and their products in
+    PCL's recurrence order, per-pixel covariance, eigen33, curvature) against the oracle's restatement of it: normals, curvature,
+    labels, planes and clouds bit for bit; clean, noisy, non-finite depth, a batch, and 1280x720."""
+    e = api.PlaneExtractor(debug=True, max_frames=8, normal_method=1)
+    for k in (2, 5):
+        d = seq[k] if k != 5 else scenes.add_noise(seq[k], FRAMES[k])
+        if k == 5:
+            d = d.copy(); d[100:120, 200:260] = np.nan; d[300, 400:420] = np.inf
+        fp = e.extract(d)
+        orc = oracle_lib.Oracle(normal_method=1).run(d)
+        rep = compare_frame(e, orc, d, fp, expect_sat_exact=False)
+        assert rep["normals_bit_exact"] and rep["labels_bit_exact"], rep
+        cv, cr = e.curvature(0, orc.n), orc.curvature()
+        assert np.array_equal(np.isnan(cv), np.isnan(cr)) and np.array_equal(cv[~np.isnan(cv)].view(np.uint32), cr[~np.isnan(cr)].view(np.uint32))
+    # the two methods are different estimators: the normals differ, the dominant planes agree
+    grad = api.PlaneExtractor(debug=True)
+    a, b = grad.extract(seq[2]), e.extract(seq[2])
+    assert a.mnRealPlaneNum == b.mnRealPlaneNum
+    assert not np.array_equal(grad.normals(0, 214 * 160)[0], e.normals(0, 214 * 160)[0])
+    grad.close()
+    res = e.extract_batch(seq)
+    for k in (0, 7):
+        compare_frame(e, oracle_lib.Oracle(normal_method=1).run(seq[k]), seq[k], res.frame(k), frame=k, expect_sat_exact=False)
+    with pytest.raises(api.SpxError):
+        grad2 = api.PlaneExtractor(debug=True); grad2.extract(seq[2]); grad2.curvature(0, 214 * 160)
+    e.close()
+    it = scenes.REALSENSE
+    big = scenes.add_noise(scenes.realsense_sequence(1, start=40)[0], 40, "realsense")
+    kw = dict(fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy, max_x=float(it.width), max_y=float(it.height))
+    e = api.PlaneExtractor(debug=True, max_rows=720, max_cols=1280, normal_method=1, **kw)
+    fp = e.extract(big)
+    rep = compare_frame(e, oracle_lib.Oracle(normal_method=1, **kw).run(big), big, fp, expect_sat_exact=False)
+    assert rep["normals_bit_exact"] and rep["labels_bit_exact"], rep
+    e.close()

@@ -222,3 +222,27 @@ def test_sat_sums_are_exact_for_depth_data(oracle_lib):
         if noisy:
             d = scenes.add_noise(d, f)
         assert oracle_lib.Oracle(enable_supposed=0).run(d).sat_exact()
+
+
+def test_covariance_matrix_method_on_an_analytic_plane(oracle_lib):
+    """IntegralImageNormalEstimation::COVARIANCE_MATRIX (normal_method = 1, the method BASELINE.json's north_star words; the
+    reference selects AVERAGE_3D_GRADIENT): on an exact plane the smallest eigenvector is the plane normal and the curvature
+    is ~0; the 10-pixel NaN border and the NaN curvature of the gradient method are as in PCL."""
+    it = scenes.TUM1
+    n = np.array([0.2, -0.1, -1.0]); n /= np.linalg.norm(n)
+    v, u = np.mgrid[0:480, 0:640].astype(np.float64)
+    rays = np.stack([(u - it.cx) / it.fx, (v - it.cy) / it.fy, np.ones_like(u)], -1)
+    depth = (-2.5 / (rays @ n)).astype(np.float32)          # plane n . p + 2.5 = 0
+    o = oracle_lib.Oracle(normal_method=1, enable_supposed=0).run(depth)
+    nrm, cv = o.normals(), o.curvature()
+    ok = ~np.isnan(nrm[0])
+    assert ok.sum() == (214 - 20) * (160 - 20)
+    ang = np.arccos(np.clip(np.abs(nrm[:, ok].T @ n), 0, 1))
+    assert ang.max() < 2e-3 and np.median(ang) < 2e-4
+    assert np.all(cv[ok] >= 0) and np.median(cv[ok]) < 1e-4
+    assert o.n_real == 1
+    g = oracle_lib.Oracle(enable_supposed=0).run(depth)
+    assert np.all(np.isnan(g.curvature()))                 # AVERAGE_3D_GRADIENT never sets the curvature
+    # the two recalled details of this method are switches as well
+    a = oracle_lib.Oracle(normal_method=1, enable_supposed=0, alt=oracle_lib.ALT_COV_TRACE).run(depth).curvature()
+    assert not np.array_equal(a[ok], cv[ok])
