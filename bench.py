@@ -479,7 +479,8 @@ def _main(out):
             ad = api.SequenceAdapter(api.default_config(max_frames=F, **kw), n_threads=max(1, ncpu // world - 1))
             ad_s, _ = timed_host(lambda: ad.process_ptr(host.data_ptr(), F, rows, cols), args.steps)
             n_pl, n_pt, n_bd, nbytes = ad.summary()
-            adapter = {"seconds": ad_s, "threads": ad.threads, "planes": n_pl, "points": n_pt, "boundary_points": n_bd,
+            adc_s, _ = timed_host(lambda: ad.process_clouds_ptr(host.data_ptr(), F, rows, cols), args.steps)
+            adapter = {"seconds": ad_s, "seconds_clouds": adc_s, "threads": ad.threads, "planes": n_pl, "points": n_pt, "boundary_points": n_bd,
                        "bytes_filled_per_step": nbytes}
             ad.close()
         except Exception as e:   # noqa: BLE001  (reported, never hidden)
@@ -566,10 +567,11 @@ def _main(out):
         cfg720 = measure_720p(stream, not args.no_cpu_baseline)
 
     t = torch.tensor([ms, e2e_s * 1e3, (e2e16_s or 0.0) * 1e3, e2e_whole_s * 1e3, e2e_full_s * 1e3,
-                      (adapter or {}).get("seconds", 0.0) * 1e3, strong_ms or 0.0], dtype=torch.float64, device="cuda")
+                      (adapter or {}).get("seconds", 0.0) * 1e3, strong_ms or 0.0, (adapter or {}).get("seconds_clouds", 0.0) * 1e3],
+                     dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, e2e16_ms, e2e_whole_ms, e2e_full_ms, ad_ms, strong_ms = (float(x) for x in t)
+    ms, e2e_ms, e2e16_ms, e2e_whole_ms, e2e_full_ms, ad_ms, strong_ms, adc_ms = (float(x) for x in t)
     K = args.steps
     value = total_frames * K / (ms * 1e-3)
     per_s = lambda t_ms: total_frames * K / (t_ms * 1e-3) if t_ms else None   # noqa: E731
@@ -635,7 +637,10 @@ def _main(out):
                 "bytes_filled_per_step": adapter["bytes_filled_per_step"], "points_per_step": adapter["points"] + adapter["boundary_points"],
                 "note": "spx_host::SequencePlanes (C++): the same call, then every Frame field of every frame filled -- mvPlanePoints / "
                         "mvBoundaryPoints as 32-byte pcl::PointXYZRGB-layout clouds in pooled storage, mvPlaneCoefficients -- by host threads "
-                        "that start on a frame group as soon as it is on the host (spx_set_group_callback)"}),
+                        "that start on a frame group as soon as it is on the host (spx_set_group_callback)",
+                "clouds_transfer": {"value": per_s(adc_ms), "unit": UNIT, "ms_per_step": adc_ms / K,
+                                    "note": "the same adapter fed by spx_extract_batch: the real planes' clouds cross PCIe as 16-byte points and "
+                                            "are only widened on the host (more bytes on the link, less host arithmetic)"}}),
             "e2e_full_clouds": {"value": per_s(e2e_full_ms), "unit": UNIT, "h2d_bytes_per_step": xfer_full[0] + xfer_full[1],
                                 "d2h_bytes_per_step": xfer_full[2], "ms_per_step": e2e_full_ms / K,
                                 "note": "spx_extract_batch: all clouds back as 16-byte points (round 1's e2e)"},

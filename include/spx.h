@@ -187,10 +187,11 @@ int spx_extract_batch_u16_compact(spx_ctx *ctx, const uint16_t *depth, int n_fra
 /* what spx_extract_batch_device packs: 0 = point clouds (default; spx_fetch_results), 1 = compact (spx_fetch_compact) */
 int spx_set_result_mode(spx_ctx *ctx, int mode);
 int spx_fetch_compact(spx_ctx *ctx, spx_compact_result *out);
-/* Streaming delivery for the compact host-input calls: a batch runs as frame groups; `fn` is called on the calling thread,
- * inside spx_extract_batch*_compact, as soon as the results of frames [frame0, frame1) are final in host memory (offsets
+/* Streaming delivery for the host-input calls: a batch runs as frame groups; `fn` is called on the calling thread, inside
+ * spx_extract_batch* (compact or not), as soon as the results of frames [frame0, frame1) are final in host memory (offsets
  * already in host layout), while later groups are still on the device -- the adapter starts filling Frame fields then.
- * `view` and the arrays it points to stay valid until the next extract call on the context.  fn = NULL turns it off. */
+ * Under the 16-byte-cloud calls the view has index_width = 0, point_index = NULL and EVERY plane's points_off indexes
+ * `points`.  `view` and the arrays it points to stay valid until the next extract call on the context.  fn = NULL turns it off. */
 typedef void (*spx_group_fn)(void *user, int frame0, int frame1, const spx_compact_result *view);
 int spx_set_group_callback(spx_ctx *ctx, spx_group_fn fn, void *user);
 

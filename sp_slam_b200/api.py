@@ -611,6 +611,8 @@ def host_lib():
         H.spx_seq_last_error.restype = C.c_char_p
         H.spx_seq_process.argtypes = [vp, vp, i32, i32, i32, sz, sz]
         H.spx_seq_process.restype = C.c_double
+        H.spx_seq_process_clouds.argtypes = [vp, vp, i32, i32, i32, sz, sz]
+        H.spx_seq_process_clouds.restype = C.c_double
         H.spx_seq_process_u16.argtypes = [vp, vp, i32, i32, i32, sz, sz, C.c_float]
         H.spx_seq_process_u16.restype = C.c_double
         H.spx_seq_summary.argtypes = [vp, vp]
@@ -648,6 +650,13 @@ class SequenceAdapter:
     def process_ptr(self, host_ptr: int, n: int, rows: int, cols: int) -> float:
         """One batch of tight CV_32F frames; returns the wall time of the call in ms."""
         ms = host_lib().spx_seq_process(self._s, host_ptr, n, rows, cols, cols * 4, rows * cols * 4)
+        if ms < 0:
+            raise SpxError(SPX_ERR_CUDA, (host_lib().spx_seq_last_error() or b"").decode())
+        return ms
+
+    def process_clouds_ptr(self, host_ptr: int, n: int, rows: int, cols: int) -> float:
+        """The same with the real planes' clouds crossing PCIe as 16-byte points (spx_extract_batch) and only widened on the host."""
+        ms = host_lib().spx_seq_process_clouds(self._s, host_ptr, n, rows, cols, cols * 4, rows * cols * 4)
         if ms < 0:
             raise SpxError(SPX_ERR_CUDA, (host_lib().spx_seq_last_error() or b"").decode())
         return ms

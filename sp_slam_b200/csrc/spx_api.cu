@@ -604,11 +604,11 @@ int grow_pinned(spx_ctx *c, T **p, size_t *cap, size_t need) {
 void fill_view(const spx_ctx *c, spx_compact_result *v, int n_frames, long long n_pl, long long n_ix, long long n_pt, long long n_bd) {
     v->n_frames = n_frames;
     v->n_planes_total = int(n_pl);
-    v->index_width = c->P.idx16 ? 2 : 4;
+    v->index_width = c->compact ? (c->P.idx16 ? 2 : 4) : 0;     // 0: every plane's cloud is in `points` (the 16-byte-cloud calls)
     v->cloud_width = c->P.w; v->cloud_height = c->P.h; v->cloud_dis = c->P.dis;
     v->n_index_total = n_ix; v->n_points_total = n_pt; v->n_boundary_total = n_bd;
     v->frames = c->h_frames; v->planes = c->h_planes;
-    v->point_index = c->h_pidx; v->points = c->h_pts; v->boundary = c->h_bnd;
+    v->point_index = c->compact ? c->h_pidx : nullptr; v->points = c->h_pts; v->boundary = c->h_bnd;
 }
 
 // results of spx_extract_batch_device -> host.  cout: the compact layout (the run must have packed it), else `out`.
@@ -688,7 +688,7 @@ int fetch_groups(spx_ctx *c, spx_batch_result *out, spx_compact_result *cout) {
             pl.points_off += (cp && !pl.is_supposed) ? d_ix : d_pt;
             pl.boundary_off += d_bd;
         }
-        if (cp && c->group_fn) {
+        if (c->group_fn) {
             fill_view(c, &c->view, go.f1, host_pl[g] + n_pls[g], end_ix[g], end_pt[g], end_bd[g]);
             c->group_fn(c->group_user, go.f0, go.f1, &c->view);
         }

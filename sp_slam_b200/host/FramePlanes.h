@@ -103,14 +103,28 @@ public:
             const __m128 tail = _mm_castsi128_ps(_mm_set_epi32(0, 0, 0, int(0xff0000fau)));   // rgba | pad pad pad
             for (; k + 4 <= n; k += 4) {
                 float z[4], a[4], b[4];
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t q = rc[idx[k + j]];
-                    const uint32_t r = q >> 16, c = q & 0xffffu;
-                    z[j] = depth_at(r, c); a[j] = xf[c]; b[j] = yf[r];
+                const uint32_t i0 = idx[k];
+                const uint32_t q0 = rc[i0];
+                const uint32_t r0i = q0 >> 16, c0 = q0 & 0xffffu;
+                __m128 va, vb;
+                if (uint32_t(idx[k + 1]) == i0 + 1 && uint32_t(idx[k + 2]) == i0 + 2 && uint32_t(idx[k + 3]) == i0 + 3 && int(c0) + 3 < w_) {
+                    // four neighbours of one row (inlier lists are mostly raster runs): one table look-up, contiguous factors
+                    const char *px = frame + size_t(r0i) * rstep + size_t(c0) * cstep;
+                    for (int j = 0; j < 4; ++j, px += cstep)
+                        z[j] = src.u16 ? float(*reinterpret_cast<const uint16_t *>(px)) * src.factor : *reinterpret_cast<const float *>(px);
+                    va = _mm_loadu_ps(xf + c0);
+                    vb = _mm_set1_ps(yf[r0i]);
+                } else {
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t q = rc[idx[k + j]];
+                        const uint32_t r = q >> 16, c = q & 0xffffu;
+                        z[j] = depth_at(r, c); a[j] = xf[c]; b[j] = yf[r];
+                    }
+                    va = _mm_loadu_ps(a); vb = _mm_loadu_ps(b);
                 }
                 const __m128 vz = _mm_loadu_ps(z);
-                __m128 r0 = _mm_div_ps(_mm_mul_ps(_mm_loadu_ps(a), vz), vfx);
-                __m128 r1 = _mm_div_ps(_mm_mul_ps(_mm_loadu_ps(b), vz), vfy);
+                __m128 r0 = _mm_div_ps(_mm_mul_ps(va, vz), vfx);
+                __m128 r1 = _mm_div_ps(_mm_mul_ps(vb, vz), vfy);
                 __m128 r2 = vz, r3 = one;
                 _MM_TRANSPOSE4_PS(r0, r1, r2, r3);                                           // rows: (x, y, z, 1) of the four points
                 float *o = reinterpret_cast<float *>(dst + k);
@@ -186,7 +200,10 @@ struct PlaneFields {
             PointCloud &pc = mvPlanePoints[size_t(k)], &bc = mvBoundaryPoints[size_t(k)];
             pc.points.resize(size_t(p.n_points));
             bc.points.resize(size_t(p.n_boundary));
-            if (!p.is_supposed) {
+            if (!p.is_supposed && res.index_width == 0) {         // 16-byte clouds (spx_extract_batch): a widening copy
+                CloudExpander::copy(pc.points.data(), res.points + p.points_off, p.n_points);
+                bc.width = 0; bc.height = 0;
+            } else if (!p.is_supposed) {
                 if (res.index_width == 2) ex.Expand(pc.points.data(), static_cast<const uint16_t *>(res.point_index) + p.points_off, p.n_points, src, frame);
                 else ex.Expand(pc.points.data(), static_cast<const uint32_t *>(res.point_index) + p.points_off, p.n_points, src, frame);
                 // `boundaryPoints->points = regions[i].getContour()` (src/Frame.cc:930-932) and GenerateBoundaryPoints' push_backs

@@ -36,11 +36,15 @@ public:
     SequencePlanes(const SequencePlanes &) = delete;
     SequencePlanes &operator=(const SequencePlanes &) = delete;
 
-    // depth: CV_32F metres, frame f at depth + f * frame_stride bytes, `step` bytes per row
-    void Process(const float *depth, int n_frames, int rows, int cols, size_t step, size_t frame_stride) {
+    // depth: CV_32F metres, frame f at depth + f * frame_stride bytes, `step` bytes per row.
+    // compact = true: the real planes' clouds cross PCIe as index lists and are rebuilt here (fewer bytes, more host work);
+    // false: they arrive as 16-byte points and are only widened to pcl::PointXYZRGB (what pays on a host with few cores per GPU
+    // is measured by bench.py: e2e_adapter / e2e_adapter_clouds).
+    void Process(const float *depth, int n_frames, int rows, int cols, size_t step, size_t frame_stride, bool compact = true) {
         begin(depth, n_frames, step, frame_stride, false, 1.0f);
-        spx_compact_result res;
-        const int rc = spx_extract_batch_compact(ctx_, depth, n_frames, rows, cols, step, frame_stride, &res);
+        int rc;
+        if (compact) { spx_compact_result res; rc = spx_extract_batch_compact(ctx_, depth, n_frames, rows, cols, step, frame_stride, &res); }
+        else { spx_batch_result res; rc = spx_extract_batch(ctx_, depth, n_frames, rows, cols, step, frame_stride, &res); }
         finish(rc);
     }
     // raw CV_16U images + mDepthMapFactor (Tracking::GrabImageRGBD's convertTo, src/Tracking.cc:230-231)

@@ -37,6 +37,14 @@ double spx_seq_process(void *h, const float *depth, int n_frames, int rows, int 
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     } catch (const std::exception &e) { g_err = e.what(); return -1.0; }
 }
+// the same with the real planes' clouds transferred as 16-byte points (spx_extract_batch) instead of index lists
+double spx_seq_process_clouds(void *h, const float *depth, int n_frames, int rows, int cols, size_t step, size_t frame_stride) {
+    try {
+        const auto t0 = std::chrono::steady_clock::now();
+        static_cast<SequencePlanes *>(h)->Process(depth, n_frames, rows, cols, step, frame_stride, false);
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    } catch (const std::exception &e) { g_err = e.what(); return -1.0; }
+}
 double spx_seq_process_u16(void *h, const uint16_t *depth, int n_frames, int rows, int cols, size_t step, size_t frame_stride, float factor) {
     try {
         const auto t0 = std::chrono::steady_clock::now();

@@ -136,6 +136,10 @@ def test_sequence_adapter_fills_every_frame_field(seq):
     for f in range(n):
         a, b = ad.frame(f), full.frame(f)
         same_fields_32(a, b)
+    # the 16-byte-cloud transfer through the same adapter (group callback of spx_extract_batch): the same fields
+    h0 = ad.hash()
+    ad.process_clouds_ptr(host.data_ptr(), n, 480, 640)
+    assert ad.hash() == h0
     # 16-bit input through the adapter
     d16 = np.round(np.clip(depth, 0, 13.0).astype(np.float64) * 5000.0).astype(np.uint16)
     h16 = torch.from_numpy(d16).pin_memory()
