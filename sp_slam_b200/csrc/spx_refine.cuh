@@ -58,90 +58,126 @@ __device__ __forceinline__ void refine_pass(RefineSmem &S, const Params &P, cons
                                             const float *__restrict__ pz, int8_t *pid, int *pos, int *cnt, int *last,
                                             const int *pos_base, int lane, bool has_invalid) {
     const int w = P.w, h = P.h;
-    int a[NCH], prev[NCH], pn[NCH], pn2[NCH], mV[NCH];
+    constexpr int kD = kReverse ? -32 : 32;      // column step from chunk to chunk
+    const int rstep = kReverse ? -w : w;         // flat-index step from visited row to visited row
+    const int c0 = kReverse ? (w - 1 - lane) : lane;   // this lane's column in chunk 0
+    const unsigned lt = (1u << lane) - 1u;
+    const int ch_last = (w - 1) >> 5, lane_last = (w - 1) & 31;   // where the last visited pixel of a row lives
+    int a[NCH], prev[NCH], pn[NCH], pn2[NCH];
     float x[NCH], y[NCH], z[NCH], xn[NCH], yn[NCH], zn[NCH];
-    auto col = [&](int ch) { const int k = ch * 32 + lane; return kReverse ? (w - 1 - k) : k; };
-    auto row_of = [&](int t) { return kReverse ? (h - 1 - t) : t; };
+    // warp-uniform lane masks per chunk.  Everything below is steered by them: a chunk of a row in which no free pixel can meet a
+    // plane costs a few scalar tests, not a round of votes.
+    unsigned lab[NCH], fre[NCH];      // row being processed: pixels of a plane / free pixels (labelled by PCL, part of no plane)
+    unsigned labn[NCH], fren[NCH];    // the next row
+    unsigned labp[NCH];               // previous row, final
+    unsigned smaskp[NCH];             // claimers of the previous row that claimed sideways
+    unsigned vmask[NCH];              // pixels of this row claimed vertically
+    // running flat indices / pointers: row being processed, one row ahead (xyz), two rows ahead (plane ids)
+    int q0 = (kReverse ? (h - 1) * w : 0) + c0;  // (r, c0)
+    const float *px1 = px + q0, *py1 = py + q0, *pz1 = pz + q0;   // advanced to row t + 1 before use
+    const int8_t *pid2 = pid + q0 + rstep;                        // advanced to row t + 2 before use
     // prologue: plane ids of rows t = 0 and 1, xyz of the free pixels of row 0
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
         const bool valid = ch * 32 + lane < w;
-        const int c = col(ch);
-        pn[ch] = valid ? int(pid[row_of(0) * w + c]) : -2;
-        pn2[ch] = (valid && h > 1) ? int(pid[row_of(1) * w + c]) : -2;
-        prev[ch] = -2; mV[ch] = -1;
+        pn[ch] = valid ? int(pid[q0 + ch * kD]) : -2;
+        pn2[ch] = (valid && h > 1) ? int(pid2[ch * kD]) : -2;
+        prev[ch] = -2;
+        labp[ch] = 0u; smaskp[ch] = 0u; vmask[ch] = 0u;
         xn[ch] = yn[ch] = zn[ch] = 0.f;
     }
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-        if (pn[ch] == -1) { const int q = row_of(0) * w + col(ch); xn[ch] = px[q]; yn[ch] = py[q]; zn[ch] = pz[q]; }
-    for (int c0 = lane; c0 < w; c0 += 32) S.cmA[c0] = -1;
-    __syncwarp();
+    for (int ch = 0; ch < NCH; ++ch) {
+        labn[ch] = __ballot_sync(SPX_FULL, pn[ch] >= 0);
+        fren[ch] = __ballot_sync(SPX_FULL, pn[ch] == -1);
+        if (pn[ch] == -1) { xn[ch] = px1[ch * kD]; yn[ch] = py1[ch * kD]; zn[ch] = pz1[ch * kD]; }
+    }
+    int wrapm = -1;         // (warp uniform) reverse pass: final plane of the last visited pixel of the previous row
 
-    for (int t = 0; t < h; ++t) {
-        const int r = row_of(t);
-        // rotate the prefetch registers and issue the loads of the rows ahead
+    for (int t = 0; t < h; ++t, q0 += rstep) {
+        // rotate the prefetch registers
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) { a[ch] = pn[ch]; x[ch] = xn[ch]; y[ch] = yn[ch]; z[ch] = zn[ch]; pn[ch] = pn2[ch]; }
+        for (int ch = 0; ch < NCH; ++ch) {
+            a[ch] = pn[ch]; x[ch] = xn[ch]; y[ch] = yn[ch]; z[ch] = zn[ch]; pn[ch] = pn2[ch];
+            lab[ch] = labn[ch]; fre[ch] = fren[ch];
+        }
+        px1 += rstep; py1 += rstep; pz1 += rstep; pid2 += rstep;
+        // the next row: its masks, and the xyz of those of its free pixels that a plane can reach.  A plane grows by one row per
+        // row step and along a row only in visiting direction, so a chunk of the next row can be tested only if a plane pixel
+        // exists in the same or an earlier-visited chunk of the previous, this or the next row (reverse pass: the wrap claim
+        // also leads from the last visited chunk to the first).
         if (t + 1 < h) {
-            const int rn = row_of(t + 1);
-#pragma unroll
-            for (int ch = 0; ch < NCH; ++ch)
-                if (pn[ch] == -1) { const int q = rn * w + col(ch); xn[ch] = px[q]; yn[ch] = py[q]; zn[ch] = pz[q]; }
-        }
-        if (t + 2 < h) {
-            const int rn2 = row_of(t + 2);
-#pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) pn2[ch] = (ch * 32 + lane < w) ? int(pid[rn2 * w + col(ch)]) : -2;
-        }
-        // A) vertical claims by the previous row
-        if (t >= 1) {
+            unsigned M = 0u, Fn = 0u;
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-                mV[ch] = -1;
-                const int m = prev[ch];
-                bool cand = a[ch] == -1 && m >= 0 && (kReverse || col(ch) <= w - 2);
-                // PCL: `if (current_label < 0 || right_label < 0) continue;` also drops the claimer's vertical claim when
-                // its sideways neighbour (flat index +-1) is an unlabelled point; only frames with non-finite depth have those
-                if (has_invalid && cand) {
-                    const int cr = kReverse ? r + 1 : r - 1;
-                    if (pid[cr * w + col(ch) + (kReverse ? -1 : 1)] == -2) cand = false;
-                }
-                if (__any_sync(SPX_FULL, cand)) {   // most chunks lie inside a plane or inside nothing
-                    if (cand && refine_dist_ok(S.coef[m], x[ch], y[ch], z[ch])) { a[ch] = m; mV[ch] = m; }
-                }
+                labn[ch] = __ballot_sync(SPX_FULL, pn[ch] >= 0);
+                fren[ch] = __ballot_sync(SPX_FULL, pn[ch] == -1);
+                if (labp[ch] | lab[ch] | labn[ch]) M |= 1u << ch;
+                if (fren[ch]) Fn |= 1u << ch;
             }
-            // W) wrap claim of (r+1, 0) on (r, w-1): visiting index w-1 of the previous row claims visiting index 0
-            if (kReverse) {
-                int m0 = -1;
+            unsigned reach = M;
+            reach |= reach << 1; reach |= reach << 2; reach |= reach << 4; reach |= reach << 8;
+            if (kReverse && M) reach = ~0u;   // (a chain that reaches the end of a row wraps into the first chunk of the next)
+            const unsigned need = Fn & reach;
+            if (need) {
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch)
-                    if (ch == ((w - 1) >> 5)) m0 = __shfl_sync(SPX_FULL, prev[ch], (w - 1) & 31);
-                if (m0 >= 0 && lane == 0 && a[0] == -1 && refine_dist_ok(S.coef[m0], x[0], y[0], z[0])) {
-                    a[0] = m0; S.cmA[0] = int8_t(m0);
-                }
-                __syncwarp();
+                    if ((need >> ch) & 1u) {
+                        if (pn[ch] == -1) { xn[ch] = px1[ch * kD]; yn[ch] = py1[ch * kD]; zn[ch] = pz1[ch * kD]; }
+                    }
             }
-            // E) emission for the claimers of the previous row
-            const int claimer_row = kReverse ? r + 1 : r - 1;
+        }
+        if (t + 2 < h) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) pn2[ch] = (ch * 32 + lane < w) ? int(pid2[ch * kD]) : -2;
+        }
+        unsigned changed = 0u;   // chunks whose labels changed in this row
+        if (t >= 1) {
+            // A) vertical claims by the previous row: a free pixel under (above) a plane pixel
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-                const bool valid = ch * 32 + lane < w;
-                const int c = col(ch);
-                const int mS = valid ? int(S.cmA[c]) : -1;
-                const int mv = mV[ch];
-                unsigned todoS = __ballot_sync(SPX_FULL, mS >= 0), todoV = __ballot_sync(SPX_FULL, mv >= 0);
+                unsigned cm = fre[ch] & labp[ch];
+                if (!kReverse && ch == ch_last) cm &= ~(1u << lane_last);   // PCL's first pass visits columns 0 .. w-2
+                vmask[ch] = 0u;
+                if (cm == 0u) continue;
+                const int m = prev[ch];
+                bool cand = (cm >> lane) & 1u;
+                // PCL: `if (current_label < 0 || right_label < 0) continue;` also drops the claimer's vertical claim when
+                // its sideways neighbour (flat index +-1) is an unlabelled point; only frames with non-finite depth have those
+                if (has_invalid && cand && pid[q0 - rstep + ch * kD + (kReverse ? -1 : 1)] == -2) cand = false;
+                const bool take = cand && refine_dist_ok(S.coef[cand ? m : 0], x[ch], y[ch], z[ch]);
+                if (take) a[ch] = m;
+                const unsigned vm = __ballot_sync(SPX_FULL, take);
+                vmask[ch] = vm;
+                if (vm) { lab[ch] |= vm; fre[ch] &= ~vm; changed |= 1u << ch; }
+            }
+            // W) wrap claim of (r+1, 0) on (r, w-1): visiting index w-1 of the previous row claims visiting index 0
+            if (kReverse && wrapm >= 0 && (fre[0] & 1u)) {
+                const bool take = lane == 0 && refine_dist_ok(S.coef[wrapm], x[0], y[0], z[0]);
+                if (take) a[0] = wrapm;
+                if (__any_sync(SPX_FULL, take)) {
+                    lab[0] |= 1u; fre[0] &= ~1u; changed |= 1u;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) if (ch == ch_last) smaskp[ch] |= 1u << lane_last;
+                }
+            }
+            // E) emission for the claimers of the previous row: in visiting order claimer k issues its sideways claim and then
+            // its vertical claim; every claimed pixel gets its position in inlier_indices[model]
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                unsigned todoS = smaskp[ch], todoV = vmask[ch];
+                if ((todoS | todoV) == 0u) continue;
+                const int mS = ((todoS >> lane) & 1u) ? prev[ch] : -1;      // the claimer's own plane
+                const int mv = ((todoV >> lane) & 1u) ? a[ch] : -1;
+                const int qV = q0 + ch * kD;                                  // (r, c): below / above the claimer
+                const int qS = qV - rstep + (kReverse ? -1 : 1);              // the claimer's sideways neighbour (wraps at c == 0)
                 while (todoS | todoV) {
                     const int src = __ffs(todoS | todoV) - 1;
                     const int mine = mS >= 0 ? mS : mv;
                     const int mm = __shfl_sync(SPX_FULL, mine, src);
                     const unsigned bS = __ballot_sync(SPX_FULL, mS == mm), bV = __ballot_sync(SPX_FULL, mv == mm);
-                    const unsigned lt = (1u << lane) - 1u;
                     const int before = __popc(bS & lt) + __popc(bV & lt);
                     const int b0 = cnt[mm];
-                    int qS, qV;
-                    if (kReverse) { qS = claimer_row * w + c - 1; qV = (claimer_row - 1) * w + c; }   // left (wraps at c == 0), up
-                    else          { qS = claimer_row * w + c + 1; qV = (claimer_row + 1) * w + c; }   // right, down
                     if (mS == mm) pos[qS] = pos_base[mm] + b0 + before;
                     if (mv == mm) pos[qV] = pos_base[mm] + b0 + before + (mS == mm ? 1 : 0);
                     const int hl = 31 - __clz(bS | bV);
@@ -150,51 +186,59 @@ __device__ __forceinline__ void refine_pass(RefineSmem &S, const Params &P, cons
                     __syncwarp();
                     todoS &= ~bS; todoV &= ~bV;
                 }
-                if (valid) S.cmA[c] = -1;
             }
-            __syncwarp();
         }
-        // B) the chain inside row r (claimers: rows <= h-2 in the forward pass, rows >= 1 in the reverse pass)
-        if (kReverse ? (r >= 1) : (r <= h - 2)) {
+        // B) the chain inside row r (claimers: rows <= h-2 in the forward pass, rows >= 1 in the reverse pass): a free pixel is
+        // claimed by its already-final neighbour on the claimer side.  Only chunks in which a free pixel follows a plane pixel
+        // (or the carry) can claim anything.
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) smaskp[ch] = 0u;
+        if (t <= h - 2) {
             int carry = -1;
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-                const bool valid = ch * 32 + lane < w;
-                const int cur = a[ch];
-                const unsigned labelled = __ballot_sync(SPX_FULL, cur >= 0);
-                const unsigned freem = __ballot_sync(SPX_FULL, valid && cur == -1);
-                if (freem == 0u || (labelled == 0u && carry < 0)) {   // nothing to claim / nobody to claim it
-                    carry = __shfl_sync(SPX_FULL, cur, 31);
-                    if (carry < 0) carry = -1;
-                    continue;
+                unsigned clm = 0u;
+                if (fre[ch] & ((lab[ch] << 1) | (carry >= 0 ? 1u : 0u))) {
+                    const int cur = a[ch];
+                    const unsigned below = lab[ch] & lt;
+                    const int src_lane = below ? (31 - __clz(below)) : -1;
+                    const int m_lane = __shfl_sync(SPX_FULL, cur, src_lane < 0 ? 0 : src_lane);
+                    const int m_src = src_lane < 0 ? carry : m_lane;
+                    const bool ok = cur == -1 && m_src >= 0 && refine_dist_ok(S.coef[m_src < 0 ? 0 : m_src], x[ch], y[ch], z[ch]);
+                    // what stops a chain: a free pixel that fails the test, and a point PCL left unlabelled (non-finite; lanes
+                    // beyond the row count as such)
+                    const unsigned blocked = ~(lab[ch] | __ballot_sync(SPX_FULL, ok));
+                    // the pixels visited between src and this one: bits src_lane+1 .. lane-1
+                    const unsigned le_src = src_lane < 0 ? 0u : ((2u << src_lane) - 1u);
+                    const bool claimed = ok && (blocked & lt & ~le_src) == 0u;
+                    clm = __ballot_sync(SPX_FULL, claimed);
+                    if (claimed) a[ch] = m_src;
+                    if (clm) {
+                        lab[ch] |= clm; changed |= 1u << ch;
+                        // the claimer is the previously visited pixel
+                        smaskp[ch] |= clm >> 1;
+                        if (ch > 0 && (clm & 1u)) smaskp[ch - 1] |= 1u << 31;
+                    }
                 }
-                const unsigned below = labelled & ((1u << lane) - 1u);
-                const int src_lane = below ? (31 - __clz(below)) : -1;
-                const int m_lane = __shfl_sync(SPX_FULL, cur, src_lane < 0 ? 0 : src_lane);
-                const int m_src = src_lane < 0 ? carry : m_lane;
-                const bool isfree = valid && cur == -1;
-                const bool ok = isfree && m_src >= 0 && refine_dist_ok(S.coef[m_src], x[ch], y[ch], z[ch]);
-                const unsigned blocked = __ballot_sync(SPX_FULL, !valid || (cur == -1 && !ok));
-                // the free pixels visited between src and this one: bits src_lane+1 .. lane-1
-                const unsigned le_src = src_lane < 0 ? 0u : ((2u << src_lane) - 1u);
-                const unsigned mask = ((1u << lane) - 1u) & ~le_src;
-                const bool claimed = ok && (blocked & mask) == 0u;
-                if (claimed) {
-                    a[ch] = m_src;
-                    const int c = col(ch);
-                    S.cmA[kReverse ? c + 1 : c - 1] = int8_t(m_src);   // the claimer is the previously visited pixel
-                }
-                carry = __shfl_sync(SPX_FULL, a[ch], 31);
-                if (carry < 0) carry = -1;
+                carry = -1;
+                if (ch + 1 < NCH && (fre[ch + 1 < NCH ? ch + 1 : ch] & 1u) && ((lab[ch] >> 31) & 1u)) carry = __shfl_sync(SPX_FULL, a[ch], 31);
             }
         }
         // final labels of row r
+        if (kReverse) {
+            int lastv = a[NCH - 1];
+            if (ch_last != NCH - 1) {
+#pragma unroll
+                for (int ch = 0; ch < NCH - 1; ++ch) if (ch == ch_last) lastv = a[ch];
+            }
+            wrapm = __shfl_sync(SPX_FULL, lastv, lane_last);
+        }
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-            if (ch * 32 + lane < w) pid[r * w + col(ch)] = int8_t(a[ch]);
+            if ((changed >> ch) & 1u) { if (ch * 32 + lane < w) pid[q0 + ch * kD] = int8_t(a[ch]); }
             prev[ch] = a[ch];
+            labp[ch] = lab[ch];
         }
-        __syncwarp();
     }
 }
 
@@ -328,7 +372,7 @@ __device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, 
                 const int m_src = src_lane < 0 ? carry : m_lane;
                 const bool isfree = valid && a == -1;
                 const bool ok = isfree && m_src >= 0 && refine_dist_ok(S.coef[m_src], x, y, z);
-                const unsigned blocked = __ballot_sync(SPX_FULL, !valid || (a == -1 && !ok));
+                const unsigned blocked = __ballot_sync(SPX_FULL, !valid || a == -2 || (a == -1 && !ok));   // (-2: a point PCL left unlabelled stops a chain)
                 const unsigned le_src = src_lane < 0 ? 0u : ((2u << src_lane) - 1u);
                 const unsigned mask = ((1u << lane) - 1u) & ~le_src;
                 bool claimed = ok && (blocked & mask) == 0u;

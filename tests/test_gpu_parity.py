@@ -271,6 +271,30 @@ def test_u16_depth_ingest_equals_converted_float(seq):
     ext.close()
 
 
+def test_refine_chain_stops_at_unlabelled_points(oracle_lib, seq):
+    """A claim chain of refine() passes from pixel to pixel; a point PCL left unlabelled (NaN depth) is neither claimed nor a
+    claimer, so the free pixels behind it (NaN normals next to the gap, same wall) must wait for the reverse pass.  Full-height
+    NaN columns leave no vertical way around the gap."""
+    d = seq[4].copy()
+    for c in (300, 301, 302, 480):
+        d[:, c] = np.nan
+    d[::6, 150] = np.nan          # a broken column: vertical claims reach some rows only
+    orc = oracle_lib.Oracle().run(d)
+    ext = api.PlaneExtractor(debug=True)            # small launch: k_refine2
+    fp = ext.extract(d)
+    rep = compare_frame(ext, orc, d, fp)
+    assert rep["labels_bit_exact"], rep
+    assert fp.mnRealPlaneNum == orc.n_real >= 1
+    batch = np.repeat(seq[1][None], 70, axis=0)
+    batch[5] = d
+    big = large_batch_extractor(max_frames=70, n_streams=1)   # one-warp-per-frame k_refine
+    b = big.extract_batch(batch).frame(5)
+    assert b.mnPlaneNum == fp.mnPlaneNum and np.array_equal(b.mvPlaneCoefficients.view(np.uint32), fp.mvPlaneCoefficients.view(np.uint32))
+    for p_, q_ in zip(b.mvPlanePoints + b.mvBoundaryPoints, fp.mvPlanePoints + fp.mvBoundaryPoints):
+        assert np.array_equal(p_, q_)
+    big.close(); ext.close()
+
+
 def test_non_finite_depth(oracle_lib, seq):
     """NaN / Inf depth (never produced by a 16-bit sensor image, but legal in a CV_32F Mat): PCL leaves such points
     unlabelled, they take part in no plane, no claim and no window sum."""
