@@ -75,6 +75,7 @@ struct spx_ctx {
     bool strip_always = false;                 // test knob SPX_STRIP_ALWAYS: the strip kernel for small launches too
     int strip_occ = 4;                         // CTAs of k_normals_strip per SM the register budget is set for (tuning knob SPX_STRIP_OCC: 3 or 4)
     bool ccl_four = true;      // k_ccl_merge4 (N % 4 == 0) instead of the one-pixel-per-thread k_ccl_merge
+    bool ccl_frame = true;     // k_ccl_frame (forest of a frame in shared memory) when it fits; test knob SPX_CCL_FRAME=0: the global-memory kernels
     bool flatten_runs = true;  // k_ccl_flatten_runs (one pointer chase per row run) instead of k_ccl_flatten (one per pixel)
     bool refine_per_group = true;
     bool refine_dev_group = false;   // tuning knob SPX_REFINE_DEV_GROUP: the k_refine / k_refine2 choice per frame group on the resident path too
@@ -275,6 +276,7 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     // On the host path the groups start one upload apart instead of together, so the decision is made per group there.
     const int refine_load = ((c->group_pack && c->refine_per_group) || c->refine_dev_group) ? ng : c->P.n_frames;
     P.refine_fast = (refine_load <= c->refine_fast_max && P.h <= kRefMaxH) ? 1 : 0;   // small launches are latency bound: parallelism inside the frame
+    P.forest_in_smem = (c->ccl_frame && ccl_frame_fits(P.N)) ? 1 : 0;
     Buffers B = c->B;
     B.work = c->B.work + size_t(g) * c->work_stride;
     B.work2 = c->B.work2 + size_t(g) * c->work2_stride;
@@ -390,10 +392,15 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
         SPX_CK(c, cudaStreamWaitEvent(st_back, c->g_link[g], 0));
         st = st_back;
     }
-    if (c->ccl_four && N % 4 == 0) LAUNCH(k_ccl_merge4, dim3(cdiv(N / 4, 256), F), 256, 0, P, B);   // four pixels per thread
-    else LAUNCH(k_ccl_merge, gpix, 256, 0, P, B, 1);
-    if (c->flatten_runs) LAUNCH(k_ccl_flatten_runs, dim3(cdiv(P.w, 32), cdiv(P.h, 8 * kFlatRows), F), dim3(32, 8), 0, P, B);
-    else LAUNCH(k_ccl_flatten, gpix, 256, 0, P, B);
+    if (c->ccl_frame && ccl_frame_fits(N)) {
+        // merge + flatten of a frame's forest in shared memory (one CTA per frame)
+        LAUNCH(k_ccl_frame, F, kCFThreads, size_t(N) * sizeof(unsigned short), P, B);
+    } else {
+        if (c->ccl_four && N % 4 == 0) LAUNCH(k_ccl_merge4, dim3(cdiv(N / 4, 256), F), 256, 0, P, B);   // four pixels per thread
+        else LAUNCH(k_ccl_merge, gpix, 256, 0, P, B, 1);
+        if (c->flatten_runs) LAUNCH(k_ccl_flatten_runs, dim3(cdiv(P.w, 32), cdiv(P.h, 8 * kFlatRows), F), dim3(32, 8), 0, P, B);
+        else LAUNCH(k_ccl_flatten, gpix, 256, 0, P, B);
+    }
     LAUNCH(k_ccl_rank, F, kRankThreads, 0, P, B);
     if (c->debug) LAUNCH(k_ccl_label, gpix, 256, 0, P, B);
     LAUNCH(k_moments_fit, dim3(kMomCands, F), 96, 0, P, B);
@@ -883,6 +890,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (const char *e = std::getenv("SPX_NORMALS")) { const int v = std::atoi(e); if (v >= 0 && v <= 2) c->normals_mode = v; }   // test knob
     if (const char *e = std::getenv("SPX_CCL_FOUR")) c->ccl_four = std::atoi(e) != 0;   // test knob: the one-pixel-per-thread kernel
     if (const char *e = std::getenv("SPX_FLATTEN_RUNS")) c->flatten_runs = std::atoi(e) != 0;   // test knob
+    if (const char *e = std::getenv("SPX_CCL_FRAME")) c->ccl_frame = std::atoi(e) != 0;   // test knob
     if (const char *e = std::getenv("SPX_REFINE_PER_GROUP")) c->refine_per_group = std::atoi(e) != 0;   // tuning knob
     if (const char *e = std::getenv("SPX_REFINE_DEV_GROUP")) c->refine_dev_group = std::atoi(e) != 0;   // tuning knob
     if (const char *e = std::getenv("SPX_EDGE_WEIGHT")) { const double v = std::atof(e); if (v > 0.05 && v <= 1.0) c->edge_weight = v; }   // tuning knob
@@ -986,6 +994,8 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     SPX_CK_CREATE(cudaFuncSetAttribute(k_refine2<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kRefMaxH * 14 * 4 + kRefTableCap * 4));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_refine2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kRefMaxH * 16 * 4 + kRefTableCap * 4));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_contour, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(w + 2) * (h + 2))));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_ccl_frame, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(std::min(size_t(c->capN) * sizeof(unsigned short), size_t(72) * 1024))));
     {
         int per_sm = 0;
         SPX_CK_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lines, kLineThreads, kLinesSmem));

@@ -200,10 +200,12 @@ k_normals_strip(const __grid_constant__ CUtensorMap tmap, const float *__restric
             B.cnt[fo + lk_q] = 0;                                         // (finite frame: every point gets a label)
             if (write_normals) { B.nx[fo + lk_q] = n1x; B.ny[fo + lk_q] = n1y; B.nz[fo + lk_q] = n1z; B.pd[fo + lk_q] = d1; }
         }
-        const unsigned linked = __ballot_sync(SPX_FULL, lk_valid && L);
-        const unsigned starts = ~linked | 1u;                             // lane 0 always starts a run inside the segment
-        const int s0 = 31 - __clz(starts & (SPX_FULL >> (31 - lane)));
-        if (lk_valid) B.parent[fo + lk_q] = lk_q - lane + s0;
+        if (!P.forest_in_smem) {                                          // (k_ccl_frame rebuilds the row runs from the link bits)
+            const unsigned linked = __ballot_sync(SPX_FULL, lk_valid && L);
+            const unsigned starts = ~linked | 1u;                         // lane 0 always starts a run inside the segment
+            const int s0 = 31 - __clz(starts & (SPX_FULL >> (31 - lane)));
+            if (lk_valid) B.parent[fo + lk_q] = lk_q - lane + s0;
+        }
     };
     // ================= phase A, part 2: back-projection of cloud rows [r0 + 5, r0 + 13) =================
     auto backproject = [&](auto edge_c, auto par_c, int r0) {

@@ -594,10 +594,14 @@ __global__ void __launch_bounds__(kContourThreads) k_contour(Params P, Buffers B
     const int w = P.w, h = P.h, sw = w + 2;
     const size_t fo = size_t(f) * P.N;
     const int8_t *pid = B.pid + fo;
-    for (int i = tid; i < (h + 2) * sw; i += kContourThreads) {
-        const int y = i / sw - 1, x = i - (y + 1) * sw - 1;
-        sm_pid[i] = (x >= 0 && x < w && y >= 0 && y < h) ? pid[y * w + x] : int8_t(kPidOutside);
+    // a warp per row (no division per element); the sentinel frame separately
+    for (int y = tid >> 5; y < h; y += kContourThreads / 32) {
+        const int8_t *src = pid + y * w;
+        int8_t *dst = sm_pid + (y + 1) * sw + 1;
+        for (int x = tid & 31; x < w; x += 32) dst[x] = src[x];
     }
+    for (int i = tid; i < sw; i += kContourThreads) { sm_pid[i] = int8_t(kPidOutside); sm_pid[(h + 1) * sw + i] = int8_t(kPidOutside); }
+    for (int y = tid; y < h; y += kContourThreads) { sm_pid[(y + 1) * sw] = int8_t(kPidOutside); sm_pid[(y + 1) * sw + w + 1] = int8_t(kPidOutside); }
     __syncthreads();
     int *arena = B.contour_idx + size_t(f) * P.contour_cap;
     // offsets of the neighbours in the padded map, in the reference's direction order

@@ -224,6 +224,140 @@ __global__ void __launch_bounds__(256) k_ccl_flatten_runs(Params P, Buffers B) {
     }
 }
 
+// K4b + K4c in shared memory: one CTA per frame whose forest fits (16-bit entries: N <= 65535 and 2 N bytes of shared memory).
+// The unions of k_ccl_merge4 and the pointer chases of k_ccl_flatten_runs are chains of dependent loads; in global memory
+// every hop is an L2 round trip, here it is a shared-memory access.  Same forest, same result: a union points the larger
+// root at the smaller, so every root is its component's first raster pixel whatever the order of the unions; the output
+// is the flattened forest (parent[q] = root) and the component sizes added to cnt[root], exactly what the two kernels leave.
+//  (1) a warp takes a 32-column segment of a block of rows and rebuilds the row runs from the left-link bits (the forest
+//      k_normals_strip / k_ccl_link initialised in global memory is not read);
+//  (2) vertical unions and the left links across segment borders, with k_ccl_merge's skip rules;
+//  (3) per run: the first pixel finds the root, the run's lanes get it by shuffle, the length goes to the root's counter.
+constexpr int kCFThreads = 448;      // 14 warps: 7 segments x 2 row blocks at 214 x 160
+constexpr int kCFRows = 40;          // rows of an item (segment x row block)
+
+__device__ __forceinline__ unsigned sm_find(volatile unsigned short *lab, unsigned x) {   // path halving (see uf_find_halving)
+    while (true) {
+        const unsigned p = lab[x];
+        if (p == x) return x;
+        const unsigned gp = lab[p];
+        if (gp == p) return p;
+        lab[x] = static_cast<unsigned short>(gp);
+        x = gp;
+    }
+}
+__device__ __forceinline__ void sm_unite(unsigned short *lab, unsigned a, unsigned b) {
+    while (true) {
+        a = sm_find(lab, a);
+        b = sm_find(lab, b);
+        if (a == b) return;
+        if (a < b) { const unsigned t = a; a = b; b = t; }
+        // a is a root as far as this thread knows: point it at the smaller root unless somebody else already did
+        if (atomicCAS(lab + a, static_cast<unsigned short>(a), static_cast<unsigned short>(b)) == a) return;
+    }
+}
+
+__host__ __device__ __forceinline__ bool ccl_frame_fits(int N) { return N <= 65535 && size_t(N) * 2 <= size_t(72) * 1024; }
+
+__global__ void __launch_bounds__(kCFThreads) k_ccl_frame(Params P, Buffers B) {
+    extern __shared__ unsigned short sm_lab[];   // N entries
+    const int f = P.frame0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int w = P.w, h = P.h;
+    const size_t fo = size_t(f) * P.N;
+    const uint8_t *conn = B.conn + fo;
+    const int segs = (w + 31) >> 5, rblocks = (h + kCFRows - 1) / kCFRows, items = segs * rblocks;
+    constexpr int kWarps = kCFThreads / 32;
+    // The link bytes are read eight rows at a time (independent loads in flight together), the chains run in shared memory.
+    constexpr int kU = 8;
+    // (1) row runs
+    for (int it = wid; it < items; it += kWarps) {
+        const int seg = it % segs, rb = it / segs;
+        const int c = seg * 32 + lane;
+        const bool valid = c < w;
+        const int r1 = min(h, (rb + 1) * kCFRows);
+        for (int rr = rb * kCFRows; rr < r1; rr += kU) {
+            unsigned cbv[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) cbv[u] = (valid && rr + u < r1) ? conn[(rr + u) * w + c] : 0u;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (rr + u >= r1) break;                            // (warp uniform)
+                const int q = (rr + u) * w + c;
+                const unsigned linked = __ballot_sync(SPX_FULL, valid && (cbv[u] & 1u));
+                const unsigned starts = ~linked | 1u;               // lane 0 always starts a run inside the segment
+                const int s0 = 31 - __clz(starts & (SPX_FULL >> (31 - lane)));
+                if (valid) sm_lab[q] = static_cast<unsigned short>(q - lane + s0);
+            }
+        }
+    }
+    __syncthreads();
+    // (2) unions (k_ccl_merge's rules: a link whose union is implied by the three other links of its 2 x 2 cell is skipped)
+    for (int it = wid; it < items; it += kWarps) {
+        const int seg = it % segs, rb = it / segs;
+        const int c = seg * 32 + lane;
+        const bool valid = c < w;
+        const int rbeg = rb * kCFRows, r1 = min(h, (rb + 1) * kCFRows);
+        unsigned up = (valid && rbeg > 0) ? conn[(rbeg - 1) * w + c] : 0u;
+        for (int rr = rbeg; rr < r1; rr += kU) {
+            unsigned cbv[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) cbv[u] = (valid && rr + u < r1) ? conn[(rr + u) * w + c] : 0u;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (rr + u >= r1) break;
+                const int r = rr + u, q = r * w + c;
+                const unsigned cb = cbv[u];
+                unsigned left = __shfl_up_sync(SPX_FULL, cb, 1);
+                if (lane == 0) {
+                    left = 0u;
+                    if ((cb & 1u) && r > 0 && (cb & 2u)) left = conn[q - 1];     // only the skip test of the border link reads it
+                    if (cb & 1u) {                                                // (c > 0: column 0 has no left link)
+                        const bool skip = r > 0 && (cb & 2u) && (left & 2u) && (up & 1u);
+                        if (!skip) sm_unite(sm_lab, unsigned(q), unsigned(q - 1));
+                    }
+                }
+                if (cb & 2u) {
+                    const bool skip = lane != 0 && (cb & 1u) && (up & 1u) && (left & 2u);
+                    if (!skip) sm_unite(sm_lab, unsigned(q), unsigned(q - w));
+                }
+                up = cb;
+            }
+        }
+    }
+    __syncthreads();
+    // (3) flatten by runs, sizes to the roots
+    int *parent = B.parent + fo;
+    int *cnt = B.cnt + fo;
+    for (int it = wid; it < items; it += kWarps) {
+        const int seg = it % segs, rb = it / segs;
+        const int c = seg * 32 + lane;
+        const bool valid = c < w;
+        const int n_valid = min(32, w - seg * 32);
+        const int r1 = min(h, (rb + 1) * kCFRows);
+        for (int rr = rb * kCFRows; rr < r1; rr += kU) {
+            unsigned cbv[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) cbv[u] = (valid && rr + u < r1) ? conn[(rr + u) * w + c] : 0u;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (rr + u >= r1) break;
+                const int q = (rr + u) * w + c;
+                const unsigned linked = __ballot_sync(SPX_FULL, valid && (cbv[u] & 1u));
+                const unsigned starts = ~linked | 1u;
+                const int s0 = 31 - __clz(starts & (SPX_FULL >> (31 - lane)));
+                const unsigned above = lane == 31 ? 0u : (starts & (SPX_FULL << (lane + 1)));
+                const int next = above ? __ffs(above) - 1 : 32;
+                const bool start = valid && s0 == lane;
+                int root = 0;
+                if (start) root = int(sm_find(sm_lab, unsigned(q)));
+                root = __shfl_sync(SPX_FULL, root, s0);
+                if (valid) parent[q] = root;
+                if (start) atomicAdd(cnt + root, min(next, n_valid) - lane);
+            }
+        }
+    }
+}
+
 // K4d: one CTA per frame, one pass over the frame in 2048-pixel chunks (raster order).
 //  (1) exclusive prefix count of roots = PCL's dense label of each component; components with size > Plane.MinSize
 //      become plane candidates, in label order, and get the offset of their index list;

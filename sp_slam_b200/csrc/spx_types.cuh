@@ -31,6 +31,7 @@ struct Params {
     float fx, fy, cx, cy;
     float rfx, rfy;        // RN(1 / fx), RN(1 / fy) for the strip kernel's division by a constant
     float min_axf, min_ayf; // smallest non-zero |n - cx| / |m - cy| over the sampled columns / rows of the current image
+    int   forest_in_smem;  // k_ccl_frame rebuilds the row runs itself: the normals kernel need not initialise the forest in global memory
     int   fast_div;        // bit 0 / 1: that division was verified against the IEEE quotient for fx / fy (k_check_div)
     float min_x, max_x, min_y, max_y;
     float mdcf;            // max depth change factor
