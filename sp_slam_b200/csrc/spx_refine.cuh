@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
 // next direction from an 8-bit "same label" mask with a rotate + find-first-set.
 __constant__ int c_ddx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
 __constant__ int c_ddy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
-constexpr int kContourThreads = 128;
+constexpr int kContourThreads = 256;
 constexpr int kPidOutside = 0x7f;   // sentinel of the frame around the image: neither "same" nor an in-image "different"
 
 __global__ void __launch_bounds__(kContourThreads) k_contour(Params P, Buffers B) {
