@@ -75,7 +75,9 @@ struct spx_ctx {
     bool strip_always = false;                 // test knob SPX_STRIP_ALWAYS: the strip kernel for small launches too
     int strip_occ = 4;                         // CTAs of k_normals_strip per SM the register budget is set for (tuning knob SPX_STRIP_OCC: 3 or 4)
     bool ccl_four = true;      // k_ccl_merge4 (N % 4 == 0) instead of the one-pixel-per-thread k_ccl_merge
-    bool ccl_frame = true;     // k_ccl_frame (forest of a frame in shared memory) when it fits; test knob SPX_CCL_FRAME=0: the global-memory kernels
+    int ccl_frame = 1;         // k_ccl_frame (forest of a frame in shared memory, one CTA per frame): 1 = for launches of >= 512 frames
+                               // (0.40 vs 0.46 ms per 1000 frames; at 1 / 64 / 128 frames the many-CTA kernels win: 0.036 / 0.056 / 0.082 vs
+                               // 0.090 / 0.112 / 0.118 ms), 0 = never, 2 = whenever it fits (test knob SPX_CCL_FRAME)
     bool flatten_runs = true;  // k_ccl_flatten_runs (one pointer chase per row run) instead of k_ccl_flatten (one per pixel)
     bool refine_per_group = true;
     bool refine_dev_group = false;   // tuning knob SPX_REFINE_DEV_GROUP: the k_refine / k_refine2 choice per frame group on the resident path too
@@ -276,7 +278,7 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     // On the host path the groups start one upload apart instead of together, so the decision is made per group there.
     const int refine_load = ((c->group_pack && c->refine_per_group) || c->refine_dev_group) ? ng : c->P.n_frames;
     P.refine_fast = (refine_load <= c->refine_fast_max && P.h <= kRefMaxH) ? 1 : 0;   // small launches are latency bound: parallelism inside the frame
-    P.forest_in_smem = (c->ccl_frame && ccl_frame_fits(P.N)) ? 1 : 0;
+    P.forest_in_smem = (ccl_frame_fits(P.N) && (c->ccl_frame == 2 || (c->ccl_frame == 1 && ng >= 512))) ? 1 : 0;
     Buffers B = c->B;
     B.work = c->B.work + size_t(g) * c->work_stride;
     B.work2 = c->B.work2 + size_t(g) * c->work2_stride;
@@ -392,7 +394,7 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
         SPX_CK(c, cudaStreamWaitEvent(st_back, c->g_link[g], 0));
         st = st_back;
     }
-    if (c->ccl_frame && ccl_frame_fits(N)) {
+    if (P.forest_in_smem) {
         // merge + flatten of a frame's forest in shared memory (one CTA per frame)
         LAUNCH(k_ccl_frame, F, kCFThreads, size_t(N) * sizeof(unsigned short), P, B);
     } else {
@@ -890,7 +892,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (const char *e = std::getenv("SPX_NORMALS")) { const int v = std::atoi(e); if (v >= 0 && v <= 2) c->normals_mode = v; }   // test knob
     if (const char *e = std::getenv("SPX_CCL_FOUR")) c->ccl_four = std::atoi(e) != 0;   // test knob: the one-pixel-per-thread kernel
     if (const char *e = std::getenv("SPX_FLATTEN_RUNS")) c->flatten_runs = std::atoi(e) != 0;   // test knob
-    if (const char *e = std::getenv("SPX_CCL_FRAME")) c->ccl_frame = std::atoi(e) != 0;   // test knob
+    if (const char *e = std::getenv("SPX_CCL_FRAME")) c->ccl_frame = std::atoi(e);   // test knob
     if (const char *e = std::getenv("SPX_REFINE_PER_GROUP")) c->refine_per_group = std::atoi(e) != 0;   // tuning knob
     if (const char *e = std::getenv("SPX_REFINE_DEV_GROUP")) c->refine_dev_group = std::atoi(e) != 0;   // tuning knob
     if (const char *e = std::getenv("SPX_EDGE_WEIGHT")) { const double v = std::atof(e); if (v > 0.05 && v <= 1.0) c->edge_weight = v; }   // tuning knob

@@ -603,6 +603,26 @@ def test_sparse_upload_without_supposed_planes(seq):
     full.close(); e.close()
 
 
+def test_forest_in_shared_memory_equals_the_global_kernels(seq, oracle_lib):
+    """k_ccl_frame (union-find + flatten of a frame's forest in shared memory; default only for launches of >= 512 frames)
+    against the oracle and against k_ccl_merge4 + k_ccl_flatten_runs: clean, noisy and non-finite frames, one frame and a batch."""
+    a = extractor_with_env({"SPX_CCL_FRAME": "2", "SPX_STRIP_ALWAYS": "1"}, debug=True, max_frames=8)
+    b = extractor_with_env({"SPX_CCL_FRAME": "0"}, debug=True, max_frames=8)
+    nanf = seq[3].copy(); nanf[100:140, 200:260] = np.nan; nanf[240:243, :] = np.nan
+    for d in (seq[0], scenes.add_noise(seq[5], FRAMES[5]), nanf):
+        fa, fb = a.extract(d), b.extract(d)
+        orc = oracle_lib.Oracle().run(d)
+        rep = compare_frame(a, orc, d, fa)
+        assert rep["labels_bit_exact"], rep
+        assert fa.mnPlaneNum == fb.mnPlaneNum and np.array_equal(fa.mvPlaneCoefficients.view(np.uint32), fb.mvPlaneCoefficients.view(np.uint32))
+        for p_, q_ in zip(fa.mvPlanePoints + fa.mvBoundaryPoints, fb.mvPlanePoints + fb.mvBoundaryPoints):
+            assert np.array_equal(p_, q_)
+    ra, rb = a.extract_batch(seq), b.extract_batch(seq)
+    assert np.array_equal(ra.frames, rb.frames) and np.array_equal(ra.planes, rb.planes)
+    assert np.array_equal(ra.points, rb.points) and np.array_equal(ra.boundary, rb.boundary)
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("mode", ["0", "1", "2"])
 def test_normals_kernel_variants(seq, oracle_lib, mode):
     """K3 three ways -- the 32x16 tile kernel of round 1 (0), the strip kernel with plain loads (1, also what a depth pointer TMA
