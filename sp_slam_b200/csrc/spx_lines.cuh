@@ -380,14 +380,15 @@ struct LineShared {
     uint16_t J[624];            // draw positions of the current output block (smem path: n <= kLineCap < 65536)
     int      Jg[624];           // the same for the global-memory path
     int      att0[kTripMax], att1[kTripMax];   // shuffled[0], shuffled[1] after each draw attempt of the trip
-    Hyp      hyp[kTripMax];
+    Hyp      hyp[2][kTripMax];  // hypotheses of the trip being scored and of the next one (drawn meanwhile)
     int      counts[kTripMax];
     int      s_warp[kLineThreads / 32];
     float    stage[32 * 7];     // per-point terms of the centroid / covariance sums, staged for the ordered adds
     float    best[6], coef[6], dir[3], cen[3], cov[6];
-    int      stop, iter, have, nhyp, natt, refill, jpos, item;
+    int      stop, iter, have, nhyp[2], natt, refill, jpos, item;
     int      n_best, iterations, best_s0, best_s1;
     unsigned skipped, run_bad;
+    unsigned skipped_end[2];    // skipped_count after the attempts of the trip
     double   kk;
 };
 
@@ -437,12 +438,32 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
         const double one_over_indices = 1.0 / double(n);
         int trip = 32;        // draw attempts of the next round trip (thread 0)
         __syncthreads();
-        while (true) {
+        // One trip = a batch of draw attempts -> hypotheses -> scores -> replay of the loop condition.  Drawing is the only
+        // inherently serial part (the swaps of drawIndexSample, thread 0) and does not depend on the scores, so warp 0 draws and
+        // folds the NEXT trip while warps 1..7 score the current one; attempts drawn beyond the stop are simply not used (every
+        // segment() round starts from a fresh shuffle and a fresh generator).
+        auto draw_and_fold = [&](int buf) {          // warp 0
+            Hyp *HB = S.hyp[buf];
             // (a) thread 0: the swaps of drawIndexSample for `trip` attempts -- the only inherently serial part
             if (tid == 0) {
                 int na = 0, jp = S.jpos;
                 if (n >= 2) {
                     while (na < trip && jp < 624) {
+                    // two attempts at a time when their four positions are distinct and beyond the two sample slots (almost always):
+                    // the four loads are independent of the four stores, so the swaps do not wait for one another
+                    while (na + 1 < trip && jp + 3 < 624) {
+                        const int a0 = kSmem ? int(S.J[jp]) : S.Jg[jp], a1 = kSmem ? int(S.J[jp + 1]) : S.Jg[jp + 1];
+                        const int b0 = kSmem ? int(S.J[jp + 2]) : S.Jg[jp + 2], b1 = kSmem ? int(S.J[jp + 3]) : S.Jg[jp + 3];
+                        if (a0 <= 1 || a1 <= 1 || b0 <= 1 || b1 <= 1 || a0 == a1 || a0 == b0 || a0 == b1 || a1 == b0 || a1 == b1 || b0 == b1) break;
+                        const int ta0 = int(sh[a0]), ta1 = int(sh[a1]), tb0 = int(sh[b0]), tb1 = int(sh[b1]);
+                        sh[a0] = IdxT(v0); sh[a1] = IdxT(v1);           // attempt 1: swap(shuffled[0], shuffled[a0]); swap(shuffled[1], shuffled[a1])
+                        S.att0[na] = ta0; S.att1[na] = ta1;
+                        sh[b0] = IdxT(ta0); sh[b1] = IdxT(ta1);         // attempt 2 swaps what attempt 1 left in slots 0 and 1
+                        S.att0[na + 1] = tb0; S.att1[na + 1] = tb1;
+                        v0 = tb0; v1 = tb1;
+                        na += 2; jp += 4;
+                    }
+                    if (na < trip && jp < 624) {                       // one attempt the general way (then the pairs resume)
                         const int j0 = kSmem ? int(S.J[jp]) : S.Jg[jp];
                         const int j1 = kSmem ? int(S.J[jp + 1]) : S.Jg[jp + 1];
                         jp += 2;
@@ -453,10 +474,11 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
                         S.att0[na] = v0; S.att1[na] = v1;
                         ++na;
                     }
+                    }
                 }
                 S.natt = na; S.jpos = jp; S.refill = (n >= 2 && jp >= 624) ? 1 : 0;
             }
-            __syncthreads();
+            __syncwarp();
             // (b) warp 0: isSampleGood / the degeneracy test of computeModelCoefficients for every attempt, then the
             // attempts are folded into hypotheses in order (getSamples gives up after 1000 bad draws in a row)
             if (wid == 0) {
@@ -478,41 +500,55 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
                     int nh = 0;
                     unsigned skipped = S.skipped, run_bad = S.run_bad;
                     bool ended = false;
-                    if (n < 2) { S.hyp[0].state = 1; S.hyp[0].skipped = skipped; nh = 1; ended = true; }
+                    if (n < 2) { HB[0].state = 1; HB[0].skipped = skipped; nh = 1; ended = true; }
                     for (int t = 0; t < na && !ended; ++t) {
                         const bool g = (good[t >> 5] >> (t & 31)) & 1u, dg = (degen[t >> 5] >> (t & 31)) & 1u;
                         if (!g) {
-                            if (++run_bad >= 1000u) { S.hyp[nh].state = 1; S.hyp[nh].skipped = skipped; ++nh; ended = true; }
+                            if (++run_bad >= 1000u) { HB[nh].state = 1; HB[nh].skipped = skipped; ++nh; ended = true; }
                             continue;
                         }
                         run_bad = 0u;
                         if (dg) {
                             ++skipped;
-                            if (skipped >= max_skip) { S.hyp[nh].state = 1; S.hyp[nh].skipped = skipped; ++nh; ended = true; }
+                            if (skipped >= max_skip) { HB[nh].state = 1; HB[nh].skipped = skipped; ++nh; ended = true; }
                             continue;
                         }
-                        Hyp &H = S.hyp[nh];
+                        Hyp &H = HB[nh];
                         H.s0 = S.att0[t]; H.s1 = S.att1[t]; H.state = 0; H.skipped = skipped;
                         ++nh;
                     }
-                    S.nhyp = nh; S.skipped = skipped; S.run_bad = run_bad;
+                    S.nhyp[buf] = nh; S.skipped = skipped; S.run_bad = run_bad; S.skipped_end[buf] = skipped;
                 }
             }
-            __syncthreads();
-            const int nh = S.nhyp;
-            // (c) score: warp `wid` takes hypotheses wid, wid+8, ...
-            for (int hh = wid; hh < nh; hh += kLineThreads / 32) {
-                if (S.hyp[hh].state != 0) continue;
-                float c[6], dir[3];
-                line_model(A[S.hyp[hh].s0], A[S.hyp[hh].s1], c);
-                line_prep_dir(c, dir);
-                int cnt = 0;
-                for (int i = lane; i < n; i += 32) {
-                    const float4 p = A[i];
-                    cnt += line_within(c, dir, p.x, p.y, p.z, thr_f) ? 1 : 0;
+            __syncwarp();
+        };
+        if (wid == 0) draw_and_fold(0);
+        __syncthreads();
+        for (int cur = 0;; cur ^= 1) {
+            const int nh = S.nhyp[cur];
+            const Hyp *HC = S.hyp[cur];
+            if (wid == 0) {
+                // the next trip (unless the generator block is used up: the refill below comes first)
+                if (tid == 0) {
+                    const double left = S.kk - double(S.iterations) - double(nh);
+                    trip = left >= double(kTripMax) ? kTripMax : (left <= 8.0 ? 8 : int(left) + 1);
                 }
-                cnt = __reduce_add_sync(SPX_FULL, cnt);
-                if (lane == 0) S.counts[hh] = cnt;
+                draw_and_fold(cur ^ 1);
+            } else {
+                // (c) score: warps 1..7 take hypotheses wid-1, wid-1+7, ...
+                for (int hh = wid - 1; hh < nh; hh += kLineThreads / 32 - 1) {
+                    if (HC[hh].state != 0) continue;
+                    float c[6], dir[3];
+                    line_model(A[HC[hh].s0], A[HC[hh].s1], c);
+                    line_prep_dir(c, dir);
+                    int cnt = 0;
+                    for (int i = lane; i < n; i += 32) {
+                        const float4 p = A[i];
+                        cnt += line_within(c, dir, p.x, p.y, p.z, thr_f) ? 1 : 0;
+                    }
+                    cnt = __reduce_add_sync(SPX_FULL, cnt);
+                    if (lane == 0) S.counts[hh] = cnt;
+                }
             }
             __syncthreads();
             // (d) warp 0 replays `while (iterations_ < k && skipped_count < max_skip)` over the scored hypotheses:
@@ -524,7 +560,7 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
                 for (int h0 = 0; h0 < nh && !stop; h0 += 32) {
                     const int hh = h0 + lane;
                     const bool valid = hh < nh;
-                    const int st = valid ? S.hyp[hh].state : 1;
+                    const int st = valid ? HC[hh].state : 1;
                     const int cnt = (valid && st == 0) ? S.counts[hh] : -INT_MAX;
                     int run = cnt;
 #pragma unroll
@@ -543,7 +579,7 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
                     double k_before = __shfl_up_sync(SPX_FULL, k_after, 1);
                     if (lane == 0) k_before = kk;
                     const int it_before = iterations + lane;
-                    const bool enter = valid && (double(it_before) < k_before) && (S.hyp[valid ? hh : 0].skipped < max_skip) && st == 0;
+                    const bool enter = valid && (double(it_before) < k_before) && (HC[valid ? hh : 0].skipped < max_skip) && st == 0;
                     const bool brk_after = enter && (it_before + 1 > P.ransac_max_iter);
                     const unsigned m_noenter = __ballot_sync(SPX_FULL, valid && !enter);
                     const unsigned m_brk = __ballot_sync(SPX_FULL, brk_after);
@@ -562,18 +598,14 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
                     }
                 }
                 if (lane == 0) {
-                    if (!stop && !(double(iterations) < kk && S.skipped < max_skip)) stop = 1;
+                    if (!stop && !(double(iterations) < kk && S.skipped_end[cur] < max_skip)) stop = 1;
                     S.n_best = n_best; S.iterations = iterations; S.kk = kk;
-                    if (have_new >= 0) { S.have = 1; S.best_s0 = S.hyp[have_new].s0; S.best_s1 = S.hyp[have_new].s1; }
+                    if (have_new >= 0) { S.have = 1; S.best_s0 = HC[have_new].s0; S.best_s1 = HC[have_new].s1; }
                     S.stop = stop; S.iter = iterations;
                 }
             }
             __syncthreads();
             if (S.stop) break;
-            if (tid == 0) {
-                const double left = S.kk - double(S.iterations);
-                trip = left >= double(kTripMax) ? kTripMax : (left <= 8.0 ? 8 : int(left) + 1);
-            }
             if (S.refill) {   // the 624 outputs of the block are used up: twist and re-derive the draw positions
                 mt_twist_cta(S.mt);
                 for (int i = tid; i < 624; i += kLineThreads) {
@@ -581,7 +613,7 @@ __device__ void lines_item(LineShared &S, float4 *A, IdxT *sh, IdxT *inl, const 
                     const unsigned j = i01 + (mt_temper(S.mt[i]) >> 1) % unsigned(n - int(i01));
                     if (kSmem) S.J[i] = uint16_t(j); else S.Jg[i] = int(j);
                 }
-                if (tid == 0) S.jpos = 0;
+                if (tid == 0) { S.jpos = 0; S.refill = 0; }
                 __syncthreads();
             }
         }
