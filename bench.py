@@ -59,6 +59,7 @@ def algorithmic_bytes_per_frame(rows=ROWS, cols=COLS, dis=3):
         "k_ccl_merge4": n * 1 + n * 4,                   # (the four-pixels-per-thread variant of the same pass)
         "k_ccl_flatten": n * 4 + n * 4 + n * 4,          # forest in/out, counts
         "k_ccl_flatten_runs": n * 4 + n * 4 + n * 4,          # forest in/out, counts
+        "k_ccl_frame": n * 1 + n * 4 + n * 4,                 # link bits in, flattened forest out, counts (the forest itself stays in shared memory)
         "k_ccl_rank": n * 8 + n * 2 + n * 8,             # forest + sizes in, index lists + positions out (upper bound)
         "k_ccl_label": n * 8,
         "k_moments_fit": n * 4 + n * 12,                 # index list + xyz of the members in
