@@ -246,7 +246,7 @@ __device__ __forceinline__ unsigned sm_find(volatile unsigned short *lab, unsign
         x = gp;
     }
 }
-__device__ __forceinline__ void sm_unite(unsigned short *lab, unsigned a, unsigned b) {
+__device__ __noinline__ void sm_unite(unsigned short *lab, unsigned a, unsigned b) {
     while (true) {
         a = sm_find(lab, a);
         b = sm_find(lab, b);
@@ -276,14 +276,14 @@ __global__ void __launch_bounds__(kCFThreads) k_ccl_frame(Params P, Buffers B) {
         const bool valid = c < w;
         const int r1 = min(h, (rb + 1) * kCFRows);
         for (int rr = rb * kCFRows; rr < r1; rr += kU) {
-            unsigned cbv[kU];
+            unsigned long long pack = 0ull;                         // the eight link bytes, one per row
 #pragma unroll
-            for (int u = 0; u < kU; ++u) cbv[u] = (valid && rr + u < r1) ? conn[(rr + u) * w + c] : 0u;
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
+            for (int u = 0; u < kU; ++u) pack |= static_cast<unsigned long long>((valid && rr + u < r1) ? conn[(rr + u) * w + c] : 0u) << (8 * u);
+#pragma unroll 1
+            for (int u = 0; u < kU; ++u, pack >>= 8) {
                 if (rr + u >= r1) break;                            // (warp uniform)
                 const int q = (rr + u) * w + c;
-                const unsigned linked = __ballot_sync(SPX_FULL, valid && (cbv[u] & 1u));
+                const unsigned linked = __ballot_sync(SPX_FULL, valid && (unsigned(pack) & 1u));
                 const unsigned starts = ~linked | 1u;               // lane 0 always starts a run inside the segment
                 const int s0 = 31 - __clz(starts & (SPX_FULL >> (31 - lane)));
                 if (valid) sm_lab[q] = static_cast<unsigned short>(q - lane + s0);
@@ -299,14 +299,14 @@ __global__ void __launch_bounds__(kCFThreads) k_ccl_frame(Params P, Buffers B) {
         const int rbeg = rb * kCFRows, r1 = min(h, (rb + 1) * kCFRows);
         unsigned up = (valid && rbeg > 0) ? conn[(rbeg - 1) * w + c] : 0u;
         for (int rr = rbeg; rr < r1; rr += kU) {
-            unsigned cbv[kU];
+            unsigned long long pack = 0ull;                         // the eight link bytes, one per row
 #pragma unroll
-            for (int u = 0; u < kU; ++u) cbv[u] = (valid && rr + u < r1) ? conn[(rr + u) * w + c] : 0u;
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
+            for (int u = 0; u < kU; ++u) pack |= static_cast<unsigned long long>((valid && rr + u < r1) ? conn[(rr + u) * w + c] : 0u) << (8 * u);
+#pragma unroll 1
+            for (int u = 0; u < kU; ++u, pack >>= 8) {
                 if (rr + u >= r1) break;
                 const int r = rr + u, q = r * w + c;
-                const unsigned cb = cbv[u];
+                const unsigned cb = unsigned(pack) & 0xffu;
                 unsigned left = __shfl_up_sync(SPX_FULL, cb, 1);
                 if (lane == 0) {
                     left = 0u;
@@ -335,14 +335,14 @@ __global__ void __launch_bounds__(kCFThreads) k_ccl_frame(Params P, Buffers B) {
         const int n_valid = min(32, w - seg * 32);
         const int r1 = min(h, (rb + 1) * kCFRows);
         for (int rr = rb * kCFRows; rr < r1; rr += kU) {
-            unsigned cbv[kU];
+            unsigned long long pack = 0ull;                         // the eight link bytes, one per row
 #pragma unroll
-            for (int u = 0; u < kU; ++u) cbv[u] = (valid && rr + u < r1) ? conn[(rr + u) * w + c] : 0u;
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
+            for (int u = 0; u < kU; ++u) pack |= static_cast<unsigned long long>((valid && rr + u < r1) ? conn[(rr + u) * w + c] : 0u) << (8 * u);
+#pragma unroll 1
+            for (int u = 0; u < kU; ++u, pack >>= 8) {
                 if (rr + u >= r1) break;
                 const int q = (rr + u) * w + c;
-                const unsigned linked = __ballot_sync(SPX_FULL, valid && (cbv[u] & 1u));
+                const unsigned linked = __ballot_sync(SPX_FULL, valid && (unsigned(pack) & 1u));
                 const unsigned starts = ~linked | 1u;
                 const int s0 = 31 - __clz(starts & (SPX_FULL >> (31 - lane)));
                 const unsigned above = lane == 31 ? 0u : (starts & (SPX_FULL << (lane + 1)));
