@@ -253,6 +253,35 @@ k_normals_strip(const __grid_constant__ CUtensorMap tmap, const float *__restric
         const int wrap_at = kSRing - nb;                                  // row i == wrap_at of this batch wraps around the node ring
         double *nd = nd_base + cs_nd + nb * kNdRow;
         const float *const cl0 = cl_base + cs_cl;
+        if (!kEdge) {
+            // steady batch: every row is an interior row of the frame.  Branch-free per row: the column test becomes a select (the
+            // ring holds zeros outside the frame, so the loads are always in bounds), the d/dx - d/dy split is taken once, the ring
+            // wrap is a choice between two base pointers with compile-time row offsets.
+            double *const ndw = nd - kSRing * kNdRow;
+            if (cs_dx) {
+#pragma unroll
+                for (int i = 0; i < kSB; ++i) {
+                    const float *p = cl0 + ((8 * kPar + 4 + i) & (kSCRing - 1)) * kClRow;
+                    const float dd = p[1] - p[-1];
+                    const float d = cs_colok ? dd : 0.0f;
+                    colsum += double(d);
+                    sabs += cs_owncol ? fabsf(d) : 0.0f;
+                    (i >= wrap_at ? ndw : nd)[i * kNdRow] = colsum;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kSB; ++i) {
+                    const float dy_p = cl0[((8 * kPar + 5 + i) & (kSCRing - 1)) * kClRow];
+                    const float dd = dy_p - dy_m;
+                    const float d = cs_colok ? dd : 0.0f;
+                    dy_m = dy_0; dy_0 = dy_p;
+                    colsum += double(d);
+                    sabs += cs_owncol ? fabsf(d) : 0.0f;
+                    (i >= wrap_at ? ndw : nd)[i * kNdRow] = colsum;
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < kSB; ++i) {
             const int y = r0 + 4 + i;                                     // (row tests are uniform over the CTA)
