@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from sp_slam_b200 import api, scenes
-from tests.parity import compare_frame
+from tests.parity import compare_frame, same_f32
 
 pytestmark = pytest.mark.gpu
 
@@ -560,6 +560,37 @@ def test_full_size_batch_is_consistent():
         at += k
     assert at == len(a.planes) and int(a.frames["n_planes"].sum()) > 2000
     ext.close(); small.close()
+
+
+def test_full_size_batch_against_the_oracle(oracle_lib):
+    """BASELINE configs[1] at full size against the oracle, frame by frame: every Frame field of all 1000 frames of the bench
+    workload -- plane counts, coefficients, clouds and boundary clouds -- bit for bit (device-resident path, default frame
+    groups; compact results on every 7th frame group boundary are covered by test_gpu_compact)."""
+    import torch
+    n = 1000
+    d = scenes.boxroom_sequence(n)
+    dev = torch.from_numpy(d).cuda()
+    ext = api.PlaneExtractor(max_frames=n)
+    ext.extract_device(dev.data_ptr(), n, 480, 640)
+    res = ext.fetch()
+    assert len(res) == n and not res.frames["flags"].any()
+    orc = oracle_lib.Oracle()
+    n_planes = n_points = 0
+    for f in range(n):
+        orc.run(d[f])
+        fp = res.frame(f)
+        pr = orc.planes()
+        assert fp.mnRealPlaneNum == orc.n_real and fp.mnPlaneNum == orc.n_planes == len(pr), f
+        for i, b in enumerate(pr):
+            assert same_f32(fp.mvPlaneCoefficients[i], b["coef"]), (f, i)
+            assert int(fp.src[i]) == b["src"], (f, i)
+            assert len(fp.mvPlanePoints[i]) == len(b["points"]) and len(fp.mvBoundaryPoints[i]) == len(b["boundary"]), (f, i)
+            assert fp.mvPlanePoints[i].tobytes() == b["points"].tobytes(), (f, i, "points")
+            assert fp.mvBoundaryPoints[i].tobytes() == b["boundary"].tobytes(), (f, i, "boundary")
+            n_points += len(b["points"])
+        n_planes += len(pr)
+    assert n_planes > 2000 and n_points > 20_000_000
+    ext.close()
 
 
 def test_one_pixel_per_thread_ccl_merge(seq, oracle_lib):
