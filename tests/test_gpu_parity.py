@@ -593,6 +593,35 @@ def test_full_size_batch_against_the_oracle(oracle_lib):
     ext.close()
 
 
+def test_720p_sequence_against_the_oracle(oracle_lib):
+    """BASELINE configs[3] as bench.py measures it (120 noisy 1280x720 RealSense-shaped clutter frames, 12 planes per frame, 32-bit
+    inlier indices): every Frame field of every frame against the oracle, bit for bit, through the host path with compact results
+    rebuilt by the Python mirror of the adapter."""
+    import torch
+    n, rows, cols = 120, 720, 1280
+    it = scenes.REALSENSE
+    d = scenes.realsense_sequence(n)
+    d = np.stack([scenes.add_noise(d[k], k, "realsense") for k in range(n)])
+    host = torch.from_numpy(d).pin_memory()
+    kw = dict(fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy, max_x=float(it.width), max_y=float(it.height))
+    ext = api.PlaneExtractor(max_frames=n, max_rows=rows, max_cols=cols, **kw)
+    res = ext.extract_batch_ptr(host.data_ptr(), n, rows, cols, copy=True)
+    orc = oracle_lib.Oracle(**kw)
+    n_planes = 0
+    for f in range(n):
+        orc.run(d[f])
+        fp = res.frame(f)
+        pr = orc.planes()
+        assert fp.mnRealPlaneNum == orc.n_real and fp.mnPlaneNum == orc.n_planes == len(pr), f
+        for i, b in enumerate(pr):
+            assert same_f32(fp.mvPlaneCoefficients[i], b["coef"]), (f, i)
+            assert fp.mvPlanePoints[i].tobytes() == b["points"].tobytes(), (f, i, "points")
+            assert fp.mvBoundaryPoints[i].tobytes() == b["boundary"].tobytes(), (f, i, "boundary")
+        n_planes += len(pr)
+    assert n_planes > 1000
+    ext.close()
+
+
 def test_one_pixel_per_thread_ccl_merge(seq, oracle_lib):
     """the fallback union kernel (organized clouds whose size is not a multiple of 4 use it) on the standard frames"""
     e = extractor_with_env({"SPX_CCL_FOUR": "0"}, debug=True)
