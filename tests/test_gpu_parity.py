@@ -594,9 +594,8 @@ def test_full_size_batch_against_the_oracle(oracle_lib):
 
 
 def test_720p_sequence_against_the_oracle(oracle_lib):
-    """BASELINE configs[3] as bench.py measures it (120 noisy 1280x720 RealSense-shaped clutter frames, 12 planes per frame, 32-bit
-    inlier indices): every Frame field of every frame against the oracle, bit for bit, through the host path with compact results
-    rebuilt by the Python mirror of the adapter."""
+    """BASELINE configs[3] as bench.py measures it (120 noisy 1280x720 RealSense-shaped clutter frames, 12 planes per frame): every
+    Frame field of every frame against the oracle, bit for bit, through the host path (sparse upload, frame groups)."""
     import torch
     n, rows, cols = 120, 720, 1280
     it = scenes.REALSENSE
