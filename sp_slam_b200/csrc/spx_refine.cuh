@@ -27,7 +27,6 @@ struct RefineSmem {
     int    n0[SPX_MAX_MODELS];
     int    cnt1[SPX_MAX_MODELS], cnt2[SPX_MAX_MODELS];
     int    last1[SPX_MAX_MODELS], last2[SPX_MAX_MODELS];
-    int8_t cmA[kMaxW];                 // model claimed sideways by claimer column c  (pass 1: right, pass 2: left)
 };
 
 __device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
@@ -50,9 +49,12 @@ __device__ __forceinline__ bool refine_dist_ok(const float *cf, float x, float y
 //      sideways claim and then its vertical claim; every claimed pixel gets its position in inlier_indices[model],
 //   B) the chain inside row r: a free pixel is claimed by its already-final neighbour on the claimer side.  With
 //      src = nearest labelled pixel on that side (or the carry from the previous chunk), a free pixel is claimed iff
-//      it and every free pixel between src and itself lie within 0.02 m of src's plane -- ballots and bit masks only.
+//      every pixel between src and itself is free and it and they lie within 0.02 m of src's plane (a point PCL left
+//      unlabelled stops the chain) -- ballots and bit masks only.
 // Row r+1's plane ids and the xyz of its free pixels are prefetched into registers while row r is processed (plane ids
 // two rows ahead), so no global-load latency sits on the row-to-row dependency chain.
+// All of it is steered by warp-uniform lane masks per chunk (plane pixels / free pixels of the previous, this and the next
+// row; the claims of the previous row's claimers): where a mask is zero the chunk costs a scalar test.
 template <int NCH, bool kReverse>
 __device__ __forceinline__ void refine_pass(RefineSmem &S, const Params &P, const float *__restrict__ px, const float *__restrict__ py,
                                             const float *__restrict__ pz, int8_t *pid, int *pos, int *cnt, int *last,
