@@ -121,7 +121,11 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_edge_chamfer(const float
 
     // ---- phase 1: mask bits of rows [ra, rb) ----
     {
-        float zU[NCH], zC[NCH], zD[NCH], zN[NCH];
+        // PCL marks BOTH pixels of a pair whose depth change exceeds the threshold of the pair's first pixel (right and lower
+        // neighbour, pixels with r <= h-2 and c <= w-2).  Every pixel evaluates its own two tests once; the marks a pixel receives
+        // from its left / upper neighbour are those neighbours' ballots, shifted by one lane / kept from the previous row.
+        float zC[NCH], zD[NCH], zN[NCH];
+        unsigned downPrev[NCH];                         // lower-neighbour tests of the previous row
         auto load_row = [&](int r, float (&dst)[NCH]) {
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
@@ -132,37 +136,33 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_edge_chamfer(const float
             }
         };
         auto thr = [&](float z) -> float { return (P.mdcf * (fabsf(z) + 1.0f)) * 2.0f; };
-        load_row(ra - 1, zU); load_row(ra, zC); load_row(ra + 1, zD);
+        const int rs = ra >= 1 ? ra - 1 : ra;          // one row early: its lower-neighbour tests mark row ra
+        load_row(rs, zC); load_row(rs + 1, zD);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) downPrev[ch] = 0u;
         bool nonfinite = false;
-        for (int r = ra; r < rb; ++r) {
+        for (int r = rs; r < rb; ++r) {
             load_row(r + 2, zN);
+            unsigned rightPrev = 0u;                   // right-neighbour tests of the previous chunk of this row
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int c = ch * 32 + lane;
                 const float z = zC[ch];
-                if (c < w && !isfinite(z)) nonfinite = true;
-                float zR = __shfl_down_sync(SPX_FULL, z, 1), zL = __shfl_up_sync(SPX_FULL, z, 1);
-                if (ch + 1 < NCH) { const float t = __shfl_sync(SPX_FULL, zC[ch + 1 < NCH ? ch + 1 : ch], 0); if (lane == 31) zR = t; }
-                if (ch >= 1) { const float t = __shfl_sync(SPX_FULL, zC[ch >= 1 ? ch - 1 : ch], 31); if (lane == 0) zL = t; }
-                bool edge = false;
                 const bool zf = isfinite(z);
-                if (r <= h - 2 && c <= w - 2) {
-                    const float zDn = zD[ch], t = thr(z);
-                    if (fabsf(z - zR) > t || !zf || !isfinite(zR)) edge = true;
-                    if (fabsf(z - zDn) > t || !zf || !isfinite(zDn)) edge = true;
-                }
-                if (c >= 1 && r <= h - 2) {
-                    if (fabsf(zL - z) > thr(zL) || !zf || !isfinite(zL)) edge = true;
-                }
-                if (r >= 1 && c <= w - 2) {
-                    const float zUp = zU[ch];
-                    if (fabsf(zUp - z) > thr(zUp) || !zf || !isfinite(zUp)) edge = true;
-                }
-                const unsigned bits = __ballot_sync(SPX_FULL, c < w && edge);
-                if (lane == 0) mbits[(r - ra) * NCH + ch] = bits;
+                if (c < w && !zf) nonfinite = true;
+                float zR = __shfl_down_sync(SPX_FULL, z, 1);
+                if (ch + 1 < NCH) { const float t = __shfl_sync(SPX_FULL, zC[ch + 1 < NCH ? ch + 1 : ch], 0); if (lane == 31) zR = t; }
+                const float zDn = zD[ch], t = thr(z);
+                const bool dom = r <= h - 2 && c <= w - 2;
+                const bool eR = dom && (fabsf(z - zR) > t || !zf || !isfinite(zR));
+                const bool eD = dom && (fabsf(z - zDn) > t || !zf || !isfinite(zDn));
+                const unsigned bR = __ballot_sync(SPX_FULL, eR), bD = __ballot_sync(SPX_FULL, eD);
+                const unsigned bits = bR | bD | (bR << 1) | (rightPrev >> 31) | downPrev[ch];
+                if (lane == 0 && r >= ra) mbits[(r - ra) * NCH + ch] = bits;
+                rightPrev = bR; downPrev[ch] = bD;
             }
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) { zU[ch] = zC[ch]; zC[ch] = zD[ch]; zD[ch] = zN[ch]; }
+            for (int ch = 0; ch < NCH; ++ch) { zC[ch] = zD[ch]; zD[ch] = zN[ch]; }
         }
         // a frame with NaN / Inf depth is flagged and queued for k_normals_link_list (finite-count integral images); the strip
         // kernel skips it
