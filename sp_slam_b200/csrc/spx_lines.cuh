@@ -266,6 +266,11 @@ __global__ void __launch_bounds__(256) k_border_fetch(const DepthT *__restrict__
     }
 }
 
+// IsBorderPoint counts a window sample when `d > 0.05` (float against a double literal).  0.05 is not a float; 0.05f lies above it and
+// the float below 0.05f lies below it, so the test is `d >= 0.05f` without the conversion.
+constexpr float kMinDepthF = 0.05f;
+static_assert(double(kMinDepthF) > 0.05 && double(0.049999997f) < 0.05, "0.05f must be the smallest float above the double 0.05");
+
 __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__restrict__ depth, Params P, Buffers B) {
     __shared__ float s_win[kBorderWarps][2][32][21];
     __shared__ int4 s_geo[kBorderWarps][32];
@@ -310,7 +315,9 @@ __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__res
                 if (live) {
                     for (int k = 0; k < 21; ++k) { if (i0 + k < ue) ++ncol; if (j0 + k < ve) ++nrow; }
                 }
-                s_geo[wid][lane] = make_int4(i0, j0, ncol, nrow);   // a dead point has an empty window
+                // (bit 8 of the column count: the whole 21 x 21 window lies inside the image -- no bounds test per sample)
+                const bool inside = live && i0 >= 0 && i0 + 20 < P.cols && j0 >= 0 && j0 + 20 < P.rows;
+                s_geo[wid][lane] = make_int4(i0, j0, ncol | (inside ? 256 : 0), nrow);   // a dead point has an empty window
             }
             __syncwarp();
             auto load_row = [&](int t, int buf) {
@@ -325,8 +332,8 @@ __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__res
                         const int qj = gq.y + t, i = gq.x + lane;
                         wr[k] = t < gq.w && lane < 21;
                         d[k] = 0.0f;   // invalid sample
-                        if (wr[k] && lane < gq.z) {
-                            if (qj >= 0 && qj < P.rows && i >= 0 && i < P.cols) {
+                        if (wr[k] && lane < (gq.z & 255)) {
+                            if ((gq.z & 256) || (qj >= 0 && qj < P.rows && i >= 0 && i < P.cols)) {
                                 d[k] = img[qj * pitch_f + i];
                             } else {
                                 const long long fidx = (long long)qj * P.cols + i;   // flat index on the continuous cv::Mat
@@ -352,7 +359,7 @@ __global__ void __launch_bounds__(kBorderWarps * 32) k_border(const float *__res
                     for (int k = 0; k < 21; ++k) {
                         if (i0 + k < ue) {
                             const float d = row[k];
-                            if (double(d) > 0.05) { res += d; num++; }
+                            if (d >= kMinDepthF) { res += d; num++; }   // == (double(d) > 0.05): 0.05f is the smallest float above 0.05
                             else { nan++; }
                         }
                     }
