@@ -71,6 +71,8 @@ __device__ __forceinline__ float div_const(float a, float b, float rb, int fast)
         const float r = __fmaf_rn(-q, b, a);
         return __fmaf_rn(r, rb, q);
     }
+    // a zero (the depth of an invalid pixel is 0): +-0 / b = +-0 with the product's sign -- no division on the sensor's dropouts
+    if (fast && aa == 0.0f) return __fmul_rn(a, rb);
     return a / b;
 }
 
