@@ -368,6 +368,10 @@ def _main(out):
     kw = dict(max_rows=rows, max_cols=cols, device=local_rank, fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy,
               max_x=float(it.width), max_y=float(it.height))
     ext = api.PlaneExtractor(max_frames=max(F, frames_cap), n_streams=args.streams, **kw)
+    # host threads of the library's gathered upload route: half of this rank's share of the host's cores (the library's own default
+    # is half of ALL cores, which is right for one process per host only)
+    gather_threads = max(1, min(16, ((os.cpu_count() or 1) // world) // 2))
+    ext.set_gather_threads(gather_threads)
     if not args.profile_groups and (args.streams == 0 or args.streams > 1):
         # the per-kernel table comes from one extra profiled step in which the batch runs as ONE group (kernels back to
         # back on one stream, so their CUDA-event times add up to the step and can be compared with an ncu launch list)
@@ -468,6 +472,11 @@ def _main(out):
         planes_per_frame = float(res.frames["n_planes"].mean())
         overflow = int((res.frames["flags"] & api.SPX_FRAME_OVERFLOW != 0).sum())
         d2h_compact = res.nbytes
+        # ---- the same with the sampled rows of every group through the copy engine (no host threads: last round's e2e) ----
+        ext.set_upload_mode(2)
+        e2e_rows_s, _ = timed_host(lambda: ext.extract_batch_compact_ptr(host.data_ptr(), F, rows, cols), args.steps)
+        xfer_rows = ext.transfer_bytes()
+        ext.set_upload_mode(0)
         # ---- the same with 16-byte point clouds back (round 1's e2e) ----
         e2e_full_s, resf = timed_host(lambda: ext.extract_batch_ptr(host.data_ptr(), F, rows, cols), args.steps)
         xfer_full = ext.transfer_bytes()
@@ -570,11 +579,11 @@ def _main(out):
         cfg720 = measure_720p(stream, not args.no_cpu_baseline)
 
     t = torch.tensor([ms, e2e_s * 1e3, (e2e16_s or 0.0) * 1e3, e2e_whole_s * 1e3, e2e_full_s * 1e3,
-                      (adapter or {}).get("seconds", 0.0) * 1e3, strong_ms or 0.0, (adapter or {}).get("seconds_clouds", 0.0) * 1e3],
+                      (adapter or {}).get("seconds", 0.0) * 1e3, strong_ms or 0.0, (adapter or {}).get("seconds_clouds", 0.0) * 1e3, e2e_rows_s * 1e3],
                      dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, e2e16_ms, e2e_whole_ms, e2e_full_ms, ad_ms, strong_ms, adc_ms = (float(x) for x in t)
+    ms, e2e_ms, e2e16_ms, e2e_whole_ms, e2e_full_ms, ad_ms, strong_ms, adc_ms, e2e_rows_ms = (float(x) for x in t)
     K = args.steps
     value = total_frames * K / (ms * 1e-3)
     per_s = lambda t_ms: total_frames * K / (t_ms * 1e-3) if t_ms else None   # noqa: E731
@@ -630,8 +639,11 @@ def _main(out):
             "e2e": {"value": per_s(e2e_ms), "unit": UNIT, "h2d_bytes_per_step": xfer[0] + xfer[1],
                     "d2h_bytes_per_step": xfer[2], "ms_per_step": e2e_ms / K,
                     "h2d_copied": xfer[0], "h2d_read_in_place": xfer[1], "result_bytes": d2h_compact, "gpu_launches_per_step": launches_e2e,
-                    "note": "spx_extract_batch_compact on the pinned CV_32F batch: the rows the organized cloud samples (every Cloud.Dis-th) "
-                            "are uploaded with one strided copy per frame group, the sectors of the 21x21 full-resolution windows the "
+                    "host_gather_threads": gather_threads,
+                    "note": "spx_extract_batch_compact on the pinned CV_32F batch, two upload routes at once: the first frame groups' sampled rows "
+                            "(every Cloud.Dis-th) go through the copy engine, one strided copy per group, while host threads inside the library "
+                            "gather the organized cloud's samples (every Cloud.Dis-th row AND column) of the last groups into a pinned staging "
+                            "buffer, of which only those samples are uploaded; the sectors of the 21x21 full-resolution windows the "
                             "border tests read are fetched from the pinned image over PCIe by k_border_fetch (h2d_read_in_place); back come "
                             "frame headers, plane records, boundary clouds, the supposed planes' clouds and -- instead of the real planes' "
                             "clouds -- their ordered inlier index lists, from which the host adapter rebuilds pcl::PointXYZRGB bit-exactly"},
@@ -644,6 +656,10 @@ def _main(out):
                 "clouds_transfer": {"value": per_s(adc_ms), "unit": UNIT, "ms_per_step": adc_ms / K,
                                     "note": "the same adapter fed by spx_extract_batch: the real planes' clouds cross PCIe as 16-byte points and "
                                             "are only widened on the host (more bytes on the link, less host arithmetic)"}}),
+            "e2e_sampled_rows": {"value": per_s(e2e_rows_ms), "unit": UNIT, "h2d_bytes_per_step": xfer_rows[0] + xfer_rows[1],
+                                 "d2h_bytes_per_step": xfer_rows[2], "ms_per_step": e2e_rows_ms / K,
+                                 "note": "the compact call with every group's sampled rows through the copy engine and no host threads "
+                                         "(spx_set_upload_mode 2; the e2e of the previous bench lines)"},
             "e2e_full_clouds": {"value": per_s(e2e_full_ms), "unit": UNIT, "h2d_bytes_per_step": xfer_full[0] + xfer_full[1],
                                 "d2h_bytes_per_step": xfer_full[2], "ms_per_step": e2e_full_ms / K,
                                 "note": "spx_extract_batch: all clouds back as 16-byte points (round 1's e2e)"},

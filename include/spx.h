@@ -128,9 +128,26 @@ int spx_extract_batch(spx_ctx *ctx, const float *depth, int n_frames, int rows, 
  * (src/Frame.cc:1038-1052).  When the caller's image is page-locked (cudaHostAlloc, cudaHostRegister or
  * spx_host_register below) the library uploads only the sampled rows (1/Cloud.Dis of the bytes, one strided copy) and the
  * window sectors the border tests will read are fetched from the image over PCIe by a kernel, each once; a pageable
- * image is uploaded whole.  Results are identical.
- * mode 0 = automatic (default), 1 = always upload the whole image, 2 = sparse whenever the image is page-locked. */
+ * image is uploaded whole.  Float batches of 64 frames or more use a second route beside it: a pool of host threads
+ * inside the library copies the h x w samples themselves (1/Cloud.Dis^2 of the image; the copy engine can skip rows but
+ * not columns) of the LAST frame groups of the batch into a page-locked staging buffer while the copy engine moves the
+ * sampled rows of the first groups, and only those samples are uploaded for the gathered groups (138 instead of 410 KB
+ * per frame at 640x480, Cloud.Dis 3).  Results are identical.
+ * mode 0 = automatic (default), 1 = always upload the whole image, 2 = sampled rows whenever the image is page-locked,
+ * 3 = every group gathered whenever the image is page-locked and float. */
 int spx_set_upload_mode(spx_ctx *ctx, int mode);
+/* host threads of the gathered route: 0 (default) = half the hardware threads, at most 16; also SPX_GATHER_THREADS */
+int spx_set_gather_threads(spx_ctx *ctx, int n_threads);
+/* automatic mode: the share of a batch's frames (its tail) that takes the gathered route, 0 .. 1; negative (default) =
+ * chosen from the thread count t as t / (t + 4), where the copy engine and the host threads finish together on the
+ * machines measured; also SPX_GATHER_SHARE */
+int spx_set_gather_share(spx_ctx *ctx, double share);
+/* the gather step on its own (host code, no device): the organized cloud's samples depth[f][m * dis][n * dis]
+ * (src/Frame.cc:857-872) of `n_frames` frames, as the upload path of mode 3 stages them -- out[f][m][n] with rows of
+ * `out_row_floats` floats (>= the cloud width; the tail is zeroed), the frames cut into `n_groups` groups and handed to
+ * `n_threads` threads.  For tests and for hosts that want to stage the samples themselves. */
+int spx_host_gather_samples(const float *depth, int n_frames, int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes,
+                            int cloud_dis, int n_groups, int n_threads, float *out, size_t out_row_floats);
 /* page-lock / release a caller-owned host buffer (e.g. the cv::Mat data of the depth images a loader recycles) */
 int spx_host_register(void *ptr, size_t bytes);
 int spx_host_unregister(void *ptr);

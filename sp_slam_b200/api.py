@@ -49,7 +49,7 @@ EXPORTS = (
     "spx_set_profile", "spx_get_kernel_times", "spx_get_kernel_timeline", "spx_get_device_results",
     "spx_get_cloud", "spx_get_distance_map", "spx_get_normals", "spx_get_curvature", "spx_get_labels_raw", "spx_get_plane_ids",
     "spx_get_models", "spx_get_model_inliers", "spx_get_model_contour", "spx_get_lines",
-    "spx_set_upload_mode", "spx_host_register", "spx_host_unregister", "spx_get_transfer_bytes",
+    "spx_set_upload_mode", "spx_set_gather_threads", "spx_set_gather_share", "spx_host_gather_samples", "spx_host_register", "spx_host_unregister", "spx_get_transfer_bytes",
     "spx_get_group_timeline",
     "spx_extract_batch_compact", "spx_extract_batch_u16_compact", "spx_set_result_mode", "spx_fetch_compact",
     "spx_set_group_callback",
@@ -166,6 +166,9 @@ def lib():
         L.spx_pose_optimize_planes.argtypes = [vp, vp, i32, i32, i32, vp, vp, C.POINTER(i32)]
         L.spx_plane_edge_errors.argtypes = [vp, vp, i32, vp]
         L.spx_set_upload_mode.argtypes = [vp, i32]
+        L.spx_set_gather_threads.argtypes = [vp, i32]
+        L.spx_set_gather_share.argtypes = [vp, C.c_double]
+        L.spx_host_gather_samples.argtypes = [vp, i32, i32, i32, sz, sz, i32, i32, i32, vp, sz]
         L.spx_host_register.argtypes = [vp, sz]
         L.spx_host_unregister.argtypes = [vp]
         u64p = C.POINTER(C.c_ulonglong)
@@ -186,6 +189,23 @@ def host_register(arr: np.ndarray):
     rc = lib().spx_host_register(arr.ctypes.data, arr.nbytes)
     if rc != SPX_OK:
         raise SpxError(rc, (lib().spx_last_error(None) or b"").decode())
+
+
+def gather_samples(depth: np.ndarray, cloud_dis: int = 5, n_groups: int = 1, n_threads: int = 2, row_floats: int | None = None) -> np.ndarray:
+    """spx_host_gather_samples: the organized cloud's samples depth[f, ::dis, ::dis] (src/Frame.cc:857-872) of a float batch
+    (frames, rows, cols; the last axis contiguous), staged as the gathered upload stages them.  Host code only."""
+    if depth.ndim == 2:
+        depth = depth[None]
+    assert depth.dtype == np.float32 and depth.ndim == 3 and depth.strides[2] == 4
+    n, rows, cols = depth.shape
+    h, w = -(-rows // cloud_dis), -(-cols // cloud_dis)
+    rf = (w + 3) & ~3 if row_floats is None else row_floats
+    out = np.full((n, h, rf), np.nan, np.float32)
+    rc = lib().spx_host_gather_samples(depth.ctypes.data, n, rows, cols, depth.strides[1], depth.strides[0] if n > 1 else depth.strides[1] * rows,
+                                       cloud_dis, n_groups, n_threads, out.ctypes.data, rf)
+    if rc != SPX_OK:
+        raise SpxError(rc, "spx_host_gather_samples")
+    return out
 
 
 def host_unregister(arr: np.ndarray):
@@ -469,8 +489,17 @@ class PlaneExtractor:
         return lib().spx_last_launch_count(self._h)
 
     def set_upload_mode(self, mode: int):
-        """0 automatic, 1 whole image, 2 sparse (sampled rows uploaded, border-test window sectors fetched on demand) when page-locked."""
+        """0 automatic, 1 whole image, 2 sparse (sampled rows uploaded, border-test window sectors fetched on demand) when page-locked,
+        3 gathered (host threads stage the organized cloud's samples, only those are uploaded) when page-locked and float."""
         self._ck(lib().spx_set_upload_mode(self._h, mode))
+
+    def set_gather_threads(self, n: int):
+        """host threads of the gathered route (0 = half the hardware threads, at most 16)"""
+        self._ck(lib().spx_set_gather_threads(self._h, n))
+
+    def set_gather_share(self, share: float):
+        """automatic upload mode: share of a batch (its last frame groups) that takes the gathered route"""
+        self._ck(lib().spx_set_gather_share(self._h, float(share)))
 
     def transfer_bytes(self):
         """(bytes uploaded by copies, bytes fetched from the caller's pinned image by the device, bytes copied back) of the last

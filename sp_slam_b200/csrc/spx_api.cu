@@ -7,7 +7,11 @@
 // There is no CPU fallback: without a usable CUDA device spx_create fails with SPX_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 #include <algorithm>
 #include <cmath>
@@ -47,6 +51,106 @@ struct DevArena {
 template <typename T>
 size_t padded(size_t n) { return (n * sizeof(T) + 255) & ~size_t(255); }
 
+// ---- upload mode 3: the organized cloud's samples are picked out of the caller's image by host threads ---------------
+// The sampling kernels read every Cloud.Dis-th row AND column of the depth image (src/Frame.cc:857-872): 1 / Dis^2 of its
+// bytes.  The copy engine can skip rows (a pitch) but not columns, so the sparse upload still moves whole sampled rows (410 MB per
+// 1000 frames at 640x480, 8 ms of PCIe).  Here a small pool of host threads copies the h x w samples of every frame into a
+// page-locked staging buffer (49 MB per 1000 frames), frame group by frame group, while the device works on the groups
+// that are complete; the kernels read that buffer with a column step of one (Params::samp_cstep).
+struct GatherPool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    unsigned long long epoch = 0;       // bumped per job
+    bool stop = false;
+    int busy = 0;                       // workers still inside the current job
+    // the job
+    const char *src = nullptr; size_t pitch = 0, fstride = 0;
+    float *dst = nullptr;
+    int n_frames = 0, h = 0, w = 0, sw = 0, dis = 1;
+    std::atomic<int> next{0};
+    std::vector<int> group_of;          // frame -> group
+    std::vector<int> left;              // frames of group g not yet gathered (guarded by m)
+
+    template <int kDis>
+    static void gather_rows(const char *s0, size_t pitch, float *d0, int h, int w, int sw, int dis_rt) {
+        const int dis = kDis ? kDis : dis_rt;
+        for (int r = 0; r < h; ++r) {
+            const float *s = reinterpret_cast<const float *>(s0 + size_t(r) * size_t(dis) * pitch);
+            float *d = d0 + size_t(r) * size_t(sw);
+            // every sampled row is a fresh 40-line stream the hardware prefetcher has to find again: the lines of the sampled row
+            // two below are requested while this one is copied (a prefetch never faults; +30 % per thread measured)
+            const char *ahead = reinterpret_cast<const char *>(s) + 2 * size_t(dis) * pitch;
+            int c = 0;
+            for (; c + 16 <= w; c += 16) {
+                const char *pf = ahead + size_t(c) * size_t(dis) * sizeof(float);
+                for (int k = 0; k < 16 * dis * int(sizeof(float)); k += 64) __builtin_prefetch(pf + k, 0, 3);
+                for (int k = 0; k < 16; ++k) d[c + k] = s[size_t(c + k) * size_t(dis)];
+            }
+            for (; c < w; ++c) d[c] = s[size_t(c) * size_t(dis)];
+            for (c = w; c < sw; ++c) d[c] = 0.0f;
+        }
+    }
+    void run_worker(unsigned long long seen) {
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_work.wait(lk, [&] { return stop || epoch != seen; });
+                if (stop) return;
+                seen = epoch;
+            }
+            for (;;) {
+                const int f = next.fetch_add(1, std::memory_order_relaxed);
+                if (f >= n_frames) break;
+                const char *s0 = src + size_t(f) * fstride;
+                float *d0 = dst + size_t(f) * size_t(h) * size_t(sw);
+                if (dis == 5) gather_rows<5>(s0, pitch, d0, h, w, sw, 5);
+                else gather_rows<0>(s0, pitch, d0, h, w, sw, dis);
+                std::lock_guard<std::mutex> lk(m);
+                if (--left[size_t(group_of[size_t(f)])] == 0) cv_done.notify_all();
+            }
+            std::lock_guard<std::mutex> lk(m);
+            if (--busy == 0) cv_done.notify_all();
+        }
+    }
+    void start(int n_threads) {      // (between jobs only)
+        unsigned long long now;
+        { std::lock_guard<std::mutex> lk(m); now = epoch; }
+        while (int(workers.size()) < n_threads) workers.emplace_back([this, now] { run_worker(now); });
+    }
+    // frames [bounds[g], bounds[g + 1]) form group g; returns at once, wait_group(g) blocks until group g is in `dst`
+    void post(const char *src_, size_t pitch_, size_t fstride_, float *dst_, int h_, int w_, int sw_, int dis_, const std::vector<int> &bounds) {
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return busy == 0; });     // (no worker may still be leaving the previous job)
+        src = src_; pitch = pitch_; fstride = fstride_; dst = dst_; h = h_; w = w_; sw = sw_; dis = dis_;
+        const int G = int(bounds.size()) - 1;
+        n_frames = bounds[size_t(G)];
+        group_of.assign(size_t(n_frames), 0);
+        left.assign(size_t(G), 0);
+        for (int g = 0; g < G; ++g) {
+            left[size_t(g)] = bounds[size_t(g) + 1] - bounds[size_t(g)];
+            for (int f = bounds[size_t(g)]; f < bounds[size_t(g) + 1]; ++f) group_of[size_t(f)] = g;
+        }
+        next.store(0);
+        busy = int(workers.size());
+        ++epoch;
+        cv_work.notify_all();
+    }
+    void wait_group(int g) {
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return left[size_t(g)] == 0; });
+    }
+    void wait_idle() {
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return busy == 0; });
+    }
+    ~GatherPool() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv_work.notify_all();
+        for (std::thread &t : workers) t.join();
+    }
+};
+
 }  // namespace
 
 struct spx_ctx {
@@ -85,8 +189,24 @@ struct spx_ctx {
     double edge_weight = 0.5;   // host path: size of the first and the last frame group relative to the others
     int group_prio = 1;      // 1: group g's stream gets a priority that falls with g (earlier groups finish first)
     int border_grid_cap = 0;
-    int upload_mode = 0;     // host input: 0 auto (sparse upload for pinned images of batches >= sparse_min_frames), 1 whole image, 2 sparse whenever possible
+    int upload_mode = 0;     // host input: 0 auto (pinned images: gathered samples for float batches >= gather_min_frames, else the sparse
+                             // upload for batches >= sparse_min_frames), 1 whole image, 2 sparse whenever possible, 3 gathered whenever possible
     int sparse_min_frames = 1;
+    int gather_min_frames = 64;   // a few frames are latency bound: one strided copy of the sampled rows is the shorter path
+    int gather_threads = 0;       // 0 = half the host's hardware threads, at most 16 (spx_set_gather_threads, SPX_GATHER_THREADS)
+    // automatic mode: both routes at once.  The first frame groups take the sampled-rows copy (the copy engine starts at once and
+    // needs no host thread), the last `gather_share` of the batch is gathered meanwhile; mode 3 gathers every group.
+    double gather_share = -1.0;   // < 0: from the thread count, t / (t + 4) -- the copy engine moves a frame's sampled rows in 8.1 us, one host
+                                  // thread gathers them in ~39 us (measured on the GPU box), so both routes end together near that share
+                                  // (8 threads: 0.67; measured optimum 0.6 .. 0.7).  spx_set_gather_share, SPX_GATHER_SHARE
+    int gather_first = 0;         // first gathered group of the current call
+    size_t g_rstep = 0, g_fstride = 0;   // layout of the gathered buffer (Params::samp_* of the gathered groups)
+    CUtensorMap tmap_g;           // ... and its tensor map
+    bool tmap_g_ok = false;
+    GatherPool *pool = nullptr;
+    float *h_samp = nullptr;      // page-locked staging of the gathered samples: frames x h x samp_w floats
+    size_t h_samp_cap = 0;
+    float *d_samp = nullptr;      // ... and its device copy (what the sampling kernels read in upload mode 3)
     bool use_prio = false;   // back stream with higher priority: measured slower (co-running kernels slow each other), kept as a knob
     std::vector<cudaStream_t> g_streams;      // front: upload, chamfer, normals (low priority)
     std::vector<cudaStream_t> g_hstreams;     // host path: group g's stream, priority falling with g (the groups start one upload
@@ -218,7 +338,7 @@ int set_geometry(spx_ctx *c, int n_frames, int rows, int cols, size_t pitch, siz
     if (n_frames > 1 && frame_stride < pitch * size_t(rows)) return fail(c, SPX_ERR_ARG, "bad frame stride");
     Params &P = c->P;
     P.rows = rows; P.cols = cols; P.pitch = pitch; P.frame_stride = frame_stride; P.n_frames = n_frames;
-    P.samp_rstep = size_t(P.dis) * pitch; P.samp_fstride = frame_stride; P.full_alpha = 1.0f;
+    P.samp_rstep = size_t(P.dis) * pitch; P.samp_fstride = frame_stride; P.samp_cstep = P.dis; P.samp_cols = cols; P.full_alpha = 1.0f;
     cloud_dims(rows, cols, P.dis, &P.w, &P.h);
     P.N = P.w * P.h;
     // smallest non-zero |n - cx|, |m - cy| over the sampled columns / rows (the exactness bound of k_models)
@@ -246,6 +366,8 @@ struct HostSrc {           // host depth of the batch (null: the depth is alread
     // from the caller's pinned image (`mapped` = its device-visible address)
     bool sparse = false;
     const void *mapped = nullptr;
+    // upload mode 3 (implies sparse): host threads gather the organized cloud's samples, only those are uploaded
+    bool gather = false;
 };
 
 int n_groups_for(const spx_ctx *c, int n_frames) {
@@ -278,7 +400,15 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     // On the host path the groups start one upload apart instead of together, so the decision is made per group there.
     const int refine_load = ((c->group_pack && c->refine_per_group) || c->refine_dev_group) ? ng : c->P.n_frames;
     P.refine_fast = (refine_load <= c->refine_fast_max && P.h <= kRefMaxH) ? 1 : 0;   // small launches are latency bound: parallelism inside the frame
-    P.forest_in_smem = (ccl_frame_fits(P.N) && (c->ccl_frame == 2 || (c->ccl_frame == 1 && ng >= 512))) ? 1 : 0;
+    // (resident batches run their groups side by side, a throughput regime: the batch size decides there -- 3.87 against 4.03 ms per 1000 frames)
+    P.forest_in_smem = (ccl_frame_fits(P.N) && (c->ccl_frame == 2 || (c->ccl_frame == 1 && (c->group_pack ? ng : c->P.n_frames) >= 512))) ? 1 : 0;
+    const bool gathered = src.gather && g >= c->gather_first;
+    if (gathered) {               // this group's samples come from the gathered buffer
+        depth_dev = c->d_samp;
+        P.samp_cstep = 1; P.samp_cols = P.w; P.samp_rstep = c->g_rstep; P.samp_fstride = c->g_fstride;
+        P.fetch_skip_sampled = 0;   // the device image holds nothing of this group yet: the windows fetch every row they touch
+    }
+    const bool tmap_ok = gathered ? c->tmap_g_ok : c->tmap_ok;
     Buffers B = c->B;
     B.work = c->B.work + size_t(g) * c->work_stride;
     B.work2 = c->B.work2 + size_t(g) * c->work2_stride;
@@ -297,7 +427,11 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
 
     cudaStream_t compute_st = st;
     if (src.depth && c->group_pack && c->last_groups > 1) st = c->up_stream;   // copies: the upload stream
-    if (src.depth && src.sparse) {   // host depth of this group: the sampled rows only, at their place in the device image
+    if (src.depth && gathered) {     // host depth of this group: its gathered samples (c->pool filled the staging buffer; run_pipeline waited)
+        const size_t per = size_t(P.h) * (P.samp_rstep / sizeof(float));
+        c->xfer_h2d += per * sizeof(float) * size_t(ng);
+        SPX_CK(c, cudaMemcpyAsync(c->d_samp + per * size_t(f0), c->h_samp + per * size_t(f0), per * sizeof(float) * size_t(ng), cudaMemcpyHostToDevice, st));
+    } else if (src.depth && src.sparse) {   // host depth of this group: the sampled rows only, at their place in the device image
         const size_t esz = src.u16 ? sizeof(uint16_t) : sizeof(float);
         const size_t tight = size_t(P.cols) * esz;
         c->xfer_h2d += tight * size_t(P.h) * size_t(ng);
@@ -378,9 +512,9 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
         } else {
             const dim3 sgrid(cdiv(P.w, kStW), F);
             void (*k_normals_strip_fn)(const CUtensorMap, const float *, Params, Buffers, int) =
-                c->tmap_ok ? (c->strip_occ == 3 ? k_normals_strip<true, 3> : k_normals_strip<true, 4>)
-                           : (c->strip_occ == 3 ? k_normals_strip<false, 3> : k_normals_strip<false, 4>);
-            LAUNCH(k_normals_strip_fn, sgrid, kSThreads, strip_smem_bytes(P.dis, c->tmap_ok), c->tmap, depth_dev, P, B, dbg);
+                tmap_ok ? (c->strip_occ == 3 ? k_normals_strip<true, 3> : k_normals_strip<true, 4>)
+                        : (c->strip_occ == 3 ? k_normals_strip<false, 3> : k_normals_strip<false, 4>);
+            LAUNCH(k_normals_strip_fn, sgrid, kSThreads, strip_smem_bytes(P.samp_cstep, tmap_ok), gathered ? c->tmap_g : c->tmap, depth_dev, P, B, dbg);
             // frames with NaN / Inf depth (queued by k_edge_chamfer; none on sensor data: the CTAs leave at once)
             LAUNCH(k_normals_link_list, std::min(c->list_grid, F * cdiv(P.w, kTW) * cdiv(P.h, kTH)), kNormThreads, kNormalsSmem, depth_dev, P, B, dbg);
         }
@@ -495,17 +629,29 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, boo
     // the depth batch as a 3-d tensor for the strip kernel's TMA loads: (image columns, SAMPLED rows, frames) -- the row stride
     // is Cloud.Dis image rows, so only the rows the organized cloud samples are ever touched
     c->tmap_ok = false;
-    if (!normals_given && c->normals_mode == 2 && c->encode_tiled && strip_tma_ok(c->P.dis) && reinterpret_cast<uintptr_t>(depth_dev) % 16 == 0 &&
+    if (!normals_given && c->normals_mode == 2 && c->encode_tiled && strip_tma_ok(c->P.samp_cstep) && reinterpret_cast<uintptr_t>(depth_dev) % 16 == 0 &&
         c->P.samp_rstep % 16 == 0 && (c->P.n_frames == 1 || c->P.samp_fstride % 16 == 0)) {
         const Params &Q = c->P;
-        const cuuint64_t gdim[3] = {cuuint64_t(Q.cols), cuuint64_t(Q.h), cuuint64_t(Q.n_frames)};
+        const cuuint64_t gdim[3] = {cuuint64_t(Q.samp_cols), cuuint64_t(Q.h), cuuint64_t(Q.n_frames)};
         const cuuint64_t gstr[2] = {cuuint64_t(Q.samp_rstep), cuuint64_t(Q.n_frames == 1 ? Q.samp_rstep * size_t(Q.h) : Q.samp_fstride)};
-        const cuuint32_t box[3] = {cuuint32_t(strip_box_w(Q.dis)), cuuint32_t(kSB), 1u};
+        const cuuint32_t box[3] = {cuuint32_t(strip_box_w(Q.samp_cstep)), cuuint32_t(kSB), 1u};
         const cuuint32_t es[3] = {1u, 1u, 1u};
         const CUresult r = c->encode_tiled(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(depth_dev), gdim, gstr, box, es,
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         c->tmap_ok = r == CUDA_SUCCESS;
+    }
+    c->tmap_g_ok = false;
+    if (src.gather && c->normals_mode == 2 && c->encode_tiled) {      // the gathered buffer: rows of samp_w floats, a column step of one
+        const Params &Q = c->P;
+        const cuuint64_t gdim[3] = {cuuint64_t(Q.w), cuuint64_t(Q.h), cuuint64_t(Q.n_frames)};
+        const cuuint64_t gstr[2] = {cuuint64_t(c->g_rstep), cuuint64_t(Q.n_frames == 1 ? c->g_rstep * size_t(Q.h) : c->g_fstride)};
+        const cuuint32_t box[3] = {cuuint32_t(strip_box_w(1)), cuuint32_t(kSB), 1u};
+        const cuuint32_t es[3] = {1u, 1u, 1u};
+        const CUresult r = c->encode_tiled(&c->tmap_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c->d_samp, gdim, gstr, box, es,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        c->tmap_g_ok = r == CUDA_SUCCESS;
     }
     const int F = c->P.n_frames;
     c->P.frame0 = 0;
@@ -534,15 +680,35 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, boo
         }
         bounds[size_t(G)] = F;
     }
+    c->gather_first = 0;
+    if (src.gather) {
+        // mode 3: every group is gathered.  Automatic mode: the first groups take the sampled-rows copy, the tail of the batch
+        // (about gather_share of the frames) is gathered by the host threads meanwhile.
+        if (c->upload_mode != 3) {
+            const int nt = int(c->pool->workers.size());
+            const double share = c->gather_share >= 0.0 ? c->gather_share : double(nt) / double(nt + 4);
+            const int f_split = int(double(F) * (1.0 - share) + 0.5);
+            while (c->gather_first < G && bounds[size_t(c->gather_first)] < f_split) ++c->gather_first;
+        }
+        if (c->gather_first < G) {
+            std::vector<int> gb(bounds.begin() + c->gather_first, bounds.end());      // frames [gb[0], F): groups gather_first .. G - 1
+            const int fa = gb[0];
+            for (int &v : gb) v -= fa;
+            const size_t per = size_t(c->P.h) * (c->g_rstep / sizeof(float));
+            c->pool->post(static_cast<const char *>(src.depth) + src.frame_stride * size_t(fa), src.pitch, src.frame_stride, c->h_samp + per * size_t(fa),
+                          c->P.h, c->P.w, int(c->g_rstep / sizeof(float)), c->P.dis, gb);
+        }
+    }
     for (int g = 0; g < G; ++g) {
         const int f0 = bounds[size_t(g)], f1 = bounds[size_t(g) + 1];
+        if (src.gather && g >= c->gather_first) c->pool->wait_group(g - c->gather_first);   // (the workers carry on with the later groups)
         cudaStream_t st = (G == 1) ? main_st : (group_pack ? c->g_hstreams[g] : c->g_streams[g]);
         cudaStream_t st_back = (G == 1) ? main_st : (c->use_prio ? c->g_back[g] : st);
         if (G > 1) SPX_CK(c, cudaStreamWaitEvent(st, c->ev[0], 0));
         SPX_CK(c, cudaEventRecord(c->g_ev[3 * g + 0], st));
         c->g_host_ms[2 * g] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - c->t_call).count();
         int rc = run_group(c, depth_dev, depth_full, normals_given, g, f0, f1 - f0, st, st_back, src);
-        if (rc != SPX_OK) return rc;
+        if (rc != SPX_OK) { if (src.gather) c->pool->wait_idle(); return rc; }   // (the job reads the caller's image)
         if (G > 1 && group_pack) SPX_CK(c, cudaStreamWaitEvent(main_st, c->g_ev[3 * g + 2], 0));
     }
     if (!group_pack && G > 1) {
@@ -888,6 +1054,9 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (const char *e = std::getenv("SPX_LINES_GLOBAL")) c->P.lines_in_global = std::atoi(e) != 0 ? 1 : 0;   // test knob
     if (const char *e = std::getenv("SPX_UPLOAD")) c->upload_mode = std::atoi(e);   // test / tuning knob (see spx_ctx::upload_mode)
     if (const char *e = std::getenv("SPX_SPARSE_MIN_FRAMES")) c->sparse_min_frames = std::atoi(e);   // tuning knob
+    if (const char *e = std::getenv("SPX_GATHER_MIN_FRAMES")) c->gather_min_frames = std::atoi(e);   // tuning knob
+    if (const char *e = std::getenv("SPX_GATHER_THREADS")) c->gather_threads = std::atoi(e);         // tuning knob (spx_set_gather_threads)
+    if (const char *e = std::getenv("SPX_GATHER_SHARE")) { const double v = std::atof(e); if (v <= 1.0) c->gather_share = v; }   // tuning knob
     if (const char *e = std::getenv("SPX_STRIP_OCC")) { const int v = std::atoi(e); if (v == 3 || v == 4) c->strip_occ = v; }   // tuning knob
     if (const char *e = std::getenv("SPX_NORMALS")) { const int v = std::atoi(e); if (v >= 0 && v <= 2) c->normals_mode = v; }   // test knob
     if (const char *e = std::getenv("SPX_CCL_FOUR")) c->ccl_four = std::atoi(e) != 0;   // test knob: the one-pixel-per-thread kernel
@@ -961,6 +1130,8 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     const size_t cov_nodes = cfg->normal_method == 1 ? F * size_t(w + 1) * size_t(h + 1) : 0;
     total += padded<double>(cov_nodes * kCovCh) + padded<unsigned>(cov_nodes) + padded<float>(cfg->normal_method == 1 ? FN : 0);
     total += padded<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4) + padded<uint16_t>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
+    const size_t samp_floats = F * size_t(h) * ((size_t(w) + 3) & ~size_t(3)) + 4;
+    total += padded<float>(samp_floats);
     SPX_CK_CREATE(cudaMalloc(reinterpret_cast<void **>(&c->arena.base), total));
     c->arena.size = total;
     DevArena &A = c->arena;
@@ -983,6 +1154,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (cfg->normal_method == 1) { c->d_cov_sat = A.take<double>(cov_nodes * kCovCh); c->d_cov_cnt = A.take<unsigned>(cov_nodes); c->d_curv = A.take<float>(FN); }
     c->d_depth = A.take<float>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
     c->d_depth16 = A.take<uint16_t>(F * size_t(cfg->max_rows) * size_t(cfg->max_cols) + 4);
+    c->d_samp = A.take<float>(samp_floats);
     if (A.used > A.size) { fail(nullptr, SPX_ERR_ARG, "internal: arena accounting"); spx_destroy(c); return SPX_ERR_ARG; }
 
     uint32_t mt[624], mt_out[624];
@@ -1060,6 +1232,8 @@ void spx_destroy(spx_ctx *c) {
     if (c->h_pts) cudaFreeHost(c->h_pts);
     if (c->h_bnd) cudaFreeHost(c->h_bnd);
     if (c->h_pidx) cudaFreeHost(c->h_pidx);
+    delete c->pool;                      // (joins the gather threads)
+    if (c->h_samp) cudaFreeHost(c->h_samp);
     for (void *p : c->graveyard) cudaFreeHost(p);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
@@ -1157,10 +1331,25 @@ static int extract_host(spx_ctx *c, const void *depth, bool u16, float depth_map
         c->P.host_pitch = pitch_bytes; c->P.host_fstride = frame_stride_bytes; c->P.fetch_skip_sampled = 1;
         if (u16) c->P.full_alpha = depth_map_factor;
         c->P.fetch_vec = (reinterpret_cast<uintptr_t>(src.mapped) % 16 == 0 && pitch_bytes % 16 == 0 && frame_stride_bytes % 16 == 0 && cols % 8 == 0) ? 1 : 0;
+        // float images: the samples themselves instead of the sampled rows (gathered by host threads, see GatherPool)
+        // (automatic mode: for the compact call only -- with 16-byte clouds coming back the call is bound by the downloads, and the
+        // gather threads' memory traffic then costs more than the smaller upload saves: 14.5 against 12.5 ms per 1000 frames)
+        if (!u16 && (c->upload_mode == 3 || (c->upload_mode == 0 && cout != nullptr && n_frames >= c->gather_min_frames))) {
+            const size_t sw = (size_t(c->P.w) + 3) & ~size_t(3);             // rows of the staging buffer start on 16 bytes (TMA)
+            if ((rc = grow_pinned(c, &c->h_samp, &c->h_samp_cap, size_t(n_frames) * size_t(c->P.h) * sw)) != SPX_OK) return rc;
+            if (!c->pool) c->pool = new (std::nothrow) GatherPool();
+            if (!c->pool) return fail(c, SPX_ERR_ARG, "out of host memory");
+            int nt = c->gather_threads;
+            if (nt <= 0) { nt = int(std::thread::hardware_concurrency()) / 2; if (nt > 16) nt = 16; }   // (the caller's own threads need cores too)
+            c->pool->start(nt < 1 ? 1 : nt);
+            src.gather = true;                                                // (which groups: run_pipeline; their layout: run_group)
+            c->g_rstep = sw * sizeof(float); c->g_fstride = sw * sizeof(float) * size_t(c->P.h);
+        }
     } else {
         src.sparse = false;
     }
     if ((rc = run_pipeline(c, c->d_depth, full, false, src, true, cout != nullptr)) != SPX_OK) return rc;
+    if (src.gather) c->pool->wait_idle();
     return fetch_groups(c, out, cout);
 }
 
@@ -1281,8 +1470,40 @@ int spx_get_transfer_bytes(const spx_ctx *c, unsigned long long *h2d_copied, uns
 }
 
 int spx_set_upload_mode(spx_ctx *c, int mode) {
-    if (!c || mode < 0 || mode > 2) return SPX_ERR_ARG;
+    if (!c || mode < 0 || mode > 3) return SPX_ERR_ARG;
     c->upload_mode = mode;
+    return SPX_OK;
+}
+
+int spx_set_gather_threads(spx_ctx *c, int n_threads) {
+    if (!c || n_threads < 0 || n_threads > 256) return SPX_ERR_ARG;
+    if (c->pool && n_threads > 0 && int(c->pool->workers.size()) > n_threads) {   // shrink: the pool is rebuilt at the next call
+        delete c->pool;
+        c->pool = nullptr;
+    }
+    c->gather_threads = n_threads;
+    return SPX_OK;
+}
+
+int spx_set_gather_share(spx_ctx *c, double share) {
+    if (!c || !(share <= 1.0)) return SPX_ERR_ARG;      // (negative: chosen from the thread count)
+    c->gather_share = share;
+    return SPX_OK;
+}
+
+int spx_host_gather_samples(const float *depth, int n_frames, int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes, int cloud_dis,
+                            int n_groups, int n_threads, float *out, size_t out_row_floats) {
+    if (!depth || !out || n_frames < 1 || rows < 1 || cols < 1 || cloud_dis < 1 || n_groups < 1 || n_threads < 1 || n_threads > 256) return SPX_ERR_ARG;
+    int w = 0, h = 0;
+    cloud_dims(rows, cols, cloud_dis, &w, &h);
+    if (out_row_floats < size_t(w) || pitch_bytes < size_t(cols) * sizeof(float)) return SPX_ERR_ARG;
+    GatherPool pool;
+    pool.start(n_threads);
+    std::vector<int> bounds(size_t(n_groups) + 1, 0);
+    for (int g = 1; g <= n_groups; ++g) bounds[size_t(g)] = std::max(bounds[size_t(g) - 1], int((long long)n_frames * g / n_groups));
+    pool.post(reinterpret_cast<const char *>(depth), pitch_bytes, frame_stride_bytes, out, h, w, int(out_row_floats), cloud_dis, bounds);
+    for (int g = 0; g < n_groups; ++g) pool.wait_group(g);      // in group order, as the upload path does
+    pool.wait_idle();
     return SPX_OK;
 }
 

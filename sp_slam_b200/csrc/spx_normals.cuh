@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) k_backproject(const float *__restrict__ d
     if (i >= P.N) return;
     const int r = i / P.w, c = i - r * P.w;
     const char *img = reinterpret_cast<const char *>(depth) + size_t(f) * P.samp_fstride;
-    const float z = *reinterpret_cast<const float *>(img + size_t(r) * P.samp_rstep + size_t(c) * P.dis * sizeof(float));
+    const float z = *reinterpret_cast<const float *>(img + size_t(r) * P.samp_rstep + size_t(c) * P.samp_cstep * sizeof(float));
     const float x = (float(c * P.dis) - P.cx) * z / P.fx;
     const float y = (float(r * P.dis) - P.cy) * z / P.fy;
     const size_t o = size_t(f) * P.N + i;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kChamferWarps * 32) k_edge_chamfer(const float
             for (int ch = 0; ch < NCH; ++ch) {
                 const int c = ch * 32 + lane;
                 dst[ch] = (r >= 0 && r < h && c < w)
-                              ? *reinterpret_cast<const float *>(img + size_t(r) * P.samp_rstep + size_t(c) * P.dis * sizeof(float))
+                              ? *reinterpret_cast<const float *>(img + size_t(r) * P.samp_rstep + size_t(c) * P.samp_cstep * sizeof(float))
                               : 0.0f;
             }
         };
@@ -300,7 +300,7 @@ __device__ __forceinline__ void normals_tile(const float *__restrict__ depth, co
         const int c = tc - 7 + lx;
         const bool cin = c >= 0 && c < w;
         const float xfac = float(c * P.dis) - P.cx;
-        const char *colp = img + size_t(cin ? c : 0) * P.dis * sizeof(float);
+        const char *colp = img + size_t(cin ? c : 0) * P.samp_cstep * sizeof(float);
         const size_t rstep = P.samp_rstep;
         const bool cown = lx >= 7 && lx < 7 + kTW;
         float zz[6];

@@ -54,7 +54,7 @@ struct StripSmem {
 // 16-byte boundary of the row (tools/tma_probe3.cu: any other start coordinate raises "illegal instruction"), so the
 // segment begins at the multiple of four columns at or below the strip's first sample and is up to three floats longer.
 constexpr size_t kStripStageOff = (sizeof(StripSmem) + 127) / 128 * 128;
-inline int strip_box_w(int dis) { return ((kSCW - 1) * dis + 1 + 3 + 3) & ~3; }
+inline int strip_box_w(int cstep) { return ((kSCW - 1) * cstep + 1 + 3 + 3) & ~3; }      // cstep = Params::samp_cstep
 inline size_t strip_smem_bytes(int dis, bool tma) { return kStripStageOff + (tma ? size_t(kSB) * strip_box_w(dis) * 4 : 0); }
 inline bool strip_tma_ok(int dis) { return strip_box_w(dis) <= 256; }
 
@@ -107,9 +107,9 @@ k_normals_strip(const __grid_constant__ CUtensorMap tmap, const float *__restric
     constexpr int kClRow = 3 * kSCW, kNdRow = 6 * kSSW, kNrRow = 5 * kSNW;     // elements per ring row
 
     float *const stage = reinterpret_cast<float *>(strip_raw + kStripStageOff);
-    const int x_first = (tc - 7) * P.dis;                       // image column of the strip's first sample
+    const int x_first = (tc - 7) * P.samp_cstep;                // column of the strip's first sample in the sampling buffer
     const int x_box = x_first & ~3;                             // where the staged row segment starts (16-byte aligned)
-    const int bw = ((kSCW - 1) * P.dis + 7) & ~3;               // floats per staged row (strip_box_w)
+    const int bw = ((kSCW - 1) * P.samp_cstep + 7) & ~3;        // floats per staged row (strip_box_w)
     if (kTMA && tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(strip_smem_u32(&S.bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -140,8 +140,8 @@ k_normals_strip(const __grid_constant__ CUtensorMap tmap, const float *__restric
     const int rstep_f = int(P.samp_rstep / sizeof(float));
     float *const gx = B.px + fo, *const gy = B.py + fo, *const gz = B.pz + fo;
     int bp_go = (5 - kSB + bp_rr) * w + bp_c;                   // index of the thread's first point of the chunk in the cloud arrays
-    int bp_so = kTMA ? bp_rr * bw + (x_first - x_box) + bp_lx * P.dis      // its sample in the staged chunk ...
-                     : (5 - kSB + bp_rr) * rstep_f + bp_c * P.dis;         // ... or in the frame's image (plain loads)
+    int bp_so = kTMA ? bp_rr * bw + (x_first - x_box) + bp_lx * P.samp_cstep      // its sample in the staged chunk ...
+                     : (5 - kSB + bp_rr) * rstep_f + bp_c * P.samp_cstep;         // ... or in the frame's image (plain loads)
     float bp_z0 = 0.f, bp_z1 = 0.f;                             // plain loads: the samples of the next chunk, fetched one phase round ahead
     unsigned zmin = 0x7f800000u;                                // smallest non-zero |z| the thread has seen (as bits)
     // column sums: warps 0..3 = d/dx (channels 0..2 of x y z), warps 4..7 = d/dy (channels 3..5); 42 difference columns each

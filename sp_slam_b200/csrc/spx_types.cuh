@@ -15,6 +15,10 @@ struct Params {
     // bytes between consecutive SAMPLED rows / between frames.  The full image: dis * pitch, frame_stride; a staging
     // buffer that holds only the sampled rows (host input, sparse upload): its row pitch, h * pitch.
     size_t samp_rstep, samp_fstride;
+    // ... and floats between consecutive SAMPLED columns / floats per row of that buffer.  The full image and the sampled-rows
+    // buffer: dis, cols; the buffer of gathered samples (host input, upload mode 3: host threads pick the h x w samples out
+    // of the caller's image and only those cross the bus): 1, w.
+    int samp_cstep, samp_cols;
     // sparse upload (k_border_fetch): the caller's page-locked image the missing window sectors are fetched from
     size_t host_pitch, host_fstride;   // bytes
     float  full_alpha;     // 16-bit host image: depth = float(d) * full_alpha (mDepthMapFactor)

@@ -520,6 +520,112 @@ def test_sparse_upload_1280x720(realsense_frames):
     e.close()
 
 
+def test_gathered_upload_equals_whole_image_upload(seq, realsense_frames):
+    """Upload mode 3: host threads inside the library stage the organized cloud's samples (every Cloud.Dis-th row AND column)
+    and only those are uploaded; the sampling kernels read that buffer with a column step of one (TMA strip kernel, plain
+    loads, the tile kernel, the chamfer), the border windows fetch every row they touch from the caller's image.  Same
+    results as uploading the whole image, for several thread counts, a pitched ROI whose cloud width is not a multiple of
+    four, the 1280x720 frames, the compact call, and the automatic mode (from 64 frames on: the first frame groups as
+    sampled rows through the copy engine, the last ones gathered meanwhile)."""
+    n = 70
+    d = np.ascontiguousarray(scenes.boxroom_sequence(n, start=150))
+    ext = api.PlaneExtractor(max_frames=n, n_streams=4)
+    ext.set_upload_mode(1)
+    whole = ext.extract_batch(d)
+    up_whole = ext.transfer_bytes()
+    assert int((whole.planes["is_supposed"] == 1).sum()) > 0
+    api.host_register(d)
+    try:
+        for threads in (1, 3, 8):
+            _poison(ext, d.shape)
+            ext.set_upload_mode(3)
+            ext.set_gather_threads(threads)
+            got = ext.extract_batch(d)
+            up = ext.transfer_bytes()
+            assert up[0] == n * 160 * 216 * 4 and 0 < up[1] < d.nbytes // 2 and up[2] == up_whole[2]
+            assert _same_batch(got, whole), threads
+        # automatic mode from 64 frames on: the first groups as sampled rows, the last ones gathered; sampled rows only below
+        rows_b, gath_b = 160 * 640 * 4, 160 * 216 * 4
+        ext.set_upload_mode(1)
+        cw = ext.extract_batch_compact(d)
+        for share, k_want in ((-1.0, None), (0.5, None), (0.0, n), (1.0, 0)):
+            _poison(ext, d.shape)
+            ext.set_upload_mode(0)
+            ext.set_gather_share(share)
+            cg = ext.extract_batch_compact(d)
+            k, rem = divmod(ext.transfer_bytes()[0] - n * gath_b, rows_b - gath_b)      # frames that went as sampled rows
+            assert rem == 0 and (0 < k < n if k_want is None else k == k_want), (share, k)
+            for name in ("frames", "planes", "point_index", "points", "boundary"):
+                assert np.array_equal(getattr(cw, name), getattr(cg, name)), (share, name)
+        ext.set_gather_share(-1.0)
+        got = ext.extract_batch(d)                                      # 16-byte clouds back: sampled rows only (download bound)
+        assert ext.transfer_bytes()[0] == n * rows_b and _same_batch(got, whole)
+        few = ext.extract_batch_compact(d[:40])
+        assert ext.transfer_bytes()[0] == 40 * 160 * 640 * 4
+        assert np.array_equal(few.frames["n_planes"], whole.frames["n_planes"][:40])
+        # a single frame and the compact call
+        ext.set_upload_mode(3)
+        one = ext.extract(d[7])
+        ref = whole.frame(7)
+        assert one.mnPlaneNum == ref.mnPlaneNum and np.array_equal(one.mvPlaneCoefficients.view(np.uint32), ref.mvPlaneCoefficients.view(np.uint32))
+        for p, q in zip(one.mvPlanePoints + one.mvBoundaryPoints, ref.mvPlanePoints + ref.mvBoundaryPoints):
+            assert np.array_equal(p, q)
+        ext.set_upload_mode(3)
+        cg = ext.extract_batch_compact(d)
+        assert ext.transfer_bytes()[0] == n * 160 * 216 * 4
+        for name in ("frames", "planes", "point_index", "points", "boundary"):
+            assert np.array_equal(getattr(cw, name), getattr(cg, name)), name
+    finally:
+        api.host_unregister(d)
+    # the other normals kernels on the gathered buffer (plain loads / the 32x16 tile kernel)
+    for knob in ("1", "0"):
+        e1 = extractor_with_env({"SPX_NORMALS": knob}, max_frames=n, n_streams=4)     # (same frame groups: the arenas are ordered per group)
+        api.host_register(d)
+        try:
+            e1.set_upload_mode(3)
+            assert _same_batch(e1.extract_batch(d), whole), knob
+        finally:
+            api.host_unregister(d)
+        e1.close()
+    ext.close()
+    # pitched ROI, rows not a multiple of Cloud.Dis; cloud width 168 -> staging rows of 168 floats, 167 -> padded to 168
+    for cols in (504, 500):
+        m = 6
+        padded = np.zeros((m, 482, 700), np.float32)
+        padded[:, :401, :cols] = d[:m, :401, :cols]
+        view = padded[:, :401, :cols]
+        e2 = api.PlaneExtractor(max_frames=m, max_rows=401, max_cols=cols, max_x=float(cols), max_y=401.0)
+        e2.set_upload_mode(1)
+        a = e2.extract_batch(view)
+        api.host_register(padded)
+        try:
+            _poison(e2, (m, 401, cols))
+            e2.set_upload_mode(3)
+            b = e2.extract_batch(view)
+            assert e2.transfer_bytes()[0] == m * 134 * 168 * 4
+            assert _same_batch(a, b) and len(a.planes) > 0
+        finally:
+            api.host_unregister(padded)
+        e2.close()
+    # 1280x720 clutter frames
+    it = scenes.REALSENSE
+    d7 = np.ascontiguousarray(np.stack([scenes.add_noise(f, 100 + k, "realsense") if k else f for k, f in enumerate(realsense_frames)]))
+    e = api.PlaneExtractor(max_frames=len(d7), max_rows=720, max_cols=1280, fx=it.fx, fy=it.fy, cx=it.cx, cy=it.cy,
+                           max_x=float(it.width), max_y=float(it.height))
+    e.set_upload_mode(1)
+    whole7 = e.extract_batch(d7)
+    api.host_register(d7)
+    try:
+        _poison(e, d7.shape)
+        e.set_upload_mode(3)
+        g7 = e.extract_batch(d7)
+        assert e.transfer_bytes()[0] == len(d7) * e.cloud_dims(720, 1280)[1] * ((e.cloud_dims(720, 1280)[0] + 3) & ~3) * 4
+    finally:
+        api.host_unregister(d7)
+    assert _same_batch(g7, whole7) and int((whole7.planes["is_supposed"] == 1).sum()) > 0
+    e.close()
+
+
 def test_full_size_batch_is_consistent():
     """BASELINE configs[1] at full size: the 1000-frame batch gives the same Frame fields through the host-input path
     (page-locked image, sparse upload, 8 frame groups with unequal sizes, early downloads), through the device-resident
@@ -531,7 +637,7 @@ def test_full_size_batch_is_consistent():
     host = torch.from_numpy(d).pin_memory()
     ext = api.PlaneExtractor(max_frames=n)
     a = ext.extract_batch_ptr(host.data_ptr(), n, 480, 640, copy=True)
-    assert ext.transfer_bytes()[0] == n * 160 * 640 * 4                 # the sparse path was taken
+    assert ext.transfer_bytes()[0] == n * 160 * 640 * 4                 # the sparse path was taken (sampled rows; 16-byte clouds back)
     dev = host.cuda()
     ext.extract_device(dev.data_ptr(), n, 480, 640)
     b = ext.fetch()
