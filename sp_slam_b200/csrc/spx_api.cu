@@ -161,6 +161,8 @@ struct spx_ctx {
     // another, so a group's copies never queue behind another group's kernels (the device has few hardware queues:
     // streams beyond CUDA_DEVICE_MAX_CONNECTIONS share one and serialise)
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    cudaStream_t up2_stream = nullptr;    // the gathered groups' uploads: ready at their own pace, they do not queue behind the sampled rows
+    bool up2 = true;                      // (tuning knob SPX_UP2)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // frame groups: internal streams + per group events (start, end of the plane section, end of the supposed-plane section)
     int n_streams = 1, min_group = 32, last_groups = 1;
@@ -426,7 +428,7 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     } while (0)
 
     cudaStream_t compute_st = st;
-    if (src.depth && c->group_pack && c->last_groups > 1) st = c->up_stream;   // copies: the upload stream
+    if (src.depth && c->group_pack && c->last_groups > 1) st = (gathered && c->up2) ? c->up2_stream : c->up_stream;   // copies: the upload streams
     if (src.depth && gathered) {     // host depth of this group: its gathered samples (c->pool filled the staging buffer; run_pipeline waited)
         const size_t per = size_t(P.h) * (P.samp_rstep / sizeof(float));
         c->xfer_h2d += per * sizeof(float) * size_t(ng);
@@ -664,7 +666,7 @@ int run_pipeline(spx_ctx *c, const float *depth_dev, const void *depth_full, boo
     SPX_CK(c, cudaEventRecord(c->ev[0], main_st));
     c->t_call = std::chrono::steady_clock::now();
     c->g_host_ms.assign(size_t(2 * G), 0.f);
-    if (group_pack && G > 1) SPX_CK(c, cudaStreamWaitEvent(c->up_stream, c->ev[0], 0));
+    if (group_pack && G > 1) { SPX_CK(c, cudaStreamWaitEvent(c->up_stream, c->ev[0], 0)); SPX_CK(c, cudaStreamWaitEvent(c->up2_stream, c->ev[0], 0)); }
     // Host path: the first group is what the device waits for and the last is what the host waits for, so both are
     // smaller than the ones in between (weights edge_w : 1 ... 1 : edge_w).
     std::vector<int> bounds(size_t(G) + 1, 0);
@@ -1046,6 +1048,8 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     SPX_CK_CREATE(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     SPX_CK_CREATE(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+    SPX_CK_CREATE(cudaStreamCreateWithFlags(&c->up2_stream, cudaStreamNonBlocking));
+    if (const char *e = std::getenv("SPX_UP2")) c->up2 = std::atoi(e) != 0;   // tuning knob
     SPX_CK_CREATE(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) SPX_CK_CREATE(cudaEventCreate(&c->ev[i]));
     c->n_streams = cfg->n_streams > 0 ? (cfg->n_streams > 32 ? 32 : cfg->n_streams) : 8;
@@ -1247,6 +1251,7 @@ void spx_destroy(spx_ctx *c) {
     for (cudaEvent_t e : c->g_link) cudaEventDestroy(e);
     for (cudaEvent_t e : c->g_side) cudaEventDestroy(e);
     if (c->up_stream) { cudaStreamSynchronize(c->up_stream); cudaStreamDestroy(c->up_stream); }
+    if (c->up2_stream) { cudaStreamSynchronize(c->up2_stream); cudaStreamDestroy(c->up2_stream); }
     if (c->down_stream) { cudaStreamSynchronize(c->down_stream); cudaStreamDestroy(c->down_stream); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
