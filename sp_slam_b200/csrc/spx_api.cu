@@ -547,9 +547,9 @@ int run_group(spx_ctx *c, const float *depth_dev, const void *depth_full, bool n
     else LAUNCH(k_pid_init, gpix, 256, 0, P, B);
     {
         if (P.refine_fast) {
-            if (P.w <= 224) LAUNCH(k_refine2<7>, F, 7 * 32, size_t(2) * P.h * 7 * 4 + kRefTableCap * 4, P, B);
-            else if (P.w <= 448) LAUNCH(k_refine2<14>, F, 14 * 32, size_t(2) * P.h * 14 * 4 + kRefTableCap * 4, P, B);
-            else LAUNCH(k_refine2<16>, F, 16 * 32, size_t(2) * P.h * 16 * 4 + kRefTableCap * 4, P, B);
+            if (P.w <= 224) LAUNCH(k_refine2<7>, F, 7 * 32, refine2_smem_bytes(P.h, 7), P, B);
+            else if (P.w <= 448) LAUNCH(k_refine2<14>, F, 14 * 32, refine2_smem_bytes(P.h, 14), P, B);
+            else LAUNCH(k_refine2<16>, F, 16 * 32, refine2_smem_bytes(P.h, 16), P, B);
         }
     }
     // (a three-warp variant of this kernel -- loader / propagate / emit warps around a shared-memory ring -- was measured
@@ -1168,9 +1168,9 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_mt_state1, mt, sizeof(mt)));
     SPX_CK_CREATE(cudaMemcpyToSymbol(c_mt_out0, mt_out, sizeof(mt_out)));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLinesSmem)));
-    SPX_CK_CREATE(cudaFuncSetAttribute(k_refine2<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kRefMaxH * 7 * 4 + kRefTableCap * 4));
-    SPX_CK_CREATE(cudaFuncSetAttribute(k_refine2<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kRefMaxH * 14 * 4 + kRefTableCap * 4));
-    SPX_CK_CREATE(cudaFuncSetAttribute(k_refine2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kRefMaxH * 16 * 4 + kRefTableCap * 4));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_refine2<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(refine2_smem_bytes(kRefMaxH, 7))));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_refine2<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(refine2_smem_bytes(kRefMaxH, 14))));
+    SPX_CK_CREATE(cudaFuncSetAttribute(k_refine2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(refine2_smem_bytes(kRefMaxH, 16))));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_contour, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(w + 2) * (h + 2))));
     SPX_CK_CREATE(cudaFuncSetAttribute(k_ccl_frame, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        int(std::min(size_t(c->capN) * sizeof(unsigned short), size_t(72) * 1024))));

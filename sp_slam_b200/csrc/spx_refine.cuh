@@ -304,16 +304,25 @@ struct Refine2Smem {
     int      n0[SPX_MAX_MODELS];
     int      cnt[2][SPX_MAX_MODELS];
     unsigned long long lastkey[2][SPX_MAX_MODELS];
-    int      carry[2][16];
-    int      rowlast[2];              // final label of the last visited pixel of a row (reverse pass: column 0)
-    uint16_t T[kRefMaxH];             // start step of every row of the reverse pass
     uint8_t  wrapflag[kRefMaxH];      // rows that wait for the row below (wrap claim possible)
     uint8_t  wrapcand[kRefMaxH];      // rows whose first visited pixel is free and close to some model plane
-    int      total_steps;
 };
+// hand-over between the warps of a frame (dynamic shared memory, behind the count table): carryq[i * NW + k] = label the chain
+// carries out of chunk k of row i (pass order), rowlastq[i] = final label of the last visited pixel of row i; kRefPending
+// until the owning warp has posted it
+constexpr int kRefPending = -128;
+__host__ __device__ __forceinline__ size_t refine2_smem_bytes(int h, int nw) {
+    return (size_t(2) * h * nw + kRefTableCap) * sizeof(unsigned) + ((size_t(h) * (nw + 1) + 15) & ~size_t(15));
+}
+__device__ __forceinline__ int refine2_wait(const volatile signed char *q) {
+    int v = *q;
+    while (v == kRefPending) { __nanosleep(20); v = *q; }
+    return v;
+}
 
 template <int NW, bool kReverse>
-__device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, unsigned *Vb, const Params &P, const float *__restrict__ px,
+__device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, unsigned *Vb, volatile signed char *carryq,
+                                                  volatile signed char *rowlastq, const Params &P, const float *__restrict__ px,
                                                   const float *__restrict__ py, const float *__restrict__ pz, int8_t *pid, bool has_invalid) {
     const int w = P.w, h = P.h;
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -321,10 +330,9 @@ __device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, 
     const bool valid = v < w;
     const int c = kReverse ? (w - 1 - v) : v;
     auto row_of = [&](int i) { return kReverse ? (h - 1 - i) : i; };
-    const int total_steps = kReverse ? S.total_steps : (h + NW - 1);
     const int k_last = (w - 1) >> 5, lane_last = (w - 1) & 31;   // where the last visited pixel of a row lives
     // statically rotated prefetch registers: plane ids 8 rows ahead, xyz of the free pixels 4 rows ahead -- a load has
-    // at least four steps to land and no register holding a pending load is ever moved
+    // at least four rows to land and no register holding a pending load is ever moved
     int pr[8];
     float xr[4], yr[4], zr[4];
 #pragma unroll
@@ -335,67 +343,72 @@ __device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, 
         if (u < h && pr[u] == -1) { const int q = row_of(u) * w + c; xr[u] = px[q]; yr[u] = py[q]; zr[u] = pz[q]; }
     }
     int prev = -2;
-    int s = 0;   // barriers passed = current step
+    // Data flow instead of a lock-step schedule: warp k works down the rows of its chunk on its own and waits only where it
+    // needs something another warp produces -- the label the chain carries out of chunk k-1 of the same row (and, in the
+    // reverse pass, the wrap claim of the row below into the first chunk of a waiting row).  A chunk without a free pixel has
+    // nothing to claim and nothing to wait for: it posts the label of its last pixel and moves on.
     for (int ib = 0; ib < h; ib += 8) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = ib + u;
             if (i >= h) break;
-            const int Ti = kReverse ? int(S.T[i]) : i;
-            while (s < Ti + k) { cta_bar(); ++s; }
             const int r = row_of(i);
             int a = pr[u];
-            const float x = xr[u & 3], y = yr[u & 3], z = zr[u & 3];
-            // A) vertical claim by the previous row (same column)
-            bool cV = false;
-            {
-                bool cand = i >= 1 && a == -1 && prev >= 0 && (kReverse || c <= w - 2);
-                if (has_invalid && cand) {   // (see k_refine: an unlabelled sideways neighbour of the claimer cancels its vertical claim)
-                    const int cr = kReverse ? r + 1 : r - 1;
-                    if (pid[cr * w + c + (kReverse ? -1 : 1)] == -2) cand = false;
-                }
-                if (__any_sync(SPX_FULL, cand)) {
-                    if (cand && refine_dist_ok(S.coef[prev], x, y, z)) { a = prev; cV = true; }
-                }
-            }
-            // B) chain along the row: claimers are rows <= h-2 (forward) / rows >= 1 (reverse); in the reverse pass the
-            // carry into the first chunk is the wrap claim of the row below
-            bool cH = false;
-            int carry = -1;
-            if (k > 0) carry = S.carry[i & 1][k - 1];
-            else if (kReverse && i >= 1 && S.wrapflag[r]) carry = S.rowlast[(i - 1) & 1];
             const bool chain_on = kReverse ? (r >= 1) : (r <= h - 2);
-            const unsigned labelled = __ballot_sync(SPX_FULL, a >= 0);
-            const unsigned freem = __ballot_sync(SPX_FULL, valid && a == -1);
-            if (freem != 0u && (chain_on ? (labelled != 0u || carry >= 0) : (k == 0 && carry >= 0))) {
-                const unsigned below = chain_on ? (labelled & ((1u << lane) - 1u)) : 0u;
-                const int src_lane = below ? (31 - __clz(below)) : -1;
-                const int m_lane = __shfl_sync(SPX_FULL, a, src_lane < 0 ? 0 : src_lane);
-                const int m_src = src_lane < 0 ? carry : m_lane;
-                const bool isfree = valid && a == -1;
-                const bool ok = isfree && m_src >= 0 && refine_dist_ok(S.coef[m_src], x, y, z);
-                const unsigned blocked = __ballot_sync(SPX_FULL, !valid || a == -2 || (a == -1 && !ok));   // (-2: a point PCL left unlabelled stops a chain)
-                const unsigned le_src = src_lane < 0 ? 0u : ((2u << src_lane) - 1u);
-                const unsigned mask = ((1u << lane) - 1u) & ~le_src;
-                bool claimed = ok && (blocked & mask) == 0u;
-                if (!chain_on) claimed = claimed && lane == 0;   // row 0 of the reverse pass: only the wrap claim itself
-                if (claimed) { a = m_src; cH = true; }
+            unsigned hb = 0u, vb = 0u;
+            if (__any_sync(SPX_FULL, valid && a == -1)) {
+                const float x = xr[u & 3], y = yr[u & 3], z = zr[u & 3];
+                // A) vertical claim by the previous row (same column)
+                bool cV = false;
+                {
+                    bool cand = i >= 1 && a == -1 && prev >= 0 && (kReverse || c <= w - 2);
+                    if (has_invalid && cand) {   // (see k_refine: an unlabelled sideways neighbour of the claimer cancels its vertical claim)
+                        const int cr = kReverse ? r + 1 : r - 1;
+                        if (pid[cr * w + c + (kReverse ? -1 : 1)] == -2) cand = false;
+                    }
+                    if (__any_sync(SPX_FULL, cand)) {
+                        if (cand && refine_dist_ok(S.coef[prev], x, y, z)) { a = prev; cV = true; }
+                    }
+                }
+                // B) chain along the row: claimers are rows <= h-2 (forward) / rows >= 1 (reverse); in the reverse pass the
+                // carry into the first chunk is the wrap claim of the row below
+                bool cH = false;
+                const unsigned freem = __ballot_sync(SPX_FULL, valid && a == -1);
+                if (freem != 0u && (chain_on || k == 0)) {
+                    int carry = -1;
+                    if (k > 0) { if (chain_on) carry = refine2_wait(carryq + i * NW + k - 1); }
+                    else if (kReverse && i >= 1 && S.wrapflag[r]) carry = refine2_wait(rowlastq + i - 1);
+                    const unsigned labelled = __ballot_sync(SPX_FULL, a >= 0);
+                    if (chain_on ? (labelled != 0u || carry >= 0) : (k == 0 && carry >= 0)) {
+                        const unsigned below = chain_on ? (labelled & ((1u << lane) - 1u)) : 0u;
+                        const int src_lane = below ? (31 - __clz(below)) : -1;
+                        const int m_lane = __shfl_sync(SPX_FULL, a, src_lane < 0 ? 0 : src_lane);
+                        const int m_src = src_lane < 0 ? carry : m_lane;
+                        const bool isfree = valid && a == -1;
+                        const bool ok = isfree && m_src >= 0 && refine_dist_ok(S.coef[m_src], x, y, z);
+                        const unsigned blocked = __ballot_sync(SPX_FULL, !valid || a == -2 || (a == -1 && !ok));   // (-2: a point PCL left unlabelled stops a chain)
+                        const unsigned le_src = src_lane < 0 ? 0u : ((2u << src_lane) - 1u);
+                        const unsigned mask = ((1u << lane) - 1u) & ~le_src;
+                        bool claimed = ok && (blocked & mask) == 0u;
+                        if (!chain_on) claimed = claimed && lane == 0;   // row 0 of the reverse pass: only the wrap claim itself
+                        if (claimed) { a = m_src; cH = true; }
+                    }
+                }
+                hb = __ballot_sync(SPX_FULL, cH); vb = __ballot_sync(SPX_FULL, cV);
+                if (valid && (cH || cV)) pid[r * w + c] = int8_t(a);
             }
-            const unsigned hb = __ballot_sync(SPX_FULL, cH), vb = __ballot_sync(SPX_FULL, cV);
             const int last_lbl = __shfl_sync(SPX_FULL, a, (k == k_last) ? lane_last : 31);
             if (lane == 0) {
+                carryq[i * NW + k] = (signed char)(chain_on ? (last_lbl < 0 ? -1 : last_lbl) : -1);
+                if (k == k_last) rowlastq[i] = (signed char)(last_lbl < 0 ? -1 : last_lbl);
                 Hb[i * NW + k] = hb; Vb[i * NW + k] = vb;
-                S.carry[i & 1][k] = chain_on ? (last_lbl < 0 ? -1 : last_lbl) : -1;
-                if (k == k_last) S.rowlast[i & 1] = last_lbl < 0 ? -1 : last_lbl;
             }
-            if (valid && (cH || cV)) pid[r * w + c] = int8_t(a);
             prev = a;
             // refill the slots just consumed: plane ids of row i+8, xyz of row i+4 (its plane ids arrived long ago)
             pr[u] = (valid && i + 8 < h) ? int(pid[row_of(i + 8) * w + c]) : -2;
             if (i + 4 < h && pr[(u + 4) & 7] == -1) { const int q = row_of(i + 4) * w + c; xr[u & 3] = px[q]; yr[u & 3] = py[q]; zr[u & 3] = pz[q]; }
         }
     }
-    while (s < total_steps) { cta_bar(); ++s; }
 }
 
 // emission of one pass; kCount: accumulate the per-(row, model) counts, else assign positions from the prefixed table
@@ -466,6 +479,8 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
     const bool has_invalid = (ctl.flags & unsigned(SPX_FRAME_NONFINITE)) != 0u;
     unsigned *table = Vb + h * NW;
     const int tid = threadIdx.x;
+    volatile signed char *carryq = reinterpret_cast<volatile signed char *>(table + kRefTableCap), *rowlastq = carryq + h * NW;
+    auto reset_handover = [&]() { for (int i = tid; i < h * (NW + 1); i += NW * 32) carryq[i] = (signed char)kRefPending; };
     const size_t fo = size_t(f) * P.N;
     const float *px = B.px + fo, *py = B.py + fo, *pz = B.pz + fo;
     int8_t *pid = B.pid + fo;
@@ -476,10 +491,11 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
         S.n0[m] = M.n0; S.cnt[0][m] = 0; S.cnt[1][m] = 0; S.lastkey[0][m] = 0ull; S.lastkey[1][m] = 0ull;
     }
     for (int i = tid; i < h * nm; i += NW * 32) table[i] = 0;
+    reset_handover();
     __syncthreads();
 
     // ---------------- pass 1 ----------------
-    refine2_propagate<NW, false>(S, Hb, Vb, P, px, py, pz, pid, has_invalid);
+    refine2_propagate<NW, false>(S, Hb, Vb, carryq, rowlastq, P, px, py, pz, pid, has_invalid);
     __threadfence_block();
     __syncthreads();
     refine2_emit<NW, false, true>(S, Hb, Vb, table, nm, P, pid, pos, S.n0, 0);
@@ -521,12 +537,9 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
         if ((P.N & 15) == 0) { for (int i = tid; i < P.N / 16; i += NW * 32) reinterpret_cast<uint4 *>(bak)[i] = reinterpret_cast<const uint4 *>(pid)[i]; }
         else { for (int i = tid; i < P.N; i += NW * 32) bak[i] = pid[i]; }
     }
-    if (tid == 0) {
-        for (int i = 0; i < h; ++i) S.T[i] = uint16_t(i);
-        S.total_steps = h + NW - 1;
-    }
+    reset_handover();
     __syncthreads();
-    refine2_propagate<NW, true>(S, Hb, Vb, P, px, py, pz, pid, has_invalid);
+    refine2_propagate<NW, true>(S, Hb, Vb, carryq, rowlastq, P, px, py, pz, pid, has_invalid);
     __threadfence_block();
     __syncthreads();
     if (any_cand) {
@@ -544,18 +557,10 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
             if ((P.N & 15) == 0) { for (int i = tid; i < P.N / 16; i += NW * 32) reinterpret_cast<uint4 *>(pid)[i] = reinterpret_cast<const uint4 *>(bak)[i]; }
             else { for (int i = tid; i < P.N; i += NW * 32) pid[i] = bak[i]; }
             for (int r = tid; r < h; r += NW * 32) S.wrapflag[r] = S.wrapcand[r];
+            reset_handover();
             __threadfence_block();
             __syncthreads();
-            if (tid == 0) {
-                int t = 0;
-                for (int i = 0; i < h; ++i) {
-                    if (i > 0) t += S.wrapflag[h - 1 - i] ? NW : 1;
-                    S.T[i] = uint16_t(t);
-                }
-                S.total_steps = t + NW;
-            }
-            __syncthreads();
-            refine2_propagate<NW, true>(S, Hb, Vb, P, px, py, pz, pid, has_invalid);
+            refine2_propagate<NW, true>(S, Hb, Vb, carryq, rowlastq, P, px, py, pz, pid, has_invalid);
             __threadfence_block();
             __syncthreads();
         }
