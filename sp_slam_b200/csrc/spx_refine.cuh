@@ -312,7 +312,7 @@ struct Refine2Smem {
 // until the owning warp has posted it
 constexpr int kRefPending = -128;
 __host__ __device__ __forceinline__ size_t refine2_smem_bytes(int h, int nw) {
-    return (size_t(2) * h * nw + kRefTableCap) * sizeof(unsigned) + ((size_t(h) * (nw + 1) + 15) & ~size_t(15));
+    return (size_t(3) * h * nw + kRefTableCap) * sizeof(unsigned) + ((size_t(h) * (nw + 1) + 15) & ~size_t(15));   // (3 h nw >= 2 h nw + h: rowmask)
 }
 __device__ __forceinline__ int refine2_wait(const volatile signed char *q) {
     int v = *q;
@@ -321,7 +321,7 @@ __device__ __forceinline__ int refine2_wait(const volatile signed char *q) {
 }
 
 template <int NW, bool kReverse>
-__device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, unsigned *Vb, volatile signed char *carryq,
+__device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, unsigned *Vb, unsigned *rowmask, volatile signed char *carryq,
                                                   volatile signed char *rowlastq, const Params &P, const float *__restrict__ px,
                                                   const float *__restrict__ py, const float *__restrict__ pz, int8_t *pid, bool has_invalid) {
     const int w = P.w, h = P.h;
@@ -402,6 +402,7 @@ __device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, 
                 carryq[i * NW + k] = (signed char)(chain_on ? (last_lbl < 0 ? -1 : last_lbl) : -1);
                 if (k == k_last) rowlastq[i] = (signed char)(last_lbl < 0 ? -1 : last_lbl);
                 Hb[i * NW + k] = hb; Vb[i * NW + k] = vb;
+                if (hb | vb) atomicOr(&rowmask[i], 1u << k);      // chunks of the row that hold claimed pixels (what the emission visits)
             }
             prev = a;
             // refill the slots just consumed: plane ids of row i+8, xyz of row i+4 (its plane ids arrived long ago)
@@ -413,15 +414,21 @@ __device__ __forceinline__ void refine2_propagate(Refine2Smem &S, unsigned *Hb, 
 
 // emission of one pass; kCount: accumulate the per-(row, model) counts, else assign positions from the prefixed table
 template <int NW, bool kReverse, bool kCount>
-__device__ __forceinline__ void refine2_emit(Refine2Smem &S, const unsigned *Hb, const unsigned *Vb, unsigned *table, int nm, const Params &P,
+__device__ __forceinline__ void refine2_emit(Refine2Smem &S, const unsigned *Hb, const unsigned *Vb, const unsigned *rowmask, unsigned *table, int nm, const Params &P,
                                              const int8_t *pid, int *pos, const int *pos_base, int pass) {
     const int w = P.w, h = P.h;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k_last = (w - 1) >> 5, lane_last = (w - 1) & 31;
     for (int i = wid; i < h; i += NW) {           // claimer row i (pass order)
         const int r = kReverse ? (h - 1 - i) : i;
-#pragma unroll
-        for (int k = 0; k < NW; ++k) {
+        // chunks that can hold a claimer of row i with a claim: a sideways target in chunk k or k + 1 of this row (the wrap target
+        // is bit 0 of the next row), a vertical target in chunk k of the next row
+        unsigned cm = rowmask[i];
+        cm |= cm >> 1;
+        if (i + 1 < h) { const unsigned m1 = rowmask[i + 1]; cm |= m1; if (kReverse && (m1 & 1u)) cm |= 1u << k_last; }
+        while (cm) {
+            const int k = __ffs(cm) - 1;
+            cm &= cm - 1u;
             // sideways targets of the claimers of chunk k: visiting index v + 1 (the wrap target is bit 0 of the next row)
             unsigned sm = Hb[i * NW + k] >> 1;
             if (k + 1 < NW) sm |= Hb[i * NW + k + 1] << 31;
@@ -479,8 +486,12 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
     const bool has_invalid = (ctl.flags & unsigned(SPX_FRAME_NONFINITE)) != 0u;
     unsigned *table = Vb + h * NW;
     const int tid = threadIdx.x;
-    volatile signed char *carryq = reinterpret_cast<volatile signed char *>(table + kRefTableCap), *rowlastq = carryq + h * NW;
-    auto reset_handover = [&]() { for (int i = tid; i < h * (NW + 1); i += NW * 32) carryq[i] = (signed char)kRefPending; };
+    unsigned *rowmask = table + kRefTableCap;         // [h]: chunks of a row with claimed pixels
+    volatile signed char *carryq = reinterpret_cast<volatile signed char *>(rowmask + h), *rowlastq = carryq + h * NW;
+    auto reset_handover = [&]() {
+        for (int i = tid; i < h * (NW + 1); i += NW * 32) carryq[i] = (signed char)kRefPending;
+        for (int i = tid; i < h; i += NW * 32) rowmask[i] = 0u;
+    };
     const size_t fo = size_t(f) * P.N;
     const float *px = B.px + fo, *py = B.py + fo, *pz = B.pz + fo;
     int8_t *pid = B.pid + fo;
@@ -495,10 +506,10 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
     __syncthreads();
 
     // ---------------- pass 1 ----------------
-    refine2_propagate<NW, false>(S, Hb, Vb, carryq, rowlastq, P, px, py, pz, pid, has_invalid);
+    refine2_propagate<NW, false>(S, Hb, Vb, rowmask, carryq, rowlastq, P, px, py, pz, pid, has_invalid);
     __threadfence_block();
     __syncthreads();
-    refine2_emit<NW, false, true>(S, Hb, Vb, table, nm, P, pid, pos, S.n0, 0);
+    refine2_emit<NW, false, true>(S, Hb, Vb, rowmask, table, nm, P, pid, pos, S.n0, 0);
     __syncthreads();
     for (int m = tid; m < nm; m += NW * 32) {     // exclusive prefix over the rows
         int run = 0;
@@ -506,7 +517,7 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
         S.cnt[0][m] = run;
     }
     __syncthreads();
-    refine2_emit<NW, false, false>(S, Hb, Vb, table, nm, P, pid, pos, S.n0, 0);
+    refine2_emit<NW, false, false>(S, Hb, Vb, rowmask, table, nm, P, pid, pos, S.n0, 0);
     __syncthreads();
 
     // ---------------- pass 2 ----------------
@@ -539,7 +550,7 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
     }
     reset_handover();
     __syncthreads();
-    refine2_propagate<NW, true>(S, Hb, Vb, carryq, rowlastq, P, px, py, pz, pid, has_invalid);
+    refine2_propagate<NW, true>(S, Hb, Vb, rowmask, carryq, rowlastq, P, px, py, pz, pid, has_invalid);
     __threadfence_block();
     __syncthreads();
     if (any_cand) {
@@ -560,12 +571,12 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
             reset_handover();
             __threadfence_block();
             __syncthreads();
-            refine2_propagate<NW, true>(S, Hb, Vb, carryq, rowlastq, P, px, py, pz, pid, has_invalid);
+            refine2_propagate<NW, true>(S, Hb, Vb, rowmask, carryq, rowlastq, P, px, py, pz, pid, has_invalid);
             __threadfence_block();
             __syncthreads();
         }
     }
-    refine2_emit<NW, true, true>(S, Hb, Vb, table, nm, P, pid, pos, S.n0, 1);
+    refine2_emit<NW, true, true>(S, Hb, Vb, rowmask, table, nm, P, pid, pos, S.n0, 1);
     __syncthreads();
     for (int m = tid; m < nm; m += NW * 32) {
         int run = 0;
@@ -573,7 +584,7 @@ __global__ void __launch_bounds__(NW * 32) k_refine2(Params P, Buffers B) {
         S.cnt[1][m] = run;
     }
     __syncthreads();
-    refine2_emit<NW, true, false>(S, Hb, Vb, table, nm, P, pid, pos, S.n0, 1);
+    refine2_emit<NW, true, false>(S, Hb, Vb, rowmask, table, nm, P, pid, pos, S.n0, 1);
     __syncthreads();
     for (int m = tid; m < nm; m += NW * 32) {
         Model &M = ctl.models[m];
