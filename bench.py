@@ -370,7 +370,7 @@ def _main(out):
     ext = api.PlaneExtractor(max_frames=max(F, frames_cap), n_streams=args.streams, **kw)
     # host threads of the library's gathered upload route: half of this rank's share of the host's cores (the library's own default
     # is half of ALL cores, which is right for one process per host only)
-    gather_threads = max(1, min(16, ((os.cpu_count() or 1) // world) // 2))
+    gather_threads = int(os.environ.get("BENCH_GATHER_THREADS", "0")) or max(1, min(16, ((os.cpu_count() or 1) // world) // 2))
     ext.set_gather_threads(gather_threads)
     if not args.profile_groups and (args.streams == 0 or args.streams > 1):
         # the per-kernel table comes from one extra profiled step in which the batch runs as ONE group (kernels back to
@@ -466,6 +466,10 @@ def _main(out):
             return time.perf_counter() - t0, r
 
         # ---- e2e: host buffers through the C ABI, copies inside the timed region; compact results ----
+        # Several ranks on one host share its cores and its memory system: the gathered route then takes from the copy engines what it
+        # saves them (2 GPUs: 187 k frames/s with 4 gather threads per rank, 190 k without; 176 k with 8), so it is the single-process setting.
+        if world > 1:
+            ext.set_upload_mode(2)
         e2e_s, res = timed_host(lambda: ext.extract_batch_compact_ptr(host.data_ptr(), F, rows, cols), args.steps)
         launches_e2e = ext.launches
         xfer = ext.transfer_bytes()   # (uploaded by copies, read in place from the pinned image, copied back) of the last step
@@ -473,17 +477,20 @@ def _main(out):
         overflow = int((res.frames["flags"] & api.SPX_FRAME_OVERFLOW != 0).sum())
         d2h_compact = res.nbytes
         # ---- the same with the sampled rows of every group through the copy engine (no host threads: last round's e2e) ----
-        ext.set_upload_mode(2)
-        e2e_rows_s, _ = timed_host(lambda: ext.extract_batch_compact_ptr(host.data_ptr(), F, rows, cols), args.steps)
-        xfer_rows = ext.transfer_bytes()
-        ext.set_upload_mode(0)
+        if world == 1:
+            ext.set_upload_mode(2)
+            e2e_rows_s, _ = timed_host(lambda: ext.extract_batch_compact_ptr(host.data_ptr(), F, rows, cols), args.steps)
+            xfer_rows = ext.transfer_bytes()
+        else:
+            e2e_rows_s, xfer_rows = e2e_s, xfer
+        ext.set_upload_mode(0 if world == 1 else 2)
         # ---- the same with 16-byte point clouds back (round 1's e2e) ----
         e2e_full_s, resf = timed_host(lambda: ext.extract_batch_ptr(host.data_ptr(), F, rows, cols), args.steps)
         xfer_full = ext.transfer_bytes()
         # ---- the same with the whole image uploaded (what a pageable caller buffer gets) ----
         ext.set_upload_mode(1)
         e2e_whole_s, _ = timed_host(lambda: ext.extract_batch_compact_ptr(host.data_ptr(), F, rows, cols), args.steps)
-        ext.set_upload_mode(0)
+        ext.set_upload_mode(0 if world == 1 else 2)
         # ---- through the C++ host adapter until every Frame field of every frame is filled ----
         adapter = None
         try:
@@ -639,7 +646,9 @@ def _main(out):
             "e2e": {"value": per_s(e2e_ms), "unit": UNIT, "h2d_bytes_per_step": xfer[0] + xfer[1],
                     "d2h_bytes_per_step": xfer[2], "ms_per_step": e2e_ms / K,
                     "h2d_copied": xfer[0], "h2d_read_in_place": xfer[1], "result_bytes": d2h_compact, "gpu_launches_per_step": launches_e2e,
-                    "host_gather_threads": gather_threads,
+                    "host_gather_threads": gather_threads if world == 1 else 0,
+                    "upload": "two routes (copy engine: sampled rows of the first groups; host threads: gathered samples of the last groups)" if world == 1
+                              else "sampled rows through the copy engine only (several ranks share the host's cores and memory system)",
                     "note": "spx_extract_batch_compact on the pinned CV_32F batch, two upload routes at once: the first frame groups' sampled rows "
                             "(every Cloud.Dis-th) go through the copy engine, one strided copy per group, while host threads inside the library "
                             "gather the organized cloud's samples (every Cloud.Dis-th row AND column) of the last groups into a pinned staging "

@@ -128,7 +128,8 @@ int spx_extract_batch(spx_ctx *ctx, const float *depth, int n_frames, int rows, 
  * (src/Frame.cc:1038-1052).  When the caller's image is page-locked (cudaHostAlloc, cudaHostRegister or
  * spx_host_register below) the library uploads only the sampled rows (1/Cloud.Dis of the bytes, one strided copy) and the
  * window sectors the border tests will read are fetched from the image over PCIe by a kernel, each once; a pageable
- * image is uploaded whole.  Float batches of 64 frames or more use a second route beside it: a pool of host threads
+ * image is uploaded whole.  Large float batches (64 frames or more and at least 200 MB of sampled rows, i.e. calls that
+ * are bound by the upload) use a second route beside it: a pool of host threads
  * inside the library copies the h x w samples themselves (1/Cloud.Dis^2 of the image; the copy engine can skip rows but
  * not columns) of the LAST frame groups of the batch into a page-locked staging buffer while the copy engine moves the
  * sampled rows of the first groups, and only those samples are uploaded for the gathered groups (138 instead of 410 KB

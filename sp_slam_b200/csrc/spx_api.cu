@@ -195,6 +195,8 @@ struct spx_ctx {
                              // upload for batches >= sparse_min_frames), 1 whole image, 2 sparse whenever possible, 3 gathered whenever possible
     int sparse_min_frames = 1;
     int gather_min_frames = 64;   // a few frames are latency bound: one strided copy of the sampled rows is the shorter path
+    size_t gather_min_bytes = size_t(200) << 20;   // ... and so is a batch whose sampled rows cross the bus in a few milliseconds: the call is
+                                  // then bound by the device (120 frames 1280x720, 147 MB: 7.1 ms with the gathered route, 6.7 without)
     int gather_threads = 0;       // 0 = half the host's hardware threads, at most 16 (spx_set_gather_threads, SPX_GATHER_THREADS)
     // automatic mode: both routes at once.  The first frame groups take the sampled-rows copy (the copy engine starts at once and
     // needs no host thread), the last `gather_share` of the batch is gathered meanwhile; mode 3 gathers every group.
@@ -1059,6 +1061,7 @@ int spx_create(const spx_config *cfg, spx_ctx **out) {
     if (const char *e = std::getenv("SPX_UPLOAD")) c->upload_mode = std::atoi(e);   // test / tuning knob (see spx_ctx::upload_mode)
     if (const char *e = std::getenv("SPX_SPARSE_MIN_FRAMES")) c->sparse_min_frames = std::atoi(e);   // tuning knob
     if (const char *e = std::getenv("SPX_GATHER_MIN_FRAMES")) c->gather_min_frames = std::atoi(e);   // tuning knob
+    if (const char *e = std::getenv("SPX_GATHER_MIN_MB")) c->gather_min_bytes = size_t(std::atoi(e)) << 20;   // tuning / test knob
     if (const char *e = std::getenv("SPX_GATHER_THREADS")) c->gather_threads = std::atoi(e);         // tuning knob (spx_set_gather_threads)
     if (const char *e = std::getenv("SPX_GATHER_SHARE")) { const double v = std::atof(e); if (v <= 1.0) c->gather_share = v; }   // tuning knob
     if (const char *e = std::getenv("SPX_STRIP_OCC")) { const int v = std::atoi(e); if (v == 3 || v == 4) c->strip_occ = v; }   // tuning knob
@@ -1339,7 +1342,8 @@ static int extract_host(spx_ctx *c, const void *depth, bool u16, float depth_map
         // float images: the samples themselves instead of the sampled rows (gathered by host threads, see GatherPool)
         // (automatic mode: for the compact call only -- with 16-byte clouds coming back the call is bound by the downloads, and the
         // gather threads' memory traffic then costs more than the smaller upload saves: 14.5 against 12.5 ms per 1000 frames)
-        if (!u16 && (c->upload_mode == 3 || (c->upload_mode == 0 && cout != nullptr && n_frames >= c->gather_min_frames))) {
+        if (!u16 && (c->upload_mode == 3 || (c->upload_mode == 0 && cout != nullptr && n_frames >= c->gather_min_frames &&
+                                             size_t(n_frames) * size_t(c->P.h) * size_t(cols) * sizeof(float) >= c->gather_min_bytes))) {
             const size_t sw = (size_t(c->P.w) + 3) & ~size_t(3);             // rows of the staging buffer start on 16 bytes (TMA)
             if ((rc = grow_pinned(c, &c->h_samp, &c->h_samp_cap, size_t(n_frames) * size_t(c->P.h) * sw)) != SPX_OK) return rc;
             if (!c->pool) c->pool = new (std::nothrow) GatherPool();

@@ -25,10 +25,9 @@ public:
         spx_set_group_callback(ctx_, &SequencePlanes::on_group, this);
         if (n_threads <= 0) n_threads = int(std::thread::hardware_concurrency()) - 1;   // the calling thread drives the device
         if (n_threads < 1) n_threads = 1;
-        // the library's gathered upload route runs on host threads of its own: it gets the cores the workers leave (at least one thread;
-        // the share of the batch that takes that route follows the thread count)
-        const int spare = int(std::thread::hardware_concurrency()) - 1 - n_threads;
-        spx_set_gather_threads(ctx_, spare < 1 ? 1 : (spare > 16 ? 16 : spare));
+        // the library's gathered upload route would run on host threads of its own; here the workers already load the host's cores and
+        // memory system (they write ~0.9 GB of clouds per 1000 frames), so the depth goes up as sampled rows through the copy engine
+        spx_set_upload_mode(ctx_, 2);
         for (int t = 0; t < n_threads; ++t) workers_.emplace_back([this] { work(); });
     }
     ~SequencePlanes() {

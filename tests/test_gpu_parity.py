@@ -529,7 +529,7 @@ def test_gathered_upload_equals_whole_image_upload(seq, realsense_frames):
     sampled rows through the copy engine, the last ones gathered meanwhile)."""
     n = 70
     d = np.ascontiguousarray(scenes.boxroom_sequence(n, start=150))
-    ext = api.PlaneExtractor(max_frames=n, n_streams=4)
+    ext = extractor_with_env({"SPX_GATHER_MIN_MB": "0"}, max_frames=n, n_streams=4)     # (automatic mode: no minimum batch size in bytes)
     ext.set_upload_mode(1)
     whole = ext.extract_batch(d)
     up_whole = ext.transfer_bytes()
@@ -563,6 +563,10 @@ def test_gathered_upload_equals_whole_image_upload(seq, realsense_frames):
         few = ext.extract_batch_compact(d[:40])
         assert ext.transfer_bytes()[0] == 40 * 160 * 640 * 4
         assert np.array_equal(few.frames["n_planes"], whole.frames["n_planes"][:40])
+        dflt = api.PlaneExtractor(max_frames=n, n_streams=4)             # default threshold: 70 frames are 29 MB of sampled rows
+        dflt.extract_batch_compact(d)
+        assert dflt.transfer_bytes()[0] == n * 160 * 640 * 4
+        dflt.close()
         # a single frame and the compact call
         ext.set_upload_mode(3)
         one = ext.extract(d[7])
