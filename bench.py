@@ -602,7 +602,7 @@ def _main(out):
         step_kernel_ms = sum(ktimes.values())
         achieved = kbytes.get(top, 0) * F / (ktimes[top] * 1e-3) / 1e9
         traffic, path_traffic = None, None
-        tpath = os.path.join(ROOT, "profiles", "r2_traffic_all.json")
+        tpath = os.path.join(ROOT, "profiles", "r5_traffic_all.json")
         if os.path.exists(tpath) and rows == ROWS and cols == COLS:
             # dram__bytes_read.sum + dram__bytes_write.sum per kernel from one ncu pass over a 1000-frame single-group step
             tj = json.load(open(tpath))
