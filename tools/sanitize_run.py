@@ -49,3 +49,25 @@ pm.update_boundary_from_result(1 % fr.mnPlaneNum, np.eye(4), 12, 0, len(f12.mvBo
 a2 = pm.associate(s1.frame(12).mvPlaneCoefficients)
 pm.close(); e4.close()
 print("next rows", [len(o) for o in outs][:4], len(r5.boundary), a[0], a2[0])
+# gathered upload route (host threads stage the samples; second tensor map; border windows fetch every row), every group gathered
+# and the mixed mode, compact results; the ROI case whose cloud width is not a multiple of four; k_refine2's data-flow hand-over
+e5 = api.PlaneExtractor(max_frames=66, n_streams=3)
+e5.set_upload_mode(3)
+e5.set_gather_threads(3)
+g1 = e5.extract_batch_compact_ptr(hp.data_ptr(), 66, 480, 640)
+g2 = e5.extract_batch_ptr(hp.data_ptr(), 66, 480, 640, copy=True)
+os.environ["SPX_GATHER_MIN_MB"] = "0"
+e6 = api.PlaneExtractor(max_frames=66, n_streams=3)
+os.environ.pop("SPX_GATHER_MIN_MB", None)
+g3 = e6.extract_batch_compact_ptr(hp.data_ptr(), 66, 480, 640)
+print("gathered", len(g1.planes), len(g2.planes), len(g3.planes), e5.transfer_bytes()[0], e6.transfer_bytes()[0])
+e5.close(); e6.close()
+pad = np.zeros((4, 482, 700), np.float32)
+pad[:, :401, :500] = dd[:4, :401, :500]
+api.host_register(pad)
+e7 = api.PlaneExtractor(max_frames=4, max_rows=401, max_cols=500, max_x=500.0, max_y=401.0)
+e7.set_upload_mode(3)
+g4 = e7.extract_batch(pad[:, :401, :500])
+print("gathered roi", len(g4.planes), e7.transfer_bytes()[0] == 4 * 134 * 168 * 4)
+e7.close()
+api.host_unregister(pad)
