@@ -1357,8 +1357,9 @@ static int extract_host(spx_ctx *c, const void *depth, bool u16, float depth_map
     } else {
         src.sparse = false;
     }
-    if ((rc = run_pipeline(c, c->d_depth, full, false, src, true, cout != nullptr)) != SPX_OK) return rc;
-    if (src.gather) c->pool->wait_idle();
+    rc = run_pipeline(c, c->d_depth, full, false, src, true, cout != nullptr);
+    if (src.gather) c->pool->wait_idle();     // (whatever happened: the host threads read the caller's image)
+    if (rc != SPX_OK) return rc;
     return fetch_groups(c, out, cout);
 }
 
